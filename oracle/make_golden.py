@@ -1,0 +1,205 @@
+"""Generate tests/golden/reference_golden.json by running the REFERENCE's own functions.
+
+TEST INFRASTRUCTURE.  Runs only where ``/root/reference`` exists (the build container); the
+output is committed so that the GPU box (which has no reference tree) can check against it.
+
+    python oracle/make_golden.py            # rewrites tests/golden/reference_golden.json
+
+Recipe: ``np.random.seed(s)`` immediately before every reference call;
+for the adv/intermediate scripts ``nEvPerLoop`` and ``data_x`` are patched in the exec'd
+namespace so that the draw count is test-sized; the stopping model is the script's own
+``simpleBethe`` (I = 19.2 keV as written) or the physical I = 19.2e-3 variant.
+The oracle reproduces every value from ``RandomState(s).standard_normal`` streams.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+
+warnings.simplefilter("ignore")
+
+
+def f(x):
+    """JSON-safe float (repr round-trips float64 exactly; inf/nan as strings)."""
+    x = float(x)
+    if np.isnan(x):
+        return "nan"
+    if np.isinf(x):
+        return "inf" if x > 0 else "-inf"
+    return x
+
+
+def fl(a):
+    return [f(v) for v in np.asarray(a, dtype=np.float64).ravel()]
+
+
+def kats():
+    ref = ref_loader.load_utilities()
+    uu, ion = ref.utilities, ref.ionStopping
+    E = np.array([250., 500., 900., 1500., 2500.])
+    En = uu.getDDneutronEnergy(E)
+    xs = uu.ddnXSinterpolator()
+    xs_in = np.array([15, 20, 25, 95, 125, 900, 1234.5, 2950, 9999, 12000.])
+    zd = uu.zeroDegreeTimingSpread()
+    zt, zw = zd.getTimesAndWeights(2500.0)
+    out = {
+        "E": fl(E),
+        "getDDneutronEnergy": fl(En),
+        "getTOF_neutron_516.625": fl(uu.getTOF(939565.0, En, 516.625)),
+        "getTOF_deuteron_1.43": fl(uu.getTOF(1.8756e+06, (1500 + E) / 2, 1.43)),
+        "dEdx_I19.2e-3": fl(ion.ionStopping.simpleBethe([1, 2, 8.565e-5, 1, 19.2e-3]).dEdx(E)),
+        "dEdx_I19.2": fl(ion.ionStopping.simpleBethe([1, 2, 8.565e-5, 1, 19.2]).dEdx(E)),
+        "dEdx_oneBD": fl(ion.ionStopping.simpleBethe([1, 2, 4 * 8.565e-5, 1, 19.2e-3]).dEdx(E)),
+        "xs_in": fl(xs_in),
+        "xs_out": fl(xs.evaluate(xs_in.copy())),
+        "xs_dense_in": fl(np.linspace(20.0, 10000.0, 2001)),
+        "xs_dense_out": fl(xs.evaluate(np.linspace(20.0, 10000.0, 2001))),
+        "beamTiming_taps": fl(uu._beamTiming_instance.timingDistribution),
+        "gaussianTiming_2.7_4_taps": fl(uu.beamTimingShape.gaussianTiming(2.7, 4).timingDistribution),
+        "zeroDeg_En2500_times": fl(zt),
+        "zeroDeg_En2500_weights": fl(zw),
+        "standoffs": {"mid": f(ref.constants.distances.tunlSSA_CsI.standoffMid),
+                      "close": f(ref.constants.distances.tunlSSA_CsI.standoffClose),
+                      "far": f(ref.constants.distances.tunlSSA_CsI.standoffFar),
+                      "tunl": f(ref.constants.distances.tunlSSA_CsI.standoff_TUNLruns)},
+    }
+    return out
+
+
+def simple():
+    ns = ref_loader.load("simpleTOFmodel")
+    np.random.seed(11)
+    fd = ns["generateModelData"]([1100, -100, 50], 10000)
+    obs = np.histogram(fd[:, 3], 25, (175, 200))[0]
+    cases = []
+    for seed, theta, nd in [(12, [1111, -110, 40], 1000000), (12, [1111, -110, 40], 1024),
+                            (13, [1090, -95, 55], 20000), (14, [1100, -100, 50], 20000),
+                            (15, [700, -100, 50], 20000), (16, [1100, -100, 99.5], 5000)]:
+        np.random.seed(seed)
+        if nd == 1000000:
+            val = ns["lnprob"](theta, obs)
+            kind = "lnprob"
+        else:
+            val = ns["lnlike"](theta, obs, nDraws=nd)
+            kind = "lnlike"
+        cases.append({"seed": seed, "theta": theta, "nDraws": nd, "kind": kind, "value": f(val)})
+    return {"obs": [int(v) for v in obs], "cases": cases}
+
+
+def adv(excitation, label):
+    ns = ref_loader.load("advIntermediateTOFmodel")
+    ref = ref_loader.load_utilities()
+    n_ev = 1024
+    ns["nEvPerLoop"] = n_ev
+    ns["data_x"] = np.repeat(ns["x_binCenters"], n_ev)
+    model = ref.ionStopping.ionStopping.simpleBethe([1, 2, 8.565e-5, 1, excitation])
+    ns["stoppingModel"] = model
+    standoff = ns["standoff"][0]
+    np.random.seed(7)
+    raw = ns["generateModelData"]([1050, .1], standoff, ns["ddnXSinstance"], model.dEdx, 1024, True)
+    obs = np.rint(ns["beamTiming"].applySpreading(raw) * 5e4)
+    cases = []
+    for seed, theta, nd in [(7, [1050, .10], 1024), (8, [1060, .11], 1024), (9, [1040, .09], 1024),
+                            (10, [1055, .12], 2048), (21, [1045.5, .105], 4096),
+                            (8, [1060, .11], 100000)]:
+        np.random.seed(seed)
+        if nd == 100000:
+            val = ns["lnprob"](theta, obs)      # default nDraws=1e5 -> 97 loops x 1024
+            kind = "lnprob"
+        else:
+            val = ns["lnlike"](theta, obs, nDraws=nd)
+            kind = "lnlike"
+        cases.append({"seed": seed, "theta": theta, "nDraws": nd, "kind": kind, "value": f(val)})
+    # raw spectra (generateModelData getPDF=True/False) for stage-level parity
+    spectra = []
+    for seed, theta in [(7, [1050, .10]), (31, [1100, .2])]:
+        np.random.seed(seed)
+        pdf = ns["generateModelData"](theta, standoff, ns["ddnXSinstance"], model.dEdx, 1024, True)
+        np.random.seed(seed)
+        cnt = ns["generateModelData"](theta, standoff, ns["ddnXSinstance"], model.dEdx, 1024, False)
+        spectra.append({"seed": seed, "theta": theta, "pdf": fl(pdf), "counts": fl(cnt)})
+    return {"label": label, "mean_excitation": excitation, "n_ev_per_loop": n_ev, "obs": fl(obs),
+            "cases": cases, "spectra": spectra}
+
+
+def sweep():
+    """adv model at the benchmark shape: 1024 draws, 2048 TOF bins on [128,256)."""
+    ns = ref_loader.load("advIntermediateTOFmodel")
+    ref = ref_loader.load_utilities()
+    ns["nEvPerLoop"] = 1024
+    ns["data_x"] = np.repeat(ns["x_binCenters"], 1024)
+    ns["tof_nBins"] = 2048
+    ns["tof_range"] = (128.0, 256.0)
+    model = ref.ionStopping.ionStopping.simpleBethe([1, 2, 8.565e-5, 1, 19.2e-3])
+    ns["stoppingModel"] = model
+    standoff = ns["standoff"][0]
+    np.random.seed(7)
+    raw = ns["generateModelData"]([1050, .1], standoff, ns["ddnXSinstance"], model.dEdx, 1024, True)
+    obs = np.rint(1e5 * ns["beamTiming"].applySpreading(raw))
+    seed = 20260101
+    thetas = np.array([1050, 0.10]) + np.array([10, 1e-2]) * np.random.RandomState(1).standard_normal((24, 2))
+    vals, pdfs = [], []
+    for th in thetas:
+        np.random.seed(seed)
+        vals.append(f(ns["lnprob"](list(th), obs)) if False else f(ns["lnlike"](list(th), obs, nDraws=1024)))
+    np.random.seed(seed)
+    pdf0 = ns["beamTiming"].applySpreading(
+        ns["generateModelData"](list(thetas[0]), standoff, ns["ddnXSinstance"], model.dEdx, 1024, True))
+    nz = np.nonzero(pdf0)[0]
+    return {"draw_seed": seed, "obs_nonzero_idx": [int(i) for i in np.nonzero(obs)[0]],
+            "obs_nonzero_val": fl(obs[np.nonzero(obs)[0]]), "thetas": [fl(t) for t in thetas],
+            "lnlike": vals, "pdf0_nonzero_idx": [int(i) for i in nz], "pdf0_nonzero_val": fl(pdf0[nz])}
+
+
+def simult(full=True):
+    ns = ref_loader.load("simultFit")
+    theta = [1878.4, 850, 170, 0.5, 3e4, 2e4, 2e4, 4e4, 4e4]
+    out = {"theta": theta, "cases": []}
+    for n_ev, n_draws, seed_obs, seed_eval in ([(1000, 4000, 3, 4), (1000, 3500, 5, 6)] +
+                                               ([(50000, 200000, 3, 4)] if full else [])):
+        ns["nEvPerLoop"] = n_ev
+        np.random.seed(seed_obs)
+        obs = []
+        for r in range(5):
+            p = theta[:4] + [theta[4 + r]]
+            obs.append(np.rint(ns["generateModelData"](p, ns["standoffs"][r], ns["tof_range"][r],
+                                                       ns["tofRunBins"][r], ns["ddnXSinstance"],
+                                                       ns["stoppingModel"].dEdx, ns["beamTiming"],
+                                                       n_draws, True)))
+        np.random.seed(seed_eval)
+        val = ns["lnprob"](theta, [o.copy() for o in obs], ns["standoffs"], ns["tof_range"],
+                           ns["tofRunBins"], n_draws)
+        out["cases"].append({"n_ev_per_loop": n_ev, "n_draws": n_draws, "seed_obs": seed_obs,
+                             "seed_eval": seed_eval, "obs": [fl(o) for o in obs], "lnprob": f(val)})
+    return out
+
+
+def main():
+    gold = {
+        "_about": "values produced by the unmodified reference functions via oracle/ref_loader.py; "
+                  "numpy %s" % np.__version__,
+        "kat": kats(),
+        "simple": simple(),
+        "adv_as_written": adv(19.2, "I=19.2 keV as written (adv:94)"),
+        "adv_physical": adv(19.2e-3, "I=19.2e-3 keV (physical)"),
+        "sweep": sweep(),
+        "simult": simult(full="--quick" not in sys.argv),
+    }
+    path = os.path.join(ROOT, "tests", "golden", "reference_golden.json")
+    with open(path, "w") as fh:
+        json.dump(gold, fh, indent=0, separators=(",", ":"))
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

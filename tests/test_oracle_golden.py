@@ -1,0 +1,163 @@
+"""Pin the CPU oracle to values produced by the reference's own functions
+(tests/golden/reference_golden.json, made by oracle/make_golden.py)."""
+import math
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import tof_oracle as O
+from conftest import parse_floats
+
+warnings.simplefilter("ignore")
+
+
+def rel(a, b):
+    if a == b:
+        return 0.0
+    if not (math.isfinite(a) and math.isfinite(b)):
+        return float("inf")
+    return abs(a - b) / max(abs(a), abs(b))
+
+
+def test_kat_kinematics_and_stopping(golden):
+    k = golden["kat"]
+    E = parse_floats(k["E"])
+    En = O.getDDneutronEnergy(E)
+    assert np.array_equal(En, parse_floats(k["getDDneutronEnergy"]))
+    assert np.array_equal(O.getTOF(O.M_NEUTRON, En, 516.625), parse_floats(k["getTOF_neutron_516.625"]))
+    assert np.array_equal(O.getTOF(O.M_DEUTERON, (1500 + E) / 2, 1.43), parse_floats(k["getTOF_deuteron_1.43"]))
+    for key, mat in [("dEdx_I19.2e-3", (1, 2, 8.565e-5, 19.2e-3)), ("dEdx_I19.2", (1, 2, 8.565e-5, 19.2)),
+                     ("dEdx_oneBD", (1, 2, 4 * 8.565e-5, 19.2e-3))]:
+        sb = O.SimpleBethe([mat])
+        assert np.array_equal(sb.dEdx(E), parse_floats(k[key])), key
+        (A, B), = sb.reduced()
+        np.testing.assert_allclose(-(A / E) * np.log(B * E), parse_floats(k[key]), rtol=2e-14)
+    assert O.STANDOFF_MID == k["standoffs"]["mid"] and O.STANDOFF_CLOSE == k["standoffs"]["close"]
+    assert O.STANDOFF_FAR == k["standoffs"]["far"] and O.STANDOFF_TUNL == k["standoffs"]["tunl"]
+
+
+def test_kat_xs_and_timing(golden):
+    k = golden["kat"]
+    xs = O.DDNXS()
+    assert np.array_equal(xs.evaluate(parse_floats(k["xs_in"])), parse_floats(k["xs_out"]))
+    assert np.array_equal(xs.evaluate(parse_floats(k["xs_dense_in"])), parse_floats(k["xs_dense_out"]))
+    assert np.array_equal(O.beam_timing_taps(), parse_floats(k["beamTiming_taps"]))
+    assert np.array_equal(O.gaussian_timing_taps(2.7), parse_floats(k["gaussianTiming_2.7_4_taps"]))
+    zt, zw = O.ZeroDegreeTimingSpread().getTimesAndWeights(2500.0)
+    assert np.array_equal(zt, parse_floats(k["zeroDeg_En2500_times"]))
+    assert np.array_equal(zw, parse_floats(k["zeroDeg_En2500_weights"]))
+
+
+def test_simple_model_goldens(golden, pf):
+    g = golden["simple"]
+    obs = np.array(g["obs"], dtype=np.float64)
+    m = O.SimpleModel()
+    for c in g["cases"]:
+        if c["nDraws"] > 100000:
+            continue  # the 1e6-draw case runs in test_simple_model_full_size
+        rs = np.random.RandomState(c["seed"])
+        u = rs.random_sample(c["nDraws"])
+        z = rs.standard_normal(c["nDraws"])
+        got = m.lnlike(c["theta"], obs, u, z)
+        want = pf(c["value"])
+        assert rel(got, want) <= 1e-13 or (math.isnan(got) and math.isnan(want)), (c, got)
+
+
+def test_simple_model_full_size(golden, pf):
+    g = golden["simple"]
+    obs = np.array(g["obs"], dtype=np.float64)
+    c = [c for c in g["cases"] if c["nDraws"] == 1000000][0]
+    rs = np.random.RandomState(c["seed"])
+    u = rs.random_sample(c["nDraws"])
+    z = rs.standard_normal(c["nDraws"])
+    assert rel(O.SimpleModel().lnprob(c["theta"], obs, u, z), pf(c["value"])) <= 1e-13
+
+
+@pytest.mark.parametrize("key", ["adv_as_written", "adv_physical"])
+def test_adv_model_goldens(golden, pf, key):
+    g = golden[key]
+    obs = parse_floats(g["obs"])
+    xs = O.DDNXS()
+    exact = 0
+    cases = [c for c in g["cases"] if c["nDraws"] <= 4096]
+    for c in cases:
+        nd = c["nDraws"]
+        m = O.adv_model(0, mean_excitation=g["mean_excitation"], n_ev_per_loop=g["n_ev_per_loop"], n_samples=nd)
+        z = np.random.RandomState(c["seed"]).standard_normal(m.n_loops * m.n_ev_per_loop)
+        got = m.lnlike(c["theta"], obs, z, xs)
+        want = pf(c["value"])
+        # the reference's LSODA runs at rtol~1.5e-8, the oracle's RK4 is accurate to ~1e-12: a draw
+        # within that distance of an E-bin edge can flip one integer cell count (~1e-5 relative).
+        assert rel(got, want) <= 1e-4, (c, got)
+        exact += rel(got, want) <= 1e-12
+    assert exact >= len(cases) - 1
+    for s in g["spectra"]:
+        m = O.adv_model(0, mean_excitation=g["mean_excitation"], n_ev_per_loop=1024, n_samples=1024)
+        z = np.random.RandomState(s["seed"]).standard_normal(1024)
+        assert np.array_equal(m.raw_tof(s["theta"], z, xs, density=False), parse_floats(s["counts"]))
+        np.testing.assert_allclose(m.raw_tof(s["theta"], z, xs, density=True), parse_floats(s["pdf"]), rtol=1e-14)
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("key", ["adv_as_written", "adv_physical"])
+def test_adv_model_default_ndraws(golden, pf, key):
+    """lnprob at the script's default nDraws=1e5 (97 loops x 1024): single-count flips allowed."""
+    g = golden[key]
+    obs = parse_floats(g["obs"])
+    c = [c for c in g["cases"] if c["nDraws"] == 100000][0]
+    m = O.adv_model(0, mean_excitation=g["mean_excitation"], n_ev_per_loop=1024, n_samples=100000)
+    z = np.random.RandomState(c["seed"]).standard_normal(97 * 1024)
+    got = m.lnprob(c["theta"], obs, z)
+    assert rel(got, pf(c["value"])) <= 5e-6, got
+
+
+def test_sweep_shape_goldens(golden, pf):
+    g = golden["sweep"]
+    m = O.sweep_model()
+    obs = np.zeros(2048)
+    obs[g["obs_nonzero_idx"]] = parse_floats(g["obs_nonzero_val"])
+    z = np.random.RandomState(g["draw_seed"]).standard_normal(1024)
+    xs = O.DDNXS()
+    n_exact = 0
+    for th, want in zip(g["thetas"], g["lnlike"]):
+        got = m.lnlike(th, obs, z, xs)
+        want = pf(want)
+        if got == want or rel(got, want) <= 1e-12:
+            n_exact += 1
+        else:
+            assert math.isfinite(got) == math.isfinite(want)
+    assert n_exact >= len(g["thetas"]) - 1
+    pdf0 = m.model_pdf(g["thetas"][0], z, xs)
+    want0 = np.zeros(2048)
+    want0[g["pdf0_nonzero_idx"]] = parse_floats(g["pdf0_nonzero_val"])
+    np.testing.assert_allclose(pdf0, want0, rtol=1e-13, atol=0)
+
+
+def test_simult_goldens_small(golden, pf):
+    g = golden["simult"]
+    for c in g["cases"]:
+        if c["n_draws"] > 10000:
+            continue
+        m = O.SimultModel(n_ev_per_loop=c["n_ev_per_loop"], n_samples=c["n_draws"])
+        obs = [parse_floats(o) for o in c["obs"]]
+        # observables themselves: regenerate through the oracle with the obs seed
+        draws = O.GlobalStateDraws(np.random.RandomState(c["seed_obs"]))
+        th = g["theta"]
+        for r in range(5):
+            ev = m.model(th[:4] + [th[4 + r]], r, draws)
+            assert np.abs(np.rint(ev) - obs[r]).max() <= 1.0, r
+        draws = O.GlobalStateDraws(np.random.RandomState(c["seed_eval"]))
+        got = m.lnprob(th, obs, draws)
+        assert rel(got, pf(c["lnprob"])) <= 1e-4, (got, c["lnprob"])
+
+
+@pytest.mark.slow
+def test_simult_golden_full(golden, pf):
+    g = golden["simult"]
+    c = [c for c in g["cases"] if c["n_draws"] == 200000][0]
+    m = O.SimultModel()
+    obs = [parse_floats(o) for o in c["obs"]]
+    draws = O.GlobalStateDraws(np.random.RandomState(c["seed_eval"]))
+    got = m.lnprob(g["theta"], obs, draws)
+    assert rel(got, pf(c["lnprob"])) <= 1e-4, (got, c["lnprob"])

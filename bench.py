@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the lnprob hot path: walker lnprob evaluations / second, adv TOF model.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]    # CPU arm: the oracle port on host cores
+
+Workload (BASELINE.json configs[4] / SURVEY.md 8d, fits one GPU): adv model, 262144 walkers x 2048 TOF
+bins x 1024 Monte-Carlo draws, synthetic observables.  One *step* is one ensemble MCMC step = two
+red/blue half-steps = 262144 lnprob evaluations (propose -> forward model + likelihood -> accept
+-> all-gather of the updated half when N > 1).  Walkers are sharded over ranks (strong scaling:
+the ensemble size is fixed by the named config).
+
+Prints ONE JSON line (rank 0).  ``value`` is device-resident throughput; ``e2e`` is the same metric
+through the reference-facing host API (`TofLnProb.batch` = C-ABI `tof_lnprob_batch` with HOST buffers,
+host<->device copies inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_WALKERS = 262144
+N_DRAWS = 1024
+N_TOF_BINS = 2048
+THETA_STAR = (1050.0, 0.10)
+DRAW_SEED = 20260101
+
+# algorithmic FP64 work per evaluation, SURVEY.md 8(d):  F = 174*D*X + 14*X*E + 26*E + (31+2K)*T
+FLOP_PER_EVAL = 174 * N_DRAWS * 100 + 14 * 100 * 240 + 26 * 240 + (31 + 2 * 16) * N_TOF_BINS
+BYTES_PER_EVAL = 8 * (2 + 1)   # theta in, lnprob out
+NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
+
+
+def workload(om_mod):
+    """Synthetic inputs of the named shape, produced with the oracle (checker side)."""
+    om = om_mod.sweep_model()
+    z = np.random.RandomState(DRAW_SEED).standard_normal(N_DRAWS)
+    zstar = np.random.RandomState(7).standard_normal(N_DRAWS)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        obs = np.rint(1e5 * om.model_pdf(list(THETA_STAR), zstar))
+    thetas = np.array(THETA_STAR) + np.array([10, 1e-2]) * np.random.RandomState(1).standard_normal((N_WALKERS, 2))
+    thetas[:, 0] = np.clip(thetas[:, 0], 1000.0 + 1e-6, 2600.0 - 1e-6)   # into the prior (adv:81-82)
+    thetas[:, 1] = np.clip(thetas[:, 1], 0.02 + 1e-9, 0.5 - 1e-9)
+    return om, z, obs, thetas
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(z, obs):
+    from oracle import tof_oracle as O
+    warnings.simplefilter("ignore")
+    _W["m"] = O.sweep_model()
+    _W["xs"] = O.DDNXS()
+    _W["z"], _W["obs"] = z, obs
+
+
+def _cpu_eval(theta):
+    return float(_W["m"].lnprob(theta, _W["obs"], _W["z"], _W["xs"]))
+
+
+def cpu_rate(z, obs, thetas, procs, per_proc, chunksize=None):
+    """Evaluations/s of the oracle through a process pool (emcee `threads=P`, adv:300-302)."""
+    import multiprocessing as mp
+    n = procs * per_proc
+    sample = [list(t) for t in thetas[:n]]
+    if procs == 1:
+        _cpu_init(z, obs)
+        _cpu_eval(sample[0])
+        t0 = time.perf_counter()
+        for t in sample:
+            _cpu_eval(t)
+        return n / (time.perf_counter() - t0)
+    with mp.get_context("fork").Pool(procs, initializer=_cpu_init, initargs=(z, obs)) as pool:
+        pool.map(_cpu_eval, sample[:procs])                       # warm-up: imports, first call
+        t0 = time.perf_counter()
+        if chunksize:
+            list(pool.imap(_cpu_eval, sample, chunksize=chunksize))
+        else:
+            pool.map(_cpu_eval, sample)
+        return n / (time.perf_counter() - t0)
+
+
+def run_cpu_baseline():
+    """The `cpu_baseline` object of the GPU arm: serial, process pool (emcee threads=P) and an
+    MPI-pool-shaped task farm, each on a bounded sample (~10-30 s of CPU work in total)."""
+    from oracle import tof_oracle as O
+    om, z, obs, thetas = workload(O)
+    procs = os.cpu_count() or 1
+    serial = cpu_rate(z, obs, thetas, 1, 48)
+    pooled = cpu_rate(z, obs, thetas, procs, 24)
+    mpi_like = cpu_rate(z, obs, thetas, max(procs - 1, 1), 24, chunksize=1) if procs > 1 else serial
+    print(json.dumps({
+        "value": pooled, "unit": "evals/s", "cores": procs, "kind": "port",
+        "sample": "%d evaluations (24 per process) of the same workload, numpy oracle" % (24 * procs),
+        "serial_evals_per_s": serial, "mpi_pool_emulation_evals_per_s": mpi_like,
+        "mpi_pool_emulation": "1 master + %d workers, one task per message (multiprocessing imap, chunksize=1); "
+                              "mpi4py is not installed" % max(procs - 1, 1)}))
+    return 0
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import tof_oracle as O
+    om, z, obs, thetas = workload(O)
+    procs = os.cpu_count() or 1
+    per_proc = 12
+    rates = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_rate(z, obs, thetas[i * procs * per_proc:], procs, per_proc)
+        if i >= args.warmup:
+            rates.append(r)
+    value = statistics.mean(rates)
+    sample = "%d evaluations per step (%d per process x %d processes) of the %d-walker workload" % (
+        procs * per_proc, per_proc, procs, N_WALKERS)
+    line = {
+        "impl": "reference", "metric": "walker lnprob evals/sec (adv TOF model)", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * procs * per_proc / value, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "adv TOF model sweep: %d walkers x %d TOF bins x %d MC draws" % (N_WALKERS, N_TOF_BINS, N_DRAWS),
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Polls SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.sm_max = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import mcmctoffitting_b200 as M
+    from mcmctoffitting_b200.ensemble import EnsembleSampler
+    from oracle import tof_oracle as O     # checker side only: builds the synthetic observables / CPU baseline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    om, z, obs, thetas = workload(O)
+    cfg = M.config.sweep()
+    fn = M.make_lnprob(cfg, obs, z, device=local_rank, sort_draws=True)
+    model = fn.model
+    sampler = EnsembleSampler(N_WALKERS, 2, fn, seed=1234, store_chain=False)
+
+    pos = torch.from_numpy(thetas).to(device)
+    lp = sampler.initial_lnprob(pos)
+    torch.cuda.synchronize()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = model.stats()["kernel_launches"]
+    for _ in range(args.warmup):
+        sampler.run_device(pos, lp, 1)
+    barrier()
+    launches_warm = model.stats()["kernel_launches"]
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    model.set_timing(True)
+    kernel_ms = []
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()                      # L2 flush between timed steps, outside the event bracket
+        starts[i].record()
+        sampler.run_device(pos, lp, 1)
+        stops[i].record()
+        stops[i].synchronize()
+        kernel_ms.append(model.last_kernel_ms())   # the second half-step's model kernel
+    barrier()
+    model.set_timing(False)
+    clock_info = clocks.finish()
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    launches_timed = model.stats()["kernel_launches"] - launches_warm
+    value = N_WALKERS * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host API (HOST buffers in, HOST lnprob out) -------------------------------
+    per_rank = N_WALKERS // world
+    host_thetas = np.ascontiguousarray(thetas[rank * per_rank:(rank + 1) * per_rank])
+    half = per_rank // 2
+    fn.batch(host_thetas[:half])
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        fn.batch(host_thetas[:half])       # one call per half-ensemble, as emcee's _get_lnprob does
+        fn.batch(host_thetas[half:])
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = N_WALKERS * e2e_steps / float(e2e_s.item())
+
+    finite_frac = float(torch.isfinite(lp).double().mean().item())
+
+    if rank == 0:
+        fp64_peak = model.measure_fp64_peak()
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        k_ms = statistics.mean(kernel_ms)
+        evals_per_launch = N_WALKERS // 2 // world
+        achieved = evals_per_launch * FLOP_PER_EVAL / (k_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+            "traffic": None,
+            "kernel": "adv_lnprob_kernel", "kernel_ms": k_ms, "evals_per_launch": evals_per_launch,
+            "flop_per_eval": FLOP_PER_EVAL, "peak_source": "DFMA microbenchmark run in this process (tof_measure_fp64_peak)",
+            "nominal_fp64_tflops": NOMINAL_FP64_TFLOPS,
+            "hbm": {"achieved_gbs": evals_per_launch * BYTES_PER_EVAL / (k_ms * 1e-3) / 1e9,
+                    "peak_gbs": peaks.get("hbm_gbs"), "bytes_per_eval": BYTES_PER_EVAL},
+            "note": "path is FP64-pipe bound (SURVEY.md 8d): neither HBM nor tensor cores limit it",
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            # a fresh interpreter: no fork of a process that holds a CUDA context
+            import subprocess
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-baseline"], stdout=subprocess.PIPE,
+                                 text=True, timeout=600)
+            cpu = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else {"error": "rc=%d" % out.returncode}
+        line = {
+            "metric": "walker lnprob evals/sec (adv TOF model)", "value": value, "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "adv TOF model sweep: %d walkers x %d TOF bins x %d MC draws" % (N_WALKERS, N_TOF_BINS, N_DRAWS),
+                       "step": "one ensemble MCMC step = 2 red/blue half-steps = %d lnprob evaluations" % N_WALKERS,
+                       "parallelism": "walkers sharded over %d rank(s); all_gather of the updated half per half-step" % world,
+                       "ode": "rk4 x%d per x-interval" % cfg.ode_substeps, "threads_per_cta": model.stats()["threads"],
+                       "l2": "flushed between timed steps (256 MiB memset outside the event bracket)",
+                       "finite_lnprob_fraction": finite_frac},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": N_WALKERS * 2 * 8,
+                    "d2h_bytes_per_step": N_WALKERS * 8},
+            "gpu_launches": launches_timed, "clocks": clock_info,
+            "kernel_stats": model.stats(),
+        }
+        print(json.dumps(line))
+    barrier()
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.cpu_baseline:
+        return run_cpu_baseline()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,193 @@
+/*
+ * tofgpu.h -- C ABI of the B200-native lnprob path for neutron time-of-flight MCMC fitting.
+ *
+ * Drop-in boundary for ONE path of gcrich/mcmcTOFfitting: the per-walker forward model +
+ * log-likelihood (`lnprob`) that emcee evaluates on every step.  The reference is pure Python,
+ * so there is no existing FFI; every entry point cites the reference function(s) whose work it
+ * replaces (paths relative to the reference tree).  The reference-side binding is the ctypes
+ * stub shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * tof_status; the message is available from tof_last_error().  All floating-point data is
+ * IEEE-754 binary64.  The library never writes caller memory except the documented outputs.
+ * There is no CPU fallback: tof_create() fails when no sm_100 device is present.
+ */
+#ifndef TOFGPU_H
+#define TOFGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOF_ABI_VERSION 1
+
+#define TOF_MAX_DIM 16       /* parameters per walker (reference max: 9, simultFit.py:444-448) */
+#define TOF_MAX_RUNS 8       /* simultaneous standoff runs (reference max: 5, simultFit.py:127-131) */
+#define TOF_MAX_MATERIALS 8  /* simpleBethe material list (ionStopping.py:71-76) */
+
+typedef enum tof_status {
+    TOF_OK = 0,
+    TOF_ERR_INVALID = -1,    /* bad argument / inconsistent config */
+    TOF_ERR_NO_DEVICE = -2,  /* no CUDA device of compute capability 10.x */
+    TOF_ERR_CUDA = -3,       /* CUDA runtime error, see tof_last_error */
+    TOF_ERR_STATE = -4,      /* observables / draws not set */
+    TOF_ERR_CAPACITY = -5    /* configuration does not fit the device (shared memory) */
+} tof_status;
+
+typedef enum tof_model_kind {
+    TOF_MODEL_SIMPLE = 1, /* tests/simpleTOFmodel.py:57-120 (and mpiTOFmodel.py:40-128)        */
+    TOF_MODEL_ADV = 2,    /* tests/advIntermediateTOFmodel.py:115-199 = intermediateTOFmodel.py */
+    TOF_MODEL_SIMULT = 3  /* tests/simultFit.py:223-300, 380-469                                */
+} tof_model_kind;
+
+typedef enum tof_ode_mode {
+    TOF_ODE_RK4 = 0,   /* classical RK4, ode_substeps per x-interval (the oracle's scheme)      */
+    TOF_ODE_RANGE = 1  /* range-energy table of the autonomous Bethe ODE staged in shared memory */
+} tof_ode_mode;
+
+/* spectrum stages returned by tof_model_batch */
+typedef enum tof_stage {
+    TOF_STAGE_COUNTS = 0, /* np.histogram(tofs, weights=cell counts)          adv:159 density=False */
+    TOF_STAGE_PDF = 1,    /* ... density=True                                 adv:159-160          */
+    TOF_STAGE_SPREAD = 2  /* beamTiming.applySpreading(pdf) [x scaleFactor]   adv:173, simultFit:300 */
+} tof_stage;
+
+/*
+ * Everything the reference scripts hold as module-level literals / objects, flattened.
+ * Tables are HOST pointers, copied by tof_create (the caller may free them afterwards).
+ */
+typedef struct tof_config {
+    int32_t abi_version;   /* = TOF_ABI_VERSION */
+    int32_t model;         /* tof_model_kind */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t ode_mode;      /* tof_ode_mode */
+    int32_t ode_substeps;  /* RK4 steps per x-interval (>=1) */
+    int32_t ode_from_zero; /* 0: E(x_0)=E0 like odeint (adv:129); 1: E(0)=E0 like dopri5 (simultFit.py:256) */
+    int32_t prior_strict;  /* 1: lo < v < hi (adv:187); 0: reject v<lo or v>hi (simultFit.py:440) */
+    int32_t nan_to_neginf; /* 1: NaN lnprob -> -inf (simultFit.py:463-468); 0: NaN is returned */
+    int32_t ndim;          /* parameters per walker */
+    int32_t n_runs;        /* 1 for simple/adv; 5 in simultFit */
+    int32_t x_bins;        /* adv:66 */
+    int32_t e_bins;        /* adv:56 */
+    int32_t n_taps;        /* timing-response taps, 16 for beamTimingShape (utilities.py:247-262) */
+    int32_t n_zero_deg;    /* 0-degree detector sub-times per cell; 0 = off, 10 in simultFit (utilities.py:161) */
+    int32_t n_materials;   /* Bethe materials */
+    int32_t n_xs;          /* cross-section data points = spline breakpoints (61, utilities.py:338-409) */
+    int64_t n_samples;     /* the multiplier in np.rint(dataHist * nSamples) (adv:146) */
+    int64_t n_ev_per_loop; /* adv:76 / simultFit.py:178; draws per run = n_loops * n_ev_per_loop */
+    int64_t n_loops;       /* adv:126 / simultFit.py:239 */
+    double x_min, x_max;   /* adv:67-68 */
+    double e_min, e_max;   /* adv:57-58 */
+    double speed_of_light; /* constants.py:13 */
+    double mass_deuteron;  /* constants.py:22 */
+    double mass_neutron;   /* constants.py:23 */
+    double mass_he3;       /* constants.py:25 */
+    double q_ddn;          /* constants.py:93 */
+    double cell_length;    /* constants.py:44 */
+    double simple_neutron_base; /* simple model: cellToZero (constants.py:43, simple:66) */
+    /* simpleBethe reduced to dE/dx = -(1/E) * sum_k A_k * ln(B_k * E)  (ionStopping.py:78-97) */
+    double bethe_A[TOF_MAX_MATERIALS];
+    double bethe_B[TOF_MAX_MATERIALS];
+    double prior_lo[TOF_MAX_DIM];
+    double prior_hi[TOF_MAX_DIM];
+    int32_t tof_bins[TOF_MAX_RUNS]; /* constants.py:105 */
+    double tof_min[TOF_MAX_RUNS];   /* constants.py:107 */
+    double tof_max[TOF_MAX_RUNS];   /* constants.py:106 */
+    const double *x_centers;      /* [x_bins]            adv:71-73 */
+    const double *e_centers;      /* [e_bins]            adv:61-63 */
+    const double *neutron_speed;  /* [e_bins]  c*sqrt(2*En_j/m_n), En_j = getDDneutronEnergy(e_centers) adv:100,110 */
+    const double *neutron_dist;   /* [n_runs][x_bins]    adv:153-155 / simultFit.py:290-291 */
+    const double *xs_breaks;      /* [n_xs]              utilities.py:338-346 */
+    const double *xs_coefs;       /* [n_xs-1][4] power basis, highest order first, about xs_breaks[i] */
+    const double *taps;           /* [n_taps]            utilities.py:262 */
+    const double *zero_deg_times;   /* [e_bins][n_zero_deg] utilities.py:185 */
+    const double *zero_deg_weights; /* [e_bins][n_zero_deg] utilities.py:188-190 */
+} tof_config;
+
+typedef struct tof_ctx tof_ctx;
+
+/* Build a context on cfg->device: copies tables, sizes kernels.  Replaces the module-level
+ * setup of the model scripts (adv:44-100; simultFit.py:121-205). */
+int tof_create(const tof_config *cfg, tof_ctx **out);
+void tof_destroy(tof_ctx *ctx);
+
+/* Last error text for ctx (or for the failed tof_create when ctx == NULL). */
+const char *tof_last_error(const tof_ctx *ctx);
+
+/* Observed TOF histogram of one run: the `observables` kwarg of lnprob (adv:300-302;
+ * simultFit.py:713-718).  Copied; the 0 -> 1 substitution of simultFit.py:391-392 is applied to
+ * the private copy only. */
+int tof_set_observables(tof_ctx *ctx, int run, const double *counts, int nbins);
+
+/* Explicit Monte-Carlo draws replacing the reference's global np.random stream.
+ *   stream 0: standard normals z[n] (adv:128; simple:64; simultFit.py:244), n = n_loops*n_ev_per_loop
+ *   stream 1: simple model: uniforms u[n] in [0,1) (simple:62);
+ *             simult model: replacement normals for the E0<=0 rejection loop (simultFit.py:245-252)
+ * Host pointers; copied to the device. */
+int tof_set_draws(tof_ctx *ctx, int run, int stream, const double *values, int64_t n);
+
+/* lnprob for n walkers: theta[n][ndim] row-major -> out[n].  HOST buffers; the call copies in,
+ * launches, copies out and synchronises.  Replaces n calls of lnprob (adv:191-199, simple:112-120,
+ * simultFit.py:444-469), i.e. one emcee `_get_lnprob` map over a half-ensemble. */
+int tof_lnprob_batch(tof_ctx *ctx, const double *theta, int64_t n, double *out);
+
+/* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t, NULL = default stream). */
+int tof_lnprob_batch_device(tof_ctx *ctx, const double *d_theta, int64_t n, double *d_out, void *stream);
+
+/* Model spectra for n parameter vectors (HOST buffers): spectra[n][tof_bins[run]] at `stage`.
+ * Replaces generateModelData (adv:115-161; simultFit.py:223-300) for parity checks and
+ * posterior-predictive generation. */
+int tof_model_batch(tof_ctx *ctx, const double *theta, int64_t n, int run, int stage, double *spectra);
+
+/* Integer (x, E) cell counts drawHist2d (adv:146; simultFit.py:283): counts[n][x_bins][e_bins]. */
+int tof_cell_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run, int64_t *counts);
+
+/* ---- ensemble driver: emcee 2.x EnsembleSampler stretch move (a = 2), red/blue halves -------- */
+
+/* Propose for a half-ensemble (DEVICE buffers, async on stream):
+ *   q[i] = c[j] - zz*(c[j] - s[i]),  zz = ((a-1)*U + 1)^2 / a,  j = randint(n_comp)
+ * Counter-based Philox keyed by (seed, step, half, global walker index) so that the chain does not
+ * depend on how walkers are sharded over GPUs.  s: [n][ndim] current positions of the slice whose
+ * first walker has global index walker0; comp: [n_comp][ndim] the complementary half.
+ * Outputs q[n][ndim], log_zz[n] = (ndim-1)*ln zz. */
+int tof_stretch_propose(tof_ctx *ctx, const double *d_s, int64_t n, int64_t walker0, const double *d_comp,
+                        int64_t n_comp, double a, uint64_t seed, int64_t step, int half, double *d_q,
+                        double *d_log_zz, void *stream);
+
+/* Accept/reject in place: accept when log_zz + new_lnprob - lnprob > ln U.  Updates s, lnprob and
+ * the per-walker acceptance counters n_accept[n] (may be NULL). */
+int tof_stretch_accept(tof_ctx *ctx, double *d_s, double *d_lnprob, int64_t n, int64_t walker0,
+                       const double *d_q, const double *d_new_lnprob, const double *d_log_zz,
+                       uint64_t seed, int64_t step, int half, int64_t *d_n_accept, void *stream);
+
+/* ---- diagnostics ----------------------------------------------------------------------------- */
+typedef struct tof_stats {
+    int64_t kernel_launches; /* kernels launched by this context since creation */
+    int64_t evaluations;     /* walker lnprob evaluations issued */
+    int64_t nan_results;     /* NaN lnprob values mapped to -inf (nan_to_neginf) -- updated by tof_lnprob_batch only */
+    int32_t sm_count;
+    int32_t smem_bytes;      /* dynamic shared memory of the main model kernel */
+    int32_t threads;         /* threads per CTA of the main model kernel */
+    int32_t ctas_per_sm;     /* resident CTAs per SM of the main model kernel */
+} tof_stats;
+int tof_get_stats(const tof_ctx *ctx, tof_stats *out);
+
+/* Device time (ms, CUDA events on the launching stream) of the model kernel(s) of the most recent
+ * tof_lnprob_batch / tof_lnprob_batch_device call made with timing enabled. */
+int tof_set_timing(tof_ctx *ctx, int enabled);
+int tof_last_kernel_ms(tof_ctx *ctx, float *ms);
+
+/* Peak FP64 FMA rate of the device measured with a register-resident DFMA loop (TFLOP/s):
+ * the roofline denominator for this FP64-pipe-bound path. */
+int tof_measure_fp64_peak(tof_ctx *ctx, double *tflops);
+
+int tof_abi_version(void);
+/* sizeof(tof_config) as compiled, so that FFI struct mirrors can be checked at load time. */
+int tof_sizeof_config(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOFGPU_H */

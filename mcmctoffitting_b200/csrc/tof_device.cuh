@@ -1,0 +1,170 @@
+// Device-side building blocks shared by the model kernels (sm_100a).
+//
+// Everything that feeds an integer decision (a histogram bin, np.rint) is written with explicit
+// round-to-nearest intrinsics in the reference's operation order, so that those decisions are
+// bit-identical to numpy's; everything else may contract to FMA.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/tofgpu.h"
+
+namespace tof {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- tables in device memory ------------------------------------------------------------------
+struct DevModel {
+    int model, ode_mode, ode_substeps, ode_from_zero, prior_strict, nan_to_neginf;
+    int ndim, n_runs, x_bins, e_bins, n_taps, conv_shift, n_zero_deg, n_materials, n_xs;
+    long long n_samples, n_ev_per_loop, n_loops, n_draws;
+    double x_min, x_max, e_min, e_max;
+    double c, m_d, m_n, m_he3, q_ddn, cell_length, simple_neutron_base;
+    double bethe_A[TOF_MAX_MATERIALS], bethe_B[TOF_MAX_MATERIALS];
+    double prior_lo[TOF_MAX_DIM], prior_hi[TOF_MAX_DIM];
+    const double *x_centers, *e_centers, *neutron_speed, *xs_breaks, *xs_coefs, *taps, *zd_times, *zd_weights;
+    const unsigned char *xs_lut;
+    int xs_lut_n;
+    double xs_lut_lo, xs_lut_inv;
+    // range-energy table (TOF_ODE_RANGE)
+    const double *rng_coefs;  // [rng_n][RNG_ORDER+1]
+    int rng_n;
+    double rng_r0, rng_inv_dr, rng_rmax, rng_sign;
+};
+
+struct DevRun {
+    int tof_bins;
+    double tof_min, tof_max;
+    const double *neutron_dist;  // [x_bins]
+    const double *z;             // stream 0
+    long long n_z;
+    const double *z1;            // stream 1
+    long long n_z1;
+    const double *obs;           // [tof_bins] (private copy, simult: 0 -> 1 applied)
+    const int *obs_nz_idx;       // compacted bins with obs != 0
+    const double *obs_nz_val;
+    int n_obs_nz;
+};
+
+// ---- reductions --------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+    return v;
+}
+
+// Sum over the CTA, result broadcast to every thread.  scratch: >= 33 elements of T in smem.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T *scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        T t = (lane < nw) ? scratch[lane] : T(0);
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+// ---- numpy-compatible uniform binning ------------------------------------------------------------
+// np.linspace(lo, hi, n+1)[k]: arange(k)*step + start with separately rounded mul and add, last
+// element forced to `hi` (numpy/_core/function_base.py).
+__device__ __forceinline__ double np_edge(int k, int n, double lo, double hi, double step) {
+    return (k == n) ? hi : __dadd_rn(__dmul_rn((double)k, step), lo);
+}
+
+// Bin of v in n uniform bins on [lo, hi] with numpy's semantics (np.histogram fast path and
+// np.histogramdd's searchsorted give the same answer): edges[k] <= v < edges[k+1], last bin closed,
+// NaN / out-of-range -> -1.  `scale` = n/(hi-lo) is only an estimate; the edge compares decide.
+__device__ __forceinline__ int np_bin(double v, int n, double lo, double hi, double step, double scale) {
+    if (!(v >= lo && v <= hi)) return -1;
+    int b = (int)((v - lo) * scale);
+    b = b < 0 ? 0 : (b > n - 1 ? n - 1 : b);
+    if (v < np_edge(b, n, lo, hi, step)) {
+        --b;
+    } else if (b != n - 1 && v >= np_edge(b + 1, n, lo, hi, step)) {
+        ++b;
+    }
+    return b;
+}
+
+// ---- D(d,n) cross section: piecewise cubic in shared memory (utilities.py:412-429) ---------------
+struct XsTab {
+    const double *bp;          // [n]
+    const double *cf;          // [n-1][4]
+    const unsigned char *lut;  // [lut_n]
+    int n, lut_n;
+    double lut_lo, lut_inv;
+};
+
+__device__ __forceinline__ double xs_eval(double E, const XsTab &t) {
+    const double lo = t.bp[0], hi = t.bp[t.n - 1];
+    if (E <= lo) E = lo;  // utilities.py:425-428 clamps in place
+    if (E >= hi) E = hi;
+    int c = (int)((E - t.lut_lo) * t.lut_inv);
+    c = c < 0 ? 0 : (c > t.lut_n - 1 ? t.lut_n - 1 : c);
+    int i = t.lut[c];
+    while (i + 2 < t.n && E >= t.bp[i + 1]) ++i;
+    while (i > 0 && E < t.bp[i]) --i;
+    const double x = E - t.bp[i];
+    const double *k = t.cf + 4 * i;
+    return ((k[0] * x + k[1]) * x + k[2]) * x + k[3];
+}
+
+// ---- Bethe stopping power, reduced form of ionStopping.py:78-97 ------------------------------------
+// dE/dx = -(1/E) * sum_k A_k ln(B_k E).  E <= 0 gives NaN, like the reference's sqrt of a negative.
+template <int NMAT>
+__device__ __forceinline__ double bethe(double E, const double *A, const double *B, int nmat) {
+    double s;
+    if (NMAT == 1) {
+        s = A[0] * log(B[0] * E);
+    } else {
+        s = 0.0;
+        for (int k = 0; k < nmat; ++k) s += A[k] * log(B[k] * E);
+    }
+    return -s / E;
+}
+
+// ---- flight time: utilities.py:64-73 in the reference's operation order ----------------------------
+__device__ __forceinline__ double speed_of(double c, double energy, double mass) {
+    return __dmul_rn(c, __dsqrt_rn(__ddiv_rn(__dmul_rn(2.0, energy), mass)));
+}
+
+// ---- Philox4x32-10 counter-based generator (Salmon et al. 2011) ------------------------------------
+struct Philox {
+    uint32_t c[4];
+    __device__ __forceinline__ Philox(uint64_t seed, uint64_t ctr_lo, uint64_t ctr_hi) {
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+        c[0] = (uint32_t)ctr_lo;
+        c[1] = (uint32_t)(ctr_lo >> 32);
+        c[2] = (uint32_t)ctr_hi;
+        c[3] = (uint32_t)(ctr_hi >> 32);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+            const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+            c[0] = n0;
+            c[1] = lo1;
+            c[2] = n2;
+            c[3] = lo0;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+    }
+    // two uniforms in [0,1) with 53 random bits each
+    __device__ __forceinline__ double u0() const {
+        return (double)((((uint64_t)c[1] << 32) | c[0]) >> 11) * (1.0 / 9007199254740992.0);
+    }
+    __device__ __forceinline__ double u1() const {
+        return (double)((((uint64_t)c[3] << 32) | c[2]) >> 11) * (1.0 / 9007199254740992.0);
+    }
+};
+
+}  // namespace tof

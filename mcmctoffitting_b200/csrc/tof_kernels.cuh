@@ -1,0 +1,404 @@
+// Model kernels (sm_100a).  One CTA evaluates one walker (one (walker, run) pair for the
+// simultaneous fit): Monte-Carlo draws are spread over the threads, every histogram lives in
+// shared memory, and only theta (in) and lnprob (out) touch HBM.
+#pragma once
+#include "tof_device.cuh"
+
+namespace tof {
+
+// Outputs requested from a model kernel.  Production: only `lnprob`.
+struct ModelOut {
+    double *lnprob;       // [n] (adv/simple) or [n][n_runs] partials (simult)
+    double *spectra;      // optional [n][T] at `stage`
+    long long *cells;     // optional [n][X][E] integer cell counts
+    int stage;
+};
+
+// ================================================================================================
+// adv / intermediate model:  tests/advIntermediateTOFmodel.py:115-199
+// ================================================================================================
+//
+// shared memory layout (doubles unless noted):
+//   H[X*E]  weighted (x,E) histogram | tofc[T] (u64) | sx[X] | sdist[X] | svd[E] | svn[E]
+//   xs_bp[n_xs] | xs_cf[(n_xs-1)*4] | staps[n_taps] | scratch[40] | xs_lut bytes
+struct AdvSmem {
+    double *H;
+    unsigned long long *tofc;
+    double *sx, *sdist, *svd, *svn, *xs_bp, *xs_cf, *staps, *scratch;
+    unsigned char *xs_lut;
+};
+
+__host__ __device__ inline size_t adv_smem_bytes(int X, int E, int T, int n_xs, int n_taps, int lut_n) {
+    size_t d = (size_t)X * E + T + 2 * (size_t)X + 2 * (size_t)E + n_xs + (size_t)(n_xs - 1) * 4 + n_taps + 40;
+    return d * 8 + (((size_t)lut_n + 15) / 16) * 16;
+}
+
+__device__ __forceinline__ AdvSmem adv_carve(unsigned char *base, const DevModel &m, int T) {
+    AdvSmem s;
+    double *p = reinterpret_cast<double *>(base);
+    s.H = p;            p += (size_t)m.x_bins * m.e_bins;
+    s.tofc = reinterpret_cast<unsigned long long *>(p); p += T;
+    s.sx = p;           p += m.x_bins;
+    s.sdist = p;        p += m.x_bins;
+    s.svd = p;          p += m.e_bins;
+    s.svn = p;          p += m.e_bins;
+    s.xs_bp = p;        p += m.n_xs;
+    s.xs_cf = p;        p += (size_t)(m.n_xs - 1) * 4;
+    s.staps = p;        p += m.n_taps;
+    s.scratch = p;      p += 40;
+    s.xs_lut = reinterpret_cast<unsigned char *>(p);
+    return s;
+}
+
+// One RK4 step of size h for DPT independent energies (interleaved for ILP).
+template <int DPT, int NMAT>
+__device__ __forceinline__ void rk4_step(double (&E)[DPT], double h, const double *A, const double *B, int nmat) {
+    double k1[DPT], k2[DPT], k3[DPT], k4[DPT];
+    const double hh = 0.5 * h, h6 = h / 6.0;
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) k1[k] = bethe<NMAT>(E[k], A, B, nmat);
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) k2[k] = bethe<NMAT>(E[k] + hh * k1[k], A, B, nmat);
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) k3[k] = bethe<NMAT>(E[k] + hh * k2[k], A, B, nmat);
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) k4[k] = bethe<NMAT>(E[k] + h * k3[k], A, B, nmat);
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) E[k] = E[k] + h6 * (k1[k] + 2.0 * k2[k] + 2.0 * k3[k] + k4[k]);
+}
+
+// Add the DPT samples of one thread at cell row `Hrow`; equal consecutive bins are merged in
+// registers first (with sorted draws neighbouring samples share a bin), so that fewer shared
+// memory atomics are issued.
+template <int DPT>
+__device__ __forceinline__ void hist_row(double *Hrow, const double (&E)[DPT], const DevModel &m, double e_step,
+                                         double e_scale, const XsTab &xs) {
+    int cur = -1;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) {
+        const int b = np_bin(E[k], m.e_bins, m.e_min, m.e_max, e_step, e_scale);
+        if (b >= 0) {
+            const double w = xs_eval(E[k], xs);  // adv:131 (only in-range samples are ever binned)
+            if (b == cur) {
+                acc += w;
+            } else {
+                if (cur >= 0) atomicAdd(Hrow + cur, acc);
+                cur = b;
+                acc = w;
+            }
+        }
+    }
+    if (cur >= 0) atomicAdd(Hrow + cur, acc);
+}
+
+// Stage common to adv and simult: timing-response convolution evaluated at bin n,
+//   np.convolve(pdf, taps, 'same')[n] = sum_k taps[k] * pdf[n + shift - k],  shift = (n_taps-1)/2
+// with pdf[t] = counts[t] / db[t] / total (np.histogram density=True, _histograms_impl.py).
+template <typename CountT>
+__device__ __forceinline__ double spread_at(int n, const CountT *cnt, double total, int T, double lo, double hi,
+                                            double step, const double *taps, int n_taps, int shift) {
+    double acc = 0.0;
+    for (int k = 0; k < n_taps; ++k) {
+        const int t = n + shift - k;
+        if (t >= 0 && t < T) {
+            const double db = __dsub_rn(np_edge(t + 1, T, lo, hi, step), np_edge(t, T, lo, hi, step));
+            const double pdf = __ddiv_rn(__ddiv_rn((double)cnt[t], db), total);
+            acc += taps[k] * pdf;
+        }
+    }
+    return acc;
+}
+
+template <int NT, int DPT, int NMAT>
+__global__ void __launch_bounds__(NT) adv_lnprob_kernel(const DevModel m, const DevRun run, const double *__restrict__ theta,
+                                                        long long n_walkers, ModelOut out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = run.tof_bins;
+    const AdvSmem s = adv_carve(smem_raw, m, T);
+    const int tid = threadIdx.x;
+    const int X = m.x_bins, EB = m.e_bins;
+    const long long w = blockIdx.x;
+    if (w >= n_walkers) return;
+
+    const double e0 = theta[w * m.ndim + 0];
+    const double sigma0 = theta[w * m.ndim + 1];
+
+    // ---- lnprior (adv:185-189): outside the box -> -inf, no model evaluation (adv:196-198) ----
+    bool inside = true;
+    for (int p = 0; p < m.ndim; ++p) {
+        const double v = theta[w * m.ndim + p];
+        inside = inside && (m.prior_strict ? (m.prior_lo[p] < v && v < m.prior_hi[p])
+                                           : !(v < m.prior_lo[p] || v > m.prior_hi[p]));
+    }
+    if (!inside && out.spectra == nullptr && out.cells == nullptr) {
+        if (tid == 0) out.lnprob[w] = -CUDART_INF;
+        return;
+    }
+
+    // ---- stage tables, zero histograms -------------------------------------------------------------
+    for (int i = tid; i < X * EB; i += NT) s.H[i] = 0.0;
+    for (int i = tid; i < T; i += NT) s.tofc[i] = 0ull;
+    for (int i = tid; i < X; i += NT) {
+        s.sx[i] = m.x_centers[i];
+        s.sdist[i] = run.neutron_dist[i];
+    }
+    for (int j = tid; j < EB; j += NT) {
+        // adv:151-152: velocity of the deuteron at the mean of e0 and the bin centre
+        const double eff = __ddiv_rn(__dadd_rn(e0, m.e_centers[j]), 2.0);
+        s.svd[j] = speed_of(m.c, eff, m.m_d);
+        s.svn[j] = m.neutron_speed[j];
+    }
+    for (int i = tid; i < m.n_xs; i += NT) s.xs_bp[i] = m.xs_breaks[i];
+    for (int i = tid; i < (m.n_xs - 1) * 4; i += NT) s.xs_cf[i] = m.xs_coefs[i];
+    for (int i = tid; i < m.n_taps; i += NT) s.staps[i] = m.taps[i];
+    for (int i = tid; i < m.xs_lut_n; i += NT) s.xs_lut[i] = m.xs_lut[i];
+    __syncthreads();
+
+    XsTab xs;
+    xs.bp = s.xs_bp; xs.cf = s.xs_cf; xs.lut = s.xs_lut; xs.n = m.n_xs; xs.lut_n = m.xs_lut_n;
+    xs.lut_lo = m.xs_lut_lo; xs.lut_inv = m.xs_lut_inv;
+
+    const double e_step = (m.e_max - m.e_min) / (double)EB;   // np.linspace step
+    const double e_scale = (double)EB / (m.e_max - m.e_min);
+    const double spread = __dmul_rn(sigma0, e0);                // np.random.normal(e0, sigma0*e0), adv:128
+
+    // ---- phase 1: energy loss through the cell + cross-section weighted (x,E) histogram ------------
+    for (long long base = (long long)tid * DPT; base < m.n_draws; base += (long long)NT * DPT) {
+        double E[DPT];
+#pragma unroll
+        for (int k = 0; k < DPT; ++k) {
+            const long long d = base + k;
+            E[k] = (d < m.n_draws) ? __dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + d))) : CUDART_NAN;
+        }
+        double x_prev = m.ode_from_zero ? 0.0 : s.sx[0];
+        for (int i = 0; i < X; ++i) {
+            if (i > 0 || m.ode_from_zero) {
+                const double h = (s.sx[i] - x_prev) / (double)m.ode_substeps;
+                for (int ss = 0; ss < m.ode_substeps; ++ss) rk4_step<DPT, NMAT>(E, h, m.bethe_A, m.bethe_B, m.n_materials);
+                x_prev = s.sx[i];
+            }
+            hist_row<DPT>(s.H + (size_t)i * EB, E, m, e_step, e_scale, xs);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: normalise (adv:143) and quantise (adv:146) ---------------------------------------
+    const double de = (m.e_max - m.e_min) / (double)EB;        // eD_binSize, adv:60
+    const double dx = (m.x_max - m.x_min) / (double)X;         // x_binSize,  adv:70
+    double part = 0.0;
+    for (int i = tid; i < X * EB; i += NT) part += __dmul_rn(__dmul_rn(s.H[i], de), dx);
+    const double S = block_sum<double>(part, s.scratch);
+
+    // ---- phase 3: every non-empty cell becomes `count` events at one flight time (adv:149-158) ------
+    const double t_step = (run.tof_max - run.tof_min) / (double)T;
+    const double t_scale = (double)T / (run.tof_max - run.tof_min);
+    const double nsamp = (double)m.n_samples;
+    for (int idx = tid; idx < X * EB; idx += NT) {
+        const double cnt = rint(__dmul_rn(__ddiv_rn(s.H[idx], S), nsamp));  // NaN when S == 0, like numpy
+        if (out.cells) out.cells[(size_t)w * X * EB + idx] = (cnt == cnt) ? (long long)cnt : LLONG_MIN;
+        if (cnt != 0.0 && cnt == cnt) {
+            const int i = idx / EB, j = idx - i * EB;
+            const double tof_d = __ddiv_rn(s.sx[i], s.svd[j]);
+            const double tof_n = __ddiv_rn(s.sdist[i], s.svn[j]);
+            const int b = np_bin(__dadd_rn(tof_d, tof_n), T, run.tof_min, run.tof_max, t_step, t_scale);
+            if (b >= 0) atomicAdd(s.tofc + b, (unsigned long long)(long long)cnt);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 4: density normalisation constant n.sum() (np.histogram density=True) -----------------
+    long long cpart = 0;
+    for (int t = tid; t < T; t += NT) cpart += (long long)s.tofc[t];
+    const long long total_i = block_sum<long long>(cpart, reinterpret_cast<long long *>(s.scratch));
+    // S == 0 or NaN (no in-range sample): numpy divides by zero -> every bin NaN -> lnlike NaN
+    const bool degenerate = !(S > 0.0) || total_i == 0;
+    const double total = (double)total_i;
+    const long long *cnts = reinterpret_cast<const long long *>(s.tofc);
+
+    if (out.spectra) {
+        double *sp = out.spectra + (size_t)w * T;
+        for (int t = tid; t < T; t += NT) {
+            double v;
+            if (out.stage == TOF_STAGE_COUNTS) {
+                v = (double)cnts[t];
+            } else if (degenerate) {
+                v = CUDART_NAN;
+            } else if (out.stage == TOF_STAGE_PDF) {
+                const double db = __dsub_rn(np_edge(t + 1, T, run.tof_min, run.tof_max, t_step),
+                                            np_edge(t, T, run.tof_min, run.tof_max, t_step));
+                v = __ddiv_rn(__ddiv_rn((double)cnts[t], db), total);
+            } else {
+                v = spread_at(t, cnts, total, T, run.tof_min, run.tof_max, t_step, s.staps, m.n_taps, m.conv_shift);
+            }
+            sp[t] = v;
+        }
+    }
+
+    // ---- phase 5: ln L = sum_{obs>0} obs * ln(model)  (adv:173-181) ----------------------------------
+    double lp = 0.0;
+    if (!degenerate) {
+        for (int q = tid; q < run.n_obs_nz; q += NT) {
+            const int t = run.obs_nz_idx[q];
+            const double ev = spread_at(t, cnts, total, T, run.tof_min, run.tof_max, t_step, s.staps, m.n_taps, m.conv_shift);
+            lp += run.obs_nz_val[q] * log(ev);  // ev == 0 -> -inf, as np.log does
+        }
+    }
+    lp = block_sum<double>(lp, s.scratch);
+    if (tid == 0 && out.lnprob) {
+        double r = degenerate ? CUDART_NAN : lp;
+        if (!inside) r = -CUDART_INF;
+        if (m.nan_to_neginf && r != r) r = -CUDART_INF;
+        out.lnprob[w] = r;
+    }
+}
+
+// ================================================================================================
+// simple model: tests/simpleTOFmodel.py:57-120  (every sample is histogrammed directly)
+// ================================================================================================
+// grid = (chunks, walkers).  counts[n][T] (u64, zeroed by the caller) accumulate across chunks.
+template <int NT>
+__global__ void __launch_bounds__(NT) simple_hist_kernel(const DevModel m, const DevRun run, const double *__restrict__ theta,
+                                                         long long n_walkers, unsigned long long *__restrict__ counts,
+                                                         int ignore_prior) {
+    __shared__ unsigned int sh[1024];
+    const int T = run.tof_bins;
+    const long long w = blockIdx.y;
+    const int tid = threadIdx.x;
+    const double e0 = theta[w * 3 + 0], e1 = theta[w * 3 + 1], sigma = theta[w * 3 + 2];
+    bool inside = true;
+    for (int p = 0; p < 3; ++p) {
+        const double v = theta[w * 3 + p];
+        inside = inside && (m.prior_strict ? (m.prior_lo[p] < v && v < m.prior_hi[p])
+                                           : !(v < m.prior_lo[p] || v > m.prior_hi[p]));
+    }
+    if (!inside && !ignore_prior) return;  // lnprob never evaluates the model outside the prior (simple:117-119)
+    for (int t = tid; t < T; t += NT) sh[t] = 0u;
+    __syncthreads();
+
+    const double t_step = (run.tof_max - run.tof_min) / (double)T;
+    const double t_scale = (double)T / (run.tof_max - run.tof_min);
+    // getDDneutronEnergy constants in the reference's order (simple:37-43)
+    const double k_mm = __dmul_rn(m.m_d, m.m_n);
+    const double k_den = __dadd_rn(m.m_n, m.m_he3);
+    const double k_dm = __dsub_rn(m.m_he3, m.m_d);
+    const double k_q = __dmul_rn(m.q_ddn, m.m_he3);
+
+    const long long per = (m.n_draws + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per;
+    const long long hi = (lo + per < m.n_draws) ? lo + per : m.n_draws;
+    for (long long d = lo + tid; d < hi; d += NT) {
+        const double x = __dmul_rn(m.cell_length, __ldg(run.z1 + d));                       // simple:62
+        const double ed = __dadd_rn(__dadd_rn(e0, __dmul_rn(e1, x)), __dmul_rn(sigma, __ldg(run.z + d)));  // simple:64
+        const double rv = __ddiv_rn(__dsqrt_rn(__dmul_rn(k_mm, ed)), k_den);               // rVal (cos 0 = 1)
+        const double sv = __ddiv_rn(__dadd_rn(__dmul_rn(ed, k_dm), k_q), k_den);           // sVal
+        const double sq = __dadd_rn(rv, __dsqrt_rn(__dadd_rn(__dmul_rn(rv, rv), sv)));
+        const double en = __dmul_rn(sq, sq);
+        const double dist = __dadd_rn(m.simple_neutron_base, __dsub_rn(m.cell_length, x));  // simple:66
+        const double tof_n = __ddiv_rn(dist, speed_of(m.c, en, m.m_n));
+        const double eff = __ddiv_rn(__dadd_rn(e0, ed), 2.0);
+        const double tof_d = __ddiv_rn(x, speed_of(m.c, eff, m.m_d));
+        const int b = np_bin(__dadd_rn(tof_n, tof_d), T, run.tof_min, run.tof_max, t_step, t_scale);
+        if (b >= 0) atomicAdd(&sh[b], 1u);
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += NT)
+        if (sh[t]) atomicAdd(counts + (size_t)w * T + t, (unsigned long long)sh[t]);
+}
+
+// One CTA per walker: density, log, dot with the observations (simple:78-102).
+template <int NT>
+__global__ void __launch_bounds__(NT) simple_finish_kernel(const DevModel m, const DevRun run, const double *__restrict__ theta,
+                                                           long long n_walkers, const unsigned long long *__restrict__ counts,
+                                                           ModelOut out) {
+    __shared__ double scratch[40];
+    const int T = run.tof_bins;
+    const long long w = blockIdx.x;
+    const int tid = threadIdx.x;
+    bool inside = true;
+    for (int p = 0; p < 3; ++p) {
+        const double v = theta[w * 3 + p];
+        inside = inside && (m.prior_strict ? (m.prior_lo[p] < v && v < m.prior_hi[p])
+                                           : !(v < m.prior_lo[p] || v > m.prior_hi[p]));
+    }
+    const unsigned long long *cw = counts + (size_t)w * T;
+    long long cpart = 0;
+    for (int t = tid; t < T; t += NT) cpart += (long long)cw[t];
+    const long long total_i = block_sum<long long>(cpart, reinterpret_cast<long long *>(scratch));
+    const double total = (double)total_i;
+    const double t_step = (run.tof_max - run.tof_min) / (double)T;
+    if (out.spectra) {
+        for (int t = tid; t < T; t += NT) {
+            const double db = __dsub_rn(np_edge(t + 1, T, run.tof_min, run.tof_max, t_step),
+                                        np_edge(t, T, run.tof_min, run.tof_max, t_step));
+            out.spectra[(size_t)w * T + t] = (out.stage == TOF_STAGE_COUNTS) ? (double)cw[t]
+                                                                               : __ddiv_rn(__ddiv_rn((double)cw[t], db), total);
+        }
+    }
+    double lp = 0.0;
+    for (int q = tid; q < run.n_obs_nz; q += NT) {
+        const int t = run.obs_nz_idx[q];
+        const double db = __dsub_rn(np_edge(t + 1, T, run.tof_min, run.tof_max, t_step),
+                                    np_edge(t, T, run.tof_min, run.tof_max, t_step));
+        const double pdf = __ddiv_rn(__ddiv_rn((double)cw[t], db), total);
+        lp += run.obs_nz_val[q] * log(pdf);
+    }
+    lp = block_sum<double>(lp, scratch);
+    if (tid == 0 && out.lnprob) {
+        double r = (total_i == 0) ? CUDART_NAN : lp;
+        if (!inside) r = -CUDART_INF;
+        if (m.nan_to_neginf && r != r) r = -CUDART_INF;
+        out.lnprob[w] = r;
+    }
+}
+
+// ================================================================================================
+// ensemble stretch move (emcee 2.x EnsembleSampler._propose_stretch, restated from Goodman & Weare)
+// ================================================================================================
+// counter layout: ctr_lo = global walker index, ctr_hi = step*4 + half*2 + kind (kind 0 propose, 1 accept)
+__global__ void stretch_propose_kernel(const double *__restrict__ s, long long n, long long walker0,
+                                       const double *__restrict__ comp, long long n_comp, int ndim, double a,
+                                       unsigned long long seed, long long step, int half, double *__restrict__ q,
+                                       double *__restrict__ log_zz) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Philox rng(seed, (uint64_t)(walker0 + i), (uint64_t)step * 4ull + (uint64_t)half * 2ull);
+    const double r = (a - 1.0) * rng.u0() + 1.0;
+    const double zz = r * r / a;
+    long long j = (long long)(rng.u1() * (double)n_comp);
+    if (j >= n_comp) j = n_comp - 1;
+    for (int p = 0; p < ndim; ++p) {
+        const double c = comp[j * ndim + p];
+        q[i * ndim + p] = c - zz * (c - s[i * ndim + p]);
+    }
+    log_zz[i] = (double)(ndim - 1) * log(zz);
+}
+
+__global__ void stretch_accept_kernel(double *__restrict__ s, double *__restrict__ lnprob, long long n, long long walker0,
+                                      const double *__restrict__ q, const double *__restrict__ new_lnprob,
+                                      const double *__restrict__ log_zz, int ndim, unsigned long long seed, long long step,
+                                      int half, long long *__restrict__ n_accept) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Philox rng(seed, (uint64_t)(walker0 + i), (uint64_t)step * 4ull + (uint64_t)half * 2ull + 1ull);
+    const double lnpdiff = log_zz[i] + new_lnprob[i] - lnprob[i];
+    if (lnpdiff > log(rng.u0())) {  // NaN and -inf proposals compare false: rejected
+        for (int p = 0; p < ndim; ++p) s[i * ndim + p] = q[i * ndim + p];
+        lnprob[i] = new_lnprob[i];
+        if (n_accept) n_accept[i] += 1;
+    }
+}
+
+// ================================================================================================
+// FP64 FMA peak microbenchmark: the roofline denominator for this path
+// ================================================================================================
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b) {
+    double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+        r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7;
+}
+
+}  // namespace tof

@@ -1,0 +1,528 @@
+// C ABI of libtofgpu.so (see include/tofgpu.h).  Host-side context management + kernel launches.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tof_kernels.cuh"
+
+using namespace tof;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct tof_ctx {
+    tof_config cfg{};
+    DevModel dm{};
+    DevRun runs[TOF_MAX_RUNS]{};
+    std::vector<void *> owned;  // device allocations freed in tof_destroy
+    DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing = false, timed = false;
+    std::string err;
+    tof_stats stats{};
+    int adv_nt = 256, adv_dpt = 4;
+    size_t adv_smem = 0;
+    int max_smem_optin = 0;
+    bool have_obs[TOF_MAX_RUNS]{};
+    bool have_z[TOF_MAX_RUNS][2]{};
+};
+
+namespace {
+
+int fail(tof_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(ctx, TOF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));      \
+    } while (0)
+
+template <typename T>
+int upload(tof_ctx *ctx, const T *host, size_t count, const T **dev) {
+    void *p = nullptr;
+    CU(ctx, cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    ctx->owned.push_back(p);
+    if (count) CU(ctx, cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = static_cast<const T *>(p);
+    return TOF_OK;
+}
+
+int ensure(tof_ctx *ctx, DeviceBuf &b, size_t bytes) {
+    if (b.bytes >= bytes) return TOF_OK;
+    if (b.p) CU(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.bytes = 0;
+    CU(ctx, cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+    return TOF_OK;
+}
+
+// ---- adv kernel variants ---------------------------------------------------------------------
+using AdvKernel = void (*)(const DevModel, const DevRun, const double *, long long, ModelOut);
+
+template <int NT, int DPT>
+AdvKernel adv_pick(int nmat) {
+    return nmat == 1 ? adv_lnprob_kernel<NT, DPT, 1> : adv_lnprob_kernel<NT, DPT, 0>;
+}
+
+AdvKernel adv_variant(int nt, int dpt, int nmat) {
+    if (nt == 128 && dpt == 8) return adv_pick<128, 8>(nmat);
+    if (nt == 256 && dpt == 4) return adv_pick<256, 4>(nmat);
+    if (nt == 256 && dpt == 2) return adv_pick<256, 2>(nmat);
+    if (nt == 512 && dpt == 2) return adv_pick<512, 2>(nmat);
+    if (nt == 512 && dpt == 1) return adv_pick<512, 1>(nmat);
+    if (nt == 1024 && dpt == 1) return adv_pick<1024, 1>(nmat);
+    return nullptr;
+}
+
+int check_run(tof_ctx *ctx, int run) {
+    if (run < 0 || run >= ctx->cfg.n_runs) return fail(ctx, TOF_ERR_INVALID, "run index out of range");
+    return TOF_OK;
+}
+
+int ready(tof_ctx *ctx, bool need_obs) {
+    for (int r = 0; r < ctx->cfg.n_runs; ++r) {
+        if (need_obs && !ctx->have_obs[r]) return fail(ctx, TOF_ERR_STATE, "observables not set for run " + std::to_string(r));
+        if (!ctx->have_z[r][0]) return fail(ctx, TOF_ERR_STATE, "draws (stream 0) not set for run " + std::to_string(r));
+        if (ctx->cfg.model == TOF_MODEL_SIMPLE && !ctx->have_z[r][1])
+            return fail(ctx, TOF_ERR_STATE, "uniform draws (stream 1) not set");
+    }
+    return TOF_OK;
+}
+
+// Launch the model for n walkers with device pointers.  `out` selects what is produced.
+int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, ModelOut out, cudaStream_t st) {
+    if (n <= 0) return TOF_OK;
+    const tof_config &c = ctx->cfg;
+    if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev0, st));
+    if (c.model == TOF_MODEL_ADV) {
+        AdvKernel k = adv_variant(ctx->adv_nt, ctx->adv_dpt, c.n_materials);
+        k<<<(unsigned)n, ctx->adv_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
+        ctx->stats.kernel_launches += 1;
+    } else if (c.model == TOF_MODEL_SIMPLE) {
+        const int T = c.tof_bins[0];
+        int rc = ensure(ctx, ctx->d_counts, (size_t)n * T * sizeof(unsigned long long));
+        if (rc) return rc;
+        CU(ctx, cudaMemsetAsync(ctx->d_counts.p, 0, (size_t)n * T * sizeof(unsigned long long), st));
+        // enough chunks to fill the machine ~4x over, but at least ~4096 draws per CTA
+        long long chunks = std::max<long long>(1, std::min<long long>((ctx->stats.sm_count * 8 + n - 1) / n,
+                                                                       (ctx->dm.n_draws + 4095) / 4096));
+        dim3 grid((unsigned)chunks, (unsigned)n);
+        simple_hist_kernel<256><<<grid, 256, 0, st>>>(ctx->dm, ctx->runs[0], d_theta, n,
+                                                      static_cast<unsigned long long *>(ctx->d_counts.p),
+                                                      out.spectra != nullptr);
+        simple_finish_kernel<32><<<(unsigned)n, 32, 0, st>>>(ctx->dm, ctx->runs[0], d_theta, n,
+                                                             static_cast<unsigned long long *>(ctx->d_counts.p), out);
+        ctx->stats.kernel_launches += 2;
+    } else {
+        return fail(ctx, TOF_ERR_INVALID, "model kind not implemented");
+    }
+    if (ctx->timing) {
+        CU(ctx, cudaEventRecord(ctx->ev1, st));
+        ctx->timed = true;
+    }
+    CU(ctx, cudaGetLastError());
+    ctx->stats.evaluations += n;
+    return TOF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tof_abi_version(void) { return TOF_ABI_VERSION; }
+int tof_sizeof_config(void) { return (int)sizeof(tof_config); }
+
+const char *tof_last_error(const tof_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int tof_create(const tof_config *cfg, tof_ctx **out) {
+    if (!cfg || !out) return fail(nullptr, TOF_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != TOF_ABI_VERSION) return fail(nullptr, TOF_ERR_INVALID, "abi_version mismatch");
+    if (cfg->model != TOF_MODEL_SIMPLE && cfg->model != TOF_MODEL_ADV && cfg->model != TOF_MODEL_SIMULT)
+        return fail(nullptr, TOF_ERR_INVALID, "unknown model kind");
+    if (cfg->ndim < 1 || cfg->ndim > TOF_MAX_DIM) return fail(nullptr, TOF_ERR_INVALID, "ndim out of range");
+    if (cfg->n_runs < 1 || cfg->n_runs > TOF_MAX_RUNS) return fail(nullptr, TOF_ERR_INVALID, "n_runs out of range");
+    if (cfg->n_loops < 1 || cfg->n_ev_per_loop < 1) return fail(nullptr, TOF_ERR_INVALID, "n_loops / n_ev_per_loop must be >= 1");
+    for (int r = 0; r < cfg->n_runs; ++r)
+        if (cfg->tof_bins[r] < 1 || !(cfg->tof_max[r] > cfg->tof_min[r]))
+            return fail(nullptr, TOF_ERR_INVALID, "bad TOF window");
+    const bool cell_model = cfg->model != TOF_MODEL_SIMPLE;
+    if (cell_model) {
+        if (cfg->x_bins < 1 || cfg->e_bins < 1 || !(cfg->x_max > cfg->x_min) || !(cfg->e_max > cfg->e_min))
+            return fail(nullptr, TOF_ERR_INVALID, "bad (x, E) binning");
+        if (cfg->n_materials < 1 || cfg->n_materials > TOF_MAX_MATERIALS) return fail(nullptr, TOF_ERR_INVALID, "n_materials out of range");
+        if (cfg->n_xs < 4) return fail(nullptr, TOF_ERR_INVALID, "cross-section table too short");
+        if (cfg->n_taps < 1) return fail(nullptr, TOF_ERR_INVALID, "n_taps must be >= 1");
+        if (cfg->ode_substeps < 1) return fail(nullptr, TOF_ERR_INVALID, "ode_substeps must be >= 1");
+        if (!cfg->x_centers || !cfg->e_centers || !cfg->neutron_speed || !cfg->neutron_dist || !cfg->xs_breaks ||
+            !cfg->xs_coefs || !cfg->taps)
+            return fail(nullptr, TOF_ERR_INVALID, "missing table pointer");
+        for (int r = 0; r < cfg->n_runs; ++r)
+            if (cfg->tof_bins[r] < cfg->n_taps) return fail(nullptr, TOF_ERR_INVALID, "tof_bins must be >= n_taps");
+        if (cfg->model == TOF_MODEL_ADV && cfg->ndim < 2) return fail(nullptr, TOF_ERR_INVALID, "adv model needs ndim >= 2");
+    } else {
+        if (cfg->ndim != 3) return fail(nullptr, TOF_ERR_INVALID, "simple model has ndim == 3");
+        if (cfg->tof_bins[0] > 1024) return fail(nullptr, TOF_ERR_INVALID, "simple model supports at most 1024 TOF bins");
+    }
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, TOF_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, TOF_ERR_NO_DEVICE, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, TOF_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, TOF_ERR_NO_DEVICE,
+                    std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                        "; libtofgpu is built for sm_100a only and has no fallback path");
+
+    tof_ctx *ctx = new tof_ctx();
+    ctx->cfg = *cfg;
+    auto bail = [&](int rc) {
+        g_create_error = ctx->err;
+        tof_destroy(ctx);
+        return rc;
+    };
+#define TRY(x)                     \
+    do {                           \
+        int rc__ = (x);            \
+        if (rc__) return bail(rc__); \
+    } while (0)
+#define CUC(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return bail(TOF_ERR_CUDA);                                                             \
+        }                                                                                          \
+    } while (0)
+
+    CUC(cudaSetDevice(cfg->device));
+    CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&ctx->ev0));
+    CUC(cudaEventCreate(&ctx->ev1));
+    ctx->stats.sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+
+    DevModel &m = ctx->dm;
+    m.model = cfg->model; m.ode_mode = cfg->ode_mode; m.ode_substeps = cfg->ode_substeps;
+    m.ode_from_zero = cfg->ode_from_zero; m.prior_strict = cfg->prior_strict; m.nan_to_neginf = cfg->nan_to_neginf;
+    m.ndim = cfg->ndim; m.n_runs = cfg->n_runs; m.x_bins = cfg->x_bins; m.e_bins = cfg->e_bins;
+    m.n_taps = cfg->n_taps; m.conv_shift = (cfg->n_taps - 1) / 2; m.n_zero_deg = cfg->n_zero_deg;
+    m.n_materials = cfg->n_materials; m.n_xs = cfg->n_xs;
+    m.n_samples = cfg->n_samples; m.n_ev_per_loop = cfg->n_ev_per_loop; m.n_loops = cfg->n_loops;
+    m.n_draws = cfg->n_loops * cfg->n_ev_per_loop;
+    m.x_min = cfg->x_min; m.x_max = cfg->x_max; m.e_min = cfg->e_min; m.e_max = cfg->e_max;
+    m.c = cfg->speed_of_light; m.m_d = cfg->mass_deuteron; m.m_n = cfg->mass_neutron; m.m_he3 = cfg->mass_he3;
+    m.q_ddn = cfg->q_ddn; m.cell_length = cfg->cell_length; m.simple_neutron_base = cfg->simple_neutron_base;
+    std::memcpy(m.bethe_A, cfg->bethe_A, sizeof(m.bethe_A));
+    std::memcpy(m.bethe_B, cfg->bethe_B, sizeof(m.bethe_B));
+    std::memcpy(m.prior_lo, cfg->prior_lo, sizeof(m.prior_lo));
+    std::memcpy(m.prior_hi, cfg->prior_hi, sizeof(m.prior_hi));
+
+    for (int r = 0; r < cfg->n_runs; ++r) {
+        ctx->runs[r].tof_bins = cfg->tof_bins[r];
+        ctx->runs[r].tof_min = cfg->tof_min[r];
+        ctx->runs[r].tof_max = cfg->tof_max[r];
+    }
+
+    if (cell_model) {
+        TRY(upload(ctx, cfg->x_centers, cfg->x_bins, &m.x_centers));
+        TRY(upload(ctx, cfg->e_centers, cfg->e_bins, &m.e_centers));
+        TRY(upload(ctx, cfg->neutron_speed, cfg->e_bins, &m.neutron_speed));
+        TRY(upload(ctx, cfg->xs_breaks, cfg->n_xs, &m.xs_breaks));
+        TRY(upload(ctx, cfg->xs_coefs, (size_t)(cfg->n_xs - 1) * 4, &m.xs_coefs));
+        TRY(upload(ctx, cfg->taps, cfg->n_taps, &m.taps));
+        for (int r = 0; r < cfg->n_runs; ++r)
+            TRY(upload(ctx, cfg->neutron_dist + (size_t)r * cfg->x_bins, cfg->x_bins, &ctx->runs[r].neutron_dist));
+        if (cfg->n_zero_deg > 0) {
+            if (!cfg->zero_deg_times || !cfg->zero_deg_weights) {
+                ctx->err = "n_zero_deg > 0 needs zero_deg_times / zero_deg_weights";
+                return bail(TOF_ERR_INVALID);
+            }
+            TRY(upload(ctx, cfg->zero_deg_times, (size_t)cfg->e_bins * cfg->n_zero_deg, &m.zd_times));
+            TRY(upload(ctx, cfg->zero_deg_weights, (size_t)cfg->e_bins * cfg->n_zero_deg, &m.zd_weights));
+        }
+        // cross-section interval lookup table: uniform cells, entry = interval holding the cell's left edge
+        {
+            const double *bp = cfg->xs_breaks;
+            const int nb = cfg->n_xs;
+            double min_gap = bp[1] - bp[0];
+            for (int i = 1; i + 1 < nb; ++i) {
+                if (!(bp[i + 1] > bp[i])) { ctx->err = "xs_breaks must increase"; return bail(TOF_ERR_INVALID); }
+                min_gap = std::min(min_gap, bp[i + 1] - bp[i]);
+            }
+            const double span = bp[nb - 1] - bp[0];
+            int lut_n = (int)std::min<double>(4096.0, std::max<double>(1.0, std::ceil(span / min_gap - 1e-9)));
+            std::vector<unsigned char> lut(lut_n);
+            if (nb - 1 > 256) { ctx->err = "at most 256 cross-section intervals"; return bail(TOF_ERR_INVALID); }
+            int iv = 0;
+            for (int cidx = 0; cidx < lut_n; ++cidx) {
+                const double left = bp[0] + span * (double)cidx / (double)lut_n;
+                while (iv + 2 < nb && left >= bp[iv + 1]) ++iv;
+                lut[cidx] = (unsigned char)iv;
+            }
+            TRY(upload(ctx, lut.data(), lut.size(), &m.xs_lut));
+            m.xs_lut_n = lut_n;
+            m.xs_lut_lo = bp[0];
+            m.xs_lut_inv = (double)lut_n / span;
+        }
+    }
+
+    if (cfg->model == TOF_MODEL_ADV) {
+        if (const char *v = std::getenv("TOFGPU_ADV_VARIANT")) {
+            int nt = 0, dpt = 0;
+            if (std::sscanf(v, "%dx%d", &nt, &dpt) == 2 && adv_variant(nt, dpt, 1)) {
+                ctx->adv_nt = nt;
+                ctx->adv_dpt = dpt;
+            } else {
+                ctx->err = std::string("TOFGPU_ADV_VARIANT='") + v + "' is not a built variant";
+                return bail(TOF_ERR_INVALID);
+            }
+        }
+        ctx->adv_smem = adv_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], cfg->n_xs, cfg->n_taps, m.xs_lut_n);
+        if ((int)ctx->adv_smem > ctx->max_smem_optin) {
+            ctx->err = "model needs " + std::to_string(ctx->adv_smem) + " B of shared memory per CTA; device offers " +
+                       std::to_string(ctx->max_smem_optin);
+            return bail(TOF_ERR_CAPACITY);
+        }
+        AdvKernel k = adv_variant(ctx->adv_nt, ctx->adv_dpt, cfg->n_materials);
+        CUC(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->adv_smem));
+        int occ = 0;
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, ctx->adv_nt, ctx->adv_smem));
+        ctx->stats.smem_bytes = (int)ctx->adv_smem;
+        ctx->stats.threads = ctx->adv_nt;
+        ctx->stats.ctas_per_sm = occ;
+    } else if (cfg->model == TOF_MODEL_SIMPLE) {
+        ctx->stats.threads = 256;
+    } else {
+        ctx->err = "simult model kernels not built yet";
+        return bail(TOF_ERR_INVALID);
+    }
+#undef TRY
+#undef CUC
+    *out = ctx;
+    return TOF_OK;
+}
+
+void tof_destroy(tof_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    for (void *p : ctx->owned) cudaFree(p);
+    for (DeviceBuf *b : {&ctx->d_theta, &ctx->d_out, &ctx->d_spectra, &ctx->d_cells, &ctx->d_counts, &ctx->d_partial})
+        if (b->p) cudaFree(b->p);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int tof_set_observables(tof_ctx *ctx, int run, const double *counts, int nbins) {
+    if (!ctx || !counts) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    if (int rc = check_run(ctx, run)) return rc;
+    if (nbins != ctx->cfg.tof_bins[run]) return fail(ctx, TOF_ERR_INVALID, "observables length != tof_bins[run]");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    std::vector<double> obs(counts, counts + nbins);
+    if (ctx->cfg.model == TOF_MODEL_SIMULT)
+        for (double &v : obs)
+            if (v == 0.0) v = 1.0;  // simultFit.py:391-392, applied to the private copy
+    std::vector<int> idx;
+    std::vector<double> val;
+    for (int t = 0; t < nbins; ++t)
+        if (obs[t] != 0.0) {  // NaN observables are kept so that they poison the sum like np.dot would
+            idx.push_back(t);
+            val.push_back(obs[t]);
+        }
+    DevRun &r = ctx->runs[run];
+    if (int rc = upload(ctx, obs.data(), obs.size(), &r.obs)) return rc;
+    if (int rc = upload(ctx, idx.data(), idx.size(), &r.obs_nz_idx)) return rc;
+    if (int rc = upload(ctx, val.data(), val.size(), &r.obs_nz_val)) return rc;
+    r.n_obs_nz = (int)idx.size();
+    ctx->have_obs[run] = true;
+    return TOF_OK;
+}
+
+int tof_set_draws(tof_ctx *ctx, int run, int stream, const double *values, int64_t n) {
+    if (!ctx || (!values && n > 0)) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    if (int rc = check_run(ctx, run)) return rc;
+    if (stream < 0 || stream > 1) return fail(ctx, TOF_ERR_INVALID, "stream must be 0 or 1");
+    const long long need = ctx->dm.n_draws;
+    if (stream == 0 && n != need)
+        return fail(ctx, TOF_ERR_INVALID, "stream 0 needs n_loops*n_ev_per_loop = " + std::to_string(need) + " draws");
+    if (stream == 1 && ctx->cfg.model == TOF_MODEL_SIMPLE && n != need)
+        return fail(ctx, TOF_ERR_INVALID, "simple model: stream 1 needs as many uniforms as normals");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const double *d = nullptr;
+    if (int rc = upload(ctx, values, (size_t)n, &d)) return rc;
+    DevRun &r = ctx->runs[run];
+    if (stream == 0) { r.z = d; r.n_z = n; } else { r.z1 = d; r.n_z1 = n; }
+    ctx->have_z[run][stream] = true;
+    return TOF_OK;
+}
+
+int tof_lnprob_batch_device(tof_ctx *ctx, const double *d_theta, int64_t n, double *d_out, void *stream) {
+    if (!ctx || (n > 0 && (!d_theta || !d_out))) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    if (n < 0) return fail(ctx, TOF_ERR_INVALID, "n < 0");
+    if (int rc = ready(ctx, true)) return rc;
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    ModelOut o{};
+    o.lnprob = d_out;
+    return launch_model(ctx, d_theta, n, 0, o, static_cast<cudaStream_t>(stream));
+}
+
+int tof_lnprob_batch(tof_ctx *ctx, const double *theta, int64_t n, double *out) {
+    if (!ctx || (n > 0 && (!theta || !out))) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    if (n < 0) return fail(ctx, TOF_ERR_INVALID, "n < 0");
+    if (n == 0) return TOF_OK;
+    if (int rc = ready(ctx, true)) return rc;
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t tb = (size_t)n * ctx->cfg.ndim * sizeof(double), ob = (size_t)n * sizeof(double);
+    if (int rc = ensure(ctx, ctx->d_theta, tb)) return rc;
+    if (int rc = ensure(ctx, ctx->d_out, ob)) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->d_theta.p, theta, tb, cudaMemcpyHostToDevice, ctx->stream));
+    ModelOut o{};
+    o.lnprob = static_cast<double *>(ctx->d_out.p);
+    if (int rc = launch_model(ctx, static_cast<const double *>(ctx->d_theta.p), n, 0, o, ctx->stream)) return rc;
+    CU(ctx, cudaMemcpyAsync(out, ctx->d_out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return TOF_OK;
+}
+
+int tof_model_batch(tof_ctx *ctx, const double *theta, int64_t n, int run, int stage, double *spectra) {
+    if (!ctx || (n > 0 && (!theta || !spectra))) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    if (int rc = check_run(ctx, run)) return rc;
+    if (stage < TOF_STAGE_COUNTS || stage > TOF_STAGE_SPREAD) return fail(ctx, TOF_ERR_INVALID, "bad stage");
+    if (ctx->cfg.model == TOF_MODEL_SIMPLE && stage == TOF_STAGE_SPREAD)
+        return fail(ctx, TOF_ERR_INVALID, "the simple model has no timing-response stage");
+    if (n <= 0) return n == 0 ? TOF_OK : fail(ctx, TOF_ERR_INVALID, "n < 0");
+    if (int rc = ready(ctx, false)) return rc;
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const int T = ctx->cfg.tof_bins[run];
+    const size_t tb = (size_t)n * ctx->cfg.ndim * sizeof(double), sb = (size_t)n * T * sizeof(double);
+    if (int rc = ensure(ctx, ctx->d_theta, tb)) return rc;
+    if (int rc = ensure(ctx, ctx->d_spectra, sb)) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->d_theta.p, theta, tb, cudaMemcpyHostToDevice, ctx->stream));
+    ModelOut o{};
+    o.spectra = static_cast<double *>(ctx->d_spectra.p);
+    o.stage = stage;
+    if (int rc = launch_model(ctx, static_cast<const double *>(ctx->d_theta.p), n, run, o, ctx->stream)) return rc;
+    CU(ctx, cudaMemcpyAsync(spectra, ctx->d_spectra.p, sb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return TOF_OK;
+}
+
+int tof_cell_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run, int64_t *counts) {
+    if (!ctx || (n > 0 && (!theta || !counts))) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    if (int rc = check_run(ctx, run)) return rc;
+    if (ctx->cfg.model == TOF_MODEL_SIMPLE) return fail(ctx, TOF_ERR_INVALID, "the simple model has no (x, E) cells");
+    if (n <= 0) return n == 0 ? TOF_OK : fail(ctx, TOF_ERR_INVALID, "n < 0");
+    if (int rc = ready(ctx, false)) return rc;
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t cells = (size_t)ctx->cfg.x_bins * ctx->cfg.e_bins;
+    const size_t tb = (size_t)n * ctx->cfg.ndim * sizeof(double), cb = (size_t)n * cells * sizeof(long long);
+    if (int rc = ensure(ctx, ctx->d_theta, tb)) return rc;
+    if (int rc = ensure(ctx, ctx->d_cells, cb)) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->d_theta.p, theta, tb, cudaMemcpyHostToDevice, ctx->stream));
+    ModelOut o{};
+    o.cells = static_cast<long long *>(ctx->d_cells.p);
+    if (int rc = launch_model(ctx, static_cast<const double *>(ctx->d_theta.p), n, run, o, ctx->stream)) return rc;
+    CU(ctx, cudaMemcpyAsync(counts, ctx->d_cells.p, cb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return TOF_OK;
+}
+
+int tof_stretch_propose(tof_ctx *ctx, const double *d_s, int64_t n, int64_t walker0, const double *d_comp, int64_t n_comp,
+                        double a, uint64_t seed, int64_t step, int half, double *d_q, double *d_log_zz, void *stream) {
+    if (!ctx || !d_s || !d_comp || !d_q || !d_log_zz) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    if (n <= 0 || n_comp <= 0 || !(a > 1.0)) return fail(ctx, TOF_ERR_INVALID, "bad stretch-move arguments");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    stretch_propose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_s, n, walker0, d_comp, n_comp, ctx->cfg.ndim, a, seed, step, half, d_q, d_log_zz);
+    ctx->stats.kernel_launches += 1;
+    CU(ctx, cudaGetLastError());
+    return TOF_OK;
+}
+
+int tof_stretch_accept(tof_ctx *ctx, double *d_s, double *d_lnprob, int64_t n, int64_t walker0, const double *d_q,
+                       const double *d_new_lnprob, const double *d_log_zz, uint64_t seed, int64_t step, int half,
+                       int64_t *d_n_accept, void *stream) {
+    if (!ctx || !d_s || !d_lnprob || !d_q || !d_new_lnprob || !d_log_zz) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    if (n <= 0) return fail(ctx, TOF_ERR_INVALID, "n <= 0");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    stretch_accept_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_s, d_lnprob, n, walker0, d_q, d_new_lnprob, d_log_zz, ctx->cfg.ndim, seed, step, half,
+        reinterpret_cast<long long *>(d_n_accept));
+    ctx->stats.kernel_launches += 1;
+    CU(ctx, cudaGetLastError());
+    return TOF_OK;
+}
+
+int tof_get_stats(const tof_ctx *ctx, tof_stats *out) {
+    if (!ctx || !out) return TOF_ERR_INVALID;
+    *out = ctx->stats;
+    return TOF_OK;
+}
+
+int tof_set_timing(tof_ctx *ctx, int enabled) {
+    if (!ctx) return TOF_ERR_INVALID;
+    ctx->timing = enabled != 0;
+    ctx->timed = false;
+    return TOF_OK;
+}
+
+int tof_last_kernel_ms(tof_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    if (!ctx->timed) return fail(ctx, TOF_ERR_STATE, "no timed launch recorded (call tof_set_timing(ctx, 1) first)");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    CU(ctx, cudaEventSynchronize(ctx->ev1));
+    CU(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return TOF_OK;
+}
+
+int tof_measure_fp64_peak(tof_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const int blocks = ctx->stats.sm_count * 16, threads = 256, iters = 1 << 16;
+    double *d = nullptr;
+    CU(ctx, cudaMalloc(&d, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t a, b;
+    CU(ctx, cudaEventCreate(&a));
+    CU(ctx, cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(ctx, cudaEventRecord(a, ctx->stream));
+        dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters, 1.0000001, 1e-9);
+        CU(ctx, cudaEventRecord(b, ctx->stream));
+        CU(ctx, cudaEventSynchronize(b));
+        float ms = 0.f;
+        CU(ctx, cudaEventElapsedTime(&ms, a, b));
+        const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    ctx->stats.kernel_launches += 5;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops = best;
+    return TOF_OK;
+}
+
+}  // extern "C"

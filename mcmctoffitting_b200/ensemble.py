@@ -1,0 +1,222 @@
+"""Ensemble driver: the emcee 2.x ``EnsembleSampler`` stretch move with walkers sharded over GPUs.
+
+The reference builds ``emcee.EnsembleSampler(nWalkers, nDim, lnprob, kwargs=..., threads=N | pool=...)``
+and iterates ``sampler.sample(p0, iterations=...)`` unpacking ``(pos, lnprob, rstate)`` each step
+(adv:300-347; simultFit.py:701-786).  emcee is a third-party dependency that is not vendored in the
+reference; its algorithm (Goodman & Weare 2010 affine-invariant stretch move, red/blue halves,
+``a = 2``) is restated here -- sampler parity is therefore statistical, not bitwise.
+
+B200 layout: one process per GPU.  Every rank keeps a full replica of the positions
+(``k * ndim * 8`` bytes); rank ``g`` of ``G`` owns rows ``[g*h/G, (g+1)*h/G)`` of EACH half
+(``h = k/2``).  Per half-step a rank proposes, evaluates ``lnprob`` and accepts for its own slice
+only, then one ``all_gather`` (NCCL over NVLink) of the updated slice -- positions and
+log-probabilities packed as ``[h/G, ndim+1]`` -- refreshes the replicas.  Proposal randomness is a
+counter-based Philox stream keyed by ``(seed, step, half, global walker index)``, so chains do not
+depend on ``G``.
+"""
+from __future__ import annotations
+
+from typing import Iterator, Optional, Tuple
+
+import numpy as np
+import torch
+
+try:  # torch.distributed is optional at import time
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    dist = None
+
+
+class CudaBackend:
+    """Stretch-move kernels + batched lnprob of one :class:`TofModel` (device pointers, current stream)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.device = torch.device("cuda", model.device)
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def propose(self, s, walker0, comp, a, seed, step, half):
+        n, ndim = s.shape
+        q = torch.empty_like(s)
+        log_zz = torch.empty(n, dtype=torch.float64, device=s.device)
+        self.model.stretch_propose(s.data_ptr(), n, walker0, comp.data_ptr(), comp.shape[0], a, seed, step, half,
+                                   q.data_ptr(), log_zz.data_ptr(), self._stream())
+        return q, log_zz
+
+    def lnprob(self, q):
+        out = torch.empty(q.shape[0], dtype=torch.float64, device=q.device)
+        self.model.lnprob_batch_device(q.data_ptr(), q.shape[0], out.data_ptr(), self._stream())
+        return out
+
+    def accept(self, s, lp, walker0, q, new_lp, log_zz, seed, step, half, n_accept):
+        self.model.stretch_accept(s.data_ptr(), lp.data_ptr(), s.shape[0], walker0, q.data_ptr(), new_lp.data_ptr(),
+                                  log_zz.data_ptr(), seed, step, half, n_accept.data_ptr(), self._stream())
+
+
+class EnsembleSampler:
+    """emcee-2.x-shaped sampler over a sharded walker ensemble.
+
+    Parameters mirror ``emcee.EnsembleSampler(nwalkers, dim, lnpostfn, a=2.0)``; ``lnpostfn`` is a
+    :class:`~mcmctoffitting_b200.lnprob.TofLnProb` (or any object exposing ``.model``), or a backend
+    is injected directly (tests run the sharding logic on CPU/gloo with a numpy backend).
+    """
+
+    def __init__(self, nwalkers: int, dim: int, lnpostfn=None, a: float = 2.0, seed: int = 0, backend=None,
+                 group=None, store_chain: bool = True):
+        if nwalkers % 2 != 0:
+            raise ValueError("The number of walkers must be even.")            # emcee's own checks
+        if nwalkers < 2 * dim:
+            raise ValueError("The number of walkers needs to be more than twice the dimension of your parameter space.")
+        self.k, self.dim, self.a, self.seed = int(nwalkers), int(dim), float(a), int(seed)
+        self.backend = backend if backend is not None else CudaBackend(lnpostfn.model)
+        self.device = self.backend.device
+        self.group = group
+        self.distributed = dist is not None and dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.world = dist.get_world_size(group) if self.distributed else 1
+        self.h = self.k // 2
+        if self.h % self.world != 0:
+            raise ValueError("half-ensemble size %d must divide evenly over %d ranks" % (self.h, self.world))
+        self.n_own = self.h // self.world
+        self.store_chain = store_chain
+        self.reset()
+        self._step = 0
+
+    # -- emcee surface ---------------------------------------------------------------------------------
+    def reset(self) -> None:
+        self._chain = []
+        self._lnprob = []
+        self.naccepted = torch.zeros(self.k, dtype=torch.int64, device=self.device)
+        self.iterations = 0
+
+    @property
+    def chain(self) -> np.ndarray:
+        """[nwalkers, steps, dim] like emcee."""
+        if not self._chain:
+            return np.empty((self.k, 0, self.dim))
+        return np.stack(self._chain, axis=1)
+
+    @property
+    def lnprobability(self) -> np.ndarray:
+        if not self._lnprob:
+            return np.empty((self.k, 0))
+        return np.stack(self._lnprob, axis=1)
+
+    @property
+    def flatchain(self) -> np.ndarray:
+        c = self.chain
+        return c.reshape(-1, self.dim)
+
+    @property
+    def acceptance_fraction(self) -> np.ndarray:
+        return self.naccepted.cpu().numpy() / max(self.iterations, 1)
+
+    # -- one red/blue half-step on device tensors ----------------------------------------------------------
+    def _half_step(self, pos: torch.Tensor, lp: torch.Tensor, half: int) -> None:
+        h, n, g = self.h, self.n_own, self.rank
+        lo = half * h
+        own = slice(lo + g * n, lo + (g + 1) * n)
+        comp = pos[(1 - half) * h:(2 - half) * h]
+        s, lps = pos[own], lp[own]
+        walker0 = lo + g * n
+        q, log_zz = self.backend.propose(s, walker0, comp, self.a, self.seed, self._step, half)
+        new_lp = self.backend.lnprob(q)
+        self.backend.accept(s, lps, walker0, q, new_lp, log_zz, self.seed, self._step, half, self.naccepted[own])
+        if self.world > 1:
+            packed = torch.cat([s, lps.unsqueeze(1)], dim=1).contiguous()           # [n, dim+1]
+            gathered = torch.empty((h, self.dim + 1), dtype=pos.dtype, device=pos.device)
+            dist.all_gather_into_tensor(gathered, packed, group=self.group)
+            pos[lo:lo + h] = gathered[:, :self.dim]
+            lp[lo:lo + h] = gathered[:, self.dim]
+
+    def _as_device(self, a, shape) -> torch.Tensor:
+        t = torch.as_tensor(np.asarray(a, dtype=np.float64) if not torch.is_tensor(a) else a, dtype=torch.float64)
+        return t.reshape(shape).to(self.device).contiguous().clone()
+
+    def initial_lnprob(self, pos: torch.Tensor) -> torch.Tensor:
+        """lnprob of every walker, each rank evaluating its share, gathered."""
+        per = self.k // self.world
+        mine = pos[self.rank * per:(self.rank + 1) * per].contiguous()
+        lp_mine = self.backend.lnprob(mine)
+        if self.world == 1:
+            return lp_mine
+        out = torch.empty(self.k, dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(out, lp_mine, group=self.group)
+        return out
+
+    def sample(self, p0, lnprob0=None, rstate0=None, iterations: int = 1, storechain: Optional[bool] = None
+               ) -> Iterator[Tuple[np.ndarray, np.ndarray, int]]:
+        """Generator yielding ``(pos, lnprob, rstate)`` per step, like emcee 2.x ``sample``.  ``rstate``
+        is the step counter of the counter-based generator (pass it back as ``rstate0`` to resume)."""
+        store = self.store_chain if storechain is None else storechain
+        pos = self._as_device(p0, (self.k, self.dim))
+        if rstate0 is not None:
+            self._step = int(rstate0)
+        lp = self._as_device(lnprob0, (self.k,)) if lnprob0 is not None else self.initial_lnprob(pos)
+        if bool(torch.isnan(lp).any()):
+            raise ValueError("The initial lnprob was NaN.")                         # emcee raises the same
+        for _ in range(int(iterations)):
+            self._half_step(pos, lp, 0)
+            self._half_step(pos, lp, 1)
+            self._step += 1
+            self.iterations += 1
+            p_host, lp_host = pos.cpu().numpy(), lp.cpu().numpy()
+            if store:
+                self._chain.append(p_host.copy())
+                self._lnprob.append(lp_host.copy())
+            yield p_host, lp_host, self._step
+
+    def run_mcmc(self, p0, N: int, rstate0=None, lnprob0=None):
+        out = None
+        for out in self.sample(p0, lnprob0, rstate0, iterations=N):
+            pass
+        return out
+
+    # -- device-resident stepping for throughput runs (no per-step host copies) ------------------------------
+    def run_device(self, pos: torch.Tensor, lp: torch.Tensor, steps: int) -> None:
+        for _ in range(int(steps)):
+            self._half_step(pos, lp, 0)
+            self._half_step(pos, lp, 1)
+            self._step += 1
+            self.iterations += 1
+
+
+# ---- chain files in the reference's text format (adv:314-317; simultFit.py:737-740) -----------------------
+def write_chain_step(path: str, pos: np.ndarray, lnprob: Optional[np.ndarray] = None) -> None:
+    """Append one step as ``"{k} {pos[k]} {lnprob[k]}\\n"`` per walker -- numpy's own array ``str`` with
+    its line wrapping, which ``utilities.readChainFromFile`` (utilities.py:432-500) parses."""
+    with open(path, "a") as fout:
+        for k in range(pos.shape[0]):
+            if lnprob is None:
+                fout.write("{} {}\n".format(k, pos[k]))                              # adv:345-346
+            else:
+                fout.write("{} {} {}\n".format(k, pos[k], lnprob[k]))                # adv:315-316
+
+
+def read_chain(path: str):
+    """Reader for the format above: ``(chain[step, walker, param], probs[step, walker], nParams,
+    nWalkers, nSteps)`` -- the return contract of utilities.readChainFromFile (utilities.py:432-500)."""
+    idx, vals, probs = [], [], []
+    with open(path, "r") as f:
+        text = f.read()
+    pos = 0
+    n = len(text)
+    while pos < n:
+        lb = text.find("[", pos)
+        if lb < 0:
+            break
+        rb = text.find("]", lb)
+        idx.append(int(float(text[pos:lb])))
+        vals.append([float(v) for v in text[lb + 1:rb].split()])
+        nl = text.find("\n", rb)
+        nl = n if nl < 0 else nl
+        tail = text[rb + 1:nl].strip()
+        probs.append(float(tail) if tail else float("nan"))
+        pos = nl + 1
+    n_walkers = max(idx) + 1
+    n_steps = len(idx) // n_walkers
+    chain = np.array(vals[:n_steps * n_walkers]).reshape(n_steps, n_walkers, -1)
+    pr = np.array(probs[:n_steps * n_walkers]).reshape(n_steps, n_walkers)
+    return chain, pr, chain.shape[2], n_walkers, n_steps

@@ -1,0 +1,203 @@
+"""TofModel: Python owner of one ``tof_ctx`` (include/tofgpu.h) -- tables in, batched lnprob out."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from . import config as cfgmod
+from .config import ModelConfig
+
+STAGES = {"counts": 0, "pdf": 1, "spread": 2}
+
+
+def _dptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _as_f64(a, shape=None) -> np.ndarray:
+    out = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if shape is not None:
+        out = out.reshape(shape)
+    return out
+
+
+class TofModel:
+    """A model configuration resident on one GPU.
+
+    ``lnprob_batch(thetas)`` evaluates what the reference evaluates one walker at a time through
+    ``lnprob(theta, observables)`` (adv:191-199 and friends); observables and the Monte-Carlo draws
+    are bound once with :meth:`set_observables` / :meth:`set_draws`.
+    """
+
+    def __init__(self, config: ModelConfig, device: int = 0):
+        config.validate()
+        self.config = config
+        self.device = int(device)
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        self._keep = []  # host tables must outlive tof_create only, kept for introspection
+        c = _lib.TofConfig()
+        c.abi_version = _lib.ABI_VERSION
+        c.model = config.kind
+        c.device = self.device
+        c.ode_mode = config.ode_mode
+        c.ode_substeps = config.ode_substeps
+        c.ode_from_zero = int(config.ode_from_zero)
+        c.prior_strict = int(config.prior_strict)
+        c.nan_to_neginf = int(config.nan_to_neginf)
+        c.ndim = config.ndim
+        c.n_runs = config.n_runs
+        c.n_samples = config.n_samples
+        c.n_ev_per_loop = config.n_ev_per_loop
+        c.n_loops = config.n_loops
+        c.speed_of_light = cfgmod.SPEED_OF_LIGHT
+        c.mass_deuteron = cfgmod.MASS_DEUTERON
+        c.mass_neutron = cfgmod.MASS_NEUTRON
+        c.mass_he3 = cfgmod.MASS_HE3
+        c.q_ddn = cfgmod.Q_DDN
+        c.cell_length = cfgmod.distances.cellLength
+        c.simple_neutron_base = cfgmod.distances.cellToZero
+        for i, (lo, hi) in enumerate(config.prior):
+            c.prior_lo[i] = lo
+            c.prior_hi[i] = hi
+        for r in range(config.n_runs):
+            c.tof_bins[r] = config.tof_bins[r]
+            c.tof_min[r], c.tof_max[r] = config.tof_ranges[r]
+        if config.kind != cfgmod.KIND_SIMPLE:
+            c.x_bins, c.e_bins = config.x_bins, config.e_bins
+            c.x_min, c.x_max = config.x_range
+            c.e_min, c.e_max = config.e_range
+            A, B = cfgmod.bethe_reduced(config.materials)
+            c.n_materials = len(A)
+            for k in range(len(A)):
+                c.bethe_A[k], c.bethe_B[k] = A[k], B[k]
+            tabs = dict(
+                x_centers=_as_f64(config.x_centers()),
+                e_centers=_as_f64(config.e_centers()),
+                neutron_speed=_as_f64(config.neutron_speed()),
+                neutron_dist=_as_f64(config.neutron_dist()),
+                xs_breaks=_as_f64(cfgmod.DDN_XS_ENERGIES),
+                xs_coefs=_as_f64(cfgmod.not_a_knot_cubic(cfgmod.DDN_XS_ENERGIES, cfgmod.DDN_XS_SIGMA0)),
+                taps=_as_f64(config.taps),
+            )
+            c.n_xs = tabs["xs_breaks"].shape[0]
+            c.n_taps = tabs["taps"].shape[0]
+            c.n_zero_deg = config.n_zero_deg
+            if config.n_zero_deg:
+                t, w = cfgmod.zero_degree_tables(cfgmod.dd_neutron_energy(config.e_centers()), config.n_zero_deg)
+                tabs["zero_deg_times"], tabs["zero_deg_weights"] = _as_f64(t), _as_f64(w)
+            for name, arr in tabs.items():
+                setattr(c, name, _dptr(arr))
+            self._keep.append(tabs)
+            self.tables = tabs
+        rc = self._lib.tof_create(C.byref(c), C.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.tof_last_error(None)
+            self._ctx = C.c_void_p()
+            raise _lib.TofError(rc, msg.decode() if msg else "")
+
+    # -- lifetime -------------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.tof_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int) -> None:
+        _lib.check(self._lib, self._ctx, rc)
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._ctx
+
+    # -- inputs ---------------------------------------------------------------------------------------
+    def set_observables(self, observables, run: int = 0) -> None:
+        obs = _as_f64(observables).ravel()
+        self._check(self._lib.tof_set_observables(self._ctx, run, _dptr(obs), obs.shape[0]))
+
+    def set_draws(self, values, run: int = 0, stream: int = 0, sort: bool = False) -> None:
+        """Bind explicit draws.  ``sort=True`` sorts stream-0 normals first: the model is a sum over
+        draws, so their order only matters for speed (neighbouring threads then hit the same
+        histogram bins and merge their updates)."""
+        v = _as_f64(values).ravel()
+        if sort:
+            v = np.sort(v)
+        self._check(self._lib.tof_set_draws(self._ctx, run, stream, _dptr(v), v.shape[0]))
+
+    # -- evaluation -----------------------------------------------------------------------------------
+    def _thetas(self, thetas) -> np.ndarray:
+        t = _as_f64(thetas)
+        if t.ndim == 1:
+            t = t.reshape(1, -1)
+        if t.ndim != 2 or t.shape[1] != self.config.ndim:
+            raise ValueError("thetas must have shape [n, %d]" % self.config.ndim)
+        return t
+
+    def lnprob_batch(self, thetas) -> np.ndarray:
+        t = self._thetas(thetas)
+        out = np.empty(t.shape[0], dtype=np.float64)
+        self._check(self._lib.tof_lnprob_batch(self._ctx, _dptr(t), t.shape[0], _dptr(out)))
+        return out
+
+    def lnprob_batch_device(self, theta_ptr: int, n: int, out_ptr: int, stream: int = 0) -> None:
+        """Device pointers (e.g. ``tensor.data_ptr()``), asynchronous on ``stream``."""
+        self._check(self._lib.tof_lnprob_batch_device(self._ctx, C.c_void_p(theta_ptr), n, C.c_void_p(out_ptr),
+                                                      C.c_void_p(stream)))
+
+    def model_batch(self, thetas, run: int = 0, stage: str = "spread") -> np.ndarray:
+        t = self._thetas(thetas)
+        out = np.empty((t.shape[0], self.config.tof_bins[run]), dtype=np.float64)
+        self._check(self._lib.tof_model_batch(self._ctx, _dptr(t), t.shape[0], run, STAGES[stage], _dptr(out)))
+        return out
+
+    def cell_counts(self, thetas, run: int = 0) -> np.ndarray:
+        t = self._thetas(thetas)
+        out = np.empty((t.shape[0], self.config.x_bins, self.config.e_bins), dtype=np.int64)
+        self._check(self._lib.tof_cell_counts_batch(self._ctx, _dptr(t), t.shape[0], run,
+                                                    out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
+    # -- sampler kernels (device pointers) ------------------------------------------------------------
+    def stretch_propose(self, s_ptr, n, walker0, comp_ptr, n_comp, a, seed, step, half, q_ptr, logzz_ptr, stream=0):
+        self._check(self._lib.tof_stretch_propose(self._ctx, C.c_void_p(s_ptr), n, walker0, C.c_void_p(comp_ptr), n_comp,
+                                                  a, seed, step, half, C.c_void_p(q_ptr), C.c_void_p(logzz_ptr),
+                                                  C.c_void_p(stream)))
+
+    def stretch_accept(self, s_ptr, lnprob_ptr, n, walker0, q_ptr, newlp_ptr, logzz_ptr, seed, step, half,
+                       naccept_ptr=0, stream=0):
+        self._check(self._lib.tof_stretch_accept(self._ctx, C.c_void_p(s_ptr), C.c_void_p(lnprob_ptr), n, walker0,
+                                                 C.c_void_p(q_ptr), C.c_void_p(newlp_ptr), C.c_void_p(logzz_ptr), seed,
+                                                 step, half, C.c_void_p(naccept_ptr), C.c_void_p(stream)))
+
+    # -- diagnostics ----------------------------------------------------------------------------------
+    def stats(self) -> dict:
+        s = _lib.TofStats()
+        self._check(self._lib.tof_get_stats(self._ctx, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def set_timing(self, enabled: bool) -> None:
+        self._check(self._lib.tof_set_timing(self._ctx, int(enabled)))
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.tof_last_kernel_ms(self._ctx, C.byref(ms)))
+        return float(ms.value)
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double()
+        self._check(self._lib.tof_measure_fp64_peak(self._ctx, C.byref(v)))
+        return float(v.value)

@@ -152,13 +152,19 @@ def sweep():
     for th in thetas:
         np.random.seed(seed)
         vals.append(f(ns["lnprob"](list(th), obs)) if False else f(ns["lnlike"](list(th), obs, nDraws=1024)))
+    counts = []
+    for th in thetas:
+        np.random.seed(seed)
+        c = ns["generateModelData"](list(th), standoff, ns["ddnXSinstance"], model.dEdx, 1024, False)
+        nzc = np.nonzero(c)[0]
+        counts.append({"idx": [int(i) for i in nzc], "val": [int(v) for v in c[nzc]]})
     np.random.seed(seed)
     pdf0 = ns["beamTiming"].applySpreading(
         ns["generateModelData"](list(thetas[0]), standoff, ns["ddnXSinstance"], model.dEdx, 1024, True))
     nz = np.nonzero(pdf0)[0]
     return {"draw_seed": seed, "obs_nonzero_idx": [int(i) for i in np.nonzero(obs)[0]],
             "obs_nonzero_val": fl(obs[np.nonzero(obs)[0]]), "thetas": [fl(t) for t in thetas],
-            "lnlike": vals, "pdf0_nonzero_idx": [int(i) for i in nz], "pdf0_nonzero_val": fl(pdf0[nz])}
+            "lnlike": vals, "counts": counts, "pdf0_nonzero_idx": [int(i) for i in nz], "pdf0_nonzero_val": fl(pdf0[nz])}
 
 
 def simult(full=True):

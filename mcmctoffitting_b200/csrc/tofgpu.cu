@@ -33,7 +33,7 @@ struct tof_ctx {
     bool timing = false, timed = false;
     std::string err;
     tof_stats stats{};
-    int adv_nt = 256, adv_dpt = 4;
+    int adv_nt = 1024, adv_dpt = 1;
     size_t adv_smem = 0;
     int max_smem_optin = 0;
     bool have_obs[TOF_MAX_RUNS]{};

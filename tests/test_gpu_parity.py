@@ -172,7 +172,7 @@ def test_adv_kernel_variants_agree(M, O):
             os.environ.pop("TOFGPU_ADV_VARIANT", None)
         else:
             os.environ["TOFGPU_ADV_VARIANT"] = old
-    base = results["256x4"]
+    base = results["1024x1"]
     for v, (lp, cc) in results.items():
         assert np.array_equal(cc, base[1]), v
         for a, b in zip(lp, base[0]):

@@ -104,6 +104,24 @@ typedef struct tof_config {
     const double *taps;           /* [n_taps]            utilities.py:262 */
     const double *zero_deg_times;   /* [e_bins][n_zero_deg] utilities.py:185 */
     const double *zero_deg_weights; /* [e_bins][n_zero_deg] utilities.py:188-190 */
+    /* ---- TOF_ODE_RANGE only: range-energy tables of the autonomous stopping ODE ------------------
+     * u(E) = int_{e_min}^{E} dE'/|dE/dx|; along a track u(E(x)) = u(E0) + rng_sign*(x - x_start).
+     * T1 gives u(E0) per draw; T2 gives, for v = u of a (draw, x) sample, the E-bin and the
+     * cross-section weight XS(E(v)) (ionStopping.py:78-97 + utilities.py:412-429 composed). */
+    int32_t t1_q;        /* T1 cells per octave of E = 2^t1_q, indexed by exponent/mantissa bits */
+    int32_t t1_key_lo;   /* (high word of E) >> (20 - t1_q) of the first T1 cell */
+    int32_t t1_n;        /* T1 cells */
+    int32_t rng_degree;  /* T2 polynomial degree (5 or 7) */
+    int32_t rng_n;       /* T2 intervals */
+    int32_t rng_lut_n;   /* uniform lookup cells over [0, rng_u_max] */
+    double rng_sign;     /* sign of dE/dx on the table domain */
+    double rng_u_max;    /* u(e_max); u(e_min) = 0 */
+    double e_tab_lo, e_tab_hi;  /* T1 domain [lo, hi) */
+    const double *t1_coefs;     /* [t1_n][8] monomials in t in [-1,1] over the cell, lowest order first */
+    const double *rng_breaks;   /* [rng_n+1] T2 breakpoints in u (every E-bin edge and XS knot is one) */
+    const int32_t *rng_bins;    /* [rng_n] E-bin of each interval */
+    const double *rng_coefs;    /* [rng_n][rng_degree+1] monomials in (v - break), lowest order first */
+    const uint16_t *rng_lut;    /* [rng_lut_n] interval holding the left edge of each lookup cell */
 } tof_config;
 
 typedef struct tof_ctx tof_ctx;

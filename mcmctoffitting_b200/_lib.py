@@ -31,6 +31,11 @@ class TofConfig(C.Structure):
         ("tof_bins", C.c_int32 * MAX_RUNS), ("tof_min", C.c_double * MAX_RUNS), ("tof_max", C.c_double * MAX_RUNS),
         ("x_centers", _dp), ("e_centers", _dp), ("neutron_speed", _dp), ("neutron_dist", _dp),
         ("xs_breaks", _dp), ("xs_coefs", _dp), ("taps", _dp), ("zero_deg_times", _dp), ("zero_deg_weights", _dp),
+        ("t1_q", C.c_int32), ("t1_key_lo", C.c_int32), ("t1_n", C.c_int32), ("rng_degree", C.c_int32),
+        ("rng_n", C.c_int32), ("rng_lut_n", C.c_int32),
+        ("rng_sign", C.c_double), ("rng_u_max", C.c_double), ("e_tab_lo", C.c_double), ("e_tab_hi", C.c_double),
+        ("t1_coefs", _dp), ("rng_breaks", _dp), ("rng_bins", C.POINTER(C.c_int32)), ("rng_coefs", _dp),
+        ("rng_lut", C.POINTER(C.c_uint16)),
     ]
 
 

@@ -27,10 +27,12 @@ struct DevModel {
     const unsigned char *xs_lut;
     int xs_lut_n;
     double xs_lut_lo, xs_lut_inv;
-    // range-energy table (TOF_ODE_RANGE)
-    const double *rng_coefs;  // [rng_n][RNG_ORDER+1]
-    int rng_n;
-    double rng_r0, rng_inv_dr, rng_rmax, rng_sign;
+    // range-energy tables (TOF_ODE_RANGE), see range_tables.py
+    const double *t1_coefs;        // [t1_n][8]
+    const double *rng_rec;         // [rng_n][P+3]: next break, bin, a0..aP
+    const unsigned short *rng_lut; // [rng_lut_n]
+    int t1_q, t1_key_lo, t1_n, rng_degree, rng_n, rng_lut_n;
+    double rng_sign, rng_u_max, rng_lut_inv, e_tab_lo, e_tab_hi;
 };
 
 struct DevRun {

@@ -402,3 +402,273 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
 }
 
 }  // namespace tof
+
+namespace tof {
+
+// ================================================================================================
+// adv / intermediate model, range-table formulation (TOF_ODE_RANGE)
+// ================================================================================================
+// The stopping ODE is autonomous, so u(E) = int dE/|f| turns "integrate every draw through every x"
+// into v = u0_d + sgn*(x_i - x_start).  With the draws sorted, v is monotone along d for a fixed row,
+// so one thread walks a run of consecutive draws with a pointer into the T2 table (bin + polynomial
+// of the cross-section weight), sums whole runs in a register and touches the (x,E) histogram once
+// per run instead of once per sample.
+constexpr int RANGE_TILE = 1024;   // draws staged in shared memory at a time
+
+__host__ __device__ inline size_t range_smem_bytes(int X, int E, int T, int rng_n, int P, int n_taps, int lut_n) {
+    size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
+    region_a = (region_a + 15) / 16 * 16;
+    size_t d = (size_t)X * E + (size_t)rng_n * (P + 3) + E + n_taps + 40;
+    return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16;
+}
+
+// u0 = u(E0): T1 cell from the exponent/mantissa bits, degree-7 Horner in t in [-1, 1].
+__device__ __forceinline__ double t1_eval(double E0, const DevModel &m) {
+    double t;
+    int idx;
+    if (!(E0 >= m.e_tab_lo)) {                 // below the table, non-positive or NaN
+        if (m.rng_sign > 0.0 && E0 > 0.0) {    // rising energies: clamp tiny E0 to the table start
+            t = -1.0;
+            idx = 0;
+        } else {
+            return -CUDART_INF;
+        }
+    } else if (E0 >= m.e_tab_hi) {
+        return CUDART_INF;
+    } else {
+        const int hi = __double2hiint(E0), lo = __double2loint(E0);
+        const int key = hi >> (20 - m.t1_q);
+        idx = key - m.t1_key_lo;
+        const double mant = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);   // [1, 2)
+        const double c = (double)(key & ((1 << m.t1_q) - 1));
+        t = (mant - 1.0) * (double)(1 << (m.t1_q + 1)) - (2.0 * c + 1.0);             // exact
+    }
+    const double *k = m.t1_coefs + 8 * idx;
+    double acc = __ldg(k + 7);
+#pragma unroll
+    for (int q = 6; q >= 0; --q) acc = fma(acc, t, __ldg(k + q));
+    return acc;
+}
+
+template <int NT, int P>
+__global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const DevRun run, const double *__restrict__ theta,
+                                                       long long n_walkers, ModelOut out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int RW = P + 3;
+    const int T = run.tof_bins, X = m.x_bins, EB = m.e_bins, M = m.rng_n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    // ---- carve --------------------------------------------------------------------------------------
+    double *H = reinterpret_cast<double *>(smem_raw);
+    size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
+    region_a = (region_a + 15) / 16 * 16;
+    unsigned char *pa = reinterpret_cast<unsigned char *>(H + (size_t)X * EB);
+    unsigned int *tofc = reinterpret_cast<unsigned int *>(pa);
+    double *u0 = reinterpret_cast<double *>(pa);                       // aliases tofc (phase 1 only)
+    double *rec = reinterpret_cast<double *>(pa + region_a);
+    double *svd = rec + (size_t)M * RW;
+    double *staps = svd + EB;
+    double *scratch = staps + m.n_taps;
+    unsigned short *lut = reinterpret_cast<unsigned short *>(scratch + 40);
+
+    const long long w = blockIdx.x;
+    if (w >= n_walkers) return;
+    const double e0 = theta[w * m.ndim + 0];
+    const double sigma0 = theta[w * m.ndim + 1];
+    bool inside = true;
+    for (int p = 0; p < m.ndim; ++p) {
+        const double v = theta[w * m.ndim + p];
+        inside = inside && (m.prior_strict ? (m.prior_lo[p] < v && v < m.prior_hi[p])
+                                           : !(v < m.prior_lo[p] || v > m.prior_hi[p]));
+    }
+    if (!inside && out.spectra == nullptr && out.cells == nullptr) {
+        if (tid == 0) out.lnprob[w] = -CUDART_INF;
+        return;
+    }
+
+    // ---- stage tables, zero the cell histogram ---------------------------------------------------------
+    for (int i = tid; i < X * EB; i += NT) H[i] = 0.0;
+    for (int i = tid; i < M * RW; i += NT) rec[i] = m.rng_rec[i];
+    for (int i = tid; i < m.rng_lut_n; i += NT) lut[i] = m.rng_lut[i];
+    for (int j = tid; j < EB; j += NT) {
+        const double eff = __ddiv_rn(__dadd_rn(e0, m.e_centers[j]), 2.0);   // adv:151
+        svd[j] = speed_of(m.c, eff, m.m_d);
+    }
+    for (int i = tid; i < m.n_taps; i += NT) staps[i] = m.taps[i];
+
+    const double spread = __dmul_rn(sigma0, e0);          // adv:128
+    const double sgn = m.rng_sign, umax = m.rng_u_max;
+    const double x_start = m.ode_from_zero ? 0.0 : m.x_centers[0];
+
+    // ---- phase 1: (x,E) histogram of cross-section weights through the range tables ---------------------
+    for (long long tile = 0; tile < m.n_draws; tile += RANGE_TILE) {
+        const int nt = (int)((m.n_draws - tile < RANGE_TILE) ? (m.n_draws - tile) : RANGE_TILE);
+        __syncthreads();                                   // previous tile fully consumed / staging done
+        for (int d = tid; d < nt; d += NT)
+            u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + tile + d))), m);
+        __syncthreads();
+        for (int row = warp; row < X; row += NW) {
+            const double delta = sgn * (__ldg(m.x_centers + row) - x_start);
+            int lo = 0, hi = nt;
+            while (lo < hi) {                              // first draw with v >= 0  (E >= e_min)
+                const int mid = (lo + hi) >> 1;
+                if (__dadd_rn(u0[mid], delta) >= 0.0) hi = mid; else lo = mid + 1;
+            }
+            const int d_lo = lo;
+            hi = nt;
+            while (lo < hi) {                              // first draw with v > u_max  (E > e_max)
+                const int mid = (lo + hi) >> 1;
+                if (__dadd_rn(u0[mid], delta) > umax) hi = mid; else lo = mid + 1;
+            }
+            const int d_hi = lo;
+            const int W = d_hi - d_lo;
+            if (W <= 0) continue;
+            const int per = ((W + 31) >> 5) | 1;           // odd stride: conflict-free u0 reads across lanes
+            const int my_lo = d_lo + lane * per;
+            const int my_hi = (my_lo + per < d_hi) ? my_lo + per : d_hi;
+            if (my_lo >= my_hi) continue;
+            double v = __dadd_rn(u0[my_lo], delta);
+            int c = (int)(v * m.rng_lut_inv);
+            c = c < 0 ? 0 : (c > m.rng_lut_n - 1 ? m.rng_lut_n - 1 : c);
+            int j = lut[c];
+            while (j + 1 < M && v >= rec[j * RW]) ++j;
+            while (j > 0 && v < rec[(j - 1) * RW]) --j;
+            // records are 16-byte aligned with an even word count: 128-bit loads, conflict-free across rows
+            const double2 *rj = reinterpret_cast<const double2 *>(rec + j * RW);
+            double2 hd = rj[0];
+            double next = hd.x;
+            double brk = j ? rec[(j - 1) * RW] : 0.0;
+            int bin = (int)hd.y;
+            double a[P + 1];
+#pragma unroll
+            for (int k = 0; k <= P; k += 2) {
+                const double2 c2 = rj[1 + (k >> 1)];
+                a[k] = c2.x;
+                a[k + 1] = c2.y;
+            }
+            double acc = 0.0;
+            double *Hrow = H + (size_t)row * EB;
+            for (int d = my_lo; d < my_hi; ++d) {
+                v = __dadd_rn(u0[d], delta);
+                if (v >= next && j + 1 < M) {
+                    do {
+                        ++j;
+                        brk = next;
+                        hd = reinterpret_cast<const double2 *>(rec + j * RW)[0];
+                        next = hd.x;
+                    } while (v >= next && j + 1 < M);
+                    const int nb = (int)hd.y;
+                    if (nb != bin) {
+                        atomicAdd(Hrow + bin, acc);
+                        acc = 0.0;
+                        bin = nb;
+                    }
+                    rj = reinterpret_cast<const double2 *>(rec + j * RW);
+#pragma unroll
+                    for (int k = 0; k <= P; k += 2) {
+                        const double2 c2 = rj[1 + (k >> 1)];
+                        a[k] = c2.x;
+                        a[k + 1] = c2.y;
+                    }
+                }
+                const double dt = v - brk;
+                double wgt = a[P];
+#pragma unroll
+                for (int k = P - 1; k >= 0; --k) wgt = fma(wgt, dt, a[k]);
+                acc += wgt;
+            }
+            atomicAdd(Hrow + bin, acc);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: normalise (adv:143) ---------------------------------------------------------------------
+    for (int i = tid; i < T; i += NT) tofc[i] = 0u;        // u0 is dead now
+    const double de = (m.e_max - m.e_min) / (double)EB;
+    const double dx = (m.x_max - m.x_min) / (double)X;
+    double part = 0.0;
+    for (int i = tid; i < X * EB; i += NT) part += __dmul_rn(__dmul_rn(H[i], de), dx);
+    const double S = block_sum<double>(part, scratch);     // includes the barrier that publishes tofc = 0
+
+    // ---- phase 3: quantise (adv:146) and scatter every non-empty cell to its flight time (adv:149-158) ----
+    const double t_step = (run.tof_max - run.tof_min) / (double)T;
+    const double t_scale = (double)T / (run.tof_max - run.tof_min);
+    const double nsamp = (double)m.n_samples;
+    for (int idx = tid; idx < X * EB; idx += NT) {
+        const double h = H[idx];
+        double cnt = 0.0;
+        if (h != 0.0 || !(S > 0.0)) cnt = rint(__dmul_rn(__ddiv_rn(h, S), nsamp));
+        if (out.cells) out.cells[(size_t)w * X * EB + idx] = (cnt == cnt) ? (long long)cnt : LLONG_MIN;
+        if (cnt > 0.0) {
+            const int i = idx / EB, j = idx - i * EB;
+            const double tof_d = __ddiv_rn(__ldg(m.x_centers + i), svd[j]);
+            const double tof_n = __ddiv_rn(__ldg(run.neutron_dist + i), __ldg(m.neutron_speed + j));
+            const int b = np_bin(__dadd_rn(tof_d, tof_n), T, run.tof_min, run.tof_max, t_step, t_scale);
+            if (b >= 0) atomicAdd(tofc + b, (unsigned int)cnt);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 4: density (np.histogram density=True) into the (now free) H region -------------------------
+    long long cpart = 0;
+    for (int t = tid; t < T; t += NT) cpart += (long long)tofc[t];
+    const long long total_i = block_sum<long long>(cpart, reinterpret_cast<long long *>(scratch));
+    const bool degenerate = !(S > 0.0) || total_i == 0;
+    const double total = (double)total_i;
+    double *pdf = H;
+    for (int t = tid; t < T; t += NT) {
+        const unsigned int cn = tofc[t];
+        double v = 0.0;
+        if (cn) {
+            const double db = __dsub_rn(np_edge(t + 1, T, run.tof_min, run.tof_max, t_step),
+                                        np_edge(t, T, run.tof_min, run.tof_max, t_step));
+            v = __ddiv_rn(__ddiv_rn((double)cn, db), total);
+        }
+        pdf[t] = v;
+    }
+    __syncthreads();
+
+    if (out.spectra) {
+        double *sp = out.spectra + (size_t)w * T;
+        for (int t = tid; t < T; t += NT) {
+            double v;
+            if (out.stage == TOF_STAGE_COUNTS) {
+                v = (double)tofc[t];
+            } else if (degenerate) {
+                v = CUDART_NAN;
+            } else if (out.stage == TOF_STAGE_PDF) {
+                v = pdf[t];
+            } else {
+                v = 0.0;
+                for (int k = 0; k < m.n_taps; ++k) {
+                    const int tt = t + m.conv_shift - k;
+                    if (tt >= 0 && tt < T) v += staps[k] * pdf[tt];
+                }
+            }
+            sp[t] = v;
+        }
+    }
+
+    // ---- phase 5: timing response at the observed bins + log-likelihood (adv:173-181) ------------------------
+    double lp = 0.0;
+    if (!degenerate) {
+        for (int q = tid; q < run.n_obs_nz; q += NT) {
+            const int t = run.obs_nz_idx[q];
+            double ev = 0.0;
+            for (int k = 0; k < m.n_taps; ++k) {
+                const int tt = t + m.conv_shift - k;
+                if (tt >= 0 && tt < T) ev += staps[k] * pdf[tt];
+            }
+            lp += run.obs_nz_val[q] * log(ev);
+        }
+    }
+    lp = block_sum<double>(lp, scratch);
+    if (tid == 0 && out.lnprob) {
+        double r = degenerate ? CUDART_NAN : lp;
+        if (!inside) r = -CUDART_INF;
+        if (m.nan_to_neginf && r != r) r = -CUDART_INF;
+        out.lnprob[w] = r;
+    }
+}
+
+}  // namespace tof

@@ -35,6 +35,7 @@ struct tof_ctx {
     tof_stats stats{};
     int adv_nt = 1024, adv_dpt = 1;
     size_t adv_smem = 0;
+    int rng_nt = 1024;
     int max_smem_optin = 0;
     bool have_obs[TOF_MAX_RUNS]{};
     bool have_z[TOF_MAX_RUNS][2]{};
@@ -92,6 +93,14 @@ AdvKernel adv_variant(int nt, int dpt, int nmat) {
     return nullptr;
 }
 
+AdvKernel range_variant(int nt, int degree) {
+    if (nt == 1024 && degree == 7) return adv_range_kernel<1024, 7>;
+    if (nt == 512 && degree == 7) return adv_range_kernel<512, 7>;
+    if (nt == 1024 && degree == 5) return adv_range_kernel<1024, 5>;
+    if (nt == 512 && degree == 5) return adv_range_kernel<512, 5>;
+    return nullptr;
+}
+
 int check_run(tof_ctx *ctx, int run) {
     if (run < 0 || run >= ctx->cfg.n_runs) return fail(ctx, TOF_ERR_INVALID, "run index out of range");
     return TOF_OK;
@@ -113,8 +122,13 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
     const tof_config &c = ctx->cfg;
     if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev0, st));
     if (c.model == TOF_MODEL_ADV) {
-        AdvKernel k = adv_variant(ctx->adv_nt, ctx->adv_dpt, c.n_materials);
-        k<<<(unsigned)n, ctx->adv_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
+        if (c.ode_mode == TOF_ODE_RANGE) {
+            AdvKernel k = range_variant(ctx->rng_nt, c.rng_degree);
+            k<<<(unsigned)n, ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
+        } else {
+            AdvKernel k = adv_variant(ctx->adv_nt, ctx->adv_dpt, c.n_materials);
+            k<<<(unsigned)n, ctx->adv_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
+        }
         ctx->stats.kernel_launches += 1;
     } else if (c.model == TOF_MODEL_SIMPLE) {
         const int T = c.tof_bins[0];
@@ -287,7 +301,54 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         }
     }
 
-    if (cfg->model == TOF_MODEL_ADV) {
+    if (cfg->model == TOF_MODEL_ADV && cfg->ode_mode == TOF_ODE_RANGE) {
+        if (!cfg->t1_coefs || !cfg->rng_breaks || !cfg->rng_bins || !cfg->rng_coefs || !cfg->rng_lut || cfg->rng_n < 1 ||
+            cfg->t1_n < 1 || cfg->rng_lut_n < 1 || !(cfg->rng_u_max > 0.0)) {
+            ctx->err = "TOF_ODE_RANGE needs the range tables (t1_*, rng_*)";
+            return bail(TOF_ERR_INVALID);
+        }
+        if (cfg->rng_degree != 5 && cfg->rng_degree != 7) { ctx->err = "rng_degree must be 5 or 7"; return bail(TOF_ERR_INVALID); }
+        if (cfg->ode_substeps < 1) { ctx->err = "ode_substeps must be >= 1"; return bail(TOF_ERR_INVALID); }
+        // np.rint counts are accumulated as u32 per TOF bin: bound the total by nSamples/(dE*dx)
+        {
+            const double de = (cfg->e_max - cfg->e_min) / cfg->e_bins, dx = (cfg->x_max - cfg->x_min) / cfg->x_bins;
+            if ((double)cfg->n_samples / (de * dx) * 1.01 + cfg->x_bins * (double)cfg->e_bins > 4.0e9) {
+                ctx->err = "n_samples too large for the 32-bit TOF counters of the range kernel; use TOF_ODE_RK4";
+                return bail(TOF_ERR_CAPACITY);
+            }
+        }
+        const int P = cfg->rng_degree, RW = P + 3, Mi = cfg->rng_n;
+        std::vector<double> rec((size_t)Mi * RW);
+        for (int j = 0; j < Mi; ++j) {
+            rec[(size_t)j * RW + 0] = cfg->rng_breaks[j + 1];
+            rec[(size_t)j * RW + 1] = (double)cfg->rng_bins[j];
+            for (int k = 0; k <= P; ++k) rec[(size_t)j * RW + 2 + k] = cfg->rng_coefs[(size_t)j * (P + 1) + k];
+        }
+        TRY(upload(ctx, rec.data(), rec.size(), &m.rng_rec));
+        TRY(upload(ctx, cfg->t1_coefs, (size_t)cfg->t1_n * 8, &m.t1_coefs));
+        TRY(upload(ctx, cfg->rng_lut, (size_t)cfg->rng_lut_n, &m.rng_lut));
+        m.t1_q = cfg->t1_q; m.t1_key_lo = cfg->t1_key_lo; m.t1_n = cfg->t1_n; m.rng_degree = P; m.rng_n = Mi;
+        m.rng_lut_n = cfg->rng_lut_n; m.rng_sign = cfg->rng_sign; m.rng_u_max = cfg->rng_u_max;
+        m.rng_lut_inv = (double)cfg->rng_lut_n / cfg->rng_u_max; m.e_tab_lo = cfg->e_tab_lo; m.e_tab_hi = cfg->e_tab_hi;
+        if (const char *v = std::getenv("TOFGPU_RANGE_THREADS")) {
+            const int nt = std::atoi(v);
+            if (!range_variant(nt, P)) { ctx->err = "TOFGPU_RANGE_THREADS must be 512 or 1024"; return bail(TOF_ERR_INVALID); }
+            ctx->rng_nt = nt;
+        }
+        ctx->adv_smem = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], Mi, P, cfg->n_taps, cfg->rng_lut_n);
+        if ((int)ctx->adv_smem > ctx->max_smem_optin) {
+            ctx->err = "range kernel needs " + std::to_string(ctx->adv_smem) + " B of shared memory per CTA; device offers " +
+                       std::to_string(ctx->max_smem_optin);
+            return bail(TOF_ERR_CAPACITY);
+        }
+        AdvKernel k = range_variant(ctx->rng_nt, P);
+        CUC(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->adv_smem));
+        int occ = 0;
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, ctx->rng_nt, ctx->adv_smem));
+        ctx->stats.smem_bytes = (int)ctx->adv_smem;
+        ctx->stats.threads = ctx->rng_nt;
+        ctx->stats.ctas_per_sm = occ;
+    } else if (cfg->model == TOF_MODEL_ADV) {
         if (const char *v = std::getenv("TOFGPU_ADV_VARIANT")) {
             int nt = 0, dpt = 0;
             if (std::sscanf(v, "%dx%d", &nt, &dpt) == 2 && adv_variant(nt, dpt, 1)) {
@@ -371,7 +432,14 @@ int tof_set_draws(tof_ctx *ctx, int run, int stream, const double *values, int64
         return fail(ctx, TOF_ERR_INVALID, "simple model: stream 1 needs as many uniforms as normals");
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     const double *d = nullptr;
-    if (int rc = upload(ctx, values, (size_t)n, &d)) return rc;
+    if (stream == 0 && ctx->cfg.ode_mode == TOF_ODE_RANGE && ctx->cfg.model == TOF_MODEL_ADV) {
+        // the model is a symmetric function of the draws; the range kernel walks them in ascending order
+        std::vector<double> sorted(values, values + n);
+        std::sort(sorted.begin(), sorted.end(), [](double a, double b) { return a < b || (b != b && a == a); });
+        if (int rc = upload(ctx, sorted.data(), (size_t)n, &d)) return rc;
+    } else {
+        if (int rc = upload(ctx, values, (size_t)n, &d)) return rc;
+    }
     DevRun &r = ctx->runs[run];
     if (stream == 0) { r.z = d; r.n_z = n; } else { r.z1 = d; r.n_z1 = n; }
     ctx->have_z[run][stream] = true;

@@ -93,6 +93,22 @@ class TofModel:
                 setattr(c, name, _dptr(arr))
             self._keep.append(tabs)
             self.tables = tabs
+            self.range_tables = None
+            if config.ode_mode == cfgmod.ODE_RANGE:
+                from . import range_tables as rt
+                rtab = rt.build_cached(config)
+                self.range_tables = rtab
+                c.t1_q, c.t1_key_lo, c.t1_n = rtab.t1_q, rtab.t1_key_lo, rtab.t1_n
+                c.rng_degree, c.rng_n, c.rng_lut_n = rtab.degree, len(rtab.bins), len(rtab.lut)
+                c.rng_sign, c.rng_u_max = rtab.sign, rtab.u_max
+                c.e_tab_lo, c.e_tab_hi = rtab.e_tab_lo, rtab.e_tab_hi
+                rt_arrays = dict(t1=_as_f64(rtab.t1_coefs), br=_as_f64(rtab.breaks), co=_as_f64(rtab.coefs),
+                                 bins=np.ascontiguousarray(rtab.bins, dtype=np.int32),
+                                 lut=np.ascontiguousarray(rtab.lut, dtype=np.uint16))
+                c.t1_coefs, c.rng_breaks, c.rng_coefs = _dptr(rt_arrays["t1"]), _dptr(rt_arrays["br"]), _dptr(rt_arrays["co"])
+                c.rng_bins = rt_arrays["bins"].ctypes.data_as(C.POINTER(C.c_int32))
+                c.rng_lut = rt_arrays["lut"].ctypes.data_as(C.POINTER(C.c_uint16))
+                self._keep.append(rt_arrays)
         rc = self._lib.tof_create(C.byref(c), C.byref(self._ctx))
         if rc != 0:
             msg = self._lib.tof_last_error(None)

@@ -261,3 +261,96 @@ def test_errors_are_loud(M):
             m.set_observables(np.zeros(5))         # wrong histogram length
     with pytest.raises(M.TofError):
         M.TofModel(M.config.sweep(), device=99)
+
+
+# ---------------------------------------------------------------------------------------------------
+# range-table formulation (TOF_ODE_RANGE): same model, no per-sample ODE integration
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("excitation", [19.2, 19.2e-3])
+def test_range_cell_counts_vs_oracle(M, O, excitation):
+    cfg = M.config.adv(0, n_samples=2048, n_ev_per_loop=1024, mean_excitation=excitation, ode_mode=M.config.ODE_RANGE)
+    # the oracle's closed-form stopping (Ei inversion): fixed-step RK4 is inaccurate for the rare draws with
+    # E0 of a few keV (|dE/dx| ~ 1e5 keV/cm there), where the reference's adaptive LSODA is not
+    om = O.adv_model(0, n_samples=2048, n_ev_per_loop=1024, mean_excitation=excitation, ode_scheme="exact")
+    z = np.random.RandomState(5).standard_normal(cfg.n_draws)
+    thetas = np.array([[1050, .10], [1500, .05], [2000, .3], [1200, .45], [2590, .02], [1001, .49]])
+    xs = O.DDNXS()
+    with M.TofModel(cfg) as m:
+        m.set_draws(z)
+        got = m.cell_counts(thetas)
+    for k, th in enumerate(thetas):
+        want = om.cell_counts(th, z, xs)
+        assert np.count_nonzero(got[k] != want) == 0, (k, th)
+
+
+def test_range_sweep_reference_goldens(M, O, golden, pf):
+    g = golden["sweep"]
+    cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE)
+    obs = np.zeros(2048)
+    obs[g["obs_nonzero_idx"]] = parse_floats(g["obs_nonzero_val"])
+    z = np.random.RandomState(g["draw_seed"]).standard_normal(1024)
+    thetas = np.array(g["thetas"])
+    with M.TofModel(cfg) as m:
+        m.set_observables(obs)
+        m.set_draws(z)
+        got = m.lnprob_batch(thetas)
+        counts = m.model_batch(thetas, stage="counts")
+        pdf0 = m.model_batch(thetas[:1], stage="spread")[0]
+    want = np.array([pf(v) for v in g["lnlike"]])
+    bad = [k for k in range(len(want)) if rel(float(got[k]), float(want[k])) > RTOL]
+    assert len(bad) <= 1, (bad, got[bad], want[bad])
+    n_bad = 0
+    for k, c in enumerate(g["counts"]):
+        want_c = np.zeros(2048)
+        want_c[c["idx"]] = c["val"]
+        n_bad += int(not np.array_equal(counts[k], want_c))
+    assert n_bad <= 1, n_bad
+    want0 = np.zeros(2048)
+    want0[g["pdf0_nonzero_idx"]] = parse_floats(g["pdf0_nonzero_val"])
+    np.testing.assert_allclose(pdf0, want0, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("excitation", [19.2, 19.2e-3])
+def test_range_vs_rk4_kernels_many_walkers(M, O, excitation):
+    """The two CUDA formulations on 2048 walkers spread over the whole prior box: integer TOF spectra
+    must be identical for (almost) every walker -- a draw within ~1e-9 keV of a bin edge may flip."""
+    n = 2048
+    rs = np.random.RandomState(77)
+    thetas = np.column_stack([rs.uniform(1000, 2600, n), rs.uniform(0.02, 0.5, n)])
+    z = rs.standard_normal(1024)
+    om = O.sweep_model(mean_excitation=excitation)
+    obs = np.rint(1e5 * om.model_pdf([1050, .10], np.random.RandomState(7).standard_normal(1024)))
+    res = {}
+    for mode in (M.config.ODE_RK4, M.config.ODE_RANGE):
+        cfg = M.config.sweep(mean_excitation=excitation, ode_mode=mode, ode_substeps=1 if mode == M.config.ODE_RANGE else 4)
+        with M.TofModel(cfg) as m:
+            m.set_observables(obs)
+            m.set_draws(z)
+            res[mode] = (m.lnprob_batch(thetas), m.model_batch(thetas, stage="counts"))
+    lp_a, c_a = res[M.config.ODE_RK4]
+    lp_b, c_b = res[M.config.ODE_RANGE]
+    # fixed-step RK4 is only trustworthy when no draw starts at a few keV, i.e. for sigma0 well below 1/|z_min|
+    narrow = thetas[:, 1] * (-z.min()) < 0.9
+    assert narrow.sum() > 800
+    diff_walkers = int(np.count_nonzero(np.any(c_a[narrow] != c_b[narrow], axis=1)))
+    assert diff_walkers <= 2, diff_walkers
+    n_lp_bad = sum(rel(float(a), float(b)) > RTOL for a, b in zip(lp_a[narrow], lp_b[narrow]))
+    assert n_lp_bad <= 2, n_lp_bad
+
+
+def test_range_multiple_tiles_and_loops(M, O):
+    """n_draws > the shared-memory tile (1024): 5 loops x 1000 draws, intermediate model."""
+    cfg = M.config.intermediate(1, n_samples=5000, n_ev_per_loop=1000, mean_excitation=19.2e-3, ode_mode=M.config.ODE_RANGE)
+    om = O.intermediate_model(1, n_samples=5000, n_ev_per_loop=1000, mean_excitation=19.2e-3, ode_scheme="exact")
+    z = np.random.RandomState(41).standard_normal(5000)
+    xs = O.DDNXS()
+    obs = np.rint(2e4 * om.model_pdf([900, .15], np.random.RandomState(42).standard_normal(5000), xs))
+    thetas = np.array([[900, .15], [800, .05], [1100, .16], [1199, .169]])
+    with M.TofModel(cfg) as m:
+        m.set_observables(obs)
+        m.set_draws(z)
+        got = m.lnprob_batch(thetas)
+        cc = m.cell_counts(thetas)
+    for k, th in enumerate(thetas):
+        assert np.array_equal(cc[k], om.cell_counts(th, z, xs)), k
+        assert rel(float(got[k]), float(om.lnprob(th, obs, z, xs))) <= RTOL, (k, got[k])

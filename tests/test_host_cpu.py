@@ -1,0 +1,162 @@
+"""CPU-side checks: the C ABI library loads and exports what include/tofgpu.h declares, host tables
+match the oracle / reference KATs, the range tables reproduce the oracle's integer cell counts, and
+the pool adapter behaves like emcee's pool seam.  No GPU compute here."""
+import ctypes
+import warnings
+
+import numpy as np
+import pytest
+
+import mcmctoffitting_b200 as M
+from mcmctoffitting_b200 import _lib, config as C, range_tables as R
+from oracle import tof_oracle as O
+from conftest import parse_floats
+
+warnings.simplefilter("ignore")
+
+
+def test_library_loads_and_exports_every_header_symbol():
+    lib = _lib.load()
+    names = _lib.header_symbols()
+    assert names, "no symbols parsed from include/tofgpu.h"
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(names) == sorted(_lib.SIGNATURES)
+    assert lib.tof_abi_version() == _lib.ABI_VERSION
+    assert lib.tof_sizeof_config() == ctypes.sizeof(_lib.TofConfig)
+
+
+def test_create_fails_loudly_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    with pytest.raises(M.TofError) as ei:
+        M.TofModel(C.sweep())
+    assert "no CPU fallback" in str(ei.value) or "no CUDA device" in str(ei.value)
+
+
+def test_product_does_not_import_the_oracle():
+    import os
+    import re
+    pkg = os.path.dirname(M.__file__)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+def test_config_tables_match_oracle(golden):
+    k = golden["kat"]
+    for cfg, om in [(C.adv(0), O.adv_model(0)), (C.intermediate(3), O.intermediate_model(3)), (C.sweep(), O.sweep_model())]:
+        assert np.array_equal(cfg.x_centers(), om.x_binCenters)
+        assert np.array_equal(cfg.e_centers(), om.eD_binCenters)
+        en = O.getDDneutronEnergy(om.eD_binCenters)
+        assert np.array_equal(cfg.neutron_speed(), O.SPEED_OF_LIGHT * np.sqrt(2 * en / O.M_NEUTRON))
+        want_dist = O.CELL_LENGTH - om.x_binCenters + O.ZERO_DEG_LENGTH / 2 + om.standoff
+        assert np.array_equal(cfg.neutron_dist()[0], want_dist)
+        assert cfg.n_loops == om.n_loops and cfg.prior == om.prior
+    s, so = C.simult(), O.SimultModel()
+    assert s.standoffs == so.standoffs and s.tof_ranges == so.tof_ranges and s.tof_bins == so.tof_bins
+    assert s.prior == so.prior and s.n_loops == so.n_loops
+    np.testing.assert_allclose(np.array(C.adv().taps), parse_floats(k["beamTiming_taps"]), rtol=4e-16)
+    np.testing.assert_allclose(C.gaussian_timing_taps(2.7), parse_floats(k["gaussianTiming_2.7_4_taps"]), rtol=4e-16)
+    zt, zw = C.zero_degree_tables(np.array([2500.0]))
+    assert np.array_equal(zt[0], parse_floats(k["zeroDeg_En2500_times"]))
+    assert np.array_equal(zw[0], parse_floats(k["zeroDeg_En2500_weights"]))
+    assert np.array_equal(C.dd_neutron_energy(parse_floats(k["E"])), parse_floats(k["getDDneutronEnergy"]))
+
+
+def test_bethe_reduced_matches_reference_dedx(golden):
+    k = golden["kat"]
+    E = parse_floats(k["E"])
+    for key, mat in [("dEdx_I19.2e-3", (1, 2, 8.565e-5, 19.2e-3)), ("dEdx_I19.2", (1, 2, 8.565e-5, 19.2)),
+                     ("dEdx_oneBD", (1, 2, 4 * 8.565e-5, 19.2e-3))]:
+        A, B = C.bethe_reduced([mat])
+        np.testing.assert_allclose(-(A[0] / E) * np.log(B[0] * E), parse_floats(k[key]), rtol=3e-14)
+
+
+def test_cross_section_spline_matches_reference(golden):
+    k = golden["kat"]
+    c = C.not_a_knot_cubic(C.DDN_XS_ENERGIES, C.DDN_XS_SIGMA0)
+    x = parse_floats(k["xs_dense_in"])
+    i = np.clip(np.searchsorted(C.DDN_XS_ENERGIES, x, side="right") - 1, 0, 59)
+    t = x - C.DDN_XS_ENERGIES[i]
+    y = ((c[i, 0] * t + c[i, 1]) * t + c[i, 2]) * t + c[i, 3]
+    np.testing.assert_allclose(y, parse_floats(k["xs_dense_out"]), rtol=1e-13)
+    assert y.min() > 0
+
+
+@pytest.mark.parametrize("excitation", [19.2e-3, 19.2])
+def test_range_tables_reproduce_oracle_cell_counts(excitation):
+    cfg = C.sweep(mean_excitation=excitation)
+    tab = R.build_cached(cfg)
+    assert tab.max_err_u <= 2e-12 and tab.max_err_omega <= 2e-13
+    assert tab.sign == (-1.0 if excitation < 1 else 1.0)
+    om = O.sweep_model(mean_excitation=excitation, ode_scheme="exact")
+    z = np.random.RandomState(5).standard_normal(1024)
+    xs = O.DDNXS()
+    for th in ([1050, .1], [2000, .3], [1200, .45]):
+        E0 = th[0] + (th[1] * th[0]) * z
+        H = R.emulate_cell_hist(tab, cfg, E0)
+        cnt = np.rint(H / np.sum(H * om.eD_binSize * om.x_binSize) * cfg.n_samples).astype(np.int64)
+        assert np.array_equal(cnt, om.cell_counts(th, z, xs)), th
+
+
+def test_range_tables_reject_sign_change():
+    # a medium whose dE/dx changes sign inside the histogram range cannot be tabulated
+    cfg = C.sweep(materials=((1, 2, 8.565e-5, 19.2e-3 * 60),))   # zero of f at ~1057 keV
+    with pytest.raises(ValueError):
+        R.build(cfg)
+
+
+class _FakeModel:
+    def __init__(self, cfg):
+        self.config = cfg
+        self.obs = {}
+        self.calls = []
+
+    def set_observables(self, obs, run=0):
+        self.obs[run] = np.array(obs)
+
+    def lnprob_batch(self, thetas):
+        t = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        self.calls.append(t.shape[0])
+        return -t.sum(axis=1)
+
+
+def test_pool_adapter_batches_and_refuses_foreign_functions():
+    fn = M.TofLnProb(_FakeModel(C.sweep()))
+    obs = np.arange(2048.0)
+    fn.bind_observables(obs)
+    pool = M.BatchedPool(fn)
+    pos = [np.array([1000.0 + i, 0.1]) for i in range(6)]
+
+    class Wrapper:
+        def __init__(self, f, args, kwargs):
+            self.f, self.args, self.kwargs = f, args, kwargs
+
+    out = pool.map(Wrapper(fn, [], {"observables": obs}), pos)
+    assert out == [-(1000.0 + i + 0.1) for i in range(6)]
+    assert fn.model.calls == [6]                  # ONE batched evaluation
+    assert pool.map(fn, []) == []
+    with pytest.raises(TypeError):
+        pool.map(lambda p: 0.0, pos)
+    assert pool.is_master() and pool.wait() is None and pool.close() is None
+    # scalar call, reference signature, re-binds only when the observables change
+    assert fn(pos[0], obs) == -(1000.0 + 0.1)
+    n_sets = len(fn.model.obs)
+    fn(pos[0], obs + 1)
+    assert np.array_equal(fn.model.obs[0], obs + 1) and len(fn.model.obs) == n_sets
+
+
+def test_simult_signature_geometry_is_checked():
+    cfg = C.simult()
+    fn = M.TofLnProb(_FakeModel(cfg))
+    obs = [np.ones(n) for n in cfg.tof_bins]
+    theta = np.arange(9.0)
+    assert fn(theta, obs, cfg.standoffs, cfg.tof_ranges, cfg.tof_bins, cfg.n_samples) == -theta.sum()
+    with pytest.raises(ValueError):
+        fn(theta, obs, cfg.standoffs[::-1], cfg.tof_ranges, cfg.tof_bins)
+    with pytest.raises(ValueError):
+        fn(theta, obs, cfg.standoffs, cfg.tof_ranges, cfg.tof_bins, 12345)

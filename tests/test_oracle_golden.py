@@ -174,3 +174,24 @@ def test_sweep_counts_goldens(golden):
         want[c["idx"]] = c["val"]
         n_bad += int(not np.array_equal(m.raw_tof(th, z, xs, density=False), want))
     assert n_bad <= 1, n_bad
+
+
+def test_exact_stopping_agrees_with_rk4_and_scipy():
+    """The closed-form (Ei) stopping solution against fine-step RK4 and scipy's LSODA at tight tolerance."""
+    from scipy.integrate import odeint
+    for exc in (19.2e-3, 19.2):
+        sb = O.SimpleBethe([(1, 2, 8.565e-5, exc)])
+        (A, B), = sb.reduced()
+        xc = O.adv_model().x_binCenters
+        E0 = np.array([250.0, 600.0, 1050.0, 1800.0, 2600.0, -5.0])
+        ex = O.exact_stop(E0, xc, A, B, None)
+        # the 250 keV deuteron stops to ~20 keV inside the cell, where RK4 needs many sub-steps
+        rk = O.rk4_stop(E0, xc, sb.dEdx, None, 64)
+        np.testing.assert_allclose(ex[:, 1:5], rk[:, 1:5], rtol=2e-13)
+        np.testing.assert_allclose(ex[:, 0], rk[:, 0], rtol=1e-10)
+        ls = odeint(sb.dEdx, E0[:5], xc, rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(ex[:, :5], ls, rtol=2e-9)
+        assert np.all(np.isnan(ex[:, 5]))
+        ex0 = O.exact_stop(E0[:5], xc[:10], A, B, 0.0)
+        rk0 = O.rk4_stop(E0[:5], xc[:10], sb.dEdx, 0.0, 64)
+        np.testing.assert_allclose(ex0, rk0, rtol=1e-11)

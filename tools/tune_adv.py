@@ -21,7 +21,7 @@ res = {}
 for v in variants:
     os.environ["TOFGPU_ADV_VARIANT"] = v
     for sort in (False, True):
-        cfg = M.config.sweep(**({"ode_mode": int(os.environ.get("TOF_ODE_MODE", "0"))}))
+        cfg = M.config.sweep(ode_mode=int(os.environ.get("TOF_ODE_MODE", "0")))
         with M.TofModel(cfg) as m:
             m.set_observables(obs)
             m.set_draws(z, sort=sort)

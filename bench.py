@@ -37,8 +37,16 @@ N_TOF_BINS = 2048
 THETA_STAR = (1050.0, 0.10)
 DRAW_SEED = 20260101
 
-# algorithmic FP64 work per evaluation, SURVEY.md 8(d):  F = 174*D*X + 14*X*E + 26*E + (31+2K)*T
-FLOP_PER_EVAL = 174 * N_DRAWS * 100 + 14 * 100 * 240 + 26 * 240 + (31 + 2 * 16) * N_TOF_BINS
+# Algorithmic FP64 work per evaluation ("Roofline"; convention of SURVEY.md 8d: add/mul/compare = 1,
+# FMA = 2, div = 8, log = 24).
+#  * RK4 formulation:   F_rk4   = 174*D*X + 14*X*E + 26*E + (31+2K)*T
+#  * range-table formulation (shipped): per (draw, x) sample  v = u0 + delta (1), interval compare (1),
+#    dt = v - break (1), degree-7 Horner (14), accumulate (1) = 18;  per draw the T1 lookup (7 FMA + 4) = 18
+#                                     F_range = 18*D*X + 18*D + 14*X*E + 26*E + (31+2K)*T
+X_BINS, E_BINS, N_TAPS = 100, 240, 16
+FLOP_PER_EVAL_RK4 = 174 * N_DRAWS * X_BINS + 14 * X_BINS * E_BINS + 26 * E_BINS + (31 + 2 * N_TAPS) * N_TOF_BINS
+FLOP_PER_EVAL_RANGE = (18 * N_DRAWS * X_BINS + 18 * N_DRAWS + 14 * X_BINS * E_BINS + 26 * E_BINS
+                       + (31 + 2 * N_TAPS) * N_TOF_BINS)
 BYTES_PER_EVAL = 8 * (2 + 1)   # theta in, lnprob out
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
 
@@ -122,7 +130,7 @@ def run_reference_arm(args):
     from oracle import tof_oracle as O
     om, z, obs, thetas = workload(O)
     procs = os.cpu_count() or 1
-    per_proc = 12
+    per_proc = 24
     rates = []
     for i in range(args.warmup + args.steps):
         r = cpu_rate(z, obs, thetas[i * procs * per_proc:], procs, per_proc)
@@ -220,8 +228,10 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=device)
 
     om, z, obs, thetas = workload(O)
-    cfg = M.config.sweep()
-    fn = M.make_lnprob(cfg, obs, z, device=local_rank, sort_draws=True)
+    ode = {"rk4": M.config.ODE_RK4, "range": M.config.ODE_RANGE}[args.ode]
+    cfg = M.config.sweep(ode_mode=ode)
+    flop_per_eval = FLOP_PER_EVAL_RANGE if ode == M.config.ODE_RANGE else FLOP_PER_EVAL_RK4
+    fn = M.make_lnprob(cfg, obs, z, device=local_rank)
     model = fn.model
     sampler = EnsembleSampler(N_WALKERS, 2, fn, seed=1234, store_chain=False)
 
@@ -295,12 +305,15 @@ def run_gpu_arm(args):
             pass
         k_ms = statistics.mean(kernel_ms)
         evals_per_launch = N_WALKERS // 2 // world
-        achieved = evals_per_launch * FLOP_PER_EVAL / (k_ms * 1e-3) / 1e12
+        achieved = evals_per_launch * flop_per_eval / (k_ms * 1e-3) / 1e12
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
             "traffic": None,
-            "kernel": "adv_lnprob_kernel", "kernel_ms": k_ms, "evals_per_launch": evals_per_launch,
-            "flop_per_eval": FLOP_PER_EVAL, "peak_source": "DFMA microbenchmark run in this process (tof_measure_fp64_peak)",
+            "kernel": "adv_range_kernel" if ode == M.config.ODE_RANGE else "adv_lnprob_kernel",
+            "kernel_ms": k_ms, "evals_per_launch": evals_per_launch,
+            "flop_per_eval": flop_per_eval, "flop_per_eval_rk4_formulation": FLOP_PER_EVAL_RK4,
+            "rk4_equivalent_tflops": evals_per_launch * FLOP_PER_EVAL_RK4 / (k_ms * 1e-3) / 1e12,
+            "peak_source": "DFMA microbenchmark run in this process (tof_measure_fp64_peak)",
             "nominal_fp64_tflops": NOMINAL_FP64_TFLOPS,
             "hbm": {"achieved_gbs": evals_per_launch * BYTES_PER_EVAL / (k_ms * 1e-3) / 1e9,
                     "peak_gbs": peaks.get("hbm_gbs"), "bytes_per_eval": BYTES_PER_EVAL},
@@ -320,7 +333,8 @@ def run_gpu_arm(args):
             "config": {"workload": "adv TOF model sweep: %d walkers x %d TOF bins x %d MC draws" % (N_WALKERS, N_TOF_BINS, N_DRAWS),
                        "step": "one ensemble MCMC step = 2 red/blue half-steps = %d lnprob evaluations" % N_WALKERS,
                        "parallelism": "walkers sharded over %d rank(s); all_gather of the updated half per half-step" % world,
-                       "ode": "rk4 x%d per x-interval" % cfg.ode_substeps, "threads_per_cta": model.stats()["threads"],
+                       "ode": ("range-energy tables (exact solution of the autonomous Bethe ODE)" if ode == M.config.ODE_RANGE
+                               else "rk4 x%d per x-interval" % cfg.ode_substeps), "threads_per_cta": model.stats()["threads"],
                        "l2": "flushed between timed steps (256 MiB memset outside the event bracket)",
                        "finite_lnprob_fraction": finite_frac},
             "roofline": roofline, "cpu_baseline": cpu,
@@ -343,6 +357,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--ode", choices=["range", "rk4"], default="range", help="stopping-stage formulation of the CUDA path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

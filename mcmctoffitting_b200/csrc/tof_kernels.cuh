@@ -422,6 +422,20 @@ __host__ __device__ inline size_t range_smem_bytes(int X, int E, int T, int rng_
     return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16;
 }
 
+constexpr int RANGE_CH = 40;        // runs longer than this are summed by the whole warp
+
+// Interval of the T2 table that holds v (0 <= v <= u_max); uniform lookup cell, then edge compares.
+template <int RW>
+__device__ __forceinline__ int range_interval(double v, const double *rec, const unsigned short *lut, double lut_inv,
+                                              int lut_n, int M) {
+    int c = (int)(v * lut_inv);
+    c = c < 0 ? 0 : (c > lut_n - 1 ? lut_n - 1 : c);
+    int j = lut[c];
+    while (j + 1 < M && v >= rec[j * RW]) ++j;
+    while (j > 0 && v < rec[(j - 1) * RW]) --j;
+    return j;
+}
+
 // u0 = u(E0): T1 cell from the exponent/mantissa bits, degree-7 Horner in t in [-1, 1].
 __device__ __forceinline__ double t1_eval(double E0, const DevModel &m) {
     double t;
@@ -507,77 +521,90 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
         for (int d = tid; d < nt; d += NT)
             u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + tile + d))), m);
         __syncthreads();
+        const int nsteps = 32 - __clz(nt);                 // binary-search iterations for [0, nt]
         for (int row = warp; row < X; row += NW) {
+            // Every cell of a row is owned by this warp for the whole kernel.  The row's in-range draws
+            // [d_lo, d_hi) are split into 32 equal chunks of consecutive draws; a lane walks its chunk with
+            // a pointer into the T2 table.  Runs that lie inside a chunk are added with plain stores;
+            // only the first and last run of a chunk (shared with the neighbouring lanes) use atomics,
+            // after the loop.
             const double delta = sgn * (__ldg(m.x_centers + row) - x_start);
-            int lo = 0, hi = nt;
-            while (lo < hi) {                              // first draw with v >= 0  (E >= e_min)
-                const int mid = (lo + hi) >> 1;
-                if (__dadd_rn(u0[mid], delta) >= 0.0) hi = mid; else lo = mid + 1;
+            int lo = 0, hi = nt, lo2 = 0, hi2 = nt;
+            for (int it = 0; it < nsteps; ++it) {          // uniform across the warp: broadcast reads
+                const int mid = (lo + hi) >> 1, mid2 = (lo2 + hi2) >> 1;
+                const bool ge = __dadd_rn(u0[mid < nt ? mid : nt - 1], delta) >= 0.0;       // E >= e_min
+                const bool gt = __dadd_rn(u0[mid2 < nt ? mid2 : nt - 1], delta) > umax;     // E >  e_max
+                const bool go = lo < hi, go2 = lo2 < hi2;
+                hi = (go && ge) ? mid : hi;
+                lo = (go && !ge) ? mid + 1 : lo;
+                hi2 = (go2 && gt) ? mid2 : hi2;
+                lo2 = (go2 && !gt) ? mid2 + 1 : lo2;
             }
-            const int d_lo = lo;
-            hi = nt;
-            while (lo < hi) {                              // first draw with v > u_max  (E > e_max)
-                const int mid = (lo + hi) >> 1;
-                if (__dadd_rn(u0[mid], delta) > umax) hi = mid; else lo = mid + 1;
-            }
-            const int d_hi = lo;
+            const int d_lo = lo, d_hi = lo2;
             const int W = d_hi - d_lo;
             if (W <= 0) continue;
             const int per = ((W + 31) >> 5) | 1;           // odd stride: conflict-free u0 reads across lanes
             const int my_lo = d_lo + lane * per;
             const int my_hi = (my_lo + per < d_hi) ? my_lo + per : d_hi;
-            if (my_lo >= my_hi) continue;
-            double v = __dadd_rn(u0[my_lo], delta);
-            int c = (int)(v * m.rng_lut_inv);
-            c = c < 0 ? 0 : (c > m.rng_lut_n - 1 ? m.rng_lut_n - 1 : c);
-            int j = lut[c];
-            while (j + 1 < M && v >= rec[j * RW]) ++j;
-            while (j > 0 && v < rec[(j - 1) * RW]) --j;
-            // records are 16-byte aligned with an even word count: 128-bit loads, conflict-free across rows
-            const double2 *rj = reinterpret_cast<const double2 *>(rec + j * RW);
-            double2 hd = rj[0];
-            double next = hd.x;
-            double brk = j ? rec[(j - 1) * RW] : 0.0;
-            int bin = (int)hd.y;
-            double a[P + 1];
-#pragma unroll
-            for (int k = 0; k <= P; k += 2) {
-                const double2 c2 = rj[1 + (k >> 1)];
-                a[k] = c2.x;
-                a[k + 1] = c2.y;
-            }
-            double acc = 0.0;
             double *Hrow = H + (size_t)row * EB;
-            for (int d = my_lo; d < my_hi; ++d) {
-                v = __dadd_rn(u0[d], delta);
-                if (v >= next && j + 1 < M) {
-                    do {
-                        ++j;
-                        brk = next;
-                        hd = reinterpret_cast<const double2 *>(rec + j * RW)[0];
-                        next = hd.x;
-                    } while (v >= next && j + 1 < M);
-                    const int nb = (int)hd.y;
-                    if (nb != bin) {
-                        atomicAdd(Hrow + bin, acc);
-                        acc = 0.0;
-                        bin = nb;
-                    }
-                    rj = reinterpret_cast<const double2 *>(rec + j * RW);
+            double acc = 0.0, acc_first = 0.0;
+            int bin = -1, bin_first = -1;
+            if (my_lo < my_hi) {
+                double v = __dadd_rn(u0[my_lo], delta);
+                int j = range_interval<RW>(v, rec, lut, m.rng_lut_inv, m.rng_lut_n, M);
+                const double2 *rj = reinterpret_cast<const double2 *>(rec + j * RW);
+                double2 hd = rj[0];
+                double next = hd.x;
+                double brk = j ? rec[(j - 1) * RW] : 0.0;
+                bin = hd.y < 0.0 ? (int)(-hd.y) - 1 : (int)hd.y;
+                double a[P + 1];
 #pragma unroll
-                    for (int k = 0; k <= P; k += 2) {
-                        const double2 c2 = rj[1 + (k >> 1)];
-                        a[k] = c2.x;
-                        a[k + 1] = c2.y;
-                    }
+                for (int k = 0; k <= P; k += 2) {
+                    const double2 c2 = rj[1 + (k >> 1)];
+                    a[k] = c2.x;
+                    a[k + 1] = c2.y;
                 }
-                const double dt = v - brk;
-                double wgt = a[P];
+                bool first = true;
+                for (int d = my_lo; d < my_hi; ++d) {
+                    v = __dadd_rn(u0[d], delta);
+                    if (v >= next && j + 1 < M) {
+                        do {
+                            ++j;
+                            brk = next;
+                            hd = reinterpret_cast<const double2 *>(rec + j * RW)[0];
+                            next = hd.x;
+                        } while (v >= next && j + 1 < M);
+                        const int nb = hd.y < 0.0 ? (int)(-hd.y) - 1 : (int)hd.y;
+                        if (nb != bin) {
+                            if (first) {
+                                acc_first = acc;           // boundary run: flushed after the loop
+                                bin_first = bin;
+                                first = false;
+                            } else {
+                                Hrow[bin] += acc;          // interior run: exclusively ours
+                            }
+                            acc = 0.0;
+                            bin = nb;
+                        }
+                        rj = reinterpret_cast<const double2 *>(rec + j * RW);
 #pragma unroll
-                for (int k = P - 1; k >= 0; --k) wgt = fma(wgt, dt, a[k]);
-                acc += wgt;
+                        for (int k = 0; k <= P; k += 2) {
+                            const double2 c2 = rj[1 + (k >> 1)];
+                            a[k] = c2.x;
+                            a[k + 1] = c2.y;
+                        }
+                    }
+                    const double dt = v - brk;
+                    double wgt = a[P];
+#pragma unroll
+                    for (int k = P - 1; k >= 0; --k) wgt = fma(wgt, dt, a[k]);
+                    acc += wgt;
+                }
             }
-            atomicAdd(Hrow + bin, acc);
+            __syncwarp();                                   // interior stores done before boundary atomics
+            if (bin_first >= 0) atomicAdd(Hrow + bin_first, acc_first);
+            if (bin >= 0) atomicAdd(Hrow + bin, acc);
+            __syncwarp();
         }
     }
     __syncthreads();

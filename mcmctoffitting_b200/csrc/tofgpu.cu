@@ -321,7 +321,10 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         std::vector<double> rec((size_t)Mi * RW);
         for (int j = 0; j < Mi; ++j) {
             rec[(size_t)j * RW + 0] = cfg->rng_breaks[j + 1];
-            rec[(size_t)j * RW + 1] = (double)cfg->rng_bins[j];
+            // a bin covered by several intervals is flagged by storing -(bin+1): those cells need atomics
+            const bool shared = (j > 0 && cfg->rng_bins[j - 1] == cfg->rng_bins[j]) ||
+                                (j + 1 < Mi && cfg->rng_bins[j + 1] == cfg->rng_bins[j]);
+            rec[(size_t)j * RW + 1] = shared ? -(double)(cfg->rng_bins[j] + 1) : (double)cfg->rng_bins[j];
             for (int k = 0; k <= P; ++k) rec[(size_t)j * RW + 2 + k] = cfg->rng_coefs[(size_t)j * (P + 1) + k];
         }
         TRY(upload(ctx, rec.data(), rec.size(), &m.rng_rec));

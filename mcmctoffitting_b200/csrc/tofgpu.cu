@@ -36,6 +36,7 @@ struct tof_ctx {
     int adv_nt = 1024, adv_dpt = 1;
     size_t adv_smem = 0;
     int rng_nt = 1024;
+    size_t simult_smem = 0;
     int max_smem_optin = 0;
     bool have_obs[TOF_MAX_RUNS]{};
     bool have_z[TOF_MAX_RUNS][2]{};
@@ -145,6 +146,22 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
         simple_finish_kernel<32><<<(unsigned)n, 32, 0, st>>>(ctx->dm, ctx->runs[0], d_theta, n,
                                                              static_cast<unsigned long long *>(ctx->d_counts.p), out);
         ctx->stats.kernel_launches += 2;
+    } else if (c.model == TOF_MODEL_SIMULT) {
+        DevRunSet rs;
+        for (int r = 0; r < TOF_MAX_RUNS; ++r) rs.r[r] = ctx->runs[r];
+        const bool debug = out.spectra != nullptr || out.cells != nullptr;
+        if (debug) {
+            simult_run_kernel<256><<<(unsigned)n, 256, ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, out, run);
+            ctx->stats.kernel_launches += 1;
+        } else {
+            int rc = ensure(ctx, ctx->d_partial, (size_t)n * c.n_runs * sizeof(double));
+            if (rc) return rc;
+            ModelOut po{};
+            po.lnprob = static_cast<double *>(ctx->d_partial.p);
+            simult_run_kernel<256><<<(unsigned)(n * c.n_runs), 256, ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, po, -1);
+            simult_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->dm, d_theta, n, po.lnprob, out.lnprob);
+            ctx->stats.kernel_launches += 2;
+        }
     } else {
         return fail(ctx, TOF_ERR_INVALID, "model kind not implemented");
     }
@@ -378,8 +395,21 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
     } else if (cfg->model == TOF_MODEL_SIMPLE) {
         ctx->stats.threads = 256;
     } else {
-        ctx->err = "simult model kernels not built yet";
-        return bail(TOF_ERR_INVALID);
+        if (cfg->ndim < 4 + cfg->n_runs) { ctx->err = "simult model needs ndim >= 4 + n_runs"; return bail(TOF_ERR_INVALID); }
+        if (cfg->ode_mode != TOF_ODE_RK4) { ctx->err = "the simult model supports TOF_ODE_RK4 only"; return bail(TOF_ERR_INVALID); }
+        int tmax = 0;
+        for (int r = 0; r < cfg->n_runs; ++r) tmax = std::max(tmax, cfg->tof_bins[r]);
+        ctx->simult_smem = simult_smem_bytes(256, cfg->x_bins, cfg->e_bins, tmax, cfg->n_xs, cfg->n_taps, m.xs_lut_n);
+        if ((int)ctx->simult_smem > ctx->max_smem_optin) {
+            ctx->err = "simult kernel needs " + std::to_string(ctx->simult_smem) + " B of shared memory per CTA";
+            return bail(TOF_ERR_CAPACITY);
+        }
+        CUC(cudaFuncSetAttribute(simult_run_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->simult_smem));
+        int occ = 0;
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simult_run_kernel<256>, 256, ctx->simult_smem));
+        ctx->stats.smem_bytes = (int)ctx->simult_smem;
+        ctx->stats.threads = 256;
+        ctx->stats.ctas_per_sm = occ;
     }
 #undef TRY
 #undef CUC

@@ -1,0 +1,119 @@
+"""Ensemble driver on CPU: stretch-move statistics on an analytic target, emcee-shaped surface, chain
+file round trip, and the N>1 sharding path over gloo (world size 2) with the numpy backend injected."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from mcmctoffitting_b200.ensemble import EnsembleSampler, write_chain_step, read_chain
+from oracle.stretch_oracle import NumpyBackend, philox4x32
+
+MU = np.array([1.0, -2.0, 0.5])
+SIG = np.array([0.5, 2.0, 1.0])
+
+
+def gauss_lnprob(x):
+    return -0.5 * np.sum(((x - MU) / SIG) ** 2, axis=1)
+
+
+def test_philox_known_answer():
+    # Random123 known-answer test: philox4x32-10, counter = key = 0
+    c = philox4x32(0, np.array([0], dtype=np.uint64), np.uint64(0))
+    assert [int(v[0]) for v in c] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    # counter ffffffff x4, key ffffffff x2
+    c = philox4x32(0xFFFFFFFFFFFFFFFF, np.array([0xFFFFFFFFFFFFFFFF], dtype=np.uint64), np.uint64(0xFFFFFFFFFFFFFFFF))
+    assert [int(v[0]) for v in c] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+
+
+def test_stretch_move_samples_a_gaussian():
+    k, dim = 200, 3
+    rs = np.random.RandomState(0)
+    p0 = MU + 0.1 * rs.standard_normal((k, dim))
+    s = EnsembleSampler(k, dim, backend=NumpyBackend(gauss_lnprob), seed=42)
+    pos, lp, state = s.run_mcmc(p0, 600)
+    chain = s.chain[:, 200:, :].reshape(-1, dim)
+    assert s.chain.shape == (k, 600, dim) and s.lnprobability.shape == (k, 600)
+    np.testing.assert_allclose(chain.mean(axis=0), MU, atol=0.08)
+    np.testing.assert_allclose(chain.std(axis=0), SIG, rtol=0.08)
+    af = s.acceptance_fraction
+    assert 0.3 < af.mean() < 0.8
+    np.testing.assert_allclose(lp, gauss_lnprob(pos))
+    # resume: (pos, lnprob, rstate) handed back like the reference does between burn-in and main chain (adv:337-339)
+    s.reset()
+    out = s.run_mcmc(pos, 5, rstate0=state, lnprob0=lp)
+    assert s.chain.shape == (k, 5, dim) and out[2] == state + 5
+
+
+def test_constructor_checks_match_emcee():
+    with pytest.raises(ValueError):
+        EnsembleSampler(7, 2, backend=NumpyBackend(gauss_lnprob))
+    with pytest.raises(ValueError):
+        EnsembleSampler(4, 3, backend=NumpyBackend(gauss_lnprob))
+    s = EnsembleSampler(8, 3, backend=NumpyBackend(lambda x: np.full(len(x), np.nan)))
+    with pytest.raises(ValueError):
+        s.run_mcmc(np.zeros((8, 3)), 1)
+
+
+def test_chain_file_round_trip(tmp_path):
+    k, dim, steps = 6, 9, 3
+    rs = np.random.RandomState(1)
+    path = str(tmp_path / "mainchain.dat")
+    want_c, want_p = [], []
+    for _ in range(steps):
+        pos = rs.standard_normal((k, dim)) * 1e3
+        lp = rs.standard_normal(k) * 1e5
+        write_chain_step(path, pos, lp)             # numpy wraps 9-parameter rows over two lines
+        want_c.append(pos)
+        want_p.append(lp)
+    chain, probs, n_params, n_walkers, n_steps = read_chain(path)
+    assert (n_params, n_walkers, n_steps) == (dim, k, steps)
+    np.testing.assert_allclose(chain, np.array(want_c), rtol=1e-7)   # numpy prints 8 significant digits
+    np.testing.assert_allclose(probs, np.array(want_p), rtol=1e-12)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, k, dim, steps, p0, out_q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        s = EnsembleSampler(k, dim, backend=NumpyBackend(gauss_lnprob), seed=7)
+        assert s.world == world and s.n_own == k // 2 // world
+        pos, lp, _ = s.run_mcmc(p0, steps)
+        out_q.put((rank, pos, lp, s.naccepted.numpy().copy()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_sampler_over_gloo_matches_single_process():
+    k, dim, steps = 64, 3, 25
+    p0 = MU + 0.1 * np.random.RandomState(3).standard_normal((k, dim))
+    ref = EnsembleSampler(k, dim, backend=NumpyBackend(gauss_lnprob), seed=7)
+    pos1, lp1, _ = ref.run_mcmc(p0, steps)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, k, dim, steps, p0, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, pos2, lp2, nacc in results:
+        # chains do not depend on the number of ranks: counter-based RNG keyed by the global walker index
+        assert np.array_equal(pos2, pos1), rank
+        assert np.array_equal(lp2, lp1), rank
+    # acceptance counters are per-owner: summed over ranks they equal the single-process counters
+    total = sum(r[3] for r in results)
+    assert np.array_equal(total, ref.naccepted.numpy())

@@ -354,3 +354,158 @@ def test_range_multiple_tiles_and_loops(M, O):
     for k, th in enumerate(thetas):
         assert np.array_equal(cc[k], om.cell_counts(th, z, xs)), k
         assert rel(float(got[k]), float(om.lnprob(th, obs, z, xs))) <= RTOL, (k, got[k])
+
+
+# ---------------------------------------------------------------------------------------------------
+# ensemble driver kernels
+# ---------------------------------------------------------------------------------------------------
+def test_stretch_kernels_match_numpy_restatement(M):
+    import torch
+    from oracle import stretch_oracle as S
+    cfg = M.config.sweep()
+    n, ncomp, ndim = 1000, 777, 2
+    rs = np.random.RandomState(11)
+    s = rs.standard_normal((n, ndim)) * 10 + 1000
+    comp = rs.standard_normal((ncomp, ndim)) * 10 + 1000
+    lp = rs.standard_normal(n) * 5 - 100
+    new_lp = rs.standard_normal(n) * 5 - 100
+    new_lp[::7] = -np.inf
+    dev = torch.device("cuda", 0)
+    with M.TofModel(cfg) as m:
+        ts, tc = torch.from_numpy(s).to(dev), torch.from_numpy(comp).to(dev)
+        q = torch.empty_like(ts)
+        lz = torch.empty(n, dtype=torch.float64, device=dev)
+        m.stretch_propose(ts.data_ptr(), n, 12345, tc.data_ptr(), ncomp, 2.0, 99, 17, 1, q.data_ptr(), lz.data_ptr())
+        torch.cuda.synchronize()
+        q_ref, lz_ref = S.propose(s, 12345, comp, 2.0, 99, 17, 1)
+        np.testing.assert_allclose(q.cpu().numpy(), q_ref, rtol=1e-14)
+        np.testing.assert_allclose(lz.cpu().numpy(), lz_ref, rtol=1e-13, atol=1e-15)
+        tlp, tnew = torch.from_numpy(lp).to(dev), torch.from_numpy(new_lp).to(dev)
+        nacc = torch.zeros(n, dtype=torch.int64, device=dev)
+        m.stretch_accept(ts.data_ptr(), tlp.data_ptr(), n, 12345, q.data_ptr(), tnew.data_ptr(), lz.data_ptr(), 99, 17, 1,
+                         nacc.data_ptr())
+        torch.cuda.synchronize()
+        s2, lp2, nacc_ref = s.copy(), lp.copy(), np.zeros(n, dtype=np.int64)
+        ok = S.accept(s2, lp2, 12345, q.cpu().numpy(), new_lp, lz.cpu().numpy(), 99, 17, 1, nacc_ref)
+        assert np.array_equal(nacc.cpu().numpy(), nacc_ref)
+        assert np.array_equal(ts.cpu().numpy(), s2) and np.array_equal(tlp.cpu().numpy(), lp2)
+        assert 0 < ok.sum() < n and not ok[::7].any()
+
+
+def test_gpu_sampler_runs_and_respects_the_prior(M, O):
+    from mcmctoffitting_b200.ensemble import EnsembleSampler
+    cfg = M.config.adv(0, n_samples=4096, n_ev_per_loop=4096, mean_excitation=19.2e-3, ode_mode=M.config.ODE_RANGE)
+    om = O.adv_model(0, n_samples=4096, n_ev_per_loop=4096, mean_excitation=19.2e-3)
+    obs = np.rint(5e4 * om.model_pdf([1050, .10], np.random.RandomState(7).standard_normal(4096)))
+    z = np.random.RandomState(8).standard_normal(4096)
+    fn = M.make_lnprob(cfg, obs, z)
+    k = 64
+    p0 = np.array([1050, 0.10]) + np.array([10, 1e-2]) * np.random.RandomState(9).standard_normal((k, 2))
+    s = EnsembleSampler(k, 2, fn, seed=5)
+    pos, lp, _ = s.run_mcmc(p0, 30)
+    assert s.chain.shape == (k, 30, 2)
+    assert np.all(np.isfinite(lp))
+    assert np.all((pos[:, 0] > 1000) & (pos[:, 0] < 2600) & (pos[:, 1] > 0.02) & (pos[:, 1] < 0.5))
+    # stored lnprob is the lnprob of the stored position (same draws -> deterministic)
+    np.testing.assert_allclose(fn.batch(pos), lp, rtol=1e-12)
+    assert lp.mean() > fn.batch(p0).mean()          # the ensemble moved uphill from its start
+    fn.model.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# simultaneous multi-standoff fit (config 4): tests/simultFit.py
+# ---------------------------------------------------------------------------------------------------
+class _Recorder:
+    """DrawSource wrapper that records what the oracle consumes, in consumption order."""
+
+    def __init__(self, inner, n_runs):
+        self.inner = inner
+        self.rec_main = [[] for _ in range(n_runs)]
+        self.rec_extra = [[] for _ in range(n_runs)]
+
+    def main(self, run, loop, n):
+        v = self.inner.main(run, loop, n)
+        self.rec_main[run].append(np.array(v))
+        return v
+
+    def extra(self, run, loop, n):
+        v = self.inner.extra(run, loop, n)
+        self.rec_extra[run].append(np.array(v))
+        return v
+
+
+def _simult_tables(O, cfg, seed, extra_per_run=4000):
+    rs = np.random.RandomState(seed)
+    z_main = [rs.standard_normal((cfg.n_loops, cfg.n_ev_per_loop)) for _ in range(cfg.n_runs)]
+    z_extra = [rs.standard_normal(extra_per_run) for _ in range(cfg.n_runs)]
+    return z_main, z_extra
+
+
+def test_simult_vs_oracle(M, O):
+    cfg = M.config.simult(n_samples=4000, n_ev_per_loop=1000)
+    om = O.SimultModel(n_samples=4000, n_ev_per_loop=1000)
+    z_main, z_extra = _simult_tables(O, cfg, 123)
+    xs = O.DDNXS()
+    theta_star = [1878.4, 850, 170, 0.5, 3e4, 2e4, 2e4, 4e4, 4e4]
+    td = O.TableDraws(z_main, z_extra)
+    obs = [np.rint(om.model(theta_star[:4] + [theta_star[4 + r]], r, td, xs)) for r in range(5)]
+    thetas = np.array([theta_star,
+                       [1900.0, 700, 100, 0.3, 2.5e4, 2.2e4, 1.9e4, 4.1e4, 3.9e4],
+                       [1825.0, 1000, 300, 1.2, 3e4, 2e4, 2e4, 4e4, 4e4],      # ~20 % of the draws are redrawn
+                       [1850.0, 900, 250, 0.9, 1e3, 5e5, 2e4, 4e4, 1e6],
+                       [1800.0, 850, 170, 0.5, 3e4, 2e4, 2e4, 4e4, 4e4],       # outside the prior
+                       [1878.4, 850, 170, 0.5, 3e4, 2e4, 2e4, 4e4, 1.1e6]])    # outside the prior
+    fn = M.make_lnprob(cfg, obs, [z.ravel() for z in z_main], extra_draws=z_extra)
+    got = fn.batch(thetas)
+    for k, th in enumerate(thetas):
+        td.reset()
+        want = om.lnprob(list(th), obs, td, xs)
+        assert rel(float(got[k]), float(want)) <= RTOL, (k, got[k], want)
+    assert got[4] == -np.inf and got[5] == -np.inf
+    # stage-level: integer cell counts and spectra of every run for two walkers
+    for k in (0, 2):
+        th = list(thetas[k])
+        for r in range(5):
+            td.reset()
+            counts, e0mean = om.cell_counts(th[:4] + [th[4 + r]], r, td, xs)
+            got_c = fn.model.cell_counts(thetas[k:k + 1], run=r)[0]
+            assert np.array_equal(got_c, counts), (k, r)
+            td.reset()
+            want_s = om.model(th[:4] + [th[4 + r]], r, td, xs)
+            got_s = fn.model.model_batch(thetas[k:k + 1], run=r, stage="spread")[0]
+            np.testing.assert_allclose(got_s, want_s, rtol=1e-11)
+    # the reference signature (simultFit.py:444) works and checks the baked-in geometry
+    v = fn(thetas[0], obs, cfg.standoffs, cfg.tof_ranges, cfg.tof_bins, cfg.n_samples)
+    assert rel(v, float(got[0])) <= 1e-11      # shared-memory double atomics: summation order varies run to run
+    fn.model.close()
+
+
+def test_simult_reference_goldens(M, O, golden, pf):
+    """Seed-pinned lnprob values produced by the reference's own simultFit functions (scipy dopri5 there)."""
+    g = golden["simult"]
+    th = g["theta"]
+    for c in g["cases"]:
+        if c["n_draws"] > 10000:
+            continue
+        cfg = M.config.simult(n_samples=c["n_draws"], n_ev_per_loop=c["n_ev_per_loop"])
+        om = O.SimultModel(n_samples=c["n_draws"], n_ev_per_loop=c["n_ev_per_loop"])
+        obs = [parse_floats(o) for o in c["obs"]]
+        rec = _Recorder(O.GlobalStateDraws(np.random.RandomState(c["seed_eval"])), 5)
+        want_oracle = om.lnprob(th, obs, rec)
+        z_main = [np.concatenate(m) for m in rec.rec_main]
+        z_extra = [np.concatenate(e) if e else np.zeros(0) for e in rec.rec_extra]
+        fn = M.make_lnprob(cfg, obs, z_main, extra_draws=z_extra)
+        got = float(fn.batch([th])[0])
+        fn.model.close()
+        assert rel(got, float(want_oracle)) <= RTOL
+        assert rel(got, pf(c["lnprob"])) <= RTOL, (got, c["lnprob"])
+
+
+def test_simult_exhausted_replacement_stream_is_neg_inf(M, O):
+    cfg = M.config.simult(n_samples=2000, n_ev_per_loop=1000)
+    z_main, z_extra = _simult_tables(O, cfg, 5, extra_per_run=3)      # far too few replacement draws
+    obs = [np.ones(n) for n in cfg.tof_bins]
+    fn = M.make_lnprob(cfg, obs, [z.ravel() for z in z_main], extra_draws=z_extra)
+    got = fn.batch([[1825.0, 1000, 300, 1.2, 3e4, 2e4, 2e4, 4e4, 4e4]])
+    assert got[0] == -np.inf                                             # NaN -> -inf (simultFit.py:463-468)
+    fn.model.close()

@@ -1,0 +1,60 @@
+"""Time the BASELINE.json configs C1-C4 on one GPU (device-resident thetas, CUDA-event kernel time)."""
+import os, sys, time, warnings
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import mcmctoffitting_b200 as M
+warnings.simplefilter("ignore")
+which = sys.argv[1:] or ["simple", "intermediate", "adv", "simult"]
+dev = torch.device("cuda", 0)
+rs = np.random.RandomState(0)
+
+
+def run(name, cfg, thetas, draws, extra=None, reps=2):
+    obs = [np.ones(n) * 100 for n in cfg.tof_bins]
+    obs = obs[0] if cfg.n_runs == 1 else obs
+    t0 = time.time()
+    fn = M.make_lnprob(cfg, obs, draws, extra_draws=extra)
+    setup = time.time() - t0
+    m = fn.model
+    th = torch.from_numpy(np.ascontiguousarray(thetas)).to(dev)
+    out = torch.empty(len(thetas), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    m.lnprob_batch_device(th.data_ptr(), len(thetas), out.data_ptr(), st)
+    torch.cuda.synchronize()
+    m.set_timing(True)
+    best = 1e30
+    for _ in range(reps):
+        m.lnprob_batch_device(th.data_ptr(), len(thetas), out.data_ptr(), st)
+        torch.cuda.synchronize()
+        best = min(best, m.last_kernel_ms())
+    fin = float(torch.isfinite(out).double().mean())
+    print("%-14s walkers=%6d draws/run=%8d  %10.2f ms  %12.1f evals/s  finite=%.2f  setup=%.1fs ctas/sm=%d" % (
+        name, len(thetas), cfg.n_draws, best, len(thetas) / (best * 1e-3), fin, setup, m.stats()["ctas_per_sm"]), flush=True)
+    m.close()
+
+
+if "simple" in which:
+    cfg = M.config.simple(1000000)
+    th = np.column_stack([rs.uniform(900, 1150, 32), rs.uniform(-150, -50, 32), rs.uniform(20, 90, 32)])
+    run("C1 simple", cfg, th, (rs.random_sample(cfg.n_draws), rs.standard_normal(cfg.n_draws)))
+if "intermediate" in which:
+    for mode, nm in ((M.config.ODE_RK4, "rk4"), (M.config.ODE_RANGE, "range")):
+        cfg = M.config.intermediate(0, ode_mode=mode)
+        th = np.column_stack([rs.uniform(850, 1000, 256), rs.uniform(0.05, 0.16, 256)])
+        run("C2 interm/" + nm, cfg, th, rs.standard_normal(cfg.n_draws), reps=1)
+if "adv" in which:
+    for mode, nm in ((M.config.ODE_RK4, "rk4"), (M.config.ODE_RANGE, "range")):
+        cfg = M.config.adv(0, ode_mode=mode)
+        n = 4096 if mode == M.config.ODE_RANGE else 592
+        th = np.column_stack([rs.uniform(1020, 1100, n), rs.uniform(0.08, 0.12, n)])
+        run("C3 adv/" + nm, cfg, th, rs.standard_normal(cfg.n_draws), reps=1)
+if "simult" in which:
+    cfg = M.config.simult()
+    n = int(os.environ.get("SIMULT_N", "148"))
+    th = np.tile([1878.4, 850, 170, 0.5, 3e4, 2e4, 2e4, 4e4, 4e4], (n, 1)) * (1 + 0.01 * rs.standard_normal((n, 9)))
+    th[:, 0] = np.clip(th[:, 0], 1826, 1924)
+    draws = [rs.standard_normal(cfg.n_draws) for _ in range(5)]
+    extra = [rs.standard_normal(20000) for _ in range(5)]
+    run("C4 simult/rk4", cfg, th, draws, extra, reps=1)

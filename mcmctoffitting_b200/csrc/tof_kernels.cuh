@@ -414,12 +414,13 @@ namespace tof {
 // of the cross-section weight), sums whole runs in a register and touches the (x,E) histogram once
 // per run instead of once per sample.
 constexpr int RANGE_TILE = 1024;   // draws staged in shared memory at a time
+constexpr int RANGE_ULUT = 1024;   // cells of the per-tile draw-index lookup table
 
 __host__ __device__ inline size_t range_smem_bytes(int X, int E, int T, int rng_n, int P, int n_taps, int lut_n) {
     size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
     region_a = (region_a + 15) / 16 * 16;
-    size_t d = (size_t)X * E + (size_t)rng_n * (P + 3) + E + n_taps + 40;
-    return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16;
+    size_t d = (size_t)X * E + (size_t)rng_n * (P + 3) + E + n_taps + 40 + X /* per-row offsets */;
+    return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16 + RANGE_ULUT * 2;
 }
 
 constexpr int RANGE_CH = 40;        // runs longer than this are summed by the whole warp
@@ -483,7 +484,9 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
     double *svd = rec + (size_t)M * RW;
     double *staps = svd + EB;
     double *scratch = staps + m.n_taps;
-    unsigned short *lut = reinterpret_cast<unsigned short *>(scratch + 40);
+    double *sdelta = scratch + 40;                                      // [X] sgn*(x_i - x_start)
+    unsigned short *lut = reinterpret_cast<unsigned short *>(sdelta + X);
+    unsigned short *ulut = lut + ((m.rng_lut_n + 7) / 8) * 8;           // [RANGE_ULUT]
 
     const long long w = blockIdx.x;
     if (w >= n_walkers) return;
@@ -513,8 +516,10 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
     const double spread = __dmul_rn(sigma0, e0);          // adv:128
     const double sgn = m.rng_sign, umax = m.rng_u_max;
     const double x_start = m.ode_from_zero ? 0.0 : m.x_centers[0];
+    for (int i = tid; i < X; i += NT) sdelta[i] = sgn * (m.x_centers[i] - x_start);
 
     // ---- phase 1: (x,E) histogram of cross-section weights through the range tables ---------------------
+    int bin_lo_all = EB, bin_hi_all = -1;                  // E-bins any draw of any tile can have touched (uniform)
     for (long long tile = 0; tile < m.n_draws; tile += RANGE_TILE) {
         const int nt = (int)((m.n_draws - tile < RANGE_TILE) ? (m.n_draws - tile) : RANGE_TILE);
         __syncthreads();                                   // previous tile fully consumed / staging done
@@ -522,89 +527,131 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
             u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + tile + d))), m);
         __syncthreads();
         const int nsteps = 32 - __clz(nt);                 // binary-search iterations for [0, nt]
-        for (int row = warp; row < X; row += NW) {
-            // Every cell of a row is owned by this warp for the whole kernel.  The row's in-range draws
-            // [d_lo, d_hi) are split into 32 equal chunks of consecutive draws; a lane walks its chunk with
-            // a pointer into the T2 table.  Runs that lie inside a chunk are added with plain stores;
-            // only the first and last run of a chunk (shared with the neighbouring lanes) use atomics,
-            // after the loop.
-            const double delta = sgn * (__ldg(m.x_centers + row) - x_start);
+        // valid (finite) part of the sorted tile: -inf (never in range) first, +inf last
+        int v_lo = 0, v_hi = nt;
+        {
             int lo = 0, hi = nt, lo2 = 0, hi2 = nt;
-            for (int it = 0; it < nsteps; ++it) {          // uniform across the warp: broadcast reads
+            for (int it = 0; it < nsteps; ++it) {
                 const int mid = (lo + hi) >> 1, mid2 = (lo2 + hi2) >> 1;
-                const bool ge = __dadd_rn(u0[mid < nt ? mid : nt - 1], delta) >= 0.0;       // E >= e_min
-                const bool gt = __dadd_rn(u0[mid2 < nt ? mid2 : nt - 1], delta) > umax;     // E >  e_max
+                const bool ge = u0[mid < nt ? mid : nt - 1] > -CUDART_INF;
+                const bool gt = u0[mid2 < nt ? mid2 : nt - 1] >= CUDART_INF;
                 const bool go = lo < hi, go2 = lo2 < hi2;
                 hi = (go && ge) ? mid : hi;
                 lo = (go && !ge) ? mid + 1 : lo;
                 hi2 = (go2 && gt) ? mid2 : hi2;
                 lo2 = (go2 && !gt) ? mid2 + 1 : lo2;
             }
-            const int d_lo = lo, d_hi = lo2;
-            const int W = d_hi - d_lo;
-            if (W <= 0) continue;
-            const int per = ((W + 31) >> 5) | 1;           // odd stride: conflict-free u0 reads across lanes
-            const int my_lo = d_lo + lane * per;
-            const int my_hi = (my_lo + per < d_hi) ? my_lo + per : d_hi;
-            double *Hrow = H + (size_t)row * EB;
-            double acc = 0.0, acc_first = 0.0;
-            int bin = -1, bin_first = -1;
-            if (my_lo < my_hi) {
-                double v = __dadd_rn(u0[my_lo], delta);
-                int j = range_interval<RW>(v, rec, lut, m.rng_lut_inv, m.rng_lut_n, M);
-                const double2 *rj = reinterpret_cast<const double2 *>(rec + j * RW);
-                double2 hd = rj[0];
-                double next = hd.x;
-                double brk = j ? rec[(j - 1) * RW] : 0.0;
-                bin = hd.y < 0.0 ? (int)(-hd.y) - 1 : (int)hd.y;
-                double a[P + 1];
-#pragma unroll
-                for (int k = 0; k <= P; k += 2) {
-                    const double2 c2 = rj[1 + (k >> 1)];
-                    a[k] = c2.x;
-                    a[k + 1] = c2.y;
+            v_lo = lo;
+            v_hi = lo2;
+        }
+        if (v_hi <= v_lo) continue;                        // uniform: no usable draw in this tile
+        const double tu_min = u0[v_lo], tu_max = u0[v_hi - 1];
+        const double tu_inv = (tu_max > tu_min) ? (double)RANGE_ULUT / (tu_max - tu_min) : 0.0;
+        // per-tile lookup: ulut[c] = first draw with u0 >= tu_min + c*cell
+        for (int c = tid; c < RANGE_ULUT; c += NT) {
+            const double x = tu_min + (double)c * ((tu_max - tu_min) / (double)RANGE_ULUT);
+            int lo = v_lo, hi = v_hi;
+            for (int it = 0; it < nsteps; ++it) {
+                const int mid = (lo + hi) >> 1;
+                const bool ge = u0[mid < nt ? mid : nt - 1] >= x;
+                const bool go = lo < hi;
+                hi = (go && ge) ? mid : hi;
+                lo = (go && !ge) ? mid + 1 : lo;
+            }
+            ulut[c] = (unsigned short)lo;
+        }
+        // band of T2 intervals any row of this tile can touch
+        double dmin = sdelta[0], dmax = sdelta[0];
+        {
+            const double dl = sdelta[X - 1];
+            dmin = dl < dmin ? dl : dmin;
+            dmax = dl > dmax ? dl : dmax;                  // delta is monotone in the row index
+        }
+        const double vmin = __dadd_rn(tu_min, dmin), vmax = __dadd_rn(tu_max, dmax);
+        __syncthreads();
+        if (!(vmax >= 0.0) || vmin > umax) continue;       // uniform
+        const int band_lo = range_interval<RW>(vmin > 0.0 ? vmin : 0.0, rec, lut, m.rng_lut_inv, m.rng_lut_n, M);
+        const int band_hi = range_interval<RW>(vmax < umax ? vmax : umax, rec, lut, m.rng_lut_inv, m.rng_lut_n, M);
+        bin_lo_all = min(bin_lo_all, __double2loint(rec[band_lo * RW + 1]));
+        bin_hi_all = max(bin_hi_all, __double2loint(rec[band_hi * RW + 1]));
+        // One task = 32 (row, interval) cells.  Type A: one T2 interval x 32 consecutive rows (lane = row; all
+        // lanes use the same polynomial).  Type B, for the X % 32 leftover rows: R rows x (32/R) consecutive
+        // intervals.  A lane's draws are the contiguous range [lb, ub) found through the per-tile lookup.
+        // Cell (row, bin) is produced by exactly one lane: plain read-modify-write, fixed summation order.
+        const int Gf = X >> 5, R = X & 31;
+        const int n_iv = band_hi - band_lo + 1;
+        const int per_b = R ? 32 / R : 1;
+        const int nA = n_iv * Gf, nB = R ? (n_iv + per_b - 1) / per_b : 0;
+        // (jj, g) of type-A task `task` without a division in the loop
+        const int GfD = Gf > 0 ? Gf : 1;
+        int a_jj = warp / GfD, a_g = warp - a_jj * GfD;
+        const int step_j = NW / GfD, step_g = NW - step_j * GfD;
+        for (int task = warp; task < nA + nB; task += NW) {
+            int row, j;
+            bool active;
+            if (task < nA) {
+                row = (a_g << 5) + lane;
+                j = band_lo + a_jj;
+                active = true;
+                a_jj += step_j;
+                a_g += step_g;
+                if (a_g >= GfD) {
+                    a_g -= GfD;
+                    ++a_jj;
                 }
-                bool first = true;
-                for (int d = my_lo; d < my_hi; ++d) {
-                    v = __dadd_rn(u0[d], delta);
-                    if (v >= next && j + 1 < M) {
-                        do {
-                            ++j;
-                            brk = next;
-                            hd = reinterpret_cast<const double2 *>(rec + j * RW)[0];
-                            next = hd.x;
-                        } while (v >= next && j + 1 < M);
-                        const int nb = hd.y < 0.0 ? (int)(-hd.y) - 1 : (int)hd.y;
-                        if (nb != bin) {
-                            if (first) {
-                                acc_first = acc;           // boundary run: flushed after the loop
-                                bin_first = bin;
-                                first = false;
-                            } else {
-                                Hrow[bin] += acc;          // interior run: exclusively ours
-                            }
-                            acc = 0.0;
-                            bin = nb;
-                        }
-                        rj = reinterpret_cast<const double2 *>(rec + j * RW);
+            } else {
+                const int isub = lane / R;
+                row = (Gf << 5) + (lane - isub * R);
+                j = band_lo + (task - nA) * per_b + isub;
+                active = isub < per_b && j <= band_hi;
+                j = j <= band_hi ? j : band_hi;
+            }
+            const double2 *rj = reinterpret_cast<const double2 *>(rec + j * RW);
+            const double2 hd = rj[0];
+            const double left = j ? rec[(j - 1) * RW] : 0.0;
+            const bool last = (j == M - 1);
+            const double right = last ? umax : hd.x;
+            const int bin = __double2loint(hd.y);
+            double a[P + 1];
 #pragma unroll
-                        for (int k = 0; k <= P; k += 2) {
-                            const double2 c2 = rj[1 + (k >> 1)];
-                            a[k] = c2.x;
-                            a[k + 1] = c2.y;
-                        }
+            for (int k = 0; k <= P; k += 2) {
+                const double2 c2 = rj[1 + (k >> 1)];
+                a[k] = c2.x;
+                a[k + 1] = c2.y;
+            }
+            if (active) {
+                const double delta = sdelta[row];
+                // first draw with v >= left
+                int c = (int)((left - delta - tu_min) * tu_inv);
+                c = c < 0 ? 0 : (c > RANGE_ULUT - 1 ? RANGE_ULUT - 1 : c);
+                int lb = ulut[c];
+                while (lb > v_lo && __dadd_rn(u0[lb - 1], delta) >= left) --lb;
+                while (lb < v_hi && !(__dadd_rn(u0[lb], delta) >= left)) ++lb;
+                // first draw beyond the interval: v >= right (v > u_max for the last interval, which is closed)
+                c = (int)((right - delta - tu_min) * tu_inv);
+                c = c < 0 ? 0 : (c > RANGE_ULUT - 1 ? RANGE_ULUT - 1 : c);
+                int ub = ulut[c];
+                if (last) {
+                    while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) > right) --ub;
+                    while (ub < v_hi && !(__dadd_rn(u0[ub], delta) > right)) ++ub;
+                } else {
+                    while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) >= right) --ub;
+                    while (ub < v_hi && !(__dadd_rn(u0[ub], delta) >= right)) ++ub;
+                }
+                if (ub > lb) {
+                    double acc = 0.0;
+                    for (int d = lb; d < ub; ++d) {
+                        const double dt = __dadd_rn(u0[d], delta) - left;
+                        double wgt = a[P];
+#pragma unroll
+                        for (int k = P - 1; k >= 0; --k) wgt = fma(wgt, dt, a[k]);
+                        acc += wgt;
                     }
-                    const double dt = v - brk;
-                    double wgt = a[P];
-#pragma unroll
-                    for (int k = P - 1; k >= 0; --k) wgt = fma(wgt, dt, a[k]);
-                    acc += wgt;
+                    double *cell = H + (size_t)row * EB + bin;
+                    if (__double2hiint(hd.y) < 0) atomicAdd(cell, acc);  // bin split over several intervals (sign-bit flag)
+                    else *cell += acc;
                 }
             }
-            __syncwarp();                                   // interior stores done before boundary atomics
-            if (bin_first >= 0) atomicAdd(Hrow + bin_first, acc_first);
-            if (bin >= 0) atomicAdd(Hrow + bin, acc);
-            __syncwarp();
         }
     }
     __syncthreads();
@@ -613,25 +660,37 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
     for (int i = tid; i < T; i += NT) tofc[i] = 0u;        // u0 is dead now
     const double de = (m.e_max - m.e_min) / (double)EB;
     const double dx = (m.x_max - m.x_min) / (double)X;
+    // only bins bin_lo_all..bin_hi_all can be non-zero
+    const int nbw = bin_hi_all - bin_lo_all + 1;
     double part = 0.0;
-    for (int i = tid; i < X * EB; i += NT) part += __dmul_rn(__dmul_rn(H[i], de), dx);
+    for (int row = warp; row < X; row += NW)
+        for (int jb = lane; jb < nbw; jb += 32) part += __dmul_rn(__dmul_rn(H[(size_t)row * EB + bin_lo_all + jb], de), dx);
     const double S = block_sum<double>(part, scratch);     // includes the barrier that publishes tofc = 0
 
     // ---- phase 3: quantise (adv:146) and scatter every non-empty cell to its flight time (adv:149-158) ----
     const double t_step = (run.tof_max - run.tof_min) / (double)T;
     const double t_scale = (double)T / (run.tof_max - run.tof_min);
     const double nsamp = (double)m.n_samples;
-    for (int idx = tid; idx < X * EB; idx += NT) {
-        const double h = H[idx];
-        double cnt = 0.0;
-        if (h != 0.0 || !(S > 0.0)) cnt = rint(__dmul_rn(__ddiv_rn(h, S), nsamp));
-        if (out.cells) out.cells[(size_t)w * X * EB + idx] = (cnt == cnt) ? (long long)cnt : LLONG_MIN;
-        if (cnt > 0.0) {
-            const int i = idx / EB, j = idx - i * EB;
-            const double tof_d = __ddiv_rn(__ldg(m.x_centers + i), svd[j]);
-            const double tof_n = __ddiv_rn(__ldg(run.neutron_dist + i), __ldg(m.neutron_speed + j));
-            const int b = np_bin(__dadd_rn(tof_d, tof_n), T, run.tof_min, run.tof_max, t_step, t_scale);
-            if (b >= 0) atomicAdd(tofc + b, (unsigned int)cnt);
+    if (out.cells) {                                        // debug output: every cell, zeros included
+        for (int idx = tid; idx < X * EB; idx += NT) {
+            const double cnt = rint(__dmul_rn(__ddiv_rn(H[idx], S), nsamp));
+            out.cells[(size_t)w * X * EB + idx] = (cnt == cnt) ? (long long)cnt : LLONG_MIN;
+        }
+    }
+    for (int row = warp; row < X; row += NW) {
+        const double xi = __ldg(m.x_centers + row), di = __ldg(run.neutron_dist + row);
+        for (int jb = lane; jb < nbw; jb += 32) {
+            const int j = bin_lo_all + jb;
+            const double h = H[(size_t)row * EB + j];
+            if (h != 0.0 && S > 0.0) {
+                const double cnt = rint(__dmul_rn(__ddiv_rn(h, S), nsamp));
+                if (cnt > 0.0) {
+                    const double tof_d = __ddiv_rn(xi, svd[j]);
+                    const double tof_n = __ddiv_rn(di, __ldg(m.neutron_speed + j));
+                    const int b = np_bin(__dadd_rn(tof_d, tof_n), T, run.tof_min, run.tof_max, t_step, t_scale);
+                    if (b >= 0) atomicAdd(tofc + b, (unsigned int)cnt);
+                }
+            }
         }
     }
     __syncthreads();

@@ -96,6 +96,9 @@ AdvKernel adv_variant(int nt, int dpt, int nmat) {
 
 AdvKernel range_variant(int nt, int degree) {
     if (nt == 1024 && degree == 7) return adv_range_kernel<1024, 7>;
+    if (nt == 800 && degree == 7) return adv_range_kernel<800, 7>;
+    if (nt == 640 && degree == 7) return adv_range_kernel<640, 7>;
+    if (nt == 800 && degree == 5) return adv_range_kernel<800, 5>;
     if (nt == 512 && degree == 7) return adv_range_kernel<512, 7>;
     if (nt == 1024 && degree == 5) return adv_range_kernel<1024, 5>;
     if (nt == 512 && degree == 5) return adv_range_kernel<512, 5>;
@@ -337,11 +340,17 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         const int P = cfg->rng_degree, RW = P + 3, Mi = cfg->rng_n;
         std::vector<double> rec((size_t)Mi * RW);
         for (int j = 0; j < Mi; ++j) {
-            rec[(size_t)j * RW + 0] = cfg->rng_breaks[j + 1];
-            // a bin covered by several intervals is flagged by storing -(bin+1): those cells need atomics
-            const bool shared = (j > 0 && cfg->rng_bins[j - 1] == cfg->rng_bins[j]) ||
-                                (j + 1 < Mi && cfg->rng_bins[j + 1] == cfg->rng_bins[j]);
-            rec[(size_t)j * RW + 1] = shared ? -(double)(cfg->rng_bins[j] + 1) : (double)cfg->rng_bins[j];
+            // header: [break that ends the interval (+inf for the last one), E-bin as an int in the low word]
+            rec[(size_t)j * RW + 0] = (j + 1 < Mi) ? cfg->rng_breaks[j + 1] : HUGE_VAL;
+            {
+                const bool shared = (j > 0 && cfg->rng_bins[j - 1] == cfg->rng_bins[j]) ||
+                                    (j + 1 < Mi && cfg->rng_bins[j + 1] == cfg->rng_bins[j]);
+                long long bits = (long long)(unsigned int)cfg->rng_bins[j];
+                if (shared) bits |= (long long)0x8000000000000000ull;   // sign bit: cell needs atomics
+                double asd;
+                std::memcpy(&asd, &bits, sizeof(asd));
+                rec[(size_t)j * RW + 1] = asd;
+            }
             for (int k = 0; k <= P; ++k) rec[(size_t)j * RW + 2 + k] = cfg->rng_coefs[(size_t)j * (P + 1) + k];
         }
         TRY(upload(ctx, rec.data(), rec.size(), &m.rng_rec));
@@ -352,7 +361,7 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         m.rng_lut_inv = (double)cfg->rng_lut_n / cfg->rng_u_max; m.e_tab_lo = cfg->e_tab_lo; m.e_tab_hi = cfg->e_tab_hi;
         if (const char *v = std::getenv("TOFGPU_RANGE_THREADS")) {
             const int nt = std::atoi(v);
-            if (!range_variant(nt, P)) { ctx->err = "TOFGPU_RANGE_THREADS must be 512 or 1024"; return bail(TOF_ERR_INVALID); }
+            if (!range_variant(nt, P)) { ctx->err = "TOFGPU_RANGE_THREADS must be 512, 640, 800 or 1024"; return bail(TOF_ERR_INVALID); }
             ctx->rng_nt = nt;
         }
         ctx->adv_smem = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], Mi, P, cfg->n_taps, cfg->rng_lut_n);

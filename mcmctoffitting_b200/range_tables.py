@@ -280,7 +280,7 @@ def build(config: cfgmod.ModelConfig, degree: int = 7, tol_omega: float = 2e-13,
     breaks = np.array(breaks, dtype=np.float64)
     breaks[0] = 0.0
     m = len(bins)
-    lut_n = 2048
+    lut_n = 1024
     lut = np.zeros(lut_n, dtype=np.uint16)
     j = 0
     for cidx in range(lut_n):

@@ -39,7 +39,8 @@ typedef enum tof_status {
 typedef enum tof_model_kind {
     TOF_MODEL_SIMPLE = 1, /* tests/simpleTOFmodel.py:57-120 (and mpiTOFmodel.py:40-128)        */
     TOF_MODEL_ADV = 2,    /* tests/advIntermediateTOFmodel.py:115-199 = intermediateTOFmodel.py */
-    TOF_MODEL_SIMULT = 3  /* tests/simultFit.py:223-300, 380-469                                */
+    TOF_MODEL_SIMULT = 3, /* tests/simultFit.py:223-300, 380-469                                */
+    TOF_MODEL_ONEBD = 4   /* tests/csi_oneBD.py:415-521, 543-649 (production "one-BD" model)        */
 } tof_model_kind;
 
 typedef enum tof_ode_mode {
@@ -122,6 +123,16 @@ typedef struct tof_config {
     const int32_t *rng_bins;    /* [rng_n] E-bin of each interval */
     const double *rng_coefs;    /* [rng_n][rng_degree+1] monomials in (v - break), lowest order first */
     const uint16_t *rng_lut;    /* [rng_lut_n] interval holding the left edge of each lookup cell */
+    /* ---- TOF_MODEL_ONEBD only ----------------------------------------------------------------------
+     * betheApprox (ionStopping.py:102-136): E(E0, x_i) from a spline table instead of an ODE.  Evaluated at
+     * the table's own x nodes the bicubic spline reduces to one not-a-knot cubic in E0 per x column. */
+    int32_t stop_n;             /* E0 grid points (23: arange(100, 2400, 100), csi_oneBD.py:293) */
+    int32_t n_taps2;            /* causal 0-degree transit taps (7, csi_oneBD.py:407-408) */
+    double stop_lo, stop_step;  /* E0 grid origin and spacing; arguments are clamped to the grid (FITPACK) */
+    double beam_energy;         /* experimentConsts.csi_oneBD.beamReferenceEnergy (constants.py:128) */
+    const double *stop_coefs;   /* [x_bins][stop_n-1][4] power basis, highest order first, about the left node */
+    const double *attenuation;  /* [x_bins] exp(-x/20 cm) (initialization.py:35-40) */
+    const double *taps2;        /* [n_taps2] np.convolve(pdf, taps2, 'full')[:T] (csi_oneBD.py:519) */
 } tof_config;
 
 typedef struct tof_ctx tof_ctx;
@@ -142,7 +153,9 @@ int tof_set_observables(tof_ctx *ctx, int run, const double *counts, int nbins);
 /* Explicit Monte-Carlo draws replacing the reference's global np.random stream.
  *   stream 0: standard normals z[n] (adv:128; simple:64; simultFit.py:244), n = n_loops*n_ev_per_loop
  *   stream 1: simple model: uniforms u[n] in [0,1) (simple:62);
- *             simult model: replacement normals for the E0<=0 rejection loop (simultFit.py:245-252)
+ *             simult model: replacement normals for the E0<=0 rejection loop (simultFit.py:245-252);
+ *             oneBD model: the uniforms numpy's legacy Poisson sampler consumes for
+ *             np.random.poisson(bgLevel, T) (csi_oneBD.py:521), taken sequentially
  * Host pointers; copied to the device. */
 int tof_set_draws(tof_ctx *ctx, int run, int stream, const double *values, int64_t n);
 

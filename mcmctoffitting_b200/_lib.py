@@ -36,6 +36,8 @@ class TofConfig(C.Structure):
         ("rng_sign", C.c_double), ("rng_u_max", C.c_double), ("e_tab_lo", C.c_double), ("e_tab_hi", C.c_double),
         ("t1_coefs", _dp), ("rng_breaks", _dp), ("rng_bins", C.POINTER(C.c_int32)), ("rng_coefs", _dp),
         ("rng_lut", C.POINTER(C.c_uint16)),
+        ("stop_n", C.c_int32), ("n_taps2", C.c_int32), ("stop_lo", C.c_double), ("stop_step", C.c_double),
+        ("beam_energy", C.c_double), ("stop_coefs", _dp), ("attenuation", _dp), ("taps2", _dp),
     ]
 
 

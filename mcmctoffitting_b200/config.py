@@ -168,7 +168,7 @@ def zero_degree_tables(e_n: np.ndarray, n_segments: int = 10) -> Tuple[np.ndarra
 
 
 # ---- model configurations --------------------------------------------------------------------------
-KIND_SIMPLE, KIND_ADV, KIND_SIMULT = 1, 2, 3
+KIND_SIMPLE, KIND_ADV, KIND_SIMULT, KIND_ONEBD = 1, 2, 3, 4
 ODE_RK4, ODE_RANGE = 0, 1
 
 
@@ -198,6 +198,12 @@ class ModelConfig:
     n_zero_deg: int = 0
     nan_to_neginf: bool = False
     taps: Tuple[float, ...] = field(default_factory=lambda: tuple(beam_timing_taps()))
+    # oneBD only (csi_oneBD.py:226-295, 407-411)
+    beam_energy: float = 0.0
+    stop_grid: Tuple[float, float, float] = ()          # np.arange(lo, hi, step) of betheApprox (csi_oneBD.py:293)
+    stop_table: Tuple[Tuple[float, ...], ...] = ()      # [len(grid)][x_bins]; () = integrate like the reference does
+    attenuation_length: float = 0.0
+    taps2: Tuple[float, ...] = ()
 
     @property
     def n_runs(self) -> int:
@@ -231,6 +237,47 @@ class ModelConfig:
             else:
                 rows.append(distances.cellLength - xc + so)                                   # simultFit:290-291
         return np.ascontiguousarray(np.array(rows, dtype=np.float64))
+
+    # oneBD tables ---------------------------------------------------------------------------------------
+    def stop_energy_grid(self) -> np.ndarray:
+        return np.arange(*self.stop_grid, dtype=np.float64)
+
+    def stopping_table(self) -> np.ndarray:
+        """betheApprox table z[E0_k, x_i] (ionStopping.py:108-128).  The reference integrates it with scipy's
+        dopri5 at default tolerances and then interpolates THAT table, so the same integrator is used here
+        (scipy is a dependency of the reference); pass ``stop_table`` to supply one instead."""
+        if self.stop_table:
+            return np.asarray(self.stop_table, dtype=np.float64)
+        try:
+            from scipy.integrate import ode
+        except ImportError as exc:  # pragma: no cover
+            raise RuntimeError("scipy is needed to integrate the betheApprox table; pass stop_table=...") from exc
+        A, B = bethe_reduced(self.materials)
+
+        def dedx(x, y):   # simpleBethe.dEdx in its own operation order (ionStopping.py:78-97)
+            velocity = np.sqrt(2 * y / MASS_DEUTERON) * SPEED_OF_LIGHT
+            lead = 4 * np.pi * 1 ** 2 / (MASS_ELECTRON * SPEED_OF_LIGHT ** 2 * velocity ** 2)
+            frac = 0
+            for Z, Am, rho, exc_ in self.materials:
+                n_e = AVOGADRO * Z * rho / (Am * 1)
+                frac = frac + n_e * np.log(2 * MASS_ELECTRON / (SPEED_OF_LIGHT ** 2) * velocity ** 2 / exc_)
+            return -1 * lead * BETHE_FIXED_FACTOR * frac
+
+        rows = []
+        for e_zero in np.arange(*self.stop_grid):
+            solver = ode(dedx).set_integrator("dopri5").set_initial_value(e_zero)
+            rows.append(np.array([solver.integrate(x) for x in self.x_centers()]).flatten())
+        return np.array(rows)
+
+    def stop_coefs(self) -> np.ndarray:
+        """Per x column, the not-a-knot cubic in E0 through the table: what RectBivariateSpline (kx=ky=3, s=0;
+        ionStopping.py:130) evaluates to along its own x nodes.  [x_bins][n-1][4]."""
+        tab = self.stopping_table()
+        grid = self.stop_energy_grid()
+        return np.ascontiguousarray(np.array([not_a_knot_cubic(grid, tab[:, i]) for i in range(self.x_bins)]))
+
+    def attenuation(self) -> np.ndarray:
+        return np.exp(-self.x_centers() / self.attenuation_length)            # initialization.py:35-40
 
     def validate(self) -> None:
         if self.kind != KIND_SIMPLE:
@@ -316,5 +363,31 @@ def simult(n_samples: int = 200000, n_ev_per_loop: int = 50000, **overrides) -> 
               x_bins=10, x_range=(0.0, distances.cellLength), e_bins=50, e_range=(200.0, 1200.0),           # simultFit:158-175
               materials=((1, 2, 8.565e-5, 19.2 * 1e-3),), ode_substeps=4, ode_from_zero=True,               # simultFit:191-201,256
               zero_deg_half_length_in_path=False, n_zero_deg=10, nan_to_neginf=True)                         # simultFit:463-468
+    kw.update(overrides)
+    return ModelConfig(**kw)
+
+
+class distances_oneBD:
+    """constants.py:59-81 (tunlSSA_CsI_oneBD)."""
+    standoffClose = 351.3
+    standoffMid = standoffClose + (412.3 - 351.3)
+    standoffFar = standoffMid + (444.5 - 412.3)
+
+
+def onebd(n_samples: int = 200000, n_ev_per_loop: int = 10000, **overrides) -> ModelConfig:
+    """tests/csi_oneBD.py with its default flags (the production "one-BD" model)."""
+    zc = np.linspace(0, 24, 7, True)
+    taps2 = np.exp(-zc / 2.) / np.sum(np.exp(-zc / 2.))                                                     # csi_oneBD:407-408
+    kw = dict(kind=KIND_ONEBD, name="onebd", ndim=9,
+              prior=((200.0, 2000.0), (10.0, 700.0), (0.05, 3.0)) + ((1e3, 1.0e8),) * 3 + ((0.0, 1e3),) * 3,  # csi_oneBD:595-606
+              prior_strict=False,
+              tof_bins=(25, 25, 25), tof_ranges=((80.0, 180.0), (100.0, 200.0), (120.0, 220.0)),            # constants.py:114-123
+              standoffs=(distances_oneBD.standoffClose, distances_oneBD.standoffMid, distances_oneBD.standoffFar),
+              n_samples=n_samples, n_ev_per_loop=n_ev_per_loop, n_loops=int(math.ceil(n_samples / n_ev_per_loop)),
+              x_bins=10, x_range=(0.0, distances.cellLength), e_bins=100, e_range=(200.0, 2200.0),          # csi_oneBD:199-212
+              materials=((1, 2, 4 * 8.565e-5, 19.2 * 1e-3),),                                                # csi_oneBD:270-288
+              zero_deg_half_length_in_path=False, n_zero_deg=0, nan_to_neginf=True,
+              taps=tuple(gaussian_timing_taps(2.7)),                                                         # csi_oneBD:266
+              beam_energy=2490.0, stop_grid=(100, 2400, 100), attenuation_length=20.0, taps2=tuple(taps2))
     kw.update(overrides)
     return ModelConfig(**kw)

@@ -33,6 +33,10 @@ struct DevModel {
     const unsigned short *rng_lut; // [rng_lut_n]
     int t1_q, t1_key_lo, t1_n, rng_degree, rng_n, rng_lut_n;
     double rng_sign, rng_u_max, rng_lut_inv, e_tab_lo, e_tab_hi;
+    // oneBD: spline stopping table, attenuation, causal transit taps
+    const double *stop_coefs, *attenuation, *taps2;
+    int stop_n, n_taps2;
+    double stop_lo, stop_step, beam_energy;
 };
 
 struct DevRun {

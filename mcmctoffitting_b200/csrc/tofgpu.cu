@@ -36,7 +36,7 @@ struct tof_ctx {
     int adv_nt = 1024, adv_dpt = 1;
     size_t adv_smem = 0;
     int rng_nt = 1024;
-    size_t simult_smem = 0;
+    size_t simult_smem = 0, onebd_smem = 0;
     int max_smem_optin = 0;
     bool have_obs[TOF_MAX_RUNS]{};
     bool have_z[TOF_MAX_RUNS][2]{};
@@ -149,6 +149,22 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
         simple_finish_kernel<32><<<(unsigned)n, 32, 0, st>>>(ctx->dm, ctx->runs[0], d_theta, n,
                                                              static_cast<unsigned long long *>(ctx->d_counts.p), out);
         ctx->stats.kernel_launches += 2;
+    } else if (c.model == TOF_MODEL_ONEBD) {
+        DevRunSet rs;
+        for (int r = 0; r < TOF_MAX_RUNS; ++r) rs.r[r] = ctx->runs[r];
+        const bool debug = out.spectra != nullptr || out.cells != nullptr;
+        if (debug) {
+            onebd_run_kernel<256><<<(unsigned)n, 256, ctx->onebd_smem, st>>>(ctx->dm, rs, d_theta, n, out, run);
+            ctx->stats.kernel_launches += 1;
+        } else {
+            int rc = ensure(ctx, ctx->d_partial, (size_t)n * c.n_runs * sizeof(double));
+            if (rc) return rc;
+            ModelOut po{};
+            po.lnprob = static_cast<double *>(ctx->d_partial.p);
+            onebd_run_kernel<256><<<(unsigned)(n * c.n_runs), 256, ctx->onebd_smem, st>>>(ctx->dm, rs, d_theta, n, po, -1);
+            simult_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->dm, d_theta, n, po.lnprob, out.lnprob);
+            ctx->stats.kernel_launches += 2;
+        }
     } else if (c.model == TOF_MODEL_SIMULT) {
         DevRunSet rs;
         for (int r = 0; r < TOF_MAX_RUNS; ++r) rs.r[r] = ctx->runs[r];
@@ -190,7 +206,8 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
     if (!cfg || !out) return fail(nullptr, TOF_ERR_INVALID, "null argument");
     *out = nullptr;
     if (cfg->abi_version != TOF_ABI_VERSION) return fail(nullptr, TOF_ERR_INVALID, "abi_version mismatch");
-    if (cfg->model != TOF_MODEL_SIMPLE && cfg->model != TOF_MODEL_ADV && cfg->model != TOF_MODEL_SIMULT)
+    if (cfg->model != TOF_MODEL_SIMPLE && cfg->model != TOF_MODEL_ADV && cfg->model != TOF_MODEL_SIMULT &&
+        cfg->model != TOF_MODEL_ONEBD)
         return fail(nullptr, TOF_ERR_INVALID, "unknown model kind");
     if (cfg->ndim < 1 || cfg->ndim > TOF_MAX_DIM) return fail(nullptr, TOF_ERR_INVALID, "ndim out of range");
     if (cfg->n_runs < 1 || cfg->n_runs > TOF_MAX_RUNS) return fail(nullptr, TOF_ERR_INVALID, "n_runs out of range");
@@ -202,7 +219,8 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
     if (cell_model) {
         if (cfg->x_bins < 1 || cfg->e_bins < 1 || !(cfg->x_max > cfg->x_min) || !(cfg->e_max > cfg->e_min))
             return fail(nullptr, TOF_ERR_INVALID, "bad (x, E) binning");
-        if (cfg->n_materials < 1 || cfg->n_materials > TOF_MAX_MATERIALS) return fail(nullptr, TOF_ERR_INVALID, "n_materials out of range");
+        if (cfg->model != TOF_MODEL_ONEBD && (cfg->n_materials < 1 || cfg->n_materials > TOF_MAX_MATERIALS))
+            return fail(nullptr, TOF_ERR_INVALID, "n_materials out of range");
         if (cfg->n_xs < 4) return fail(nullptr, TOF_ERR_INVALID, "cross-section table too short");
         if (cfg->n_taps < 1) return fail(nullptr, TOF_ERR_INVALID, "n_taps must be >= 1");
         if (cfg->ode_substeps < 1) return fail(nullptr, TOF_ERR_INVALID, "ode_substeps must be >= 1");
@@ -403,6 +421,31 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         ctx->stats.ctas_per_sm = occ;
     } else if (cfg->model == TOF_MODEL_SIMPLE) {
         ctx->stats.threads = 256;
+    } else if (cfg->model == TOF_MODEL_ONEBD) {
+        if (cfg->ndim != 3 + 2 * cfg->n_runs) { ctx->err = "oneBD model has ndim == 3 + 2*n_runs"; return bail(TOF_ERR_INVALID); }
+        if (cfg->stop_n < 4 || !cfg->stop_coefs || !cfg->attenuation || !cfg->taps2 || cfg->n_taps2 < 1 || !(cfg->stop_step > 0.0)) {
+            ctx->err = "oneBD model needs stop_coefs / attenuation / taps2";
+            return bail(TOF_ERR_INVALID);
+        }
+        TRY(upload(ctx, cfg->stop_coefs, (size_t)cfg->x_bins * (cfg->stop_n - 1) * 4, &m.stop_coefs));
+        TRY(upload(ctx, cfg->attenuation, (size_t)cfg->x_bins, &m.attenuation));
+        TRY(upload(ctx, cfg->taps2, (size_t)cfg->n_taps2, &m.taps2));
+        m.stop_n = cfg->stop_n; m.n_taps2 = cfg->n_taps2; m.stop_lo = cfg->stop_lo; m.stop_step = cfg->stop_step;
+        m.beam_energy = cfg->beam_energy;
+        int tmax = 0;
+        for (int r = 0; r < cfg->n_runs; ++r) tmax = std::max(tmax, cfg->tof_bins[r]);
+        ctx->onebd_smem = onebd_smem_bytes(256, cfg->x_bins, cfg->e_bins, tmax, cfg->n_xs, cfg->n_taps, cfg->n_taps2, cfg->stop_n,
+                                           m.xs_lut_n);
+        if ((int)ctx->onebd_smem > ctx->max_smem_optin) {
+            ctx->err = "oneBD kernel needs " + std::to_string(ctx->onebd_smem) + " B of shared memory per CTA";
+            return bail(TOF_ERR_CAPACITY);
+        }
+        CUC(cudaFuncSetAttribute(onebd_run_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->onebd_smem));
+        int occ = 0;
+        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, onebd_run_kernel<256>, 256, ctx->onebd_smem));
+        ctx->stats.smem_bytes = (int)ctx->onebd_smem;
+        ctx->stats.threads = 256;
+        ctx->stats.ctas_per_sm = occ;
     } else {
         if (cfg->ndim < 4 + cfg->n_runs) { ctx->err = "simult model needs ndim >= 4 + n_runs"; return bail(TOF_ERR_INVALID); }
         if (cfg->ode_mode != TOF_ODE_RK4) { ctx->err = "the simult model supports TOF_ODE_RK4 only"; return bail(TOF_ERR_INVALID); }
@@ -444,7 +487,7 @@ int tof_set_observables(tof_ctx *ctx, int run, const double *counts, int nbins) 
     if (nbins != ctx->cfg.tof_bins[run]) return fail(ctx, TOF_ERR_INVALID, "observables length != tof_bins[run]");
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     std::vector<double> obs(counts, counts + nbins);
-    if (ctx->cfg.model == TOF_MODEL_SIMULT)
+    if (ctx->cfg.model == TOF_MODEL_SIMULT || ctx->cfg.model == TOF_MODEL_ONEBD)
         for (double &v : obs)
             if (v == 0.0) v = 1.0;  // simultFit.py:391-392, applied to the private copy
     std::vector<int> idx;

@@ -74,6 +74,7 @@ class TofModel:
             c.n_materials = len(A)
             for k in range(len(A)):
                 c.bethe_A[k], c.bethe_B[k] = A[k], B[k]
+            c.ode_substeps = max(config.ode_substeps, 1)
             tabs = dict(
                 x_centers=_as_f64(config.x_centers()),
                 e_centers=_as_f64(config.e_centers()),
@@ -89,6 +90,14 @@ class TofModel:
             if config.n_zero_deg:
                 t, w = cfgmod.zero_degree_tables(cfgmod.dd_neutron_energy(config.e_centers()), config.n_zero_deg)
                 tabs["zero_deg_times"], tabs["zero_deg_weights"] = _as_f64(t), _as_f64(w)
+            if config.kind == cfgmod.KIND_ONEBD:
+                tabs["stop_coefs"] = _as_f64(config.stop_coefs())
+                tabs["attenuation"] = _as_f64(config.attenuation())
+                tabs["taps2"] = _as_f64(config.taps2)
+                grid = config.stop_energy_grid()
+                c.stop_n, c.n_taps2 = len(grid), len(config.taps2)
+                c.stop_lo, c.stop_step = float(grid[0]), float(grid[1] - grid[0])
+                c.beam_energy = config.beam_energy
             for name, arr in tabs.items():
                 setattr(c, name, _dptr(arr))
             self._keep.append(tabs)

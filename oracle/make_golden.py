@@ -200,11 +200,35 @@ def main():
         "adv_physical": adv(19.2e-3, "I=19.2e-3 keV (physical)"),
         "sweep": sweep(),
         "simult": simult(full="--quick" not in sys.argv),
+        "onebd": onebd(),
     }
     path = os.path.join(ROOT, "tests", "golden", "reference_golden.json")
     with open(path, "w") as fh:
         json.dump(gold, fh, indent=0, separators=(",", ":"))
     print("wrote", path, os.path.getsize(path), "bytes")
+
+
+
+
+def onebd():
+    """tests/csi_oneBD.py through the loader (prefix 700 lines, -quitEarly 0)."""
+    ns = ref_loader.load("csi_oneBD", argv=["-quitEarly", "0"], prefix_lines=700)
+    out = {"stop_table": [fl(r) for r in ns["stoppingApprox"].z], "cases": []}
+    theta = [900.0, 170.0, 0.5, 3e4, 2e4, 4e4, 5.0, 12.0, 0.0]
+    for n_ev, n_samp, seed_obs, seed_eval in [(500, 2000, 3, 4), (1000, 3000, 5, 6)]:
+        ns["nEvPerLoop"] = n_ev
+        np.random.seed(seed_obs)
+        obs = []
+        for r in range(3):
+            p = [theta[0], theta[1], theta[2], theta[3 + r], theta[6 + r]]
+            obs.append(np.rint(ns["generateModelData"](p, ns["standoffs"][r], ns["tof_range"][r], ns["tofRunBins"][r],
+                                                       ns["ddnXSinstance"], ns["stoppingApprox"], ns["beamTiming"],
+                                                       n_samp, True)))
+        np.random.seed(seed_eval)
+        val = ns["lnprob"](theta, [o.copy() for o in obs], ns["standoffs"], ns["tof_range"], ns["tofRunBins"], n_samp)
+        out["cases"].append({"n_ev_per_loop": n_ev, "n_samples": n_samp, "seed_obs": seed_obs, "seed_eval": seed_eval,
+                             "theta": theta, "obs": [fl(o) for o in obs], "lnprob": f(val)})
+    return out
 
 
 if __name__ == "__main__":

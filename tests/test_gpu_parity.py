@@ -509,3 +509,77 @@ def test_simult_exhausted_replacement_stream_is_neg_inf(M, O):
     got = fn.batch([[1825.0, 1000, 300, 1.2, 3e4, 2e4, 2e4, 4e4, 4e4]])
     assert got[0] == -np.inf                                             # NaN -> -inf (simultFit.py:463-468)
     fn.model.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# oneBD production model: tests/csi_oneBD.py
+# ---------------------------------------------------------------------------------------------------
+def _onebd_oracle_lnprob(O, om, theta, obs, z_last, u_streams, xs, tab):
+    def bg(run, lam, T):
+        return O.poisson_from_uniforms(lam, T, O.UniformStream(u_streams[run]))
+    return om.lnprob(list(theta), obs, z_last, bg, xs, tab)
+
+
+def test_onebd_vs_oracle(M, O):
+    n_ev, n_samp = 2000, 6000
+    cfg = M.config.onebd(n_samples=n_samp, n_ev_per_loop=n_ev)
+    om = O.OneBDModel(n_samples=n_samp, n_ev_per_loop=n_ev)
+    rs = np.random.RandomState(21)
+    z = [rs.standard_normal((cfg.n_loops, n_ev)) for _ in range(3)]
+    u = [rs.random_sample(4000) for _ in range(3)]
+    xs = O.DDNXS()
+    tab = om.stop_table()
+    theta_star = [900.0, 170.0, 0.5, 3e4, 2e4, 4e4, 5.0, 12.0, 0.0]
+    z_last = [zz[-1] for zz in z]
+    obs = []
+    for r in range(3):
+        p = om.run_params(theta_star, r)
+        ev, _ = om.model(p, r, z_last[r], O.poisson_from_uniforms(p[4], 25, O.UniformStream(u[r])), xs, tab)
+        obs.append(np.rint(ev))
+    thetas = np.array([theta_star,
+                       [1200.0, 300.0, 0.8, 5e4, 1e4, 2e4, 0.5, 30.0, 250.0],
+                       [400.0, 50.0, 2.5, 2e3, 9e7, 1e5, 999.0, 0.0, 9.99],     # very wide: E0 far outside the table
+                       [2000.0, 700.0, 0.05, 1e3, 1e3, 1e3, 10.0, 10.0, 10.0],
+                       [199.0, 170.0, 0.5, 3e4, 2e4, 4e4, 5.0, 12.0, 0.0],       # outside the prior
+                       [900.0, 170.0, 0.5, 3e4, 2e4, 4e4, 5.0, 12.0, 1000.5]])   # outside the prior
+    fn = M.make_lnprob(cfg, obs, [zz.ravel() for zz in z], extra_draws=u)
+    got = fn.batch(thetas)
+    for k, th in enumerate(thetas):
+        want = _onebd_oracle_lnprob(O, om, th, obs, z_last, u, xs, tab)
+        assert rel(float(got[k]), float(want)) <= RTOL, (k, got[k], want)
+    assert got[4] == -np.inf and got[5] == -np.inf
+    for k in (0, 2):
+        for r in range(3):
+            p = om.run_params(list(thetas[k]), r)
+            bgc = O.poisson_from_uniforms(p[4], 25, O.UniformStream(u[r]))
+            want_s, want_c = om.model(p, r, z_last[r], bgc, xs, tab)
+            got_c = fn.model.cell_counts(thetas[k:k + 1], run=r)[0]
+            n_diff = int(np.count_nonzero(got_c != want_c))
+            assert n_diff == 0, (k, r, n_diff)
+            got_s = fn.model.model_batch(thetas[k:k + 1], run=r, stage="spread")[0]
+            np.testing.assert_allclose(got_s, want_s, rtol=1e-11)
+    fn.model.close()
+
+
+def test_onebd_reference_goldens(M, O, golden, pf):
+    g = golden["onebd"]
+    tab = np.array([parse_floats(r) for r in g["stop_table"]])
+    for c in g["cases"]:
+        cfg = M.config.onebd(n_samples=c["n_samples"], n_ev_per_loop=c["n_ev_per_loop"],
+                             stop_table=tuple(tuple(r) for r in tab))
+        obs = [parse_floats(o) for o in c["obs"]]
+        # replay the reference's global stream: per run n_loops*n_ev normals, then the doubles poisson() consumes
+        rs = np.random.RandomState(c["seed_eval"])
+        z, u = [], []
+        for r in range(3):
+            z.append(rs.standard_normal(cfg.n_draws))
+            lam = c["theta"][6 + r]
+            state = rs.get_state()
+            probe = np.random.RandomState()
+            probe.set_state(state)
+            u.append(probe.random_sample(2000))          # same doubles the sampler is about to consume
+            rs.poisson(lam, 25)                           # advance the real stream
+        fn = M.make_lnprob(cfg, obs, z, extra_draws=u)
+        got = float(fn.batch([c["theta"]])[0])
+        fn.model.close()
+        assert rel(got, pf(c["lnprob"])) <= RTOL, (got, c["lnprob"])

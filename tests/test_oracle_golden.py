@@ -195,3 +195,31 @@ def test_exact_stopping_agrees_with_rk4_and_scipy():
         ex0 = O.exact_stop(E0[:5], xc[:10], A, B, 0.0)
         rk0 = O.rk4_stop(E0[:5], xc[:10], sb.dEdx, 0.0, 64)
         np.testing.assert_allclose(ex0, rk0, rtol=1e-11)
+
+
+def test_poisson_restatement_matches_numpy_randomstate():
+    """numpy's legacy Poisson sampler restated on an explicit uniform stream == RandomState.poisson."""
+    for lam in (0.0, 0.3, 5.0, 9.99, 10.0, 12.0, 57.3, 999.0):
+        want = np.random.RandomState(42).poisson(lam, 300)
+        st = O.UniformStream(np.random.RandomState(42).random_sample(30000))
+        got = O.poisson_from_uniforms(lam, 300, st)
+        assert np.array_equal(got, want), lam
+
+
+def test_onebd_goldens(golden, pf):
+    """tests/csi_oneBD.py: spline stopping table and seed-pinned lnprob, reproduced bit for bit."""
+    g = golden["onebd"]
+    tab = np.array([parse_floats(r) for r in g["stop_table"]])
+    assert np.array_equal(O.OneBDModel().stop_table(), tab)
+    xs = O.DDNXS()
+    for c in g["cases"]:
+        m = O.OneBDModel(n_ev_per_loop=c["n_ev_per_loop"], n_samples=c["n_samples"])
+        obs = [parse_floats(o) for o in c["obs"]]
+        rs = np.random.RandomState(c["seed_eval"])
+        total = []
+        for r in range(3):   # the reference consumes, per run: n_loops*n_ev normals, then poisson(bg, T)
+            z_all = rs.standard_normal(m.n_loops * m.n_ev_per_loop).reshape(m.n_loops, m.n_ev_per_loop)
+            p = m.run_params(c["theta"], r)
+            ev, _ = m.model(p, r, z_all[-1], rs.poisson(p[4], m.tof_bins[r]), xs, tab)
+            total.append(m.bin_loglike(ev, obs[r]))
+        assert rel(float(np.sum(total)), pf(c["lnprob"])) <= 1e-13

@@ -10,5 +10,6 @@ from .config import ModelConfig
 from .model import TofModel
 from .lnprob import TofLnProb, BatchedPool, make_lnprob
 from ._lib import TofError
+from . import ppc
 
-__all__ = ["config", "ModelConfig", "TofModel", "TofLnProb", "BatchedPool", "make_lnprob", "TofError"]
+__all__ = ["config", "ModelConfig", "TofModel", "TofLnProb", "BatchedPool", "make_lnprob", "TofError", "ppc"]

@@ -583,3 +583,27 @@ def test_onebd_reference_goldens(M, O, golden, pf):
         got = float(fn.batch([c["theta"]])[0])
         fn.model.close()
         assert rel(got, pf(c["lnprob"])) <= RTOL, (got, c["lnprob"])
+
+
+def test_ppc_batch_generation(M, O):
+    """Posterior-predictive batch = model spectra + cell counts for sampled parameter vectors."""
+    cfg = M.config.simult(n_samples=3000, n_ev_per_loop=1000)
+    om = O.SimultModel(n_samples=3000, n_ev_per_loop=1000)
+    z_main, z_extra = _simult_tables(O, cfg, 9)
+    fn = M.make_lnprob(cfg, [np.ones(n) for n in cfg.tof_bins], [z.ravel() for z in z_main], extra_draws=z_extra)
+    rs = np.random.RandomState(2)
+    chain = np.array([1878.4, 850, 170, 0.5, 3e4, 2e4, 2e4, 4e4, 4e4]) * (1 + 0.01 * rs.standard_normal((60, 8, 9)))
+    thetas = M.ppc.sample_posterior(chain, 12, rng=np.random.RandomState(3))
+    assert thetas.shape == (12, 9)
+    spectra, cells = M.ppc.generate_ppc(fn.model, thetas)
+    assert [s.shape for s in spectra] == [(12, n) for n in cfg.tof_bins] and cells[0].shape == (12, 10, 50)
+    td = O.TableDraws(z_main, z_extra)
+    xs = O.DDNXS()
+    for k in (0, 7):
+        for r in (0, 3):
+            td.reset()
+            th = list(thetas[k])
+            np.testing.assert_allclose(spectra[r][k], om.model(th[:4] + [th[4 + r]], r, td, xs), rtol=1e-11)
+    bands = M.ppc.ppc_bands(spectra[0])
+    assert bands.shape == (3, cfg.tof_bins[0]) and np.all(bands[0] <= bands[2])
+    fn.model.close()

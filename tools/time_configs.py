@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import torch
 import mcmctoffitting_b200 as M
 warnings.simplefilter("ignore")
-which = sys.argv[1:] or ["simple", "intermediate", "adv", "simult"]
+which = sys.argv[1:] or ["simple", "intermediate", "adv", "simult", "onebd"]
 dev = torch.device("cuda", 0)
 rs = np.random.RandomState(0)
 
@@ -58,3 +58,10 @@ if "simult" in which:
     draws = [rs.standard_normal(cfg.n_draws) for _ in range(5)]
     extra = [rs.standard_normal(20000) for _ in range(5)]
     run("C4 simult/rk4", cfg, th, draws, extra, reps=1)
+if "onebd" in which:
+    cfg = M.config.onebd()
+    n = 4096
+    th = np.tile([900.0, 170.0, 0.5, 3e4, 2e4, 4e4, 5.0, 12.0, 0.5], (n, 1)) * (1 + 0.01 * rs.standard_normal((n, 9)))
+    draws = [rs.standard_normal(cfg.n_draws) for _ in range(3)]
+    extra = [rs.random_sample(4000) for _ in range(3)]
+    run("oneBD", cfg, th, draws, extra, reps=2)

@@ -415,6 +415,7 @@ namespace tof {
 // per run instead of once per sample.
 constexpr int RANGE_TILE = 1024;   // draws staged in shared memory at a time
 constexpr int RANGE_ULUT = 1024;   // cells of the per-tile draw-index lookup table
+constexpr int SIMULT_ULUT = 256;   // same for the 10-row simultaneous fit (fewer lookups per tile)
 
 __host__ __device__ inline size_t range_smem_bytes(int X, int E, int T, int rng_n, int P, int n_taps, int lut_n) {
     size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
@@ -463,6 +464,146 @@ __device__ __forceinline__ double t1_eval(double E0, const DevModel &m) {
 #pragma unroll
     for (int q = 6; q >= 0; --q) acc = fma(acc, t, __ldg(k + q));
     return acc;
+}
+
+// Phase 1 for one tile of sorted u0 values (shared memory): add the cross-section weights of every (draw, row)
+// sample to the (x,E) histogram H.  Called by all threads of the CTA (contains barriers).
+template <int NT, int P>
+__device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, const double *rec, const unsigned short *lut,
+                                                      unsigned short *ulut, int n_ulut, const double *sdelta, double *H, int X,
+                                                      int EB, int M, double umax, double lut_inv, int lut_n, int &bin_lo_all,
+                                                      int &bin_hi_all) {
+    constexpr int RW = P + 3;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nsteps = 32 - __clz(nt);                 // binary-search iterations for [0, nt]
+    // valid (finite) part of the sorted tile: -inf (never in range) first, +inf last
+    int v_lo = 0, v_hi = nt;
+    {
+        int lo = 0, hi = nt, lo2 = 0, hi2 = nt;
+        for (int it = 0; it < nsteps; ++it) {
+            const int mid = (lo + hi) >> 1, mid2 = (lo2 + hi2) >> 1;
+            const bool ge = u0[mid < nt ? mid : nt - 1] > -CUDART_INF;
+            const bool gt = u0[mid2 < nt ? mid2 : nt - 1] >= CUDART_INF;
+            const bool go = lo < hi, go2 = lo2 < hi2;
+            hi = (go && ge) ? mid : hi;
+            lo = (go && !ge) ? mid + 1 : lo;
+            hi2 = (go2 && gt) ? mid2 : hi2;
+            lo2 = (go2 && !gt) ? mid2 + 1 : lo2;
+        }
+        v_lo = lo;
+        v_hi = lo2;
+    }
+    if (v_hi <= v_lo) return;                        // uniform: no usable draw in this tile
+    const double tu_min = u0[v_lo], tu_max = u0[v_hi - 1];
+    const double tu_inv = (tu_max > tu_min) ? (double)n_ulut / (tu_max - tu_min) : 0.0;
+    // per-tile lookup: ulut[c] = first draw with u0 >= tu_min + c*cell
+    for (int c = tid; c < n_ulut; c += NT) {
+        const double x = tu_min + (double)c * ((tu_max - tu_min) / (double)n_ulut);
+        int lo = v_lo, hi = v_hi;
+        for (int it = 0; it < nsteps; ++it) {
+            const int mid = (lo + hi) >> 1;
+            const bool ge = u0[mid < nt ? mid : nt - 1] >= x;
+            const bool go = lo < hi;
+            hi = (go && ge) ? mid : hi;
+            lo = (go && !ge) ? mid + 1 : lo;
+        }
+        ulut[c] = (unsigned short)lo;
+    }
+    // band of T2 intervals any row of this tile can touch
+    double dmin = sdelta[0], dmax = sdelta[0];
+    {
+        const double dl = sdelta[X - 1];
+        dmin = dl < dmin ? dl : dmin;
+        dmax = dl > dmax ? dl : dmax;                  // delta is monotone in the row index
+    }
+    const double vmin = __dadd_rn(tu_min, dmin), vmax = __dadd_rn(tu_max, dmax);
+    __syncthreads();
+    if (!(vmax >= 0.0) || vmin > umax) return;         // uniform
+    const int band_lo = range_interval<RW>(vmin > 0.0 ? vmin : 0.0, rec, lut, lut_inv, lut_n, M);
+    const int band_hi = range_interval<RW>(vmax < umax ? vmax : umax, rec, lut, lut_inv, lut_n, M);
+    bin_lo_all = min(bin_lo_all, __double2loint(rec[band_lo * RW + 1]));
+    bin_hi_all = max(bin_hi_all, __double2loint(rec[band_hi * RW + 1]));
+    // One task = 32 (row, interval) cells.  Type A: one T2 interval x 32 consecutive rows (lane = row; all
+    // lanes use the same polynomial).  Type B, for the X % 32 leftover rows: R rows x (32/R) consecutive
+    // intervals.  A lane's draws are the contiguous range [lb, ub) found through the per-tile lookup.
+    // Cell (row, bin) is produced by exactly one lane: plain read-modify-write, fixed summation order.
+    const int Gf = X >> 5, R = X & 31;
+    const int n_iv = band_hi - band_lo + 1;
+    const int per_b = R ? 32 / R : 1;
+    const int nA = n_iv * Gf, nB = R ? (n_iv + per_b - 1) / per_b : 0;
+    // (jj, g) of type-A task `task` without a division in the loop
+    const int GfD = Gf > 0 ? Gf : 1;
+    int a_jj = warp / GfD, a_g = warp - a_jj * GfD;
+    const int step_j = NW / GfD, step_g = NW - step_j * GfD;
+    for (int task = warp; task < nA + nB; task += NW) {
+        int row, j;
+        bool active;
+        if (task < nA) {
+            row = (a_g << 5) + lane;
+            j = band_lo + a_jj;
+            active = true;
+            a_jj += step_j;
+            a_g += step_g;
+            if (a_g >= GfD) {
+                a_g -= GfD;
+                ++a_jj;
+            }
+        } else {
+            const int isub = lane / R;
+            row = (Gf << 5) + (lane - isub * R);
+            j = band_lo + (task - nA) * per_b + isub;
+            active = isub < per_b && j <= band_hi;
+            j = j <= band_hi ? j : band_hi;
+        }
+        const double2 *rj = reinterpret_cast<const double2 *>(rec + j * RW);
+        const double2 hd = rj[0];
+        const double left = j ? rec[(j - 1) * RW] : 0.0;
+        const bool last = (j == M - 1);
+        const double right = last ? umax : hd.x;
+        const int bin = __double2loint(hd.y);
+        double a[P + 1];
+#pragma unroll
+        for (int k = 0; k <= P; k += 2) {
+            const double2 c2 = rj[1 + (k >> 1)];
+            a[k] = c2.x;
+            a[k + 1] = c2.y;
+        }
+        if (active) {
+            const double delta = sdelta[row];
+            // first draw with v >= left
+            int c = (int)((left - delta - tu_min) * tu_inv);
+            c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
+            int lb = ulut[c];
+            while (lb > v_lo && __dadd_rn(u0[lb - 1], delta) >= left) --lb;
+            while (lb < v_hi && !(__dadd_rn(u0[lb], delta) >= left)) ++lb;
+            // first draw beyond the interval: v >= right (v > u_max for the last interval, which is closed)
+            c = (int)((right - delta - tu_min) * tu_inv);
+            c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
+            int ub = ulut[c];
+            if (last) {
+                while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) > right) --ub;
+                while (ub < v_hi && !(__dadd_rn(u0[ub], delta) > right)) ++ub;
+            } else {
+                while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) >= right) --ub;
+                while (ub < v_hi && !(__dadd_rn(u0[ub], delta) >= right)) ++ub;
+            }
+            if (ub > lb) {
+                double acc = 0.0;
+                for (int d = lb; d < ub; ++d) {
+                    const double dt = __dadd_rn(u0[d], delta) - left;
+                    double wgt = a[P];
+#pragma unroll
+                    for (int k = P - 1; k >= 0; --k) wgt = fma(wgt, dt, a[k]);
+                    acc += wgt;
+                }
+                double *cell = H + (size_t)row * EB + bin;
+                if (__double2hiint(hd.y) < 0) atomicAdd(cell, acc);  // bin split over several intervals (sign-bit flag)
+                else *cell += acc;
+            }
+        }
+    }
+
 }
 
 template <int NT, int P>
@@ -526,133 +667,8 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
         for (int d = tid; d < nt; d += NT)
             u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + tile + d))), m);
         __syncthreads();
-        const int nsteps = 32 - __clz(nt);                 // binary-search iterations for [0, nt]
-        // valid (finite) part of the sorted tile: -inf (never in range) first, +inf last
-        int v_lo = 0, v_hi = nt;
-        {
-            int lo = 0, hi = nt, lo2 = 0, hi2 = nt;
-            for (int it = 0; it < nsteps; ++it) {
-                const int mid = (lo + hi) >> 1, mid2 = (lo2 + hi2) >> 1;
-                const bool ge = u0[mid < nt ? mid : nt - 1] > -CUDART_INF;
-                const bool gt = u0[mid2 < nt ? mid2 : nt - 1] >= CUDART_INF;
-                const bool go = lo < hi, go2 = lo2 < hi2;
-                hi = (go && ge) ? mid : hi;
-                lo = (go && !ge) ? mid + 1 : lo;
-                hi2 = (go2 && gt) ? mid2 : hi2;
-                lo2 = (go2 && !gt) ? mid2 + 1 : lo2;
-            }
-            v_lo = lo;
-            v_hi = lo2;
-        }
-        if (v_hi <= v_lo) continue;                        // uniform: no usable draw in this tile
-        const double tu_min = u0[v_lo], tu_max = u0[v_hi - 1];
-        const double tu_inv = (tu_max > tu_min) ? (double)RANGE_ULUT / (tu_max - tu_min) : 0.0;
-        // per-tile lookup: ulut[c] = first draw with u0 >= tu_min + c*cell
-        for (int c = tid; c < RANGE_ULUT; c += NT) {
-            const double x = tu_min + (double)c * ((tu_max - tu_min) / (double)RANGE_ULUT);
-            int lo = v_lo, hi = v_hi;
-            for (int it = 0; it < nsteps; ++it) {
-                const int mid = (lo + hi) >> 1;
-                const bool ge = u0[mid < nt ? mid : nt - 1] >= x;
-                const bool go = lo < hi;
-                hi = (go && ge) ? mid : hi;
-                lo = (go && !ge) ? mid + 1 : lo;
-            }
-            ulut[c] = (unsigned short)lo;
-        }
-        // band of T2 intervals any row of this tile can touch
-        double dmin = sdelta[0], dmax = sdelta[0];
-        {
-            const double dl = sdelta[X - 1];
-            dmin = dl < dmin ? dl : dmin;
-            dmax = dl > dmax ? dl : dmax;                  // delta is monotone in the row index
-        }
-        const double vmin = __dadd_rn(tu_min, dmin), vmax = __dadd_rn(tu_max, dmax);
-        __syncthreads();
-        if (!(vmax >= 0.0) || vmin > umax) continue;       // uniform
-        const int band_lo = range_interval<RW>(vmin > 0.0 ? vmin : 0.0, rec, lut, m.rng_lut_inv, m.rng_lut_n, M);
-        const int band_hi = range_interval<RW>(vmax < umax ? vmax : umax, rec, lut, m.rng_lut_inv, m.rng_lut_n, M);
-        bin_lo_all = min(bin_lo_all, __double2loint(rec[band_lo * RW + 1]));
-        bin_hi_all = max(bin_hi_all, __double2loint(rec[band_hi * RW + 1]));
-        // One task = 32 (row, interval) cells.  Type A: one T2 interval x 32 consecutive rows (lane = row; all
-        // lanes use the same polynomial).  Type B, for the X % 32 leftover rows: R rows x (32/R) consecutive
-        // intervals.  A lane's draws are the contiguous range [lb, ub) found through the per-tile lookup.
-        // Cell (row, bin) is produced by exactly one lane: plain read-modify-write, fixed summation order.
-        const int Gf = X >> 5, R = X & 31;
-        const int n_iv = band_hi - band_lo + 1;
-        const int per_b = R ? 32 / R : 1;
-        const int nA = n_iv * Gf, nB = R ? (n_iv + per_b - 1) / per_b : 0;
-        // (jj, g) of type-A task `task` without a division in the loop
-        const int GfD = Gf > 0 ? Gf : 1;
-        int a_jj = warp / GfD, a_g = warp - a_jj * GfD;
-        const int step_j = NW / GfD, step_g = NW - step_j * GfD;
-        for (int task = warp; task < nA + nB; task += NW) {
-            int row, j;
-            bool active;
-            if (task < nA) {
-                row = (a_g << 5) + lane;
-                j = band_lo + a_jj;
-                active = true;
-                a_jj += step_j;
-                a_g += step_g;
-                if (a_g >= GfD) {
-                    a_g -= GfD;
-                    ++a_jj;
-                }
-            } else {
-                const int isub = lane / R;
-                row = (Gf << 5) + (lane - isub * R);
-                j = band_lo + (task - nA) * per_b + isub;
-                active = isub < per_b && j <= band_hi;
-                j = j <= band_hi ? j : band_hi;
-            }
-            const double2 *rj = reinterpret_cast<const double2 *>(rec + j * RW);
-            const double2 hd = rj[0];
-            const double left = j ? rec[(j - 1) * RW] : 0.0;
-            const bool last = (j == M - 1);
-            const double right = last ? umax : hd.x;
-            const int bin = __double2loint(hd.y);
-            double a[P + 1];
-#pragma unroll
-            for (int k = 0; k <= P; k += 2) {
-                const double2 c2 = rj[1 + (k >> 1)];
-                a[k] = c2.x;
-                a[k + 1] = c2.y;
-            }
-            if (active) {
-                const double delta = sdelta[row];
-                // first draw with v >= left
-                int c = (int)((left - delta - tu_min) * tu_inv);
-                c = c < 0 ? 0 : (c > RANGE_ULUT - 1 ? RANGE_ULUT - 1 : c);
-                int lb = ulut[c];
-                while (lb > v_lo && __dadd_rn(u0[lb - 1], delta) >= left) --lb;
-                while (lb < v_hi && !(__dadd_rn(u0[lb], delta) >= left)) ++lb;
-                // first draw beyond the interval: v >= right (v > u_max for the last interval, which is closed)
-                c = (int)((right - delta - tu_min) * tu_inv);
-                c = c < 0 ? 0 : (c > RANGE_ULUT - 1 ? RANGE_ULUT - 1 : c);
-                int ub = ulut[c];
-                if (last) {
-                    while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) > right) --ub;
-                    while (ub < v_hi && !(__dadd_rn(u0[ub], delta) > right)) ++ub;
-                } else {
-                    while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) >= right) --ub;
-                    while (ub < v_hi && !(__dadd_rn(u0[ub], delta) >= right)) ++ub;
-                }
-                if (ub > lb) {
-                    double acc = 0.0;
-                    for (int d = lb; d < ub; ++d) {
-                        const double dt = __dadd_rn(u0[d], delta) - left;
-                        double wgt = a[P];
-#pragma unroll
-                        for (int k = P - 1; k >= 0; --k) wgt = fma(wgt, dt, a[k]);
-                        acc += wgt;
-                    }
-                    double *cell = H + (size_t)row * EB + bin;
-                    if (__double2hiint(hd.y) < 0) atomicAdd(cell, acc);  // bin split over several intervals (sign-bit flag)
-                    else *cell += acc;
-                }
-            }
-        }
+        range_accumulate_tile<NT, P>(u0, nt, rec, lut, ulut, RANGE_ULUT, sdelta, H, X, EB, M, umax, m.rng_lut_inv,
+                                     m.rng_lut_n, bin_lo_all, bin_hi_all);
     }
     __syncthreads();
 
@@ -775,6 +791,87 @@ __host__ __device__ inline size_t simult_smem_bytes(int NT, int X, int E, int T,
     return d * 8 + (((size_t)lut_n + 15) / 16) * 16;
 }
 
+// Everything after the (x,E) histogram of one (walker, run): normalise, quantise, flight times with the
+// zero-degree sub-times, density, timing response, per-bin likelihood (simultFit.py:279-300, 389-409).
+template <int NT>
+__device__ __forceinline__ void simult_tail(const DevModel &m, const DevRun &run, int r, long long w, const ModelOut &out,
+                                            double *H, double *tofh, double *pdf, const double *sx, double *svd,
+                                            const double *staps, double *scratch, double sum_e0_last, double sf,
+                                            bool exhausted) {
+    const int T = run.tof_bins, X = m.x_bins, EB = m.e_bins, CELLS = X * EB;
+    const int tid = threadIdx.x;
+    // ---- normalise, quantise (simultFit.py:279-283) --------------------------------------------------------
+    const double de = (m.e_max - m.e_min) / (double)EB, dx = (m.x_max - m.x_min) / (double)X;
+    double part = 0.0;
+    for (int c = tid; c < CELLS; c += NT) part += __dmul_rn(__dmul_rn(H[c], de), dx);
+    const double S = block_sum<double>(part, scratch);
+    const double e0mean = __ddiv_rn(sum_e0_last, (double)m.n_ev_per_loop);
+    for (int j = tid; j < EB; j += NT) {
+        const double eff = __ddiv_rn(__dadd_rn(e0mean, m.e_centers[j]), 2.0);             // simultFit.py:288
+        svd[j] = speed_of(m.c, eff, m.m_d);
+    }
+    __syncthreads();
+
+    // ---- cells -> flight times, 10 zero-degree sub-times each (simultFit.py:286-299) -----------------------
+    const double t_step = (run.tof_max - run.tof_min) / (double)T;
+    const double t_scale = (double)T / (run.tof_max - run.tof_min);
+    const double nsamp = (double)m.n_samples;
+    const int NZ = m.n_zero_deg;
+    for (int idx = tid; idx < CELLS; idx += NT) {
+        const double cnt = rint(__dmul_rn(__ddiv_rn(H[idx], S), nsamp));
+        if (out.cells) out.cells[(size_t)w * CELLS + idx] = (cnt == cnt) ? (long long)cnt : LLONG_MIN;
+        if (cnt != 0.0 && cnt == cnt) {
+            const int i = idx / EB, j = idx - i * EB;
+            const double tof_d = __ddiv_rn(sx[i], svd[j]);
+            const double tof_n = __ddiv_rn(__ldg(run.neutron_dist + i), __ldg(m.neutron_speed + j));
+            const double base = __dadd_rn(tof_d, tof_n);
+            if (NZ == 0) {
+                const int b = np_bin(base, T, run.tof_min, run.tof_max, t_step, t_scale);
+                if (b >= 0) atomicAdd(tofh + b, cnt);
+            } else {
+                for (int k = 0; k < NZ; ++k) {
+                    const double tof = __dadd_rn(base, __ldg(m.zd_times + j * NZ + k));
+                    const int b = np_bin(tof, T, run.tof_min, run.tof_max, t_step, t_scale);
+                    if (b >= 0) atomicAdd(tofh + b, __dmul_rn(cnt, __ldg(m.zd_weights + j * NZ + k)));
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- density, timing response, per-bin likelihood (simultFit.py:298-300, 389-409) ------------------------
+    double tpart = 0.0;
+    for (int t = tid; t < T; t += NT) tpart += tofh[t];
+    const double total = block_sum<double>(tpart, scratch);
+    const bool degenerate = exhausted || !(S > 0.0) || !(total != 0.0);
+    for (int t = tid; t < T; t += NT) {
+        const double db = __dsub_rn(np_edge(t + 1, T, run.tof_min, run.tof_max, t_step),
+                                    np_edge(t, T, run.tof_min, run.tof_max, t_step));
+        pdf[t] = __ddiv_rn(__ddiv_rn(tofh[t], db), total);
+    }
+    __syncthreads();
+    double lp = 0.0;
+    for (int t = tid; t < T; t += NT) {
+        double acc = 0.0;
+        for (int k = 0; k < m.n_taps; ++k) {
+            const int tt = t + m.conv_shift - k;
+            if (tt >= 0 && tt < T) acc += staps[k] * pdf[tt];
+        }
+        double ev = __dmul_rn(sf, acc);                                                    // simultFit.py:300
+        if (out.spectra) {
+            const double v = out.stage == TOF_STAGE_COUNTS ? tofh[t] : (out.stage == TOF_STAGE_PDF ? pdf[t] : ev);
+            out.spectra[(size_t)w * T + t] = (degenerate && out.stage != TOF_STAGE_COUNTS) ? CUDART_NAN : v;
+        }
+        const double o = run.obs ? run.obs[t] : 1.0;                                       // 0 -> 1 done at upload
+        if (ev == 0.0) ev = 1.0;                                                           // simultFit.py:393-394
+        double poi = -o - lgamma(trunc(ev) + 1.0);                                         // simultFit.py:397
+        if (ev > 0.0) poi += ev * log(o);                                                  // simultFit.py:398-399
+        lp += o * poi;                                                                     // simultFit.py:400
+    }
+    lp = block_sum<double>(lp, scratch);
+    if (tid == 0 && out.lnprob) out.lnprob[w * m.n_runs + r] = degenerate ? CUDART_NAN : lp;
+}
+
 template <int NT>
 __global__ void __launch_bounds__(NT) simult_run_kernel(const DevModel m, const DevRunSet runs, const double *__restrict__ theta,
                                                         long long n_walkers, ModelOut out, int only_run) {
@@ -884,76 +981,139 @@ __global__ void __launch_bounds__(NT) simult_run_kernel(const DevModel m, const 
     }
     __syncthreads();
 
-    // ---- normalise, quantise (simultFit.py:279-283) --------------------------------------------------------
-    const double de = (m.e_max - m.e_min) / (double)EB, dx = (m.x_max - m.x_min) / (double)X;
-    double part = 0.0;
-    for (int c = tid; c < CELLS; c += NT) part += __dmul_rn(__dmul_rn(H[c], de), dx);
-    const double S = block_sum<double>(part, scratch);
-    const double e0mean = __ddiv_rn(sum_e0_last, (double)m.n_ev_per_loop);
-    for (int j = tid; j < EB; j += NT) {
-        const double eff = __ddiv_rn(__dadd_rn(e0mean, m.e_centers[j]), 2.0);             // simultFit.py:288
-        svd[j] = speed_of(m.c, eff, m.m_d);
-    }
-    __syncthreads();
+    simult_tail<NT>(m, run, r, w, out, H, tofh, pdf, sx, svd, staps, scratch, sum_e0_last, sf, exhausted);
+}
 
-    // ---- cells -> flight times, 10 zero-degree sub-times each (simultFit.py:286-299) -----------------------
-    const double t_step = (run.tof_max - run.tof_min) / (double)T;
-    const double t_scale = (double)T / (run.tof_max - run.tof_min);
-    const double nsamp = (double)m.n_samples;
-    const int NZ = m.n_zero_deg;
-    for (int idx = tid; idx < CELLS; idx += NT) {
-        const double cnt = rint(__dmul_rn(__ddiv_rn(H[idx], S), nsamp));
-        if (out.cells) out.cells[(size_t)w * CELLS + idx] = (cnt == cnt) ? (long long)cnt : LLONG_MIN;
-        if (cnt != 0.0 && cnt == cnt) {
-            const int i = idx / EB, j = idx - i * EB;
-            const double tof_d = __ddiv_rn(sx[i], svd[j]);
-            const double tof_n = __ddiv_rn(__ldg(run.neutron_dist + i), __ldg(m.neutron_speed + j));
-            const double base = __dadd_rn(tof_d, tof_n);
-            if (NZ == 0) {
-                const int b = np_bin(base, T, run.tof_min, run.tof_max, t_step, t_scale);
-                if (b >= 0) atomicAdd(tofh + b, cnt);
-            } else {
-                for (int k = 0; k < NZ; ++k) {
-                    const double tof = __dadd_rn(base, __ldg(m.zd_times + j * NZ + k));
-                    const int b = np_bin(tof, T, run.tof_min, run.tof_max, t_step, t_scale);
-                    if (b >= 0) atomicAdd(tofh + b, __dmul_rn(cnt, __ldg(m.zd_weights + j * NZ + k)));
+// Ascending bitonic sort of n <= cap doubles in shared memory (cap a power of two, tail padded with +inf).
+template <int NT>
+__device__ __forceinline__ void smem_sort(double *a, int n, int cap) {
+    for (int i = n + threadIdx.x; i < cap; i += NT) a[i] = CUDART_INF;
+    __syncthreads();
+    for (int k = 2; k <= cap; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < cap; i += NT) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const double x = a[i], y = a[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) {
+                        a[i] = y;
+                        a[ixj] = x;
+                    }
                 }
             }
+            __syncthreads();
         }
     }
+}
+
+__host__ __device__ inline size_t simult_range_smem_bytes(int X, int E, int T, int rng_n, int P, int n_taps, int lut_n) {
+    size_t d = (size_t)X * E + 2 * (size_t)T + RANGE_TILE + (size_t)rng_n * (P + 3) + X + E + n_taps + 48 + X;
+    return d * 8 + (((size_t)lut_n * 2 + 15) / 16) * 16 + SIMULT_ULUT * 2;
+}
+
+// Range-table formulation of the simultaneous fit: same model as simult_run_kernel, stopping through T1/T2.
+template <int NT, int P>
+__global__ void __launch_bounds__(NT) simult_range_kernel(const DevModel m, const DevRunSet runs, const double *__restrict__ theta,
+                                                          long long n_walkers, ModelOut out, int only_run) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int RW = P + 3;
+    const int n_launch_runs = (only_run >= 0) ? 1 : m.n_runs;
+    const long long w = blockIdx.x / n_launch_runs;
+    const int r = (only_run >= 0) ? only_run : (int)(blockIdx.x % n_launch_runs);
+    if (w >= n_walkers) return;
+    const DevRun &run = runs.r[r];
+    const int T = run.tof_bins, X = m.x_bins, EB = m.e_bins, CELLS = X * EB, M = m.rng_n;
+    const int tid = threadIdx.x;
+
+    double *H = reinterpret_cast<double *>(smem_raw);            // [CELLS]
+    double *tofh = H + CELLS;                                    // [T]
+    double *pdf = tofh + T;                                      // [T]
+    double *u0 = pdf + T;                                        // [RANGE_TILE]
+    double *rec = u0 + RANGE_TILE;                               // [M][RW]
+    double *sx = rec + (size_t)M * RW;                           // [X]
+    double *svd = sx + X;                                        // [E]
+    double *staps = svd + EB;
+    double *scratch = staps + m.n_taps;                          // [48]
+    double *sdelta = scratch + 48;                               // [X]
+    unsigned short *lut = reinterpret_cast<unsigned short *>(sdelta + X);
+    unsigned short *ulut = lut + ((m.rng_lut_n + 7) / 8) * 8;    // [SIMULT_ULUT]
+
+    const double *th = theta + w * m.ndim;
+    bool inside = true;
+    for (int p = 0; p < m.ndim; ++p) {
+        const double v = th[p];
+        inside = inside && (m.prior_strict ? (m.prior_lo[p] < v && v < m.prior_hi[p])
+                                           : !(v < m.prior_lo[p] || v > m.prior_hi[p]));
+    }
+    if (!inside && out.spectra == nullptr && out.cells == nullptr) return;
+    const double beamE = th[0], eLoss = th[1], scale = th[2], sshape = th[3], sf = th[4 + r];
+
+    const double x_start = m.ode_from_zero ? 0.0 : m.x_centers[0];
+    for (int i = tid; i < CELLS; i += NT) H[i] = 0.0;
+    for (int i = tid; i < T; i += NT) tofh[i] = 0.0;
+    for (int i = tid; i < X; i += NT) {
+        sx[i] = m.x_centers[i];
+        sdelta[i] = m.rng_sign * (m.x_centers[i] - x_start);
+    }
+    for (int i = tid; i < M * RW; i += NT) rec[i] = m.rng_rec[i];
+    for (int i = tid; i < m.rng_lut_n; i += NT) lut[i] = m.rng_lut[i];
+    for (int i = tid; i < m.n_taps; i += NT) staps[i] = m.taps[i];
     __syncthreads();
 
-    // ---- density, timing response, per-bin likelihood (simultFit.py:298-300, 389-409) ------------------------
-    double tpart = 0.0;
-    for (int t = tid; t < T; t += NT) tpart += tofh[t];
-    const double total = block_sum<double>(tpart, scratch);
-    const bool degenerate = exhausted || !(S > 0.0) || !(total != 0.0);
-    for (int t = tid; t < T; t += NT) {
-        const double db = __dsub_rn(np_edge(t + 1, T, run.tof_min, run.tof_max, t_step),
-                                    np_edge(t, T, run.tof_min, run.tof_max, t_step));
-        pdf[t] = __ddiv_rn(__ddiv_rn(tofh[t], db), total);
+    long long extra_pos = 0;
+    double sum_e0_last = 0.0;
+    bool exhausted = false;
+    int bin_lo_all = EB, bin_hi_all = -1;
+    for (long long loop = 0; loop < m.n_loops; ++loop) {
+        const double *src = run.z + loop * m.n_ev_per_loop;     // sorted by the library: E0 ascending
+        long long count = m.n_ev_per_loop;
+        bool sorted = true;
+        double loop_sum = 0.0;
+        while (count > 0) {
+            long long nbad = 0;
+            double part = 0.0;
+            for (long long tile = 0; tile < count; tile += RANGE_TILE) {
+                const int nt = (int)((count - tile < RANGE_TILE) ? (count - tile) : RANGE_TILE);
+                __syncthreads();
+                for (int d = tid; d < nt; d += NT) {
+                    const double z = __ldg(src + tile + d);
+                    const double E = __dsub_rn(beamE, __dadd_rn(__dmul_rn(exp(__dmul_rn(sshape, z)), scale), eLoss));
+                    double u = -CUDART_INF;                      // redrawn (E <= 0) or NaN: contributes nothing
+                    if (E <= 0.0) {
+                        ++nbad;
+                    } else if (E == E) {
+                        part += E;
+                        u = t1_eval(E, m);
+                    }
+                    u0[d] = u;
+                }
+                __syncthreads();
+                if (!sorted) {
+                    int cap = 1;
+                    while (cap < nt) cap <<= 1;
+                    smem_sort<NT>(u0, nt, cap);
+                }
+                range_accumulate_tile<NT, P>(u0, nt, rec, lut, ulut, SIMULT_ULUT, sdelta, H, X, EB, M, m.rng_u_max, m.rng_lut_inv,
+                                             m.rng_lut_n, bin_lo_all, bin_hi_all);
+            }
+            const long long nbad_tot = block_sum<long long>(nbad, reinterpret_cast<long long *>(scratch));
+            loop_sum += block_sum<double>(part, scratch);
+            if (nbad_tot == 0) break;
+            if (extra_pos + nbad_tot > run.n_z1) {
+                exhausted = true;
+                break;
+            }
+            src = run.z1 + extra_pos;                            // replacement draws: arbitrary order
+            extra_pos += nbad_tot;
+            count = nbad_tot;
+            sorted = false;
+        }
+        if (exhausted) break;
+        if (loop == m.n_loops - 1) sum_e0_last = loop_sum;
     }
     __syncthreads();
-    double lp = 0.0;
-    for (int t = tid; t < T; t += NT) {
-        double acc = 0.0;
-        for (int k = 0; k < m.n_taps; ++k) {
-            const int tt = t + m.conv_shift - k;
-            if (tt >= 0 && tt < T) acc += staps[k] * pdf[tt];
-        }
-        double ev = __dmul_rn(sf, acc);                                                    // simultFit.py:300
-        if (out.spectra) {
-            const double v = out.stage == TOF_STAGE_COUNTS ? tofh[t] : (out.stage == TOF_STAGE_PDF ? pdf[t] : ev);
-            out.spectra[(size_t)w * T + t] = (degenerate && out.stage != TOF_STAGE_COUNTS) ? CUDART_NAN : v;
-        }
-        const double o = run.obs ? run.obs[t] : 1.0;                                       // 0 -> 1 done at upload
-        if (ev == 0.0) ev = 1.0;                                                           // simultFit.py:393-394
-        double poi = -o - lgamma(trunc(ev) + 1.0);                                         // simultFit.py:397
-        if (ev > 0.0) poi += ev * log(o);                                                  // simultFit.py:398-399
-        lp += o * poi;                                                                     // simultFit.py:400
-    }
-    lp = block_sum<double>(lp, scratch);
-    if (tid == 0 && out.lnprob) out.lnprob[w * m.n_runs + r] = degenerate ? CUDART_NAN : lp;
+    simult_tail<NT>(m, run, r, w, out, H, tofh, pdf, sx, svd, staps, scratch, sum_e0_last, sf, exhausted);
 }
 
 // lnprob = lnprior + sum of the per-run log-likelihoods in run order (simultFit.py:412-420, 444-469).

@@ -169,15 +169,18 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
         DevRunSet rs;
         for (int r = 0; r < TOF_MAX_RUNS; ++r) rs.r[r] = ctx->runs[r];
         const bool debug = out.spectra != nullptr || out.cells != nullptr;
+        const bool rng = c.ode_mode == TOF_ODE_RANGE;
         if (debug) {
-            simult_run_kernel<256><<<(unsigned)n, 256, ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, out, run);
+            if (rng) simult_range_kernel<256, 7><<<(unsigned)n, 256, ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, out, run);
+            else simult_run_kernel<256><<<(unsigned)n, 256, ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, out, run);
             ctx->stats.kernel_launches += 1;
         } else {
             int rc = ensure(ctx, ctx->d_partial, (size_t)n * c.n_runs * sizeof(double));
             if (rc) return rc;
             ModelOut po{};
             po.lnprob = static_cast<double *>(ctx->d_partial.p);
-            simult_run_kernel<256><<<(unsigned)(n * c.n_runs), 256, ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, po, -1);
+            if (rng) simult_range_kernel<256, 7><<<(unsigned)(n * c.n_runs), 256, ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, po, -1);
+            else simult_run_kernel<256><<<(unsigned)(n * c.n_runs), 256, ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, po, -1);
             simult_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->dm, d_theta, n, po.lnprob, out.lnprob);
             ctx->stats.kernel_launches += 2;
         }
@@ -339,7 +342,8 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         }
     }
 
-    if (cfg->model == TOF_MODEL_ADV && cfg->ode_mode == TOF_ODE_RANGE) {
+    const bool use_range = cfg->ode_mode == TOF_ODE_RANGE && (cfg->model == TOF_MODEL_ADV || cfg->model == TOF_MODEL_SIMULT);
+    if (use_range) {
         if (!cfg->t1_coefs || !cfg->rng_breaks || !cfg->rng_bins || !cfg->rng_coefs || !cfg->rng_lut || cfg->rng_n < 1 ||
             cfg->t1_n < 1 || cfg->rng_lut_n < 1 || !(cfg->rng_u_max > 0.0)) {
             ctx->err = "TOF_ODE_RANGE needs the range tables (t1_*, rng_*)";
@@ -377,6 +381,9 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         m.t1_q = cfg->t1_q; m.t1_key_lo = cfg->t1_key_lo; m.t1_n = cfg->t1_n; m.rng_degree = P; m.rng_n = Mi;
         m.rng_lut_n = cfg->rng_lut_n; m.rng_sign = cfg->rng_sign; m.rng_u_max = cfg->rng_u_max;
         m.rng_lut_inv = (double)cfg->rng_lut_n / cfg->rng_u_max; m.e_tab_lo = cfg->e_tab_lo; m.e_tab_hi = cfg->e_tab_hi;
+    }
+    if (cfg->model == TOF_MODEL_ADV && use_range) {
+        const int P = cfg->rng_degree, Mi = cfg->rng_n;
         if (const char *v = std::getenv("TOFGPU_RANGE_THREADS")) {
             const int nt = std::atoi(v);
             if (!range_variant(nt, P)) { ctx->err = "TOFGPU_RANGE_THREADS must be 512, 640, 800 or 1024"; return bail(TOF_ERR_INVALID); }
@@ -448,17 +455,26 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         ctx->stats.ctas_per_sm = occ;
     } else {
         if (cfg->ndim < 4 + cfg->n_runs) { ctx->err = "simult model needs ndim >= 4 + n_runs"; return bail(TOF_ERR_INVALID); }
-        if (cfg->ode_mode != TOF_ODE_RK4) { ctx->err = "the simult model supports TOF_ODE_RK4 only"; return bail(TOF_ERR_INVALID); }
         int tmax = 0;
         for (int r = 0; r < cfg->n_runs; ++r) tmax = std::max(tmax, cfg->tof_bins[r]);
-        ctx->simult_smem = simult_smem_bytes(256, cfg->x_bins, cfg->e_bins, tmax, cfg->n_xs, cfg->n_taps, m.xs_lut_n);
+        int occ = 0;
+        if (use_range) {
+            if (cfg->rng_degree != 7) { ctx->err = "the simult range kernel is built for rng_degree 7"; return bail(TOF_ERR_INVALID); }
+            ctx->simult_smem = simult_range_smem_bytes(cfg->x_bins, cfg->e_bins, tmax, cfg->rng_n, 7, cfg->n_taps, cfg->rng_lut_n);
+        } else {
+            ctx->simult_smem = simult_smem_bytes(256, cfg->x_bins, cfg->e_bins, tmax, cfg->n_xs, cfg->n_taps, m.xs_lut_n);
+        }
         if ((int)ctx->simult_smem > ctx->max_smem_optin) {
             ctx->err = "simult kernel needs " + std::to_string(ctx->simult_smem) + " B of shared memory per CTA";
             return bail(TOF_ERR_CAPACITY);
         }
-        CUC(cudaFuncSetAttribute(simult_run_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->simult_smem));
-        int occ = 0;
-        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simult_run_kernel<256>, 256, ctx->simult_smem));
+        if (use_range) {
+            CUC(cudaFuncSetAttribute(simult_range_kernel<256, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->simult_smem));
+            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simult_range_kernel<256, 7>, 256, ctx->simult_smem));
+        } else {
+            CUC(cudaFuncSetAttribute(simult_run_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->simult_smem));
+            CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simult_run_kernel<256>, 256, ctx->simult_smem));
+        }
         ctx->stats.smem_bytes = (int)ctx->simult_smem;
         ctx->stats.threads = 256;
         ctx->stats.ctas_per_sm = occ;
@@ -517,7 +533,14 @@ int tof_set_draws(tof_ctx *ctx, int run, int stream, const double *values, int64
         return fail(ctx, TOF_ERR_INVALID, "simple model: stream 1 needs as many uniforms as normals");
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     const double *d = nullptr;
-    if (stream == 0 && ctx->cfg.ode_mode == TOF_ODE_RANGE && ctx->cfg.model == TOF_MODEL_ADV) {
+    if (stream == 0 && ctx->cfg.ode_mode == TOF_ODE_RANGE && ctx->cfg.model == TOF_MODEL_SIMULT) {
+        // E0 = beamE - (eLoss + scale*exp(s*z)) falls with z: sort every loop's block descending so that E0 ascends
+        std::vector<double> sorted(values, values + n);
+        const long long per = ctx->cfg.n_ev_per_loop;
+        for (long long l = 0; l < ctx->cfg.n_loops; ++l)
+            std::sort(sorted.begin() + l * per, sorted.begin() + (l + 1) * per, [](double a, double b) { return a > b; });
+        if (int rc = upload(ctx, sorted.data(), (size_t)n, &d)) return rc;
+    } else if (stream == 0 && ctx->cfg.ode_mode == TOF_ODE_RANGE && ctx->cfg.model == TOF_MODEL_ADV) {
         // the model is a symmetric function of the draws; the range kernel walks them in ascending order
         std::vector<double> sorted(values, values + n);
         std::sort(sorted.begin(), sorted.end(), [](double a, double b) { return a < b || (b != b && a == a); });

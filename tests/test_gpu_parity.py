@@ -441,9 +441,12 @@ def _simult_tables(O, cfg, seed, extra_per_run=4000):
     return z_main, z_extra
 
 
-def test_simult_vs_oracle(M, O):
-    cfg = M.config.simult(n_samples=4000, n_ev_per_loop=1000)
-    om = O.SimultModel(n_samples=4000, n_ev_per_loop=1000)
+@pytest.mark.parametrize("ode", ["rk4", "range"])
+def test_simult_vs_oracle(M, O, ode):
+    # RK4 kernel against the RK4 oracle (same scheme); range-table kernel against the closed-form oracle
+    cfg = M.config.simult(n_samples=4000, n_ev_per_loop=1000,
+                          ode_mode=M.config.ODE_RANGE if ode == "range" else M.config.ODE_RK4)
+    om = O.SimultModel(n_samples=4000, n_ev_per_loop=1000, ode_scheme="exact" if ode == "range" else "rk4")
     z_main, z_extra = _simult_tables(O, cfg, 123)
     xs = O.DDNXS()
     theta_star = [1878.4, 850, 170, 0.5, 3e4, 2e4, 2e4, 4e4, 4e4]
@@ -487,18 +490,19 @@ def test_simult_reference_goldens(M, O, golden, pf):
     for c in g["cases"]:
         if c["n_draws"] > 10000:
             continue
-        cfg = M.config.simult(n_samples=c["n_draws"], n_ev_per_loop=c["n_ev_per_loop"])
         om = O.SimultModel(n_samples=c["n_draws"], n_ev_per_loop=c["n_ev_per_loop"])
         obs = [parse_floats(o) for o in c["obs"]]
         rec = _Recorder(O.GlobalStateDraws(np.random.RandomState(c["seed_eval"])), 5)
         want_oracle = om.lnprob(th, obs, rec)
         z_main = [np.concatenate(m) for m in rec.rec_main]
         z_extra = [np.concatenate(e) if e else np.zeros(0) for e in rec.rec_extra]
-        fn = M.make_lnprob(cfg, obs, z_main, extra_draws=z_extra)
-        got = float(fn.batch([th])[0])
-        fn.model.close()
-        assert rel(got, float(want_oracle)) <= RTOL
-        assert rel(got, pf(c["lnprob"])) <= RTOL, (got, c["lnprob"])
+        for mode in (M.config.ODE_RK4, M.config.ODE_RANGE):
+            cfg = M.config.simult(n_samples=c["n_draws"], n_ev_per_loop=c["n_ev_per_loop"], ode_mode=mode)
+            fn = M.make_lnprob(cfg, obs, z_main, extra_draws=z_extra)
+            got = float(fn.batch([th])[0])
+            fn.model.close()
+            assert rel(got, float(want_oracle)) <= RTOL, mode
+            assert rel(got, pf(c["lnprob"])) <= RTOL, (mode, got, c["lnprob"])
 
 
 def test_simult_exhausted_replacement_stream_is_neg_inf(M, O):

@@ -51,13 +51,14 @@ if "adv" in which:
         th = np.column_stack([rs.uniform(1020, 1100, n), rs.uniform(0.08, 0.12, n)])
         run("C3 adv/" + nm, cfg, th, rs.standard_normal(cfg.n_draws), reps=1)
 if "simult" in which:
-    cfg = M.config.simult()
-    n = int(os.environ.get("SIMULT_N", "148"))
+  for mode, nm in ((M.config.ODE_RK4, "rk4"), (M.config.ODE_RANGE, "range")):
+    cfg = M.config.simult(ode_mode=mode)
+    n = int(os.environ.get("SIMULT_N", "148")) * (8 if mode == M.config.ODE_RANGE else 1)
     th = np.tile([1878.4, 850, 170, 0.5, 3e4, 2e4, 2e4, 4e4, 4e4], (n, 1)) * (1 + 0.01 * rs.standard_normal((n, 9)))
     th[:, 0] = np.clip(th[:, 0], 1826, 1924)
     draws = [rs.standard_normal(cfg.n_draws) for _ in range(5)]
     extra = [rs.standard_normal(20000) for _ in range(5)]
-    run("C4 simult/rk4", cfg, th, draws, extra, reps=1)
+    run("C4 simult/" + nm, cfg, th, draws, extra, reps=1)
 if "onebd" in which:
     cfg = M.config.onebd()
     n = 4096

@@ -308,7 +308,11 @@ def run_gpu_arm(args):
         achieved = evals_per_launch * flop_per_eval / (k_ms * 1e-3) / 1e12
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this size (131072 walkers),
+            # from the ncu --set full capture summarised in profiles/r1_range_adv_kernel_bench_size_ncu_summary.txt;
+            # algorithmic bytes per launch are evals_per_launch * 24
+            "traffic": (2211840 * evals_per_launch // 131072) if ode == M.config.ODE_RANGE else None,
+            "traffic_source": "profiles/r1_range_adv_kernel_bench_size_ncu_summary.txt (scaled by walkers per launch)",
             "kernel": "adv_range_kernel" if ode == M.config.ODE_RANGE else "adv_lnprob_kernel",
             "kernel_ms": k_ms, "evals_per_launch": evals_per_launch,
             "flop_per_eval": flop_per_eval, "flop_per_eval_rk4_formulation": FLOP_PER_EVAL_RK4,

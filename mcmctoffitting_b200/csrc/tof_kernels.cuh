@@ -421,7 +421,7 @@ __host__ __device__ inline size_t range_smem_bytes(int X, int E, int T, int rng_
     size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
     region_a = (region_a + 15) / 16 * 16;
     size_t d = (size_t)X * E + (size_t)rng_n * (P + 3) + E + n_taps + 40 + X /* per-row offsets */;
-    return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16 + RANGE_ULUT * 2;
+    return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16 + RANGE_ULUT * 2 + (((size_t)X * 4 + 15) / 16) * 16;
 }
 
 constexpr int RANGE_CH = 40;        // runs longer than this are summed by the whole warp
@@ -470,9 +470,9 @@ __device__ __forceinline__ double t1_eval(double E0, const DevModel &m) {
 // sample to the (x,E) histogram H.  Called by all threads of the CTA (contains barriers).
 template <int NT, int P>
 __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, const double *rec, const unsigned short *lut,
-                                                      unsigned short *ulut, int n_ulut, const double *sdelta, double *H, int X,
-                                                      int EB, int M, double umax, double lut_inv, int lut_n, int &bin_lo_all,
-                                                      int &bin_hi_all) {
+                                                      unsigned short *ulut, int n_ulut, const double *sdelta, int *srow,
+                                                      double *H, int X, int EB, int M, double umax, double lut_inv, int lut_n,
+                                                      int &bin_lo_all, int &bin_hi_all) {
     constexpr int RW = P + 3;
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -510,6 +510,16 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
         }
         ulut[c] = (unsigned short)lo;
     }
+    // per-row interval of the tile's median draw: rows are processed along the trajectory (interval j = k + shift(row)),
+    // so that the 32 lanes of a task look at the same slice of the draw distribution and have runs of similar length
+    {
+        const double u_med = u0[(v_lo + v_hi) >> 1];
+        for (int i = tid; i < X; i += NT) {
+            double vm = __dadd_rn(u_med, sdelta[i]);
+            vm = vm < 0.0 ? 0.0 : (vm > umax ? umax : vm);
+            srow[i] = range_interval<RW>(vm, rec, lut, lut_inv, lut_n, M);
+        }
+    }
     // band of T2 intervals any row of this tile can touch
     double dmin = sdelta[0], dmax = sdelta[0];
     {
@@ -529,7 +539,11 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
     // intervals.  A lane's draws are the contiguous range [lb, ub) found through the per-tile lookup.
     // Cell (row, bin) is produced by exactly one lane: plain read-modify-write, fixed summation order.
     const int Gf = X >> 5, R = X & 31;
-    const int n_iv = band_hi - band_lo + 1;
+    const int s_ref = srow[0];
+    const int s_a = srow[0] - s_ref, s_b = srow[X - 1] - s_ref;       // shift is monotone in the row index
+    const int s_min = s_a < s_b ? s_a : s_b, s_max = s_a < s_b ? s_b : s_a;
+    const int k_lo = band_lo - s_max;
+    const int n_iv = (band_hi - s_min) - k_lo + 1;
     const int per_b = R ? 32 / R : 1;
     const int nA = n_iv * Gf, nB = R ? (n_iv + per_b - 1) / per_b : 0;
     // (jj, g) of type-A task `task` without a division in the loop
@@ -541,7 +555,7 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
         bool active;
         if (task < nA) {
             row = (a_g << 5) + lane;
-            j = band_lo + a_jj;
+            j = k_lo + a_jj + (srow[row] - s_ref);
             active = true;
             a_jj += step_j;
             a_g += step_g;
@@ -552,10 +566,11 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
         } else {
             const int isub = lane / R;
             row = (Gf << 5) + (lane - isub * R);
-            j = band_lo + (task - nA) * per_b + isub;
-            active = isub < per_b && j <= band_hi;
-            j = j <= band_hi ? j : band_hi;
+            j = k_lo + (task - nA) * per_b + isub + (srow[row] - s_ref);
+            active = isub < per_b;
         }
+        active = active && j >= band_lo && j <= band_hi;
+        j = j < band_lo ? band_lo : (j > band_hi ? band_hi : j);
         const double2 *rj = reinterpret_cast<const double2 *>(rec + j * RW);
         const double2 hd = rj[0];
         const double left = j ? rec[(j - 1) * RW] : 0.0;
@@ -628,6 +643,7 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
     double *sdelta = scratch + 40;                                      // [X] sgn*(x_i - x_start)
     unsigned short *lut = reinterpret_cast<unsigned short *>(sdelta + X);
     unsigned short *ulut = lut + ((m.rng_lut_n + 7) / 8) * 8;           // [RANGE_ULUT]
+    int *srow = reinterpret_cast<int *>(ulut + RANGE_ULUT);             // [X]
 
     const long long w = blockIdx.x;
     if (w >= n_walkers) return;
@@ -667,7 +683,7 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
         for (int d = tid; d < nt; d += NT)
             u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + tile + d))), m);
         __syncthreads();
-        range_accumulate_tile<NT, P>(u0, nt, rec, lut, ulut, RANGE_ULUT, sdelta, H, X, EB, M, umax, m.rng_lut_inv,
+        range_accumulate_tile<NT, P>(u0, nt, rec, lut, ulut, RANGE_ULUT, sdelta, srow, H, X, EB, M, umax, m.rng_lut_inv,
                                      m.rng_lut_n, bin_lo_all, bin_hi_all);
     }
     __syncthreads();
@@ -1009,7 +1025,7 @@ __device__ __forceinline__ void smem_sort(double *a, int n, int cap) {
 
 __host__ __device__ inline size_t simult_range_smem_bytes(int X, int E, int T, int rng_n, int P, int n_taps, int lut_n) {
     size_t d = (size_t)X * E + 2 * (size_t)T + RANGE_TILE + (size_t)rng_n * (P + 3) + X + E + n_taps + 48 + X;
-    return d * 8 + (((size_t)lut_n * 2 + 15) / 16) * 16 + SIMULT_ULUT * 2;
+    return d * 8 + (((size_t)lut_n * 2 + 15) / 16) * 16 + SIMULT_ULUT * 2 + (((size_t)X * 4 + 15) / 16) * 16;
 }
 
 // Range-table formulation of the simultaneous fit: same model as simult_run_kernel, stopping through T1/T2.
@@ -1038,6 +1054,7 @@ __global__ void __launch_bounds__(NT) simult_range_kernel(const DevModel m, cons
     double *sdelta = scratch + 48;                               // [X]
     unsigned short *lut = reinterpret_cast<unsigned short *>(sdelta + X);
     unsigned short *ulut = lut + ((m.rng_lut_n + 7) / 8) * 8;    // [SIMULT_ULUT]
+    int *srow = reinterpret_cast<int *>(ulut + SIMULT_ULUT);     // [X]
 
     const double *th = theta + w * m.ndim;
     bool inside = true;
@@ -1094,7 +1111,7 @@ __global__ void __launch_bounds__(NT) simult_range_kernel(const DevModel m, cons
                     while (cap < nt) cap <<= 1;
                     smem_sort<NT>(u0, nt, cap);
                 }
-                range_accumulate_tile<NT, P>(u0, nt, rec, lut, ulut, SIMULT_ULUT, sdelta, H, X, EB, M, m.rng_u_max, m.rng_lut_inv,
+                range_accumulate_tile<NT, P>(u0, nt, rec, lut, ulut, SIMULT_ULUT, sdelta, srow, H, X, EB, M, m.rng_u_max, m.rng_lut_inv,
                                              m.rng_lut_n, bin_lo_all, bin_hi_all);
             }
             const long long nbad_tot = block_sum<long long>(nbad, reinterpret_cast<long long *>(scratch));

@@ -611,3 +611,21 @@ def test_ppc_batch_generation(M, O):
     bands = M.ppc.ppc_bands(spectra[0])
     assert bands.shape == (3, cfg.tof_bins[0]) and np.all(bands[0] <= bands[2])
     fn.model.close()
+
+
+def test_template_precomputation(M, O):
+    """devShapeTemplates.py:195-244 templates = adv pipeline with uniform initial energies per slice."""
+    cfg = M.config.intermediate(0, n_samples=4096, n_ev_per_loop=4096, mean_excitation=19.2e-3, ode_mode=M.config.ODE_RANGE)
+    om = O.intermediate_model(0, n_samples=4096, n_ev_per_loop=4096, mean_excitation=19.2e-3, ode_scheme="exact")
+    bounds = np.linspace(400, 1200, 33)                      # templateEnergyBounds, devShapeTemplates.py:252
+    u = np.random.RandomState(12).random_sample(4096)
+    with M.TofModel(cfg) as m:
+        tpl = M.templates.build_templates(m, bounds, u)
+    assert tpl.shape == (32, cfg.tof_bins[0])
+    xs = O.DDNXS()
+    th = M.templates.template_thetas(bounds)
+    for k in (0, 13, 31):
+        want = om.model_pdf(list(th[k]), u, xs)
+        np.testing.assert_allclose(tpl[k], want, rtol=1e-11, atol=1e-300)
+    coeffs = np.concatenate([[2.0], np.ones(32)])
+    np.testing.assert_allclose(M.templates.build_model_tof(coeffs, tpl), 2.0 * tpl.sum(axis=0), rtol=1e-14)

@@ -629,3 +629,21 @@ def test_template_precomputation(M, O):
         np.testing.assert_allclose(tpl[k], want, rtol=1e-11, atol=1e-300)
     coeffs = np.concatenate([[2.0], np.ones(32)])
     np.testing.assert_allclose(M.templates.build_model_tof(coeffs, tpl), 2.0 * tpl.sum(axis=0), rtol=1e-14)
+
+
+def test_api_edge_cases(M):
+    cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE)
+    with M.TofModel(cfg) as m:
+        m.set_observables(np.ones(2048))
+        m.set_draws(np.random.RandomState(0).standard_normal(1024))
+        assert m.lnprob_batch(np.zeros((0, 2))).shape == (0,)           # empty batch
+        with pytest.raises(ValueError):
+            m.lnprob_batch(np.zeros((3, 5)))                            # wrong parameter count
+        one = m.lnprob_batch([1050.0, 0.1])                             # a single vector is accepted
+        assert one.shape == (1,)
+        many = m.lnprob_batch(np.tile([1050.0, 0.1], (70000, 1)))       # more CTAs than 65535
+        assert many.shape == (70000,) and np.all(many == one[0])        # no atomics on the cell histogram: bit-reproducible
+        nanq = m.lnprob_batch([[float("nan"), 0.1], [1050.0, float("inf")]])
+        assert np.all(nanq == -np.inf)                                  # NaN/inf parameters fail the prior box
+        st = m.stats()
+        assert st["evaluations"] >= 70003 and st["ctas_per_sm"] >= 1

@@ -12,6 +12,7 @@ struct ModelOut {
     double *spectra;      // optional [n][T] at `stage`
     long long *cells;     // optional [n][X][E] integer cell counts
     int stage;
+    unsigned long long *work;  // optional global work counter (persistent CTAs take walkers dynamically)
 };
 
 // ================================================================================================
@@ -645,8 +646,21 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
     unsigned short *ulut = lut + ((m.rng_lut_n + 7) / 8) * 8;           // [RANGE_ULUT]
     int *srow = reinterpret_cast<int *>(ulut + RANGE_ULUT);             // [X]
 
-    const long long w = blockIdx.x;
-    if (w >= n_walkers) return;
+    // ---- walker-independent tables: staged once per CTA (persistent CTAs loop over walkers) ------------------
+    for (int i = tid; i < M * RW; i += NT) rec[i] = m.rng_rec[i];
+    for (int i = tid; i < m.rng_lut_n; i += NT) lut[i] = m.rng_lut[i];
+    for (int i = tid; i < m.n_taps; i += NT) staps[i] = m.taps[i];
+    const double sgn = m.rng_sign, umax = m.rng_u_max;
+    const double x_start = m.ode_from_zero ? 0.0 : m.x_centers[0];
+    for (int i = tid; i < X; i += NT) sdelta[i] = sgn * (m.x_centers[i] - x_start);
+    __shared__ long long s_next;
+    for (long long iter = 0;; ++iter) {
+    __syncthreads();                                       // the previous walker is done with shared memory
+    if (tid == 0)
+        s_next = out.work ? (long long)atomicAdd(out.work, 1ull) : (long long)blockIdx.x + iter * (long long)gridDim.x;
+    __syncthreads();
+    const long long w = s_next;
+    if (w >= n_walkers) break;
     const double e0 = theta[w * m.ndim + 0];
     const double sigma0 = theta[w * m.ndim + 1];
     bool inside = true;
@@ -657,23 +671,16 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
     }
     if (!inside && out.spectra == nullptr && out.cells == nullptr) {
         if (tid == 0) out.lnprob[w] = -CUDART_INF;
-        return;
+        continue;
     }
 
-    // ---- stage tables, zero the cell histogram ---------------------------------------------------------
+    // ---- per walker: zero the cell histogram, deuteron speeds ------------------------------------------------
     for (int i = tid; i < X * EB; i += NT) H[i] = 0.0;
-    for (int i = tid; i < M * RW; i += NT) rec[i] = m.rng_rec[i];
-    for (int i = tid; i < m.rng_lut_n; i += NT) lut[i] = m.rng_lut[i];
     for (int j = tid; j < EB; j += NT) {
         const double eff = __ddiv_rn(__dadd_rn(e0, m.e_centers[j]), 2.0);   // adv:151
         svd[j] = speed_of(m.c, eff, m.m_d);
     }
-    for (int i = tid; i < m.n_taps; i += NT) staps[i] = m.taps[i];
-
     const double spread = __dmul_rn(sigma0, e0);          // adv:128
-    const double sgn = m.rng_sign, umax = m.rng_u_max;
-    const double x_start = m.ode_from_zero ? 0.0 : m.x_centers[0];
-    for (int i = tid; i < X; i += NT) sdelta[i] = sgn * (m.x_centers[i] - x_start);
 
     // ---- phase 1: (x,E) histogram of cross-section weights through the range tables ---------------------
     int bin_lo_all = EB, bin_hi_all = -1;                  // E-bins any draw of any tile can have touched (uniform)
@@ -787,6 +794,7 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
         if (m.nan_to_neginf && r != r) r = -CUDART_INF;
         out.lnprob[w] = r;
     }
+    }   // persistent walker loop
 }
 
 }  // namespace tof

@@ -27,7 +27,7 @@ struct tof_ctx {
     DevModel dm{};
     DevRun runs[TOF_MAX_RUNS]{};
     std::vector<void *> owned;  // device allocations freed in tof_destroy
-    DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial;
+    DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial, d_work;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false, timed = false;
@@ -127,8 +127,14 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
     if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev0, st));
     if (c.model == TOF_MODEL_ADV) {
         if (c.ode_mode == TOF_ODE_RANGE) {
+            // persistent CTAs: one per resident slot, walkers handed out through a global counter
             AdvKernel k = range_variant(ctx->rng_nt, c.rng_degree);
-            k<<<(unsigned)n, ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
+            int rc = ensure(ctx, ctx->d_work, sizeof(unsigned long long));
+            if (rc) return rc;
+            CU(ctx, cudaMemsetAsync(ctx->d_work.p, 0, sizeof(unsigned long long), st));
+            out.work = static_cast<unsigned long long *>(ctx->d_work.p);
+            const long long slots = (long long)ctx->stats.sm_count * std::max(ctx->stats.ctas_per_sm, 1);
+            k<<<(unsigned)std::min<long long>(n, slots), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
         } else {
             AdvKernel k = adv_variant(ctx->adv_nt, ctx->adv_dpt, c.n_materials);
             k<<<(unsigned)n, ctx->adv_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
@@ -489,7 +495,7 @@ void tof_destroy(tof_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     for (void *p : ctx->owned) cudaFree(p);
-    for (DeviceBuf *b : {&ctx->d_theta, &ctx->d_out, &ctx->d_spectra, &ctx->d_cells, &ctx->d_counts, &ctx->d_partial})
+    for (DeviceBuf *b : {&ctx->d_theta, &ctx->d_out, &ctx->d_spectra, &ctx->d_cells, &ctx->d_counts, &ctx->d_partial, &ctx->d_work})
         if (b->p) cudaFree(b->p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

@@ -202,6 +202,9 @@ typedef struct tof_stats {
     int32_t smem_bytes;      /* dynamic shared memory of the main model kernel */
     int32_t threads;         /* threads per CTA of the main model kernel */
     int32_t ctas_per_sm;     /* resident CTAs per SM of the main model kernel */
+    int32_t band_ctas_per_sm; /* range kernel, banded launch (512 threads): resident CTAs per SM; 0 = disabled */
+    int32_t band_cells;       /* ... cell-histogram capacity of the banded launch */
+    int64_t band_queued_last; /* ... walkers of the most recent call that needed the full-size launch */
 } tof_stats;
 int tof_get_stats(const tof_ctx *ctx, tof_stats *out);
 

@@ -44,7 +44,8 @@ class TofConfig(C.Structure):
 class TofStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("evaluations", C.c_int64), ("nan_results", C.c_int64),
                 ("sm_count", C.c_int32), ("smem_bytes", C.c_int32), ("threads", C.c_int32),
-                ("ctas_per_sm", C.c_int32)]
+                ("ctas_per_sm", C.c_int32), ("band_ctas_per_sm", C.c_int32), ("band_cells", C.c_int32),
+                ("band_queued_last", C.c_int64)]
 
 
 class TofError(RuntimeError):

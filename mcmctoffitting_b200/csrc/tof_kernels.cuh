@@ -13,6 +13,11 @@ struct ModelOut {
     long long *cells;     // optional [n][X][E] integer cell counts
     int stage;
     unsigned long long *work;  // optional global work counter (persistent CTAs take walkers dynamically)
+    // range kernel, banded launch: capacity of the cell histogram (cells) and of the staged T2 records
+    int hcap, rcap;
+    int *queue_out;                  // walkers that do not fit the banded layout ...
+    unsigned long long *queue_count; // ... and how many
+    const int *queue_in;             // full-size launch: process queue_in[0 .. *queue_count)
 };
 
 // ================================================================================================
@@ -418,10 +423,11 @@ constexpr int RANGE_TILE = 1024;   // draws staged in shared memory at a time
 constexpr int RANGE_ULUT = 1024;   // cells of the per-tile draw-index lookup table
 constexpr int SIMULT_ULUT = 256;   // same for the 10-row simultaneous fit (fewer lookups per tile)
 
-__host__ __device__ inline size_t range_smem_bytes(int X, int E, int T, int rng_n, int P, int n_taps, int lut_n) {
+// hcap: cells of the (possibly banded) histogram; rcap: staged T2 records
+__host__ __device__ inline size_t range_smem_bytes(int X, int E, int T, int hcap, int rcap, int P, int n_taps, int lut_n) {
     size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
     region_a = (region_a + 15) / 16 * 16;
-    size_t d = (size_t)X * E + (size_t)rng_n * (P + 3) + E + n_taps + 40 + X /* per-row offsets */;
+    size_t d = (size_t)hcap + (size_t)rcap * (P + 3) + E + n_taps + 40 + X /* per-row offsets */;
     return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16 + RANGE_ULUT * 2 + (((size_t)X * 4 + 15) / 16) * 16;
 }
 
@@ -470,10 +476,13 @@ __device__ __forceinline__ double t1_eval(double E0, const DevModel &m) {
 // Phase 1 for one tile of sorted u0 values (shared memory): add the cross-section weights of every (draw, row)
 // sample to the (x,E) histogram H.  Called by all threads of the CTA (contains barriers).
 template <int NT, int P>
-__device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, const double *rec, const unsigned short *lut,
-                                                      unsigned short *ulut, int n_ulut, const double *sdelta, int *srow,
-                                                      double *H, int X, int EB, int M, double umax, double lut_inv, int lut_n,
-                                                      int &bin_lo_all, int &bin_hi_all) {
+// `recf`: the full T2 table (any address space) for interval searches; `rec`: the shared-memory copy of records
+// jbase.. used by the tasks; H has `hstride` bins per row starting at E-bin `hb_lo` (banded layout).
+__device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, const double *recf, const double *rec, int jbase,
+                                                      const unsigned short *lut, unsigned short *ulut, int n_ulut,
+                                                      const double *sdelta, int *srow, double *H, int hstride, int hb_lo, int X,
+                                                      int M, double umax, double lut_inv, int lut_n, int &bin_lo_all,
+                                                      int &bin_hi_all) {
     constexpr int RW = P + 3;
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -518,7 +527,7 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
         for (int i = tid; i < X; i += NT) {
             double vm = __dadd_rn(u_med, sdelta[i]);
             vm = vm < 0.0 ? 0.0 : (vm > umax ? umax : vm);
-            srow[i] = range_interval<RW>(vm, rec, lut, lut_inv, lut_n, M);
+            srow[i] = range_interval<RW>(vm, recf, lut, lut_inv, lut_n, M);
         }
     }
     // band of T2 intervals any row of this tile can touch
@@ -531,10 +540,10 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
     const double vmin = __dadd_rn(tu_min, dmin), vmax = __dadd_rn(tu_max, dmax);
     __syncthreads();
     if (!(vmax >= 0.0) || vmin > umax) return;         // uniform
-    const int band_lo = range_interval<RW>(vmin > 0.0 ? vmin : 0.0, rec, lut, lut_inv, lut_n, M);
-    const int band_hi = range_interval<RW>(vmax < umax ? vmax : umax, rec, lut, lut_inv, lut_n, M);
-    bin_lo_all = min(bin_lo_all, __double2loint(rec[band_lo * RW + 1]));
-    bin_hi_all = max(bin_hi_all, __double2loint(rec[band_hi * RW + 1]));
+    const int band_lo = range_interval<RW>(vmin > 0.0 ? vmin : 0.0, recf, lut, lut_inv, lut_n, M);
+    const int band_hi = range_interval<RW>(vmax < umax ? vmax : umax, recf, lut, lut_inv, lut_n, M);
+    bin_lo_all = min(bin_lo_all, __double2loint(rec[(band_lo - jbase) * RW + 1]));
+    bin_hi_all = max(bin_hi_all, __double2loint(rec[(band_hi - jbase) * RW + 1]));
     // One task = 32 (row, interval) cells.  Type A: one T2 interval x 32 consecutive rows (lane = row; all
     // lanes use the same polynomial).  Type B, for the X % 32 leftover rows: R rows x (32/R) consecutive
     // intervals.  A lane's draws are the contiguous range [lb, ub) found through the per-tile lookup.
@@ -572,9 +581,9 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
         }
         active = active && j >= band_lo && j <= band_hi;
         j = j < band_lo ? band_lo : (j > band_hi ? band_hi : j);
-        const double2 *rj = reinterpret_cast<const double2 *>(rec + j * RW);
+        const double2 *rj = reinterpret_cast<const double2 *>(rec + (j - jbase) * RW);
         const double2 hd = rj[0];
-        const double left = j ? rec[(j - 1) * RW] : 0.0;
+        const double left = j ? rec[(j - 1 - jbase) * RW] : 0.0;
         const bool last = (j == M - 1);
         const double right = last ? umax : hd.x;
         const int bin = __double2loint(hd.y);
@@ -613,7 +622,7 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
                     for (int k = P - 1; k >= 0; --k) wgt = fma(wgt, dt, a[k]);
                     acc += wgt;
                 }
-                double *cell = H + (size_t)row * EB + bin;
+                double *cell = H + (size_t)row * hstride + (bin - hb_lo);
                 if (__double2hiint(hd.y) < 0) atomicAdd(cell, acc);  // bin split over several intervals (sign-bit flag)
                 else *cell += acc;
             }
@@ -623,7 +632,7 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
 }
 
 template <int NT, int P>
-__global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const DevRun run, const double *__restrict__ theta,
+__global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(const DevModel m, const DevRun run, const double *__restrict__ theta,
                                                        long long n_walkers, ModelOut out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int RW = P + 3;
@@ -631,14 +640,18 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = NT / 32;
     // ---- carve --------------------------------------------------------------------------------------
+    // banded launch (out.hcap < X*EB): the cell histogram holds only the E-bins this walker can touch and only the
+    // matching T2 records are staged, so that two 512-thread CTAs fit one SM; walkers that do not fit are queued
+    // for the full-size launch
+    const bool banded = out.hcap < X * EB;
     double *H = reinterpret_cast<double *>(smem_raw);
     size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
     region_a = (region_a + 15) / 16 * 16;
-    unsigned char *pa = reinterpret_cast<unsigned char *>(H + (size_t)X * EB);
+    unsigned char *pa = reinterpret_cast<unsigned char *>(H + (size_t)out.hcap);
     unsigned int *tofc = reinterpret_cast<unsigned int *>(pa);
     double *u0 = reinterpret_cast<double *>(pa);                       // aliases tofc (phase 1 only)
     double *rec = reinterpret_cast<double *>(pa + region_a);
-    double *svd = rec + (size_t)M * RW;
+    double *svd = rec + (size_t)out.rcap * RW;
     double *staps = svd + EB;
     double *scratch = staps + m.n_taps;
     double *sdelta = scratch + 40;                                      // [X] sgn*(x_i - x_start)
@@ -647,7 +660,9 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
     int *srow = reinterpret_cast<int *>(ulut + RANGE_ULUT);             // [X]
 
     // ---- walker-independent tables: staged once per CTA (persistent CTAs loop over walkers) ------------------
-    for (int i = tid; i < M * RW; i += NT) rec[i] = m.rng_rec[i];
+    if (!banded)
+        for (int i = tid; i < M * RW; i += NT) rec[i] = m.rng_rec[i];
+    const double *recf = banded ? m.rng_rec : rec;         // full table for interval searches
     for (int i = tid; i < m.rng_lut_n; i += NT) lut[i] = m.rng_lut[i];
     for (int i = tid; i < m.n_taps; i += NT) staps[i] = m.taps[i];
     const double sgn = m.rng_sign, umax = m.rng_u_max;
@@ -659,8 +674,11 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
     if (tid == 0)
         s_next = out.work ? (long long)atomicAdd(out.work, 1ull) : (long long)blockIdx.x + iter * (long long)gridDim.x;
     __syncthreads();
-    const long long w = s_next;
-    if (w >= n_walkers) break;
+    const long long item = s_next;
+    // the full-size launch of a banded call works through the queue the banded launch filled
+    const long long n_items = out.queue_in ? (long long)*out.queue_count : n_walkers;
+    if (item >= n_items) break;
+    const long long w = out.queue_in ? (long long)out.queue_in[item] : item;
     const double e0 = theta[w * m.ndim + 0];
     const double sigma0 = theta[w * m.ndim + 1];
     bool inside = true;
@@ -674,13 +692,42 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
         continue;
     }
 
+    const double spread = __dmul_rn(sigma0, e0);          // adv:128
+    // ---- per walker: E-bins it can touch (the draws are sorted: first and last give the extremes) ------------
+    int hb_lo = 0, hstride = EB, jbase = 0;
+    if (banded) {
+        const double u_lo = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z))), m);
+        const double u_hi = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + m.n_draws - 1))), m);
+        const double d_a = sdelta[0], d_b = sdelta[X - 1];
+        double vmin = (u_lo > -CUDART_INF ? u_lo : 0.0) + (d_a < d_b ? d_a : d_b);   // -inf draws: lowest in-range v is 0
+        double vmax = u_hi + (d_a < d_b ? d_b : d_a);
+        vmin = vmin > 0.0 ? vmin : 0.0;
+        vmax = vmax < umax ? vmax : umax;
+        bool fits = true;
+        int j_lo = 0, j_hi = 0;
+        if (vmax >= vmin) {                                   // otherwise nothing is in range: any band will do
+            j_lo = range_interval<RW>(vmin, recf, lut, m.rng_lut_inv, m.rng_lut_n, M);
+            j_hi = range_interval<RW>(vmax, recf, lut, m.rng_lut_inv, m.rng_lut_n, M);
+            // one interval of slack on both sides: T1 is only monotone up to its 2e-13 cm fit error
+            j_lo = j_lo > 0 ? j_lo - 1 : 0;
+            j_hi = j_hi < M - 1 ? j_hi + 1 : M - 1;
+        }
+        jbase = j_lo > 0 ? j_lo - 1 : 0;
+        hb_lo = __double2loint(recf[j_lo * RW + 1]);
+        hstride = __double2loint(recf[j_hi * RW + 1]) - hb_lo + 1;
+        fits = (long long)X * hstride <= out.hcap && (j_hi - jbase + 1) <= out.rcap && hstride * 8 >= 0;
+        if (!fits || (size_t)T * 8 > (size_t)out.hcap * 8) {  // queue for the full-size launch
+            if (tid == 0) out.queue_out[atomicAdd(out.queue_count, 1ull)] = (int)w;
+            continue;
+        }
+        for (int i = tid; i < (j_hi - jbase + 1) * RW; i += NT) rec[i] = recf[(size_t)jbase * RW + i];
+    }
     // ---- per walker: zero the cell histogram, deuteron speeds ------------------------------------------------
-    for (int i = tid; i < X * EB; i += NT) H[i] = 0.0;
+    for (int i = tid; i < X * hstride; i += NT) H[i] = 0.0;
     for (int j = tid; j < EB; j += NT) {
         const double eff = __ddiv_rn(__dadd_rn(e0, m.e_centers[j]), 2.0);   // adv:151
         svd[j] = speed_of(m.c, eff, m.m_d);
     }
-    const double spread = __dmul_rn(sigma0, e0);          // adv:128
 
     // ---- phase 1: (x,E) histogram of cross-section weights through the range tables ---------------------
     int bin_lo_all = EB, bin_hi_all = -1;                  // E-bins any draw of any tile can have touched (uniform)
@@ -690,8 +737,8 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
         for (int d = tid; d < nt; d += NT)
             u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + tile + d))), m);
         __syncthreads();
-        range_accumulate_tile<NT, P>(u0, nt, rec, lut, ulut, RANGE_ULUT, sdelta, srow, H, X, EB, M, umax, m.rng_lut_inv,
-                                     m.rng_lut_n, bin_lo_all, bin_hi_all);
+        range_accumulate_tile<NT, P>(u0, nt, recf, rec, jbase, lut, ulut, RANGE_ULUT, sdelta, srow, H, hstride, hb_lo, X, M, umax,
+                                     m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all);
     }
     __syncthreads();
 
@@ -703,7 +750,8 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
     const int nbw = bin_hi_all - bin_lo_all + 1;
     double part = 0.0;
     for (int row = warp; row < X; row += NW)
-        for (int jb = lane; jb < nbw; jb += 32) part += __dmul_rn(__dmul_rn(H[(size_t)row * EB + bin_lo_all + jb], de), dx);
+        for (int jb = lane; jb < nbw; jb += 32)
+            part += __dmul_rn(__dmul_rn(H[(size_t)row * hstride + (bin_lo_all - hb_lo) + jb], de), dx);
     const double S = block_sum<double>(part, scratch);     // includes the barrier that publishes tofc = 0
 
     // ---- phase 3: quantise (adv:146) and scatter every non-empty cell to its flight time (adv:149-158) ----
@@ -720,7 +768,7 @@ __global__ void __launch_bounds__(NT) adv_range_kernel(const DevModel m, const D
         const double xi = __ldg(m.x_centers + row), di = __ldg(run.neutron_dist + row);
         for (int jb = lane; jb < nbw; jb += 32) {
             const int j = bin_lo_all + jb;
-            const double h = H[(size_t)row * EB + j];
+            const double h = H[(size_t)row * hstride + (j - hb_lo)];
             if (h != 0.0 && S > 0.0) {
                 const double cnt = rint(__dmul_rn(__ddiv_rn(h, S), nsamp));
                 if (cnt > 0.0) {
@@ -1119,8 +1167,8 @@ __global__ void __launch_bounds__(NT) simult_range_kernel(const DevModel m, cons
                     while (cap < nt) cap <<= 1;
                     smem_sort<NT>(u0, nt, cap);
                 }
-                range_accumulate_tile<NT, P>(u0, nt, rec, lut, ulut, SIMULT_ULUT, sdelta, srow, H, X, EB, M, m.rng_u_max, m.rng_lut_inv,
-                                             m.rng_lut_n, bin_lo_all, bin_hi_all);
+                range_accumulate_tile<NT, P>(u0, nt, rec, rec, 0, lut, ulut, SIMULT_ULUT, sdelta, srow, H, EB, 0, X, M, m.rng_u_max,
+                                             m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all);
             }
             const long long nbad_tot = block_sum<long long>(nbad, reinterpret_cast<long long *>(scratch));
             loop_sum += block_sum<double>(part, scratch);

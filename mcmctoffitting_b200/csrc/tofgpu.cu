@@ -27,7 +27,7 @@ struct tof_ctx {
     DevModel dm{};
     DevRun runs[TOF_MAX_RUNS]{};
     std::vector<void *> owned;  // device allocations freed in tof_destroy
-    DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial, d_work;
+    DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial, d_work, d_queue;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false, timed = false;
@@ -36,6 +36,10 @@ struct tof_ctx {
     int adv_nt = 1024, adv_dpt = 1;
     size_t adv_smem = 0;
     int rng_nt = 1024;
+    // banded launch of the range kernel: 512 threads, 2 CTAs/SM
+    int band_hcap = 0, band_rcap = 0, band_ctas = 0;
+    size_t band_smem = 0;
+    bool band_enabled = false;
     size_t simult_smem = 0, onebd_smem = 0;
     int max_smem_optin = 0;
     bool have_obs[TOF_MAX_RUNS]{};
@@ -127,14 +131,40 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
     if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev0, st));
     if (c.model == TOF_MODEL_ADV) {
         if (c.ode_mode == TOF_ODE_RANGE) {
-            // persistent CTAs: one per resident slot, walkers handed out through a global counter
-            AdvKernel k = range_variant(ctx->rng_nt, c.rng_degree);
-            int rc = ensure(ctx, ctx->d_work, sizeof(unsigned long long));
+            // persistent CTAs: one per resident slot, walkers handed out through global counters.
+            // d_work = {banded work counter, full-size work counter, queue length}
+            AdvKernel kfull = range_variant(ctx->rng_nt, c.rng_degree);
+            int rc = ensure(ctx, ctx->d_work, 3 * sizeof(unsigned long long));
             if (rc) return rc;
-            CU(ctx, cudaMemsetAsync(ctx->d_work.p, 0, sizeof(unsigned long long), st));
-            out.work = static_cast<unsigned long long *>(ctx->d_work.p);
-            const long long slots = (long long)ctx->stats.sm_count * std::max(ctx->stats.ctas_per_sm, 1);
-            k<<<(unsigned)std::min<long long>(n, slots), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
+            CU(ctx, cudaMemsetAsync(ctx->d_work.p, 0, 3 * sizeof(unsigned long long), st));
+            unsigned long long *cnt = static_cast<unsigned long long *>(ctx->d_work.p);
+            const long long slots_full = (long long)ctx->stats.sm_count * std::max(ctx->stats.ctas_per_sm, 1);
+            const bool debug = out.spectra != nullptr || out.cells != nullptr;
+            out.hcap = c.x_bins * c.e_bins;
+            out.rcap = c.rng_n;
+            if (ctx->band_enabled && !debug) {
+                rc = ensure(ctx, ctx->d_queue, (size_t)n * sizeof(int));
+                if (rc) return rc;
+                // 1) banded launch: every walker whose E-band fits; the others are queued
+                ModelOut ob = out;
+                ob.work = cnt + 0;
+                ob.hcap = ctx->band_hcap;
+                ob.rcap = ctx->band_rcap;
+                ob.queue_out = static_cast<int *>(ctx->d_queue.p);
+                ob.queue_count = cnt + 2;
+                AdvKernel kband = range_variant(512, c.rng_degree);
+                const long long slots_band = (long long)ctx->stats.sm_count * std::max(ctx->band_ctas, 1);
+                kband<<<(unsigned)std::min<long long>(n, slots_band), 512, ctx->band_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, ob);
+                // 2) full-size launch over the queue (exits at once when it is empty)
+                out.work = cnt + 1;
+                out.queue_in = static_cast<const int *>(ctx->d_queue.p);
+                out.queue_count = cnt + 2;
+                kfull<<<(unsigned)std::min<long long>(n, slots_full), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
+                ctx->stats.kernel_launches += 1;
+            } else {
+                out.work = cnt + 1;
+                kfull<<<(unsigned)std::min<long long>(n, slots_full), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
+            }
         } else {
             AdvKernel k = adv_variant(ctx->adv_nt, ctx->adv_dpt, c.n_materials);
             k<<<(unsigned)n, ctx->adv_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
@@ -395,7 +425,8 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
             if (!range_variant(nt, P)) { ctx->err = "TOFGPU_RANGE_THREADS must be 512, 640, 800 or 1024"; return bail(TOF_ERR_INVALID); }
             ctx->rng_nt = nt;
         }
-        ctx->adv_smem = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], Mi, P, cfg->n_taps, cfg->rng_lut_n);
+        ctx->adv_smem = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], cfg->x_bins * cfg->e_bins, Mi, P, cfg->n_taps,
+                                         cfg->rng_lut_n);
         if ((int)ctx->adv_smem > ctx->max_smem_optin) {
             ctx->err = "range kernel needs " + std::to_string(ctx->adv_smem) + " B of shared memory per CTA; device offers " +
                        std::to_string(ctx->max_smem_optin);
@@ -403,11 +434,35 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         }
         AdvKernel k = range_variant(ctx->rng_nt, P);
         CUC(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->adv_smem));
+        CUC(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int occ = 0;
         CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, ctx->rng_nt, ctx->adv_smem));
         ctx->stats.smem_bytes = (int)ctx->adv_smem;
         ctx->stats.threads = ctx->rng_nt;
         ctx->stats.ctas_per_sm = occ;
+        // banded launch: size the histogram so that two 512-thread CTAs share an SM
+        {
+            const char *env = std::getenv("TOFGPU_RANGE_BANDED");
+            const bool want = !(env && std::atoi(env) == 0);
+            AdvKernel kband = range_variant(512, P);
+            const int per_cta = (int)prop.sharedMemPerBlockOptin / 2 - 2048;   // two CTAs + the per-CTA reservation
+            const int rcap = std::min(Mi, 128);
+            const size_t fixed = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], 0, rcap, P, cfg->n_taps, cfg->rng_lut_n);
+            long long hcap = ((long long)per_cta - (long long)fixed) / 8;
+            hcap = std::min<long long>(hcap, (long long)cfg->x_bins * cfg->e_bins - 1);
+            if (want && kband && hcap >= (long long)cfg->x_bins * 8 && hcap >= cfg->tof_bins[0]) {
+                ctx->band_hcap = (int)hcap;
+                ctx->band_rcap = rcap;
+                ctx->band_smem = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], (int)hcap, rcap, P, cfg->n_taps,
+                                                  cfg->rng_lut_n);
+                CUC(cudaFuncSetAttribute(kband, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->band_smem));
+                CUC(cudaFuncSetAttribute(kband, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                int occb = 0;
+                CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, kband, 512, ctx->band_smem));
+                ctx->band_ctas = occb;
+                ctx->band_enabled = occb >= 2;
+            }
+        }
     } else if (cfg->model == TOF_MODEL_ADV) {
         if (const char *v = std::getenv("TOFGPU_ADV_VARIANT")) {
             int nt = 0, dpt = 0;
@@ -427,6 +482,7 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         }
         AdvKernel k = adv_variant(ctx->adv_nt, ctx->adv_dpt, cfg->n_materials);
         CUC(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->adv_smem));
+        CUC(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int occ = 0;
         CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, ctx->adv_nt, ctx->adv_smem));
         ctx->stats.smem_bytes = (int)ctx->adv_smem;
@@ -454,6 +510,7 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
             return bail(TOF_ERR_CAPACITY);
         }
         CUC(cudaFuncSetAttribute(onebd_run_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->onebd_smem));
+        CUC(cudaFuncSetAttribute(onebd_run_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int occ = 0;
         CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, onebd_run_kernel<256>, 256, ctx->onebd_smem));
         ctx->stats.smem_bytes = (int)ctx->onebd_smem;
@@ -479,6 +536,7 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
             CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simult_range_kernel<256, 7>, 256, ctx->simult_smem));
         } else {
             CUC(cudaFuncSetAttribute(simult_run_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->simult_smem));
+            CUC(cudaFuncSetAttribute(simult_run_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simult_run_kernel<256>, 256, ctx->simult_smem));
         }
         ctx->stats.smem_bytes = (int)ctx->simult_smem;
@@ -495,7 +553,7 @@ void tof_destroy(tof_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     for (void *p : ctx->owned) cudaFree(p);
-    for (DeviceBuf *b : {&ctx->d_theta, &ctx->d_out, &ctx->d_spectra, &ctx->d_cells, &ctx->d_counts, &ctx->d_partial, &ctx->d_work})
+    for (DeviceBuf *b : {&ctx->d_theta, &ctx->d_out, &ctx->d_spectra, &ctx->d_cells, &ctx->d_counts, &ctx->d_partial, &ctx->d_work, &ctx->d_queue})
         if (b->p) cudaFree(b->p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -660,6 +718,15 @@ int tof_stretch_accept(tof_ctx *ctx, double *d_s, double *d_lnprob, int64_t n, i
 int tof_get_stats(const tof_ctx *ctx, tof_stats *out) {
     if (!ctx || !out) return TOF_ERR_INVALID;
     *out = ctx->stats;
+    out->band_ctas_per_sm = ctx->band_enabled ? ctx->band_ctas : 0;
+    out->band_cells = ctx->band_enabled ? ctx->band_hcap : 0;
+    out->band_queued_last = 0;
+    if (ctx->band_enabled && ctx->d_work.p) {
+        unsigned long long q = 0;
+        cudaSetDevice(ctx->cfg.device);
+        if (cudaMemcpy(&q, static_cast<unsigned long long *>(ctx->d_work.p) + 2, sizeof(q), cudaMemcpyDeviceToHost) == cudaSuccess)
+            out->band_queued_last = (int64_t)q;
+    }
     return TOF_OK;
 }
 

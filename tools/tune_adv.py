@@ -37,7 +37,8 @@ for v in variants:
                 ms.append(m.last_kernel_ms())
             s = m.stats()
             res[(v, sort)] = min(ms)
-            print("variant %-7s sorted=%-5s  %8.3f ms  %10.0f evals/s  ctas/sm=%d smem=%d" % (
-                v, sort, min(ms), n / (min(ms) * 1e-3), s["ctas_per_sm"], s["smem_bytes"]), flush=True)
+            print("variant %-7s sorted=%-5s  %8.3f ms  %10.0f evals/s  ctas/sm=%d smem=%d band=%d/%d queued=%d" % (
+                v, sort, min(ms), n / (min(ms) * 1e-3), s["ctas_per_sm"], s["smem_bytes"], s["band_ctas_per_sm"],
+                s["band_cells"], s["band_queued_last"]), flush=True)
     if v == variants[0]:
         print("fp64 peak TFLOP/s", M.TofModel(M.config.sweep()).measure_fp64_peak())

@@ -421,27 +421,30 @@ namespace tof {
 // per run instead of once per sample.
 constexpr int RANGE_TILE = 1024;   // draws staged in shared memory at a time
 constexpr int RANGE_ULUT = 1024;   // cells of the per-tile draw-index lookup table
+constexpr int RANGE_SPLIT = 6;      // long runs: pieces per warp when a tile has few (row, interval) tasks
 constexpr int SIMULT_ULUT = 256;   // same for the 10-row simultaneous fit (fewer lookups per tile)
 
 // hcap: cells of the (possibly banded) histogram; rcap: staged T2 records
-__host__ __device__ inline size_t range_smem_bytes(int X, int E, int T, int hcap, int rcap, int P, int n_taps, int lut_n) {
+__host__ __device__ inline size_t range_smem_bytes(int X, int E, int T, int hcap, int rcap, int P, int n_taps, int lut_n,
+                                                   int rng_n) {
     size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
     region_a = (region_a + 15) / 16 * 16;
     size_t d = (size_t)hcap + (size_t)rcap * (P + 3) + E + n_taps + 40 + X /* per-row offsets */;
-    return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16 + RANGE_ULUT * 2 + (((size_t)X * 4 + 15) / 16) * 16;
+    return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16 + RANGE_ULUT * 2 + (((size_t)X * 8 + 15) / 16) * 16 +
+           (size_t)rng_n * 8 + (((size_t)rng_n * 2 + 15) / 16) * 16 + 16;
 }
 
 constexpr int RANGE_CH = 40;        // runs longer than this are summed by the whole warp
 
 // Interval of the T2 table that holds v (0 <= v <= u_max); uniform lookup cell, then edge compares.
-template <int RW>
-__device__ __forceinline__ int range_interval(double v, const double *rec, const unsigned short *lut, double lut_inv,
-                                              int lut_n, int M) {
+// brk[j] = break that ends interval j (brk[M-1] = +inf).
+__device__ __forceinline__ int range_interval(double v, const double *brk, const unsigned short *lut, double lut_inv, int lut_n,
+                                              int M) {
     int c = (int)(v * lut_inv);
     c = c < 0 ? 0 : (c > lut_n - 1 ? lut_n - 1 : c);
     int j = lut[c];
-    while (j + 1 < M && v >= rec[j * RW]) ++j;
-    while (j > 0 && v < rec[(j - 1) * RW]) --j;
+    while (j + 1 < M && v >= brk[j]) ++j;
+    while (j > 0 && v < brk[j - 1]) --j;
     return j;
 }
 
@@ -476,12 +479,13 @@ __device__ __forceinline__ double t1_eval(double E0, const DevModel &m) {
 // Phase 1 for one tile of sorted u0 values (shared memory): add the cross-section weights of every (draw, row)
 // sample to the (x,E) histogram H.  Called by all threads of the CTA (contains barriers).
 template <int NT, int P>
-// `recf`: the full T2 table (any address space) for interval searches; `rec`: the shared-memory copy of records
-// jbase.. used by the tasks; H has `hstride` bins per row starting at E-bin `hb_lo` (banded layout).
-__device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, const double *recf, const double *rec, int jbase,
+// `brk`: the ends of all T2 intervals (shared memory) for interval searches; `rec`: the shared-memory copy of records
+// jbase.. used by the tasks; H has `hstride` bins per row; row i starts at E-bin hlo[i] (banded layout; hlo == nullptr:
+// every row starts at bin 0).
+__device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, const double *brk, const double *rec, int jbase,
                                                       const unsigned short *lut, unsigned short *ulut, int n_ulut,
-                                                      const double *sdelta, int *srow, double *H, int hstride, int hb_lo, int X,
-                                                      int M, double umax, double lut_inv, int lut_n, int &bin_lo_all,
+                                                      const double *sdelta, int *srow, double *H, int hstride, const int *hlo,
+                                                      int X, int M, double umax, double lut_inv, int lut_n, int &bin_lo_all,
                                                       int &bin_hi_all) {
     constexpr int RW = P + 3;
     constexpr int NW = NT / 32;
@@ -527,7 +531,7 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
         for (int i = tid; i < X; i += NT) {
             double vm = __dadd_rn(u_med, sdelta[i]);
             vm = vm < 0.0 ? 0.0 : (vm > umax ? umax : vm);
-            srow[i] = range_interval<RW>(vm, recf, lut, lut_inv, lut_n, M);
+            srow[i] = range_interval(vm, brk, lut, lut_inv, lut_n, M);
         }
     }
     // band of T2 intervals any row of this tile can touch
@@ -540,8 +544,8 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
     const double vmin = __dadd_rn(tu_min, dmin), vmax = __dadd_rn(tu_max, dmax);
     __syncthreads();
     if (!(vmax >= 0.0) || vmin > umax) return;         // uniform
-    const int band_lo = range_interval<RW>(vmin > 0.0 ? vmin : 0.0, recf, lut, lut_inv, lut_n, M);
-    const int band_hi = range_interval<RW>(vmax < umax ? vmax : umax, recf, lut, lut_inv, lut_n, M);
+    const int band_lo = range_interval(vmin > 0.0 ? vmin : 0.0, brk, lut, lut_inv, lut_n, M);
+    const int band_hi = range_interval(vmax < umax ? vmax : umax, brk, lut, lut_inv, lut_n, M);
     bin_lo_all = min(bin_lo_all, __double2loint(rec[(band_lo - jbase) * RW + 1]));
     bin_hi_all = max(bin_hi_all, __double2loint(rec[(band_hi - jbase) * RW + 1]));
     // One task = 32 (row, interval) cells.  Type A: one T2 interval x 32 consecutive rows (lane = row; all
@@ -556,29 +560,9 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
     const int n_iv = (band_hi - s_min) - k_lo + 1;
     const int per_b = R ? 32 / R : 1;
     const int nA = n_iv * Gf, nB = R ? (n_iv + per_b - 1) / per_b : 0;
-    // (jj, g) of type-A task `task` without a division in the loop
-    const int GfD = Gf > 0 ? Gf : 1;
-    int a_jj = warp / GfD, a_g = warp - a_jj * GfD;
-    const int step_j = NW / GfD, step_g = NW - step_j * GfD;
-    for (int task = warp; task < nA + nB; task += NW) {
-        int row, j;
-        bool active;
-        if (task < nA) {
-            row = (a_g << 5) + lane;
-            j = k_lo + a_jj + (srow[row] - s_ref);
-            active = true;
-            a_jj += step_j;
-            a_g += step_g;
-            if (a_g >= GfD) {
-                a_g -= GfD;
-                ++a_jj;
-            }
-        } else {
-            const int isub = lane / R;
-            row = (Gf << 5) + (lane - isub * R);
-            j = k_lo + (task - nA) * per_b + isub + (srow[row] - s_ref);
-            active = isub < per_b;
-        }
+    // One (row, interval) cell for this lane; with nch > 1 the lane takes piece `piece` of the run and the pieces
+    // are combined with atomics (long runs: tiles of a big draw set cover few intervals).
+    auto do_cell = [&](int row, int j, bool active, int piece, int nch) {
         active = active && j >= band_lo && j <= band_hi;
         j = j < band_lo ? band_lo : (j > band_hi ? band_hi : j);
         const double2 *rj = reinterpret_cast<const double2 *>(rec + (j - jbase) * RW);
@@ -594,41 +578,87 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
             a[k] = c2.x;
             a[k + 1] = c2.y;
         }
-        if (active) {
-            const double delta = sdelta[row];
-            // first draw with v >= left
-            int c = (int)((left - delta - tu_min) * tu_inv);
-            c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
-            int lb = ulut[c];
-            while (lb > v_lo && __dadd_rn(u0[lb - 1], delta) >= left) --lb;
-            while (lb < v_hi && !(__dadd_rn(u0[lb], delta) >= left)) ++lb;
-            // first draw beyond the interval: v >= right (v > u_max for the last interval, which is closed)
-            c = (int)((right - delta - tu_min) * tu_inv);
-            c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
-            int ub = ulut[c];
-            if (last) {
-                while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) > right) --ub;
-                while (ub < v_hi && !(__dadd_rn(u0[ub], delta) > right)) ++ub;
-            } else {
-                while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) >= right) --ub;
-                while (ub < v_hi && !(__dadd_rn(u0[ub], delta) >= right)) ++ub;
-            }
-            if (ub > lb) {
-                double acc = 0.0;
-                for (int d = lb; d < ub; ++d) {
-                    const double dt = __dadd_rn(u0[d], delta) - left;
-                    double wgt = a[P];
+        if (!active) return;
+        const double delta = sdelta[row];
+        // first draw with v >= left
+        int c = (int)((left - delta - tu_min) * tu_inv);
+        c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
+        int lb = ulut[c];
+        while (lb > v_lo && __dadd_rn(u0[lb - 1], delta) >= left) --lb;
+        while (lb < v_hi && !(__dadd_rn(u0[lb], delta) >= left)) ++lb;
+        // first draw beyond the interval: v >= right (v > u_max for the last interval, which is closed)
+        c = (int)((right - delta - tu_min) * tu_inv);
+        c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
+        int ub = ulut[c];
+        if (last) {
+            while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) > right) --ub;
+            while (ub < v_hi && !(__dadd_rn(u0[ub], delta) > right)) ++ub;
+        } else {
+            while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) >= right) --ub;
+            while (ub < v_hi && !(__dadd_rn(u0[ub], delta) >= right)) ++ub;
+        }
+        if (nch > 1) {
+            const int len = (ub - lb + nch - 1) / nch;
+            lb += piece * len;
+            ub = (lb + len < ub) ? lb + len : ub;
+        }
+        if (ub <= lb) return;
+        double acc = 0.0;
+        for (int d = lb; d < ub; ++d) {
+            const double dt = __dadd_rn(u0[d], delta) - left;
+            double wgt = a[P];
 #pragma unroll
-                    for (int k = P - 1; k >= 0; --k) wgt = fma(wgt, dt, a[k]);
-                    acc += wgt;
+            for (int k = P - 1; k >= 0; --k) wgt = fma(wgt, dt, a[k]);
+            acc += wgt;
+        }
+        const int col = bin - (hlo ? hlo[row] : 0);
+        if ((unsigned)col >= (unsigned)hstride) return;       // cannot happen: the band has an interval of slack
+        double *cell = H + (size_t)row * hstride + col;
+        if (nch > 1 || __double2hiint(hd.y) < 0) atomicAdd(cell, acc);   // shared cell: pieces / bin split over intervals
+        else *cell += acc;
+    };
+    const int GfD = Gf > 0 ? Gf : 1;
+    const int n_tasks = nA + nB;
+    // few tasks (a tile of a big draw set spans few intervals): split every run so that all warps have work
+    int nch = 1;
+    if (n_tasks < 2 * NW) {
+        nch = (RANGE_SPLIT * NW + n_tasks - 1) / (n_tasks > 0 ? n_tasks : 1);   // ~RANGE_SPLIT pieces per warp
+        nch = nch > 64 ? 64 : nch;
+    }
+    if (nch == 1) {
+        // (jj, g) of type-A task `task` without a division in the loop
+        int a_jj = warp / GfD, a_g = warp - a_jj * GfD;
+        const int step_j = NW / GfD, step_g = NW - step_j * GfD;
+        for (int task = warp; task < n_tasks; task += NW) {
+            if (task < nA) {
+                const int row = (a_g << 5) + lane;
+                do_cell(row, k_lo + a_jj + (srow[row] - s_ref), true, 0, 1);
+                a_jj += step_j;
+                a_g += step_g;
+                if (a_g >= GfD) {
+                    a_g -= GfD;
+                    ++a_jj;
                 }
-                double *cell = H + (size_t)row * hstride + (bin - hb_lo);
-                if (__double2hiint(hd.y) < 0) atomicAdd(cell, acc);  // bin split over several intervals (sign-bit flag)
-                else *cell += acc;
+            } else {
+                const int isub = lane / R;
+                const int row = (Gf << 5) + (lane - isub * R);
+                do_cell(row, k_lo + (task - nA) * per_b + isub + (srow[row] - s_ref), isub < per_b, 0, 1);
+            }
+        }
+    } else {
+        for (int t2 = warp; t2 < n_tasks * nch; t2 += NW) {
+            const int task = t2 / nch, piece = t2 - task * nch;
+            if (task < nA) {
+                const int jj = task / GfD;
+                const int row = ((task - jj * GfD) << 5) + lane;
+                do_cell(row, k_lo + jj + (srow[row] - s_ref), true, piece, nch);
+            } else {
+                const int isub = lane / R;
+                const int row = (Gf << 5) + (lane - isub * R);
+                do_cell(row, k_lo + (task - nA) * per_b + isub + (srow[row] - s_ref), isub < per_b, piece, nch);
             }
         }
     }
-
 }
 
 template <int NT, int P>
@@ -658,11 +688,19 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     unsigned short *lut = reinterpret_cast<unsigned short *>(sdelta + X);
     unsigned short *ulut = lut + ((m.rng_lut_n + 7) / 8) * 8;           // [RANGE_ULUT]
     int *srow = reinterpret_cast<int *>(ulut + RANGE_ULUT);             // [X]
+    int *hlo_s = srow + X;                                              // [X] first E-bin of each row (banded launch)
+    double *sbrk = reinterpret_cast<double *>(hlo_s + X + (X & 1));     // [M] interval ends
+    unsigned short *sbin = reinterpret_cast<unsigned short *>(sbrk + M);  // [M] E-bin of each interval
+    __shared__ int s_band[3];                                           // widest row, first / last interval of the walker
 
     // ---- walker-independent tables: staged once per CTA (persistent CTAs loop over walkers) ------------------
     if (!banded)
         for (int i = tid; i < M * RW; i += NT) rec[i] = m.rng_rec[i];
-    const double *recf = banded ? m.rng_rec : rec;         // full table for interval searches
+    const double *recf = m.rng_rec;                        // full table in global memory
+    for (int j = tid; j < M; j += NT) {
+        sbrk[j] = recf[(size_t)j * RW];
+        sbin[j] = (unsigned short)__double2loint(recf[(size_t)j * RW + 1]);
+    }
     for (int i = tid; i < m.rng_lut_n; i += NT) lut[i] = m.rng_lut[i];
     for (int i = tid; i < m.n_taps; i += NT) staps[i] = m.taps[i];
     const double sgn = m.rng_sign, umax = m.rng_u_max;
@@ -694,33 +732,48 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
 
     const double spread = __dmul_rn(sigma0, e0);          // adv:128
     // ---- per walker: E-bins it can touch (the draws are sorted: first and last give the extremes) ------------
-    int hb_lo = 0, hstride = EB, jbase = 0;
+    int hstride = EB, jbase = 0;
+    const int *hlo = nullptr;
     if (banded) {
         const double u_lo = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z))), m);
         const double u_hi = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + m.n_draws - 1))), m);
-        const double d_a = sdelta[0], d_b = sdelta[X - 1];
-        double vmin = (u_lo > -CUDART_INF ? u_lo : 0.0) + (d_a < d_b ? d_a : d_b);   // -inf draws: lowest in-range v is 0
-        double vmax = u_hi + (d_a < d_b ? d_b : d_a);
-        vmin = vmin > 0.0 ? vmin : 0.0;
-        vmax = vmax < umax ? vmax : umax;
-        bool fits = true;
-        int j_lo = 0, j_hi = 0;
-        if (vmax >= vmin) {                                   // otherwise nothing is in range: any band will do
-            j_lo = range_interval<RW>(vmin, recf, lut, m.rng_lut_inv, m.rng_lut_n, M);
-            j_hi = range_interval<RW>(vmax, recf, lut, m.rng_lut_inv, m.rng_lut_n, M);
-            // one interval of slack on both sides: T1 is only monotone up to its 2e-13 cm fit error
-            j_lo = j_lo > 0 ? j_lo - 1 : 0;
-            j_hi = j_hi < M - 1 ? j_hi + 1 : M - 1;
+        if (tid == 0) {
+            s_band[0] = 0;
+            s_band[1] = M;
+            s_band[2] = -1;
         }
-        jbase = j_lo > 0 ? j_lo - 1 : 0;
-        hb_lo = __double2loint(recf[j_lo * RW + 1]);
-        hstride = __double2loint(recf[j_hi * RW + 1]) - hb_lo + 1;
-        fits = (long long)X * hstride <= out.hcap && (j_hi - jbase + 1) <= out.rcap && hstride * 8 >= 0;
-        if (!fits || (size_t)T * 8 > (size_t)out.hcap * 8) {  // queue for the full-size launch
+        __syncthreads();
+        // every row has its own window of E-bins: [u_lo + delta_i, u_hi + delta_i], one interval of slack on both
+        // sides (T1 is only monotone up to its 2e-13 cm fit error)
+        for (int i = tid; i < X; i += NT) {
+            double vmin = (u_lo > -CUDART_INF ? u_lo : 0.0) + sdelta[i];   // -inf draws: the lowest in-range v is 0
+            double vmax = u_hi + sdelta[i];
+            vmin = vmin > 0.0 ? vmin : 0.0;
+            vmax = vmax < umax ? vmax : umax;
+            int j_lo = 0, j_hi = 0;
+            if (vmax >= vmin) {                               // otherwise this row gets nothing: any window will do
+                j_lo = range_interval(vmin, sbrk, lut, m.rng_lut_inv, m.rng_lut_n, M);
+                j_hi = range_interval(vmax, sbrk, lut, m.rng_lut_inv, m.rng_lut_n, M);
+                j_lo = j_lo > 0 ? j_lo - 1 : 0;
+                j_hi = j_hi < M - 1 ? j_hi + 1 : M - 1;
+                atomicMin(&s_band[1], j_lo);
+                atomicMax(&s_band[2], j_hi);
+            }
+            const int b_lo = sbin[j_lo];
+            hlo_s[i] = b_lo;
+            atomicMax(&s_band[0], (int)sbin[j_hi] - b_lo + 1);
+        }
+        __syncthreads();
+        hstride = s_band[0];
+        const int j_lo_all = s_band[2] >= 0 ? s_band[1] : 0, j_hi_all = s_band[2] >= 0 ? s_band[2] : 0;
+        jbase = j_lo_all > 0 ? j_lo_all - 1 : 0;
+        hlo = hlo_s;
+        const bool fits = (long long)X * hstride <= out.hcap && (j_hi_all - jbase + 1) <= out.rcap && T <= out.hcap;
+        if (!fits) {                                          // queue for the full-size launch
             if (tid == 0) out.queue_out[atomicAdd(out.queue_count, 1ull)] = (int)w;
             continue;
         }
-        for (int i = tid; i < (j_hi - jbase + 1) * RW; i += NT) rec[i] = recf[(size_t)jbase * RW + i];
+        for (int i = tid; i < (j_hi_all - jbase + 1) * RW; i += NT) rec[i] = recf[(size_t)jbase * RW + i];
     }
     // ---- per walker: zero the cell histogram, deuteron speeds ------------------------------------------------
     for (int i = tid; i < X * hstride; i += NT) H[i] = 0.0;
@@ -737,7 +790,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
         for (int d = tid; d < nt; d += NT)
             u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + tile + d))), m);
         __syncthreads();
-        range_accumulate_tile<NT, P>(u0, nt, recf, rec, jbase, lut, ulut, RANGE_ULUT, sdelta, srow, H, hstride, hb_lo, X, M, umax,
+        range_accumulate_tile<NT, P>(u0, nt, sbrk, rec, jbase, lut, ulut, RANGE_ULUT, sdelta, srow, H, hstride, hlo, X, M, umax,
                                      m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all);
     }
     __syncthreads();
@@ -746,12 +799,14 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     for (int i = tid; i < T; i += NT) tofc[i] = 0u;        // u0 is dead now
     const double de = (m.e_max - m.e_min) / (double)EB;
     const double dx = (m.x_max - m.x_min) / (double)X;
-    // only bins bin_lo_all..bin_hi_all can be non-zero
-    const int nbw = bin_hi_all - bin_lo_all + 1;
+    // banded launch: every row holds `hstride` bins from hlo[row]; full-size launch: only bins bin_lo_all..bin_hi_all
+    // can be non-zero
+    const int nbw = hlo ? hstride : bin_hi_all - bin_lo_all + 1;
     double part = 0.0;
-    for (int row = warp; row < X; row += NW)
-        for (int jb = lane; jb < nbw; jb += 32)
-            part += __dmul_rn(__dmul_rn(H[(size_t)row * hstride + (bin_lo_all - hb_lo) + jb], de), dx);
+    for (int row = warp; row < X; row += NW) {
+        const double *Hr = H + (size_t)row * hstride + (hlo ? 0 : bin_lo_all);
+        for (int jb = lane; jb < nbw; jb += 32) part += __dmul_rn(__dmul_rn(Hr[jb], de), dx);
+    }
     const double S = block_sum<double>(part, scratch);     // includes the barrier that publishes tofc = 0
 
     // ---- phase 3: quantise (adv:146) and scatter every non-empty cell to its flight time (adv:149-158) ----
@@ -766,9 +821,12 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     }
     for (int row = warp; row < X; row += NW) {
         const double xi = __ldg(m.x_centers + row), di = __ldg(run.neutron_dist + row);
+        const int row_lo = hlo ? hlo[row] : bin_lo_all;
+        const double *Hr = H + (size_t)row * hstride + (hlo ? 0 : bin_lo_all);
         for (int jb = lane; jb < nbw; jb += 32) {
-            const int j = bin_lo_all + jb;
-            const double h = H[(size_t)row * hstride + (j - hb_lo)];
+            const int j = row_lo + jb;
+            if (j >= EB) break;
+            const double h = Hr[jb];
             if (h != 0.0 && S > 0.0) {
                 const double cnt = rint(__dmul_rn(__ddiv_rn(h, S), nsamp));
                 if (cnt > 0.0) {
@@ -1081,7 +1139,7 @@ __device__ __forceinline__ void smem_sort(double *a, int n, int cap) {
 
 __host__ __device__ inline size_t simult_range_smem_bytes(int X, int E, int T, int rng_n, int P, int n_taps, int lut_n) {
     size_t d = (size_t)X * E + 2 * (size_t)T + RANGE_TILE + (size_t)rng_n * (P + 3) + X + E + n_taps + 48 + X;
-    return d * 8 + (((size_t)lut_n * 2 + 15) / 16) * 16 + SIMULT_ULUT * 2 + (((size_t)X * 4 + 15) / 16) * 16;
+    return d * 8 + (((size_t)lut_n * 2 + 15) / 16) * 16 + SIMULT_ULUT * 2 + (((size_t)X * 4 + 15) / 16) * 16 + (size_t)rng_n * 8 + 32;
 }
 
 // Range-table formulation of the simultaneous fit: same model as simult_run_kernel, stopping through T1/T2.
@@ -1111,6 +1169,7 @@ __global__ void __launch_bounds__(NT) simult_range_kernel(const DevModel m, cons
     unsigned short *lut = reinterpret_cast<unsigned short *>(sdelta + X);
     unsigned short *ulut = lut + ((m.rng_lut_n + 7) / 8) * 8;    // [SIMULT_ULUT]
     int *srow = reinterpret_cast<int *>(ulut + SIMULT_ULUT);     // [X]
+    double *sbrk = reinterpret_cast<double *>(srow + X + (X & 1) + 2);   // [M] interval ends
 
     const double *th = theta + w * m.ndim;
     bool inside = true;
@@ -1130,6 +1189,7 @@ __global__ void __launch_bounds__(NT) simult_range_kernel(const DevModel m, cons
         sdelta[i] = m.rng_sign * (m.x_centers[i] - x_start);
     }
     for (int i = tid; i < M * RW; i += NT) rec[i] = m.rng_rec[i];
+    for (int j = tid; j < M; j += NT) sbrk[j] = m.rng_rec[(size_t)j * RW];
     for (int i = tid; i < m.rng_lut_n; i += NT) lut[i] = m.rng_lut[i];
     for (int i = tid; i < m.n_taps; i += NT) staps[i] = m.taps[i];
     __syncthreads();
@@ -1167,7 +1227,7 @@ __global__ void __launch_bounds__(NT) simult_range_kernel(const DevModel m, cons
                     while (cap < nt) cap <<= 1;
                     smem_sort<NT>(u0, nt, cap);
                 }
-                range_accumulate_tile<NT, P>(u0, nt, rec, rec, 0, lut, ulut, SIMULT_ULUT, sdelta, srow, H, EB, 0, X, M, m.rng_u_max,
+                range_accumulate_tile<NT, P>(u0, nt, sbrk, rec, 0, lut, ulut, SIMULT_ULUT, sdelta, srow, H, EB, nullptr, X, M, m.rng_u_max,
                                              m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all);
             }
             const long long nbad_tot = block_sum<long long>(nbad, reinterpret_cast<long long *>(scratch));

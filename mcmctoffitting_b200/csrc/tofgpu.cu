@@ -426,7 +426,7 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
             ctx->rng_nt = nt;
         }
         ctx->adv_smem = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], cfg->x_bins * cfg->e_bins, Mi, P, cfg->n_taps,
-                                         cfg->rng_lut_n);
+                                         cfg->rng_lut_n, Mi);
         if ((int)ctx->adv_smem > ctx->max_smem_optin) {
             ctx->err = "range kernel needs " + std::to_string(ctx->adv_smem) + " B of shared memory per CTA; device offers " +
                        std::to_string(ctx->max_smem_optin);
@@ -447,14 +447,14 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
             AdvKernel kband = range_variant(512, P);
             const int per_cta = (int)prop.sharedMemPerBlockOptin / 2 - 2048;   // two CTAs + the per-CTA reservation
             const int rcap = std::min(Mi, 128);
-            const size_t fixed = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], 0, rcap, P, cfg->n_taps, cfg->rng_lut_n);
+            const size_t fixed = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], 0, rcap, P, cfg->n_taps, cfg->rng_lut_n, Mi);
             long long hcap = ((long long)per_cta - (long long)fixed) / 8;
             hcap = std::min<long long>(hcap, (long long)cfg->x_bins * cfg->e_bins - 1);
             if (want && kband && hcap >= (long long)cfg->x_bins * 8 && hcap >= cfg->tof_bins[0]) {
                 ctx->band_hcap = (int)hcap;
                 ctx->band_rcap = rcap;
                 ctx->band_smem = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], (int)hcap, rcap, P, cfg->n_taps,
-                                                  cfg->rng_lut_n);
+                                                  cfg->rng_lut_n, Mi);
                 CUC(cudaFuncSetAttribute(kband, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->band_smem));
                 CUC(cudaFuncSetAttribute(kband, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 int occb = 0;

@@ -308,12 +308,13 @@ def run_gpu_arm(args):
         achieved = evals_per_launch * flop_per_eval / (k_ms * 1e-3) / 1e12
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this size (131072 walkers),
-            # from the ncu --set full capture summarised in profiles/r1_range_adv_kernel_bench_size_ncu_summary.txt;
-            # algorithmic bytes per launch are evals_per_launch * 24
-            "traffic": (2211840 * evals_per_launch // 131072) if ode == M.config.ODE_RANGE else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE model call at this size (131072 walkers: the banded
+            # launch <512,7> plus the full-size launch <1024,7> over its overflow queue), from the ncu --set full capture
+            # summarised in profiles/r1_range_adv_kernel_bench_size_ncu_summary.txt; algorithmic bytes are evals * 24
+            "traffic": (3113472 * evals_per_launch // 131072) if ode == M.config.ODE_RANGE else None,
             "traffic_source": "profiles/r1_range_adv_kernel_bench_size_ncu_summary.txt (scaled by walkers per launch)",
-            "kernel": "adv_range_kernel" if ode == M.config.ODE_RANGE else "adv_lnprob_kernel",
+            "kernel": ("adv_range_kernel<512,7> (banded, 2 CTAs/SM) + adv_range_kernel<1024,7> (overflow queue)"
+                       if ode == M.config.ODE_RANGE else "adv_lnprob_kernel"),
             "kernel_ms": k_ms, "evals_per_launch": evals_per_launch,
             "flop_per_eval": flop_per_eval, "flop_per_eval_rk4_formulation": FLOP_PER_EVAL_RK4,
             "rk4_equivalent_tflops": evals_per_launch * FLOP_PER_EVAL_RK4 / (k_ms * 1e-3) / 1e12,

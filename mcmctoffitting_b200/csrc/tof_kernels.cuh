@@ -421,6 +421,7 @@ namespace tof {
 // per run instead of once per sample.
 constexpr int RANGE_TILE = 1024;   // draws staged in shared memory at a time
 constexpr int RANGE_ULUT = 1024;   // cells of the per-tile draw-index lookup table
+constexpr int RANGE_STREAM_MIN = 8192;  // draws per walker from which the warp-private streaming walk is used
 constexpr int RANGE_SPLIT = 6;      // long runs: pieces per warp when a tile has few (row, interval) tasks
 constexpr int SIMULT_ULUT = 256;   // same for the 10-row simultaneous fit (fewer lookups per tile)
 
@@ -784,14 +785,80 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
 
     // ---- phase 1: (x,E) histogram of cross-section weights through the range tables ---------------------
     int bin_lo_all = EB, bin_hi_all = -1;                  // E-bins any draw of any tile can have touched (uniform)
-    for (long long tile = 0; tile < m.n_draws; tile += RANGE_TILE) {
-        const int nt = (int)((m.n_draws - tile < RANGE_TILE) ? (m.n_draws - tile) : RANGE_TILE);
-        __syncthreads();                                   // previous tile fully consumed / staging done
-        for (int d = tid; d < nt; d += NT)
-            u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + tile + d))), m);
-        __syncthreads();
-        range_accumulate_tile<NT, P>(u0, nt, sbrk, rec, jbase, lut, ulut, RANGE_ULUT, sdelta, srow, H, hstride, hlo, X, M, umax,
-                                     m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all);
+    if (m.n_draws >= RANGE_STREAM_MIN) {
+        // Big draw sets: the sorted draws of one interval are hundreds of consecutive values, so a lane that walks
+        // draws in order changes interval rarely.  Warp-private streaming, no barriers: a warp takes 128 consecutive
+        // draws (4 per lane, T1 evaluated once, kept in registers and broadcast by shuffle) and, for every group of
+        // 32 rows, lane = row walks the 128 samples with an interval pointer; runs go to H with atomics.
+        __syncthreads();                                   // staging done
+        bin_lo_all = 0;
+        bin_hi_all = EB - 1;
+        const int n_groups = (X + 31) >> 5;
+        for (long long base = (long long)warp * 128; base < m.n_draws; base += (long long)NW * 128) {
+            double ur[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const long long d = base + q * 32 + lane;
+                ur[q] = (d < m.n_draws) ? t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + d))), m) : CUDART_INF;
+            }
+            for (int g = 0; g < n_groups; ++g) {
+                const int row = (g << 5) + lane;
+                const bool rowok = row < X;
+                const double delta = rowok ? sdelta[row] : 0.0;
+                const int row_lo = (rowok && hlo) ? hlo[row] : 0;
+                double *Hrow = H + (size_t)(rowok ? row : 0) * hstride;
+                int bin = -1;
+                double next = -CUDART_INF, brk = CUDART_INF, acc = 0.0;   // forces a lookup at the first in-range sample
+                double a[P + 1];
+#pragma unroll
+                for (int k = 0; k <= P; ++k) a[k] = 0.0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    for (int k = 0; k < 32; ++k) {
+                        const double v = __dadd_rn(__shfl_sync(FULL, ur[q], k), delta);
+                        if (rowok && v >= 0.0 && v <= umax) {
+                            if (v >= next || v < brk) {          // another interval (rare: runs are long)
+                                const int j = range_interval(v, sbrk, lut, m.rng_lut_inv, m.rng_lut_n, M);
+                                const double2 *rj = reinterpret_cast<const double2 *>(rec + (j - jbase) * RW);
+                                const double2 hd = rj[0];
+                                next = hd.x;
+                                brk = j ? sbrk[j - 1] : 0.0;
+                                const int nb = __double2loint(hd.y);
+                                if (nb != bin) {
+                                    const int col = bin - row_lo;
+                                    if (bin >= 0 && (unsigned)col < (unsigned)hstride) atomicAdd(Hrow + col, acc);
+                                    acc = 0.0;
+                                    bin = nb;
+                                }
+#pragma unroll
+                                for (int c = 0; c <= P; c += 2) {
+                                    const double2 c2 = rj[1 + (c >> 1)];
+                                    a[c] = c2.x;
+                                    a[c + 1] = c2.y;
+                                }
+                            }
+                            const double dt = v - brk;
+                            double wgt = a[P];
+#pragma unroll
+                            for (int c = P - 1; c >= 0; --c) wgt = fma(wgt, dt, a[c]);
+                            acc += wgt;
+                        }
+                    }
+                }
+                const int col = bin - row_lo;
+                if (bin >= 0 && (unsigned)col < (unsigned)hstride) atomicAdd(Hrow + col, acc);
+            }
+        }
+    } else {
+        for (long long tile = 0; tile < m.n_draws; tile += RANGE_TILE) {
+            const int nt = (int)((m.n_draws - tile < RANGE_TILE) ? (m.n_draws - tile) : RANGE_TILE);
+            __syncthreads();                               // previous tile fully consumed / staging done
+            for (int d = tid; d < nt; d += NT)
+                u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + tile + d))), m);
+            __syncthreads();
+            range_accumulate_tile<NT, P>(u0, nt, sbrk, rec, jbase, lut, ulut, RANGE_ULUT, sdelta, srow, H, hstride, hlo, X, M,
+                                         umax, m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all);
+        }
     }
     __syncthreads();
 

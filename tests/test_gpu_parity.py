@@ -647,3 +647,25 @@ def test_api_edge_cases(M):
         assert np.all(nanq == -np.inf)                                  # NaN/inf parameters fail the prior box
         st = m.stats()
         assert st["evaluations"] >= 70003 and st["ctas_per_sm"] >= 1
+
+
+def test_range_streaming_big_draw_sets(M, O):
+    """>= 8192 draws per walker take the warp-private streaming walk (no tiles, no barriers)."""
+    nd = 16384
+    cfg = M.config.adv(0, n_samples=nd, n_ev_per_loop=4096, mean_excitation=19.2e-3, ode_mode=M.config.ODE_RANGE)
+    om = O.adv_model(0, n_samples=nd, n_ev_per_loop=4096, mean_excitation=19.2e-3, ode_substeps=2)
+    z = np.random.RandomState(61).standard_normal(nd)
+    xs = O.DDNXS()
+    obs = np.rint(5e4 * om.model_pdf([1050, .10], np.random.RandomState(62).standard_normal(nd), xs))
+    thetas = np.array([[1050, .10], [1100, .05], [1500, .20], [2400, .03]])     # banded and full-size walkers
+    with M.TofModel(cfg) as m:
+        m.set_observables(obs)
+        m.set_draws(z)
+        got = m.lnprob_batch(thetas)
+        cc = m.cell_counts(thetas)
+        again = m.lnprob_batch(thetas)
+    for k, th in enumerate(thetas):
+        want_c = om.cell_counts(th, z, xs)
+        assert int(np.count_nonzero(cc[k] != want_c)) == 0, k
+        assert rel(float(got[k]), float(om.lnprob(th, obs, z, xs))) <= RTOL, (k, got[k])
+        assert rel(float(got[k]), float(again[k])) <= 1e-11

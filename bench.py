@@ -278,15 +278,18 @@ def run_gpu_arm(args):
 
     # ---- end to end through the host API (HOST buffers in, HOST lnprob out) -------------------------------
     per_rank = N_WALKERS // world
-    host_thetas = np.ascontiguousarray(thetas[rank * per_rank:(rank + 1) * per_rank])
+    # pinned host buffers for the inputs (positions) and the result (lnprob)
+    pin_in = torch.from_numpy(np.ascontiguousarray(thetas[rank * per_rank:(rank + 1) * per_rank])).pin_memory()
+    pin_out = torch.empty(per_rank // 2, dtype=torch.float64).pin_memory()
+    host_thetas, host_out = pin_in.numpy(), pin_out.numpy()
     half = per_rank // 2
-    fn.batch(host_thetas[:half])
+    fn.batch(host_thetas[:half], host_out)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
     for _ in range(e2e_steps):
-        fn.batch(host_thetas[:half])       # one call per half-ensemble, as emcee's _get_lnprob does
-        fn.batch(host_thetas[half:])
+        fn.batch(host_thetas[:half], host_out)   # one call per half-ensemble, as emcee's _get_lnprob does
+        fn.batch(host_thetas[half:], host_out)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
     if world > 1:

@@ -732,12 +732,13 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     }
 
     const double spread = __dmul_rn(sigma0, e0);          // adv:128
+    const bool rev = spread < 0.0;                         // draws are sorted ascending: E0 ascends unless the spread is negative
     // ---- per walker: E-bins it can touch (the draws are sorted: first and last give the extremes) ------------
     int hstride = EB, jbase = 0;
     const int *hlo = nullptr;
     if (banded) {
-        const double u_lo = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z))), m);
-        const double u_hi = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + m.n_draws - 1))), m);
+        const double u_lo = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 : 0)))), m);
+        const double u_hi = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? 0 : m.n_draws - 1)))), m);
         if (tid == 0) {
             s_band[0] = 0;
             s_band[1] = M;
@@ -799,7 +800,8 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const long long d = base + q * 32 + lane;
-                ur[q] = (d < m.n_draws) ? t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + d))), m) : CUDART_INF;
+                ur[q] = (d < m.n_draws) ? t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 - d : d)))), m)
+                                        : CUDART_INF;
             }
             for (int g = 0; g < n_groups; ++g) {
                 const int row = (g << 5) + lane;
@@ -854,7 +856,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
             const int nt = (int)((m.n_draws - tile < RANGE_TILE) ? (m.n_draws - tile) : RANGE_TILE);
             __syncthreads();                               // previous tile fully consumed / staging done
             for (int d = tid; d < nt; d += NT)
-                u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + tile + d))), m);
+                u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 - (tile + d) : tile + d)))), m);
             __syncthreads();
             range_accumulate_tile<NT, P>(u0, nt, sbrk, rec, jbase, lut, ulut, RANGE_ULUT, sdelta, srow, H, hstride, hlo, X, M,
                                          umax, m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all);

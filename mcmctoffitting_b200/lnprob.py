@@ -56,8 +56,8 @@ class TofLnProb:
             raise ValueError("nDraws=%s differs from the configured n_samples=%d" % (nDraws, cfg.n_samples))
 
     # evaluation -------------------------------------------------------------------------------------
-    def batch(self, thetas) -> np.ndarray:
-        return self.model.lnprob_batch(thetas)
+    def batch(self, thetas, out=None) -> np.ndarray:
+        return self.model.lnprob_batch(thetas, out) if out is not None else self.model.lnprob_batch(thetas)
 
     def __call__(self, theta, observables=None, standoffDists=None, tofRanges=None, nTOFbins=None, nDraws=None):
         if observables is not None:

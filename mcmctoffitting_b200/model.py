@@ -172,9 +172,13 @@ class TofModel:
             raise ValueError("thetas must have shape [n, %d]" % self.config.ndim)
         return t
 
-    def lnprob_batch(self, thetas) -> np.ndarray:
+    def lnprob_batch(self, thetas, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """``out``: optional preallocated float64 result buffer (e.g. a view of pinned host memory)."""
         t = self._thetas(thetas)
-        out = np.empty(t.shape[0], dtype=np.float64)
+        if out is None:
+            out = np.empty(t.shape[0], dtype=np.float64)
+        elif out.dtype != np.float64 or out.shape != (t.shape[0],) or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape [n]")
         self._check(self._lib.tof_lnprob_batch(self._ctx, _dptr(t), t.shape[0], _dptr(out)))
         return out
 

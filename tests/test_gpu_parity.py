@@ -669,3 +669,17 @@ def test_range_streaming_big_draw_sets(M, O):
         assert int(np.count_nonzero(cc[k] != want_c)) == 0, k
         assert rel(float(got[k]), float(om.lnprob(th, obs, z, xs))) <= RTOL, (k, got[k])
         assert rel(float(got[k]), float(again[k])) <= 1e-11
+
+
+def test_range_negative_spread_is_handled(M, O):
+    """model_batch ignores the prior, so sigma0 < 0 can reach the kernel: E0 then DEScends with the sorted draws."""
+    cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE)
+    om = O.sweep_model(ode_scheme="exact")
+    z = np.random.RandomState(4).standard_normal(1024)
+    with M.TofModel(cfg) as m:
+        m.set_draws(z)
+        got = m.model_batch([[1050.0, -0.1]], stage="counts")[0]
+        ref = m.model_batch([[1050.0, 0.1]], stage="counts")[0]
+    want = om.raw_tof([1050.0, -0.1], z, O.DDNXS(), density=False)
+    assert np.array_equal(got, want)
+    assert got.sum() > 0 and not np.array_equal(got, ref)

@@ -10,7 +10,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libtofgpu.so")
 SOURCES = ["tofgpu.cu"]
-HEADERS = ["tof_device.cuh", "tof_kernels.cuh", os.path.join("..", "..", "include", "tofgpu.h")]
+HEADERS = ["tof_device.cuh", "tof_kernels.cuh", "tof_common.cuh", "adv_rk4.cuh", "adv_range.cuh", "simple_model.cuh",
+           "simult_model.cuh", "onebd_model.cuh", "sampler.cuh", os.path.join("..", "..", "include", "tofgpu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,0 +1,568 @@
+// adv / intermediate model, range-table formulation (TOF_ODE_RANGE).
+#pragma once
+#include "tof_common.cuh"
+#include "adv_rk4.cuh"
+
+namespace tof {
+
+// ================================================================================================
+// adv / intermediate model, range-table formulation (TOF_ODE_RANGE)
+// ================================================================================================
+// The stopping ODE is autonomous, so u(E) = int dE/|f| turns "integrate every draw through every x"
+// into v = u0_d + sgn*(x_i - x_start).  With the draws sorted, v is monotone along d for a fixed row,
+// so one thread walks a run of consecutive draws with a pointer into the T2 table (bin + polynomial
+// of the cross-section weight), sums whole runs in a register and touches the (x,E) histogram once
+// per run instead of once per sample.
+constexpr int RANGE_TILE = 1024;   // draws staged in shared memory at a time
+constexpr int RANGE_ULUT = 1024;   // cells of the per-tile draw-index lookup table
+constexpr int RANGE_STREAM_MIN = 8192;  // draws per walker from which the warp-private streaming walk is used
+constexpr int RANGE_SPLIT = 6;      // long runs: pieces per warp when a tile has few (row, interval) tasks
+constexpr int SIMULT_ULUT = 256;   // same for the 10-row simultaneous fit (fewer lookups per tile)
+
+// hcap: cells of the (possibly banded) histogram; rcap: staged T2 records
+__host__ __device__ inline size_t range_smem_bytes(int X, int E, int T, int hcap, int rcap, int P, int n_taps, int lut_n,
+                                                   int rng_n) {
+    size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
+    region_a = (region_a + 15) / 16 * 16;
+    size_t d = (size_t)hcap + (size_t)rcap * (P + 3) + E + n_taps + 40 + X /* per-row offsets */;
+    return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16 + RANGE_ULUT * 2 + (((size_t)X * 8 + 15) / 16) * 16 +
+           (size_t)rng_n * 8 + (((size_t)rng_n * 2 + 15) / 16) * 16 + 16;
+}
+
+
+// Interval of the T2 table that holds v (0 <= v <= u_max); uniform lookup cell, then edge compares.
+// brk[j] = break that ends interval j (brk[M-1] = +inf).
+__device__ __forceinline__ int range_interval(double v, const double *brk, const unsigned short *lut, double lut_inv, int lut_n,
+                                              int M) {
+    int c = (int)(v * lut_inv);
+    c = c < 0 ? 0 : (c > lut_n - 1 ? lut_n - 1 : c);
+    int j = lut[c];
+    while (j + 1 < M && v >= brk[j]) ++j;
+    while (j > 0 && v < brk[j - 1]) --j;
+    return j;
+}
+
+// u0 = u(E0): T1 cell from the exponent/mantissa bits, degree-7 Horner in t in [-1, 1].
+__device__ __forceinline__ double t1_eval(double E0, const DevModel &m) {
+    double t;
+    int idx;
+    if (!(E0 >= m.e_tab_lo)) {                 // below the table, non-positive or NaN
+        if (m.rng_sign > 0.0 && E0 > 0.0) {    // rising energies: clamp tiny E0 to the table start
+            t = -1.0;
+            idx = 0;
+        } else {
+            return -CUDART_INF;
+        }
+    } else if (E0 >= m.e_tab_hi) {
+        return CUDART_INF;
+    } else {
+        const int hi = __double2hiint(E0), lo = __double2loint(E0);
+        const int key = hi >> (20 - m.t1_q);
+        idx = key - m.t1_key_lo;
+        const double mant = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);   // [1, 2)
+        const double c = (double)(key & ((1 << m.t1_q) - 1));
+        t = (mant - 1.0) * (double)(1 << (m.t1_q + 1)) - (2.0 * c + 1.0);             // exact
+    }
+    const double *k = m.t1_coefs + 8 * idx;
+    double acc = __ldg(k + 7);
+#pragma unroll
+    for (int q = 6; q >= 0; --q) acc = fma(acc, t, __ldg(k + q));
+    return acc;
+}
+
+// Phase 1 for one tile of sorted u0 values (shared memory): add the cross-section weights of every (draw, row)
+// sample to the (x,E) histogram H.  Called by all threads of the CTA (contains barriers).
+template <int NT, int P>
+// `brk`: the ends of all T2 intervals (shared memory) for interval searches; `rec`: the shared-memory copy of records
+// jbase.. used by the tasks; H has `hstride` bins per row; row i starts at E-bin hlo[i] (banded layout; hlo == nullptr:
+// every row starts at bin 0).
+__device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, const double *brk, const double *rec, int jbase,
+                                                      const unsigned short *lut, unsigned short *ulut, int n_ulut,
+                                                      const double *sdelta, int *srow, double *H, int hstride, const int *hlo,
+                                                      int X, int M, double umax, double lut_inv, int lut_n, int &bin_lo_all,
+                                                      int &bin_hi_all) {
+    constexpr int RW = P + 3;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nsteps = 32 - __clz(nt);                 // binary-search iterations for [0, nt]
+    // valid (finite) part of the sorted tile: -inf (never in range) first, +inf last
+    int v_lo = 0, v_hi = nt;
+    {
+        int lo = 0, hi = nt, lo2 = 0, hi2 = nt;
+        for (int it = 0; it < nsteps; ++it) {
+            const int mid = (lo + hi) >> 1, mid2 = (lo2 + hi2) >> 1;
+            const bool ge = u0[mid < nt ? mid : nt - 1] > -CUDART_INF;
+            const bool gt = u0[mid2 < nt ? mid2 : nt - 1] >= CUDART_INF;
+            const bool go = lo < hi, go2 = lo2 < hi2;
+            hi = (go && ge) ? mid : hi;
+            lo = (go && !ge) ? mid + 1 : lo;
+            hi2 = (go2 && gt) ? mid2 : hi2;
+            lo2 = (go2 && !gt) ? mid2 + 1 : lo2;
+        }
+        v_lo = lo;
+        v_hi = lo2;
+    }
+    if (v_hi <= v_lo) return;                        // uniform: no usable draw in this tile
+    const double tu_min = u0[v_lo], tu_max = u0[v_hi - 1];
+    const double tu_inv = (tu_max > tu_min) ? (double)n_ulut / (tu_max - tu_min) : 0.0;
+    // per-tile lookup: ulut[c] = first draw with u0 >= tu_min + c*cell
+    for (int c = tid; c < n_ulut; c += NT) {
+        const double x = tu_min + (double)c * ((tu_max - tu_min) / (double)n_ulut);
+        int lo = v_lo, hi = v_hi;
+        for (int it = 0; it < nsteps; ++it) {
+            const int mid = (lo + hi) >> 1;
+            const bool ge = u0[mid < nt ? mid : nt - 1] >= x;
+            const bool go = lo < hi;
+            hi = (go && ge) ? mid : hi;
+            lo = (go && !ge) ? mid + 1 : lo;
+        }
+        ulut[c] = (unsigned short)lo;
+    }
+    // per-row interval of the tile's median draw: rows are processed along the trajectory (interval j = k + shift(row)),
+    // so that the 32 lanes of a task look at the same slice of the draw distribution and have runs of similar length
+    {
+        const double u_med = u0[(v_lo + v_hi) >> 1];
+        for (int i = tid; i < X; i += NT) {
+            double vm = __dadd_rn(u_med, sdelta[i]);
+            vm = vm < 0.0 ? 0.0 : (vm > umax ? umax : vm);
+            srow[i] = range_interval(vm, brk, lut, lut_inv, lut_n, M);
+        }
+    }
+    // band of T2 intervals any row of this tile can touch
+    double dmin = sdelta[0], dmax = sdelta[0];
+    {
+        const double dl = sdelta[X - 1];
+        dmin = dl < dmin ? dl : dmin;
+        dmax = dl > dmax ? dl : dmax;                  // delta is monotone in the row index
+    }
+    const double vmin = __dadd_rn(tu_min, dmin), vmax = __dadd_rn(tu_max, dmax);
+    __syncthreads();
+    if (!(vmax >= 0.0) || vmin > umax) return;         // uniform
+    const int band_lo = range_interval(vmin > 0.0 ? vmin : 0.0, brk, lut, lut_inv, lut_n, M);
+    const int band_hi = range_interval(vmax < umax ? vmax : umax, brk, lut, lut_inv, lut_n, M);
+    bin_lo_all = min(bin_lo_all, __double2loint(rec[(band_lo - jbase) * RW + 1]));
+    bin_hi_all = max(bin_hi_all, __double2loint(rec[(band_hi - jbase) * RW + 1]));
+    // One task = 32 (row, interval) cells.  Type A: one T2 interval x 32 consecutive rows (lane = row; all
+    // lanes use the same polynomial).  Type B, for the X % 32 leftover rows: R rows x (32/R) consecutive
+    // intervals.  A lane's draws are the contiguous range [lb, ub) found through the per-tile lookup.
+    // Cell (row, bin) is produced by exactly one lane: plain read-modify-write, fixed summation order.
+    const int Gf = X >> 5, R = X & 31;
+    const int s_ref = srow[0];
+    const int s_a = srow[0] - s_ref, s_b = srow[X - 1] - s_ref;       // shift is monotone in the row index
+    const int s_min = s_a < s_b ? s_a : s_b, s_max = s_a < s_b ? s_b : s_a;
+    const int k_lo = band_lo - s_max;
+    const int n_iv = (band_hi - s_min) - k_lo + 1;
+    const int per_b = R ? 32 / R : 1;
+    const int nA = n_iv * Gf, nB = R ? (n_iv + per_b - 1) / per_b : 0;
+    // One (row, interval) cell for this lane; with nch > 1 the lane takes piece `piece` of the run and the pieces
+    // are combined with atomics (long runs: tiles of a big draw set cover few intervals).
+    auto do_cell = [&](int row, int j, bool active, int piece, int nch) {
+        active = active && j >= band_lo && j <= band_hi;
+        j = j < band_lo ? band_lo : (j > band_hi ? band_hi : j);
+        const double2 *rj = reinterpret_cast<const double2 *>(rec + (j - jbase) * RW);
+        const double2 hd = rj[0];
+        const double left = j ? rec[(j - 1 - jbase) * RW] : 0.0;
+        const bool last = (j == M - 1);
+        const double right = last ? umax : hd.x;
+        const int bin = __double2loint(hd.y);
+        double a[P + 1];
+#pragma unroll
+        for (int k = 0; k <= P; k += 2) {
+            const double2 c2 = rj[1 + (k >> 1)];
+            a[k] = c2.x;
+            a[k + 1] = c2.y;
+        }
+        if (!active) return;
+        const double delta = sdelta[row];
+        // first draw with v >= left
+        int c = (int)((left - delta - tu_min) * tu_inv);
+        c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
+        int lb = ulut[c];
+        while (lb > v_lo && __dadd_rn(u0[lb - 1], delta) >= left) --lb;
+        while (lb < v_hi && !(__dadd_rn(u0[lb], delta) >= left)) ++lb;
+        // first draw beyond the interval: v >= right (v > u_max for the last interval, which is closed)
+        c = (int)((right - delta - tu_min) * tu_inv);
+        c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
+        int ub = ulut[c];
+        if (last) {
+            while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) > right) --ub;
+            while (ub < v_hi && !(__dadd_rn(u0[ub], delta) > right)) ++ub;
+        } else {
+            while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) >= right) --ub;
+            while (ub < v_hi && !(__dadd_rn(u0[ub], delta) >= right)) ++ub;
+        }
+        if (nch > 1) {
+            const int len = (ub - lb + nch - 1) / nch;
+            lb += piece * len;
+            ub = (lb + len < ub) ? lb + len : ub;
+        }
+        if (ub <= lb) return;
+        double acc = 0.0;
+        for (int d = lb; d < ub; ++d) {
+            const double dt = __dadd_rn(u0[d], delta) - left;
+            double wgt = a[P];
+#pragma unroll
+            for (int k = P - 1; k >= 0; --k) wgt = fma(wgt, dt, a[k]);
+            acc += wgt;
+        }
+        const int col = bin - (hlo ? hlo[row] : 0);
+        if ((unsigned)col >= (unsigned)hstride) return;       // cannot happen: the band has an interval of slack
+        double *cell = H + (size_t)row * hstride + col;
+        if (nch > 1 || __double2hiint(hd.y) < 0) atomicAdd(cell, acc);   // shared cell: pieces / bin split over intervals
+        else *cell += acc;
+    };
+    const int GfD = Gf > 0 ? Gf : 1;
+    const int n_tasks = nA + nB;
+    // few tasks (a tile of a big draw set spans few intervals): split every run so that all warps have work
+    int nch = 1;
+    if (n_tasks < 2 * NW) {
+        nch = (RANGE_SPLIT * NW + n_tasks - 1) / (n_tasks > 0 ? n_tasks : 1);   // ~RANGE_SPLIT pieces per warp
+        nch = nch > 64 ? 64 : nch;
+    }
+    if (nch == 1) {
+        // (jj, g) of type-A task `task` without a division in the loop
+        int a_jj = warp / GfD, a_g = warp - a_jj * GfD;
+        const int step_j = NW / GfD, step_g = NW - step_j * GfD;
+        for (int task = warp; task < n_tasks; task += NW) {
+            if (task < nA) {
+                const int row = (a_g << 5) + lane;
+                do_cell(row, k_lo + a_jj + (srow[row] - s_ref), true, 0, 1);
+                a_jj += step_j;
+                a_g += step_g;
+                if (a_g >= GfD) {
+                    a_g -= GfD;
+                    ++a_jj;
+                }
+            } else {
+                const int isub = lane / R;
+                const int row = (Gf << 5) + (lane - isub * R);
+                do_cell(row, k_lo + (task - nA) * per_b + isub + (srow[row] - s_ref), isub < per_b, 0, 1);
+            }
+        }
+    } else {
+        for (int t2 = warp; t2 < n_tasks * nch; t2 += NW) {
+            const int task = t2 / nch, piece = t2 - task * nch;
+            if (task < nA) {
+                const int jj = task / GfD;
+                const int row = ((task - jj * GfD) << 5) + lane;
+                do_cell(row, k_lo + jj + (srow[row] - s_ref), true, piece, nch);
+            } else {
+                const int isub = lane / R;
+                const int row = (Gf << 5) + (lane - isub * R);
+                do_cell(row, k_lo + (task - nA) * per_b + isub + (srow[row] - s_ref), isub < per_b, piece, nch);
+            }
+        }
+    }
+}
+
+template <int NT, int P>
+__global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(const DevModel m, const DevRun run, const double *__restrict__ theta,
+                                                       long long n_walkers, ModelOut out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int RW = P + 3;
+    const int T = run.tof_bins, X = m.x_bins, EB = m.e_bins, M = m.rng_n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NT / 32;
+    // ---- carve --------------------------------------------------------------------------------------
+    // banded launch (out.hcap < X*EB): the cell histogram holds only the E-bins this walker can touch and only the
+    // matching T2 records are staged, so that two 512-thread CTAs fit one SM; walkers that do not fit are queued
+    // for the full-size launch
+    const bool banded = out.hcap < X * EB;
+    double *H = reinterpret_cast<double *>(smem_raw);
+    size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
+    region_a = (region_a + 15) / 16 * 16;
+    unsigned char *pa = reinterpret_cast<unsigned char *>(H + (size_t)out.hcap);
+    unsigned int *tofc = reinterpret_cast<unsigned int *>(pa);
+    double *u0 = reinterpret_cast<double *>(pa);                       // aliases tofc (phase 1 only)
+    double *rec = reinterpret_cast<double *>(pa + region_a);
+    double *svd = rec + (size_t)out.rcap * RW;
+    double *staps = svd + EB;
+    double *scratch = staps + m.n_taps;
+    double *sdelta = scratch + 40;                                      // [X] sgn*(x_i - x_start)
+    unsigned short *lut = reinterpret_cast<unsigned short *>(sdelta + X);
+    unsigned short *ulut = lut + ((m.rng_lut_n + 7) / 8) * 8;           // [RANGE_ULUT]
+    int *srow = reinterpret_cast<int *>(ulut + RANGE_ULUT);             // [X]
+    int *hlo_s = srow + X;                                              // [X] first E-bin of each row (banded launch)
+    double *sbrk = reinterpret_cast<double *>(hlo_s + X + (X & 1));     // [M] interval ends
+    unsigned short *sbin = reinterpret_cast<unsigned short *>(sbrk + M);  // [M] E-bin of each interval
+    __shared__ int s_band[3];                                           // widest row, first / last interval of the walker
+
+    // ---- walker-independent tables: staged once per CTA (persistent CTAs loop over walkers) ------------------
+    if (!banded)
+        for (int i = tid; i < M * RW; i += NT) rec[i] = m.rng_rec[i];
+    const double *recf = m.rng_rec;                        // full table in global memory
+    for (int j = tid; j < M; j += NT) {
+        sbrk[j] = recf[(size_t)j * RW];
+        sbin[j] = (unsigned short)__double2loint(recf[(size_t)j * RW + 1]);
+    }
+    for (int i = tid; i < m.rng_lut_n; i += NT) lut[i] = m.rng_lut[i];
+    for (int i = tid; i < m.n_taps; i += NT) staps[i] = m.taps[i];
+    const double sgn = m.rng_sign, umax = m.rng_u_max;
+    const double x_start = m.ode_from_zero ? 0.0 : m.x_centers[0];
+    for (int i = tid; i < X; i += NT) sdelta[i] = sgn * (m.x_centers[i] - x_start);
+    __shared__ long long s_next;
+    for (long long iter = 0;; ++iter) {
+    __syncthreads();                                       // the previous walker is done with shared memory
+    if (tid == 0)
+        s_next = out.work ? (long long)atomicAdd(out.work, 1ull) : (long long)blockIdx.x + iter * (long long)gridDim.x;
+    __syncthreads();
+    const long long item = s_next;
+    // the full-size launch of a banded call works through the queue the banded launch filled
+    const long long n_items = out.queue_in ? (long long)*out.queue_count : n_walkers;
+    if (item >= n_items) break;
+    const long long w = out.queue_in ? (long long)out.queue_in[item] : item;
+    const double e0 = theta[w * m.ndim + 0];
+    const double sigma0 = theta[w * m.ndim + 1];
+    bool inside = true;
+    for (int p = 0; p < m.ndim; ++p) {
+        const double v = theta[w * m.ndim + p];
+        inside = inside && (m.prior_strict ? (m.prior_lo[p] < v && v < m.prior_hi[p])
+                                           : !(v < m.prior_lo[p] || v > m.prior_hi[p]));
+    }
+    if (!inside && out.spectra == nullptr && out.cells == nullptr) {
+        if (tid == 0) out.lnprob[w] = -CUDART_INF;
+        continue;
+    }
+
+    const double spread = __dmul_rn(sigma0, e0);          // adv:128
+    const bool rev = spread < 0.0;                         // draws are sorted ascending: E0 ascends unless the spread is negative
+    // ---- per walker: E-bins it can touch (the draws are sorted: first and last give the extremes) ------------
+    int hstride = EB, jbase = 0;
+    const int *hlo = nullptr;
+    if (banded) {
+        const double u_lo = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 : 0)))), m);
+        const double u_hi = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? 0 : m.n_draws - 1)))), m);
+        if (tid == 0) {
+            s_band[0] = 0;
+            s_band[1] = M;
+            s_band[2] = -1;
+        }
+        __syncthreads();
+        // every row has its own window of E-bins: [u_lo + delta_i, u_hi + delta_i], one interval of slack on both
+        // sides (T1 is only monotone up to its 2e-13 cm fit error)
+        for (int i = tid; i < X; i += NT) {
+            double vmin = (u_lo > -CUDART_INF ? u_lo : 0.0) + sdelta[i];   // -inf draws: the lowest in-range v is 0
+            double vmax = u_hi + sdelta[i];
+            vmin = vmin > 0.0 ? vmin : 0.0;
+            vmax = vmax < umax ? vmax : umax;
+            int j_lo = 0, j_hi = 0;
+            if (vmax >= vmin) {                               // otherwise this row gets nothing: any window will do
+                j_lo = range_interval(vmin, sbrk, lut, m.rng_lut_inv, m.rng_lut_n, M);
+                j_hi = range_interval(vmax, sbrk, lut, m.rng_lut_inv, m.rng_lut_n, M);
+                j_lo = j_lo > 0 ? j_lo - 1 : 0;
+                j_hi = j_hi < M - 1 ? j_hi + 1 : M - 1;
+                atomicMin(&s_band[1], j_lo);
+                atomicMax(&s_band[2], j_hi);
+            }
+            const int b_lo = sbin[j_lo];
+            hlo_s[i] = b_lo;
+            atomicMax(&s_band[0], (int)sbin[j_hi] - b_lo + 1);
+        }
+        __syncthreads();
+        hstride = s_band[0];
+        const int j_lo_all = s_band[2] >= 0 ? s_band[1] : 0, j_hi_all = s_band[2] >= 0 ? s_band[2] : 0;
+        jbase = j_lo_all > 0 ? j_lo_all - 1 : 0;
+        hlo = hlo_s;
+        const bool fits = (long long)X * hstride <= out.hcap && (j_hi_all - jbase + 1) <= out.rcap && T <= out.hcap;
+        if (!fits) {                                          // queue for the full-size launch
+            if (tid == 0) out.queue_out[atomicAdd(out.queue_count, 1ull)] = (int)w;
+            continue;
+        }
+        for (int i = tid; i < (j_hi_all - jbase + 1) * RW; i += NT) rec[i] = recf[(size_t)jbase * RW + i];
+    }
+    // ---- per walker: zero the cell histogram, deuteron speeds ------------------------------------------------
+    for (int i = tid; i < X * hstride; i += NT) H[i] = 0.0;
+    for (int j = tid; j < EB; j += NT) {
+        const double eff = __ddiv_rn(__dadd_rn(e0, m.e_centers[j]), 2.0);   // adv:151
+        svd[j] = speed_of(m.c, eff, m.m_d);
+    }
+
+    // ---- phase 1: (x,E) histogram of cross-section weights through the range tables ---------------------
+    int bin_lo_all = EB, bin_hi_all = -1;                  // E-bins any draw of any tile can have touched (uniform)
+    if (m.n_draws >= RANGE_STREAM_MIN) {
+        // Big draw sets: the sorted draws of one interval are hundreds of consecutive values, so a lane that walks
+        // draws in order changes interval rarely.  Warp-private streaming, no barriers: a warp takes 128 consecutive
+        // draws (4 per lane, T1 evaluated once, kept in registers and broadcast by shuffle) and, for every group of
+        // 32 rows, lane = row walks the 128 samples with an interval pointer; runs go to H with atomics.
+        __syncthreads();                                   // staging done
+        bin_lo_all = 0;
+        bin_hi_all = EB - 1;
+        const int n_groups = (X + 31) >> 5;
+        for (long long base = (long long)warp * 128; base < m.n_draws; base += (long long)NW * 128) {
+            double ur[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const long long d = base + q * 32 + lane;
+                ur[q] = (d < m.n_draws) ? t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 - d : d)))), m)
+                                        : CUDART_INF;
+            }
+            for (int g = 0; g < n_groups; ++g) {
+                const int row = (g << 5) + lane;
+                const bool rowok = row < X;
+                const double delta = rowok ? sdelta[row] : 0.0;
+                const int row_lo = (rowok && hlo) ? hlo[row] : 0;
+                double *Hrow = H + (size_t)(rowok ? row : 0) * hstride;
+                int bin = -1;
+                double next = -CUDART_INF, brk = CUDART_INF, acc = 0.0;   // forces a lookup at the first in-range sample
+                double a[P + 1];
+#pragma unroll
+                for (int k = 0; k <= P; ++k) a[k] = 0.0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    for (int k = 0; k < 32; ++k) {
+                        const double v = __dadd_rn(__shfl_sync(FULL, ur[q], k), delta);
+                        if (rowok && v >= 0.0 && v <= umax) {
+                            if (v >= next || v < brk) {          // another interval (rare: runs are long)
+                                const int j = range_interval(v, sbrk, lut, m.rng_lut_inv, m.rng_lut_n, M);
+                                const double2 *rj = reinterpret_cast<const double2 *>(rec + (j - jbase) * RW);
+                                const double2 hd = rj[0];
+                                next = hd.x;
+                                brk = j ? sbrk[j - 1] : 0.0;
+                                const int nb = __double2loint(hd.y);
+                                if (nb != bin) {
+                                    const int col = bin - row_lo;
+                                    if (bin >= 0 && (unsigned)col < (unsigned)hstride) atomicAdd(Hrow + col, acc);
+                                    acc = 0.0;
+                                    bin = nb;
+                                }
+#pragma unroll
+                                for (int c = 0; c <= P; c += 2) {
+                                    const double2 c2 = rj[1 + (c >> 1)];
+                                    a[c] = c2.x;
+                                    a[c + 1] = c2.y;
+                                }
+                            }
+                            const double dt = v - brk;
+                            double wgt = a[P];
+#pragma unroll
+                            for (int c = P - 1; c >= 0; --c) wgt = fma(wgt, dt, a[c]);
+                            acc += wgt;
+                        }
+                    }
+                }
+                const int col = bin - row_lo;
+                if (bin >= 0 && (unsigned)col < (unsigned)hstride) atomicAdd(Hrow + col, acc);
+            }
+        }
+    } else {
+        for (long long tile = 0; tile < m.n_draws; tile += RANGE_TILE) {
+            const int nt = (int)((m.n_draws - tile < RANGE_TILE) ? (m.n_draws - tile) : RANGE_TILE);
+            __syncthreads();                               // previous tile fully consumed / staging done
+            for (int d = tid; d < nt; d += NT)
+                u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 - (tile + d) : tile + d)))), m);
+            __syncthreads();
+            range_accumulate_tile<NT, P>(u0, nt, sbrk, rec, jbase, lut, ulut, RANGE_ULUT, sdelta, srow, H, hstride, hlo, X, M,
+                                         umax, m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: normalise (adv:143) ---------------------------------------------------------------------
+    for (int i = tid; i < T; i += NT) tofc[i] = 0u;        // u0 is dead now
+    const double de = (m.e_max - m.e_min) / (double)EB;
+    const double dx = (m.x_max - m.x_min) / (double)X;
+    // banded launch: every row holds `hstride` bins from hlo[row]; full-size launch: only bins bin_lo_all..bin_hi_all
+    // can be non-zero
+    const int nbw = hlo ? hstride : bin_hi_all - bin_lo_all + 1;
+    double part = 0.0;
+    for (int row = warp; row < X; row += NW) {
+        const double *Hr = H + (size_t)row * hstride + (hlo ? 0 : bin_lo_all);
+        for (int jb = lane; jb < nbw; jb += 32) part += __dmul_rn(__dmul_rn(Hr[jb], de), dx);
+    }
+    const double S = block_sum<double>(part, scratch);     // includes the barrier that publishes tofc = 0
+
+    // ---- phase 3: quantise (adv:146) and scatter every non-empty cell to its flight time (adv:149-158) ----
+    const double t_step = (run.tof_max - run.tof_min) / (double)T;
+    const double t_scale = (double)T / (run.tof_max - run.tof_min);
+    const double nsamp = (double)m.n_samples;
+    if (out.cells) {                                        // debug output: every cell, zeros included
+        for (int idx = tid; idx < X * EB; idx += NT) {
+            const double cnt = rint(__dmul_rn(__ddiv_rn(H[idx], S), nsamp));
+            out.cells[(size_t)w * X * EB + idx] = (cnt == cnt) ? (long long)cnt : LLONG_MIN;
+        }
+    }
+    for (int row = warp; row < X; row += NW) {
+        const double xi = __ldg(m.x_centers + row), di = __ldg(run.neutron_dist + row);
+        const int row_lo = hlo ? hlo[row] : bin_lo_all;
+        const double *Hr = H + (size_t)row * hstride + (hlo ? 0 : bin_lo_all);
+        for (int jb = lane; jb < nbw; jb += 32) {
+            const int j = row_lo + jb;
+            if (j >= EB) break;
+            const double h = Hr[jb];
+            if (h != 0.0 && S > 0.0) {
+                const double cnt = rint(__dmul_rn(__ddiv_rn(h, S), nsamp));
+                if (cnt > 0.0) {
+                    const double tof_d = __ddiv_rn(xi, svd[j]);
+                    const double tof_n = __ddiv_rn(di, __ldg(m.neutron_speed + j));
+                    const int b = np_bin(__dadd_rn(tof_d, tof_n), T, run.tof_min, run.tof_max, t_step, t_scale);
+                    if (b >= 0) atomicAdd(tofc + b, (unsigned int)cnt);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 4: density (np.histogram density=True) into the (now free) H region -------------------------
+    long long cpart = 0;
+    for (int t = tid; t < T; t += NT) cpart += (long long)tofc[t];
+    const long long total_i = block_sum<long long>(cpart, reinterpret_cast<long long *>(scratch));
+    const bool degenerate = !(S > 0.0) || total_i == 0;
+    const double total = (double)total_i;
+    double *pdf = H;
+    for (int t = tid; t < T; t += NT) {
+        const unsigned int cn = tofc[t];
+        double v = 0.0;
+        if (cn) {
+            const double db = __dsub_rn(np_edge(t + 1, T, run.tof_min, run.tof_max, t_step),
+                                        np_edge(t, T, run.tof_min, run.tof_max, t_step));
+            v = __ddiv_rn(__ddiv_rn((double)cn, db), total);
+        }
+        pdf[t] = v;
+    }
+    __syncthreads();
+
+    if (out.spectra) {
+        double *sp = out.spectra + (size_t)w * T;
+        for (int t = tid; t < T; t += NT) {
+            double v;
+            if (out.stage == TOF_STAGE_COUNTS) {
+                v = (double)tofc[t];
+            } else if (degenerate) {
+                v = CUDART_NAN;
+            } else if (out.stage == TOF_STAGE_PDF) {
+                v = pdf[t];
+            } else {
+                v = 0.0;
+                for (int k = 0; k < m.n_taps; ++k) {
+                    const int tt = t + m.conv_shift - k;
+                    if (tt >= 0 && tt < T) v += staps[k] * pdf[tt];
+                }
+            }
+            sp[t] = v;
+        }
+    }
+
+    // ---- phase 5: timing response at the observed bins + log-likelihood (adv:173-181) ------------------------
+    double lp = 0.0;
+    if (!degenerate) {
+        for (int q = tid; q < run.n_obs_nz; q += NT) {
+            const int t = run.obs_nz_idx[q];
+            double ev = 0.0;
+            for (int k = 0; k < m.n_taps; ++k) {
+                const int tt = t + m.conv_shift - k;
+                if (tt >= 0 && tt < T) ev += staps[k] * pdf[tt];
+            }
+            lp += run.obs_nz_val[q] * log(ev);
+        }
+    }
+    lp = block_sum<double>(lp, scratch);
+    if (tid == 0 && out.lnprob) {
+        double r = degenerate ? CUDART_NAN : lp;
+        if (!inside) r = -CUDART_INF;
+        if (m.nan_to_neginf && r != r) r = -CUDART_INF;
+        out.lnprob[w] = r;
+    }
+    }   // persistent walker loop
+}
+
+}  // namespace tof

@@ -1,0 +1,21 @@
+// Shared kernel-side declarations: what a model kernel is asked to produce.
+#pragma once
+#include "tof_device.cuh"
+
+namespace tof {
+
+// Outputs requested from a model kernel.  Production: only `lnprob`.
+struct ModelOut {
+    double *lnprob;       // [n] (adv/simple) or [n][n_runs] partials (simult)
+    double *spectra;      // optional [n][T] at `stage`
+    long long *cells;     // optional [n][X][E] integer cell counts
+    int stage;
+    unsigned long long *work;  // optional global work counter (persistent CTAs take walkers dynamically)
+    // range kernel, banded launch: capacity of the cell histogram (cells) and of the staged T2 records
+    int hcap, rcap;
+    int *queue_out;                  // walkers that do not fit the banded layout ...
+    unsigned long long *queue_count; // ... and how many
+    const int *queue_in;             // full-size launch: process queue_in[0 .. *queue_count)
+};
+
+}  // namespace tof

@@ -8,11 +8,17 @@ namespace tof {
 // ================================================================================================
 // adv / intermediate model, range-table formulation (TOF_ODE_RANGE)
 // ================================================================================================
-// The stopping ODE is autonomous, so u(E) = int dE/|f| turns "integrate every draw through every x"
-// into v = u0_d + sgn*(x_i - x_start).  With the draws sorted, v is monotone along d for a fixed row,
-// so one thread walks a run of consecutive draws with a pointer into the T2 table (bin + polynomial
-// of the cross-section weight), sums whole runs in a register and touches the (x,E) histogram once
-// per run instead of once per sample.
+// The stopping ODE (ionStopping.py:78-97) is autonomous, so u(E) = int dE/|f| turns "integrate every draw through
+// every x" (adv:129) into v = u0_d + sgn*(x_i - x_start): one T1 lookup per draw, and for every (draw, x) sample an
+// interval of the T2 table that gives both its E-bin and a polynomial for its cross-section weight
+// (range_tables.py).  The library keeps the draws sorted, so for a fixed row the samples of one interval are a
+// contiguous range of draws.  Three phase-1 strategies share the tables:
+//   * tiles (n_draws < RANGE_STREAM_MIN): 1024 draws staged in shared memory, a per-tile lookup from u to draw
+//     index, tasks of 32 (row, interval) cells with lane = row -- every cell is summed by exactly one lane, no
+//     atomics, fixed order (range_accumulate_tile);
+//   * pieces: when a tile spans few intervals each run is split over several lanes (atomics on the cell);
+//   * streaming (big draw sets): warp-private walk over 128 draws at a time, values broadcast by shuffle.
+// The cell histogram is either full (X*E doubles, 1 CTA/SM) or banded per row (2 CTAs/SM), see adv_range_kernel.
 constexpr int RANGE_TILE = 1024;   // draws staged in shared memory at a time
 constexpr int RANGE_ULUT = 1024;   // cells of the per-tile draw-index lookup table
 constexpr int RANGE_STREAM_MIN = 8192;  // draws per walker from which the warp-private streaming walk is used

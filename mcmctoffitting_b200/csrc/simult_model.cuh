@@ -241,7 +241,7 @@ __host__ __device__ inline size_t simult_range_smem_bytes(int X, int E, int T, i
 
 // Range-table formulation of the simultaneous fit: same model as simult_run_kernel, stopping through T1/T2.
 template <int NT, int P>
-__global__ void __launch_bounds__(NT) simult_range_kernel(const DevModel m, const DevRunSet runs, const double *__restrict__ theta,
+__global__ void __launch_bounds__(NT, 4) simult_range_kernel(const DevModel m, const DevRunSet runs, const double *__restrict__ theta,
                                                           long long n_walkers, ModelOut out, int only_run) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int RW = P + 3;

@@ -312,7 +312,10 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     if (tid == 0)
         s_next = out.work ? (long long)atomicAdd(out.work, 1ull) : (long long)blockIdx.x + iter * (long long)gridDim.x;
     __syncthreads();
-    const long long item = s_next;
+    // a work item is (walker, split): with few walkers and a big draw set, `n_split` CTAs share one walker's draws
+    const int NS = out.n_split > 1 ? out.n_split : 1;
+    const long long item = s_next / NS;
+    const int split = (int)(s_next - item * NS);
     // the full-size launch of a banded call works through the queue the banded launch filled
     const long long n_items = out.queue_in ? (long long)*out.queue_count : n_walkers;
     if (item >= n_items) break;
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
         hlo = hlo_s;
         const bool fits = (long long)X * hstride <= out.hcap && (j_hi_all - jbase + 1) <= out.rcap && T <= out.hcap;
         if (!fits) {                                          // queue for the full-size launch
-            if (tid == 0) out.queue_out[atomicAdd(out.queue_count, 1ull)] = (int)w;
+            if (tid == 0 && split == 0) out.queue_out[atomicAdd(out.queue_count, 1ull)] = (int)w;
             continue;
         }
         for (int i = tid; i < (j_hi_all - jbase + 1) * RW; i += NT) rec[i] = recf[(size_t)jbase * RW + i];
@@ -394,7 +397,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
         bin_lo_all = 0;
         bin_hi_all = EB - 1;
         const int n_groups = (X + 31) >> 5;
-        for (long long base = (long long)warp * 128; base < m.n_draws; base += (long long)NW * 128) {
+        for (long long base = ((long long)split * NW + warp) * 128; base < m.n_draws; base += (long long)NS * NW * 128) {
             double ur[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -462,6 +465,29 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
         }
     }
     __syncthreads();
+
+    if (NS > 1) {
+        // partial histogram -> L2-resident scratch; the CTA that arrives last adds the NS partials in split order
+        // (fixed order: the sum does not depend on which CTA finishes last) and carries on alone
+        const int ncell = X * hstride;
+        double *part_out = out.split_scratch + ((size_t)w * NS + split) * (size_t)out.split_stride;
+        for (int i = tid; i < ncell; i += NT) part_out[i] = H[i];
+        __threadfence();
+        __syncthreads();
+        __shared__ int s_last;
+        if (tid == 0) s_last = (atomicAdd(out.split_tickets + w, 1u) == (unsigned)(NS - 1));
+        __syncthreads();
+        if (!s_last) continue;
+        __threadfence();
+        const double *base_in = out.split_scratch + (size_t)w * NS * (size_t)out.split_stride;
+        for (int i = tid; i < ncell; i += NT) {
+            double v = 0.0;
+            for (int k = 0; k < NS; ++k) v += __ldcg(base_in + (size_t)k * out.split_stride + i);
+            H[i] = v;
+        }
+        if (tid == 0) out.split_tickets[w] = 0u;           // ready for the next call
+        __syncthreads();
+    }
 
     // ---- phase 2: normalise (adv:143) ---------------------------------------------------------------------
     for (int i = tid; i < T; i += NT) tofc[i] = 0u;        // u0 is dead now

@@ -16,6 +16,11 @@ struct ModelOut {
     int *queue_out;                  // walkers that do not fit the banded layout ...
     unsigned long long *queue_count; // ... and how many
     const int *queue_in;             // full-size launch: process queue_in[0 .. *queue_count)
+    // few walkers x big draw sets: n_split CTAs share a walker; partial cell histograms meet in global scratch
+    int n_split;
+    int split_stride;                // doubles per partial histogram
+    double *split_scratch;           // [n][n_split][split_stride]
+    unsigned int *split_tickets;     // [n] arrival counters (zero between calls)
 };
 
 }  // namespace tof

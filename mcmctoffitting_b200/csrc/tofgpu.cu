@@ -27,7 +27,7 @@ struct tof_ctx {
     DevModel dm{};
     DevRun runs[TOF_MAX_RUNS]{};
     std::vector<void *> owned;  // device allocations freed in tof_destroy
-    DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial, d_work, d_queue;
+    DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial, d_work, d_queue, d_split, d_tickets;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false, timed = false;
@@ -142,6 +142,28 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
             const bool debug = out.spectra != nullptr || out.cells != nullptr;
             out.hcap = c.x_bins * c.e_bins;
             out.rcap = c.rng_n;
+            // few walkers and a big (streamed) draw set: several CTAs per walker
+            out.n_split = 1;
+            if (!debug && ctx->dm.n_draws >= RANGE_STREAM_MIN) {
+                const long long slots = (long long)ctx->stats.sm_count * (ctx->band_enabled ? std::max(ctx->band_ctas, 1) : 1);
+                const long long chunks = (ctx->dm.n_draws + 128LL * 16 - 1) / (128LL * 16);   // >= one 128-draw chunk per warp
+                long long S = std::min<long long>(std::min<long long>(slots / n, 16), chunks);
+                if (S > 1) {
+                    const size_t stride = (size_t)c.x_bins * c.e_bins;
+                    rc = ensure(ctx, ctx->d_split, (size_t)n * S * stride * sizeof(double));
+                    if (rc) return rc;
+                    if (ctx->d_tickets.bytes < (size_t)n * sizeof(unsigned int)) {
+                        rc = ensure(ctx, ctx->d_tickets, (size_t)n * sizeof(unsigned int));
+                        if (rc) return rc;
+                        CU(ctx, cudaMemsetAsync(ctx->d_tickets.p, 0, ctx->d_tickets.bytes, st));
+                    }
+                    out.n_split = (int)S;
+                    out.split_stride = (int)stride;
+                    out.split_scratch = static_cast<double *>(ctx->d_split.p);
+                    out.split_tickets = static_cast<unsigned int *>(ctx->d_tickets.p);
+                }
+            }
+            const long long n_work = n * out.n_split;
             if (ctx->band_enabled && !debug) {
                 rc = ensure(ctx, ctx->d_queue, (size_t)n * sizeof(int));
                 if (rc) return rc;
@@ -154,16 +176,16 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 ob.queue_count = cnt + 2;
                 AdvKernel kband = range_variant(512, c.rng_degree);
                 const long long slots_band = (long long)ctx->stats.sm_count * std::max(ctx->band_ctas, 1);
-                kband<<<(unsigned)std::min<long long>(n, slots_band), 512, ctx->band_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, ob);
+                kband<<<(unsigned)std::min<long long>(n_work, slots_band), 512, ctx->band_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, ob);
                 // 2) full-size launch over the queue (exits at once when it is empty)
                 out.work = cnt + 1;
                 out.queue_in = static_cast<const int *>(ctx->d_queue.p);
                 out.queue_count = cnt + 2;
-                kfull<<<(unsigned)std::min<long long>(n, slots_full), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
+                kfull<<<(unsigned)std::min<long long>(n_work, slots_full), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
                 ctx->stats.kernel_launches += 1;
             } else {
                 out.work = cnt + 1;
-                kfull<<<(unsigned)std::min<long long>(n, slots_full), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
+                kfull<<<(unsigned)std::min<long long>(n_work, slots_full), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
             }
         } else {
             AdvKernel k = adv_variant(ctx->adv_nt, ctx->adv_dpt, c.n_materials);
@@ -553,7 +575,7 @@ void tof_destroy(tof_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     for (void *p : ctx->owned) cudaFree(p);
-    for (DeviceBuf *b : {&ctx->d_theta, &ctx->d_out, &ctx->d_spectra, &ctx->d_cells, &ctx->d_counts, &ctx->d_partial, &ctx->d_work, &ctx->d_queue})
+    for (DeviceBuf *b : {&ctx->d_theta, &ctx->d_out, &ctx->d_spectra, &ctx->d_cells, &ctx->d_counts, &ctx->d_partial, &ctx->d_work, &ctx->d_queue, &ctx->d_split, &ctx->d_tickets})
         if (b->p) cudaFree(b->p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

@@ -661,14 +661,16 @@ def test_range_streaming_big_draw_sets(M, O):
     with M.TofModel(cfg) as m:
         m.set_observables(obs)
         m.set_draws(z)
-        got = m.lnprob_batch(thetas)
+        got = m.lnprob_batch(thetas)            # 4 walkers: several CTAs share each walker's draws (draw split)
         cc = m.cell_counts(thetas)
         again = m.lnprob_batch(thetas)
+        many = m.lnprob_batch(np.tile(thetas, (150, 1)))   # 600 walkers: one CTA per walker
     for k, th in enumerate(thetas):
         want_c = om.cell_counts(th, z, xs)
         assert int(np.count_nonzero(cc[k] != want_c)) == 0, k
         assert rel(float(got[k]), float(om.lnprob(th, obs, z, xs))) <= RTOL, (k, got[k])
         assert rel(float(got[k]), float(again[k])) <= 1e-11
+        assert all(rel(float(got[k]), float(v)) <= 1e-11 for v in many[k::4])
 
 
 def test_range_negative_spread_is_handled(M, O):

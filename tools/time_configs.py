@@ -66,3 +66,9 @@ if "onebd" in which:
     draws = [rs.standard_normal(cfg.n_draws) for _ in range(3)]
     extra = [rs.random_sample(4000) for _ in range(3)]
     run("oneBD", cfg, th, draws, extra, reps=2)
+if "few" in which:
+    # the reference's own run sizes: a few dozen walkers per half-step, 1e5 draws
+    cfg = M.config.adv(0, ode_mode=M.config.ODE_RANGE)
+    for n in (25, 50, 128):
+        th = np.column_stack([rs.uniform(1020, 1100, n), rs.uniform(0.08, 0.12, n)])
+        run("adv few n=%d" % n, cfg, th, rs.standard_normal(cfg.n_draws), reps=2)

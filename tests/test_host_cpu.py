@@ -160,3 +160,31 @@ def test_simult_signature_geometry_is_checked():
         fn(theta, obs, cfg.standoffs[::-1], cfg.tof_ranges, cfg.tof_bins)
     with pytest.raises(ValueError):
         fn(theta, obs, cfg.standoffs, cfg.tof_ranges, cfg.tof_bins, 12345)
+
+
+def test_energy_distribution_shapes_match_numpy_and_the_reference():
+    """a18: normal / lognormal-loss / skew-normal transforms on explicit draws."""
+    import os
+    from scipy.stats import lognorm, skewnorm as sp_skewnorm
+    from mcmctoffitting_b200 import shapes
+    n = 1000
+    z = np.random.RandomState(5).standard_normal(n)
+    assert np.array_equal(shapes.normal(1050.0, 0.1 * 1050.0, z), np.random.RandomState(5).normal(1050.0, 0.1 * 1050.0, n))
+    want = np.repeat(1878.4, n) - lognorm.rvs(s=0.5, loc=850.0, scale=170.0, size=n, random_state=np.random.RandomState(5))
+    assert np.array_equal(shapes.lognormal_loss(1878.4, 0.5, 850.0, 170.0, z), want)
+    # the legacy skew-normal: restated from utilities/pdfs.py, checked against the reference itself when it is present
+    rs = np.random.RandomState(9)
+    z0, z1 = rs.standard_normal(n), rs.standard_normal(n)
+    got = shapes.skewnorm_rvs(2.5, 900.0, 75.0, z0, z1)
+    x = np.linspace(600, 1300, 50)
+    np.testing.assert_allclose(shapes.skewnorm_pdf(x, 900.0, 2.5, 75.0), sp_skewnorm.pdf(x, 2.5, loc=900.0, scale=75.0), rtol=1e-12)
+    assert abs(np.mean(got) - sp_skewnorm.mean(2.5, loc=900.0, scale=75.0)) < 4 * 75.0 / np.sqrt(n)
+    from oracle import ref_loader
+    if ref_loader.available():
+        import sys
+        sys.path.insert(0, ref_loader.REFERENCE_ROOT)
+        import utilities.pdfs as ref_pdfs
+        np.random.seed(9)
+        assert np.array_equal(ref_pdfs.skewnorm().rvs(n, a=2.5, loc=900.0, scale=75.0), got)
+        np.testing.assert_allclose(ref_pdfs.skewnorm().pdf(x, loc=900.0, a=2.5, scale=75.0),
+                                   shapes.skewnorm_pdf(x, 900.0, 2.5, 75.0), rtol=1e-12)

@@ -10,6 +10,6 @@ from .config import ModelConfig
 from .model import TofModel
 from .lnprob import TofLnProb, BatchedPool, make_lnprob
 from ._lib import TofError
-from . import ppc, templates, shapes
+from . import ppc, templates, shapes, dataio
 
-__all__ = ["config", "ModelConfig", "TofModel", "TofLnProb", "BatchedPool", "make_lnprob", "TofError", "ppc", "templates", "shapes"]
+__all__ = ["config", "ModelConfig", "TofModel", "TofLnProb", "BatchedPool", "make_lnprob", "TofError", "ppc", "templates", "shapes", "dataio"]

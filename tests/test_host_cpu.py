@@ -188,3 +188,23 @@ def test_energy_distribution_shapes_match_numpy_and_the_reference():
         assert np.array_equal(ref_pdfs.skewnorm().rvs(n, a=2.5, loc=900.0, scale=75.0), got)
         np.testing.assert_allclose(ref_pdfs.skewnorm().pdf(x, loc=900.0, a=2.5, scale=75.0),
                                    shapes.skewnorm_pdf(x, 900.0, 2.5, 75.0), rtol=1e-12)
+
+
+def test_tof_data_file_round_trip(tmp_path):
+    """utilities.readMultiStandoffTOFdata format + the window selection of adv:219-224 / simultFit.py:528-532."""
+    from mcmctoffitting_b200 import dataio
+    edges = np.arange(100.0, 300.0, 1.0)
+    counts = np.random.RandomState(1).poisson(50, (len(edges), 5)).astype(float)
+    path = str(tmp_path / "multistandoff.dat")
+    dataio.write_multi_standoff_tof(path, edges, counts)
+    data = dataio.read_multi_standoff_tof(path, n_runs=5)
+    assert data.shape == (200, 6) and np.array_equal(data[:, 0], edges) and np.array_equal(data[:, 1:], counts)
+    cfg = C.simult()
+    obs = dataio.observables_for(cfg, data)
+    assert [len(o) for o in obs] == list(cfg.tof_bins)            # 1-ns bins: window width == bin count
+    assert np.array_equal(obs[0], counts[75:125, 0]) and np.array_equal(obs[3], counts[90:160, 3])
+    ref_mod = None
+    from oracle import ref_loader
+    if ref_loader.available():
+        ref_mod = ref_loader.load_utilities().utilities
+        assert np.array_equal(ref_mod.readMultiStandoffTOFdata(path, nRuns=5), data)

@@ -117,3 +117,20 @@ def test_sharded_sampler_over_gloo_matches_single_process():
     # acceptance counters are per-owner: summed over ranks they equal the single-process counters
     total = sum(r[3] for r in results)
     assert np.array_equal(total, ref.naccepted.numpy())
+
+
+def test_chain_file_is_readable_by_the_reference_reader(tmp_path):
+    """utilities.readChainFromFile (utilities.py:432-500) parses what write_chain_step writes."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    uu = ref_loader.load_utilities().utilities
+    k, dim, steps = 8, 9, 4
+    rs = np.random.RandomState(2)
+    path = str(tmp_path / "burninchain.dat")
+    for _ in range(steps):
+        write_chain_step(path, rs.standard_normal((k, dim)) * 1e3, rs.standard_normal(k) * 1e4)
+    chain_ref, probs_ref, n_params, n_walkers, n_steps = uu.readChainFromFile(path)
+    chain, probs, p2, w2, s2 = read_chain(path)
+    assert (n_params, n_walkers, n_steps) == (p2, w2, s2) == (dim, k, steps)
+    assert np.array_equal(chain_ref, chain) and np.array_equal(probs_ref, probs)

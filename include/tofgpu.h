@@ -112,7 +112,7 @@ typedef struct tof_config {
     int32_t t1_q;        /* T1 cells per octave of E = 2^t1_q, indexed by exponent/mantissa bits */
     int32_t t1_key_lo;   /* (high word of E) >> (20 - t1_q) of the first T1 cell */
     int32_t t1_n;        /* T1 cells */
-    int32_t rng_degree;  /* T2 polynomial degree (5 or 7) */
+    int32_t rng_degree;  /* T2 polynomial degree (7) */
     int32_t rng_n;       /* T2 intervals */
     int32_t rng_lut_n;   /* uniform lookup cells over [0, rng_u_max] */
     double rng_sign;     /* sign of dE/dx on the table domain */

@@ -102,10 +102,7 @@ AdvKernel range_variant(int nt, int degree) {
     if (nt == 1024 && degree == 7) return adv_range_kernel<1024, 7>;
     if (nt == 800 && degree == 7) return adv_range_kernel<800, 7>;
     if (nt == 640 && degree == 7) return adv_range_kernel<640, 7>;
-    if (nt == 800 && degree == 5) return adv_range_kernel<800, 5>;
     if (nt == 512 && degree == 7) return adv_range_kernel<512, 7>;
-    if (nt == 1024 && degree == 5) return adv_range_kernel<1024, 5>;
-    if (nt == 512 && degree == 5) return adv_range_kernel<512, 5>;
     return nullptr;
 }
 
@@ -407,7 +404,7 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
             ctx->err = "TOF_ODE_RANGE needs the range tables (t1_*, rng_*)";
             return bail(TOF_ERR_INVALID);
         }
-        if (cfg->rng_degree != 5 && cfg->rng_degree != 7) { ctx->err = "rng_degree must be 5 or 7"; return bail(TOF_ERR_INVALID); }
+        if (cfg->rng_degree != 7) { ctx->err = "rng_degree must be 7 (the built kernels evaluate degree-7 weight polynomials)"; return bail(TOF_ERR_INVALID); }
         if (cfg->ode_substeps < 1) { ctx->err = "ode_substeps must be >= 1"; return bail(TOF_ERR_INVALID); }
         // np.rint counts are accumulated as u32 per TOF bin: bound the total by nSamples/(dE*dx)
         {

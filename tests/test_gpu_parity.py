@@ -685,3 +685,24 @@ def test_range_negative_spread_is_handled(M, O):
     want = om.raw_tof([1050.0, -0.1], z, O.DDNXS(), density=False)
     assert np.array_equal(got, want)
     assert got.sum() > 0 and not np.array_equal(got, ref)
+
+
+def test_range_bins_split_by_cross_section_knots(M, O):
+    """20-keV E bins: several cross-section knots fall inside bins, so some bins are covered by two T2 intervals
+    (cells shared between lanes -> atomics) in both the banded and the full-size launch."""
+    kw = dict(e_bins=120, n_samples=2048, n_ev_per_loop=1024)
+    cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE, **kw)
+    om = O.sweep_model(eD_bins=120, n_samples=2048, n_ev_per_loop=1024, ode_scheme="exact")
+    z = np.random.RandomState(8).standard_normal(2048)
+    xs = O.DDNXS()
+    thetas = np.array([[1050, .10], [1500, .05], [1300, .40]])
+    with M.TofModel(cfg) as m:
+        m.set_observables(np.ones(2048))
+        m.set_draws(z)
+        cc = m.cell_counts(thetas)
+        lp = m.lnprob_batch(thetas)
+        counts = m.model_batch(thetas, stage="counts")
+    for k, th in enumerate(thetas):
+        assert np.array_equal(cc[k], om.cell_counts(th, z, xs)), k
+        assert np.array_equal(counts[k], om.raw_tof(th, z, xs, density=False)), k
+        assert rel(float(lp[k]), float(om.lnprob(th, np.ones(2048), z, xs))) <= RTOL

@@ -197,7 +197,7 @@ int tof_stretch_accept(tof_ctx *ctx, double *d_s, double *d_lnprob, int64_t n, i
 typedef struct tof_stats {
     int64_t kernel_launches; /* kernels launched by this context since creation */
     int64_t evaluations;     /* walker lnprob evaluations issued */
-    int64_t nan_results;     /* NaN lnprob values mapped to -inf (nan_to_neginf) -- updated by tof_lnprob_batch only */
+    int64_t nan_results;     /* reserved (always 0 in this version) */
     int32_t sm_count;
     int32_t smem_bytes;      /* dynamic shared memory of the main model kernel */
     int32_t threads;         /* threads per CTA of the main model kernel */

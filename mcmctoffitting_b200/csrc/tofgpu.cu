@@ -28,6 +28,8 @@ struct tof_ctx {
     DevRun runs[TOF_MAX_RUNS]{};
     std::vector<void *> owned;  // device allocations freed in tof_destroy
     DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial, d_work, d_queue, d_split, d_tickets;
+    // rebindable inputs: reused across tof_set_draws / tof_set_observables calls (no growth when draws are refreshed)
+    DeviceBuf d_z[TOF_MAX_RUNS][2], d_obs[TOF_MAX_RUNS], d_obs_idx[TOF_MAX_RUNS], d_obs_val[TOF_MAX_RUNS];
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false, timed = false;
@@ -67,6 +69,19 @@ int upload(tof_ctx *ctx, const T *host, size_t count, const T **dev) {
     ctx->owned.push_back(p);
     if (count) CU(ctx, cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
     *dev = static_cast<const T *>(p);
+    return TOF_OK;
+}
+
+int ensure(tof_ctx *ctx, DeviceBuf &b, size_t bytes);
+
+// Copy host data into a reusable device buffer (grown when needed); *dev receives the device pointer.
+template <typename T>
+int upload_into(tof_ctx *ctx, DeviceBuf &b, const T *host, size_t count, const T **dev) {
+    if (int rc = ensure(ctx, b, std::max<size_t>(count, 1) * sizeof(T))) return rc;
+    // make sure no kernel of this context still reads the previous contents
+    CU(ctx, cudaDeviceSynchronize());
+    if (count) CU(ctx, cudaMemcpy(b.p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = static_cast<const T *>(b.p);
     return TOF_OK;
 }
 
@@ -574,6 +589,9 @@ void tof_destroy(tof_ctx *ctx) {
     for (void *p : ctx->owned) cudaFree(p);
     for (DeviceBuf *b : {&ctx->d_theta, &ctx->d_out, &ctx->d_spectra, &ctx->d_cells, &ctx->d_counts, &ctx->d_partial, &ctx->d_work, &ctx->d_queue, &ctx->d_split, &ctx->d_tickets})
         if (b->p) cudaFree(b->p);
+    for (int r = 0; r < TOF_MAX_RUNS; ++r)
+        for (DeviceBuf *b : {&ctx->d_z[r][0], &ctx->d_z[r][1], &ctx->d_obs[r], &ctx->d_obs_idx[r], &ctx->d_obs_val[r]})
+            if (b->p) cudaFree(b->p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -597,9 +615,9 @@ int tof_set_observables(tof_ctx *ctx, int run, const double *counts, int nbins) 
             val.push_back(obs[t]);
         }
     DevRun &r = ctx->runs[run];
-    if (int rc = upload(ctx, obs.data(), obs.size(), &r.obs)) return rc;
-    if (int rc = upload(ctx, idx.data(), idx.size(), &r.obs_nz_idx)) return rc;
-    if (int rc = upload(ctx, val.data(), val.size(), &r.obs_nz_val)) return rc;
+    if (int rc = upload_into(ctx, ctx->d_obs[run], obs.data(), obs.size(), &r.obs)) return rc;
+    if (int rc = upload_into(ctx, ctx->d_obs_idx[run], idx.data(), idx.size(), &r.obs_nz_idx)) return rc;
+    if (int rc = upload_into(ctx, ctx->d_obs_val[run], val.data(), val.size(), &r.obs_nz_val)) return rc;
     r.n_obs_nz = (int)idx.size();
     ctx->have_obs[run] = true;
     return TOF_OK;
@@ -622,14 +640,14 @@ int tof_set_draws(tof_ctx *ctx, int run, int stream, const double *values, int64
         const long long per = ctx->cfg.n_ev_per_loop;
         for (long long l = 0; l < ctx->cfg.n_loops; ++l)
             std::sort(sorted.begin() + l * per, sorted.begin() + (l + 1) * per, [](double a, double b) { return a > b; });
-        if (int rc = upload(ctx, sorted.data(), (size_t)n, &d)) return rc;
+        if (int rc = upload_into(ctx, ctx->d_z[run][stream], sorted.data(), (size_t)n, &d)) return rc;
     } else if (stream == 0 && ctx->cfg.ode_mode == TOF_ODE_RANGE && ctx->cfg.model == TOF_MODEL_ADV) {
         // the model is a symmetric function of the draws; the range kernel walks them in ascending order
         std::vector<double> sorted(values, values + n);
         std::sort(sorted.begin(), sorted.end(), [](double a, double b) { return a < b || (b != b && a == a); });
-        if (int rc = upload(ctx, sorted.data(), (size_t)n, &d)) return rc;
+        if (int rc = upload_into(ctx, ctx->d_z[run][stream], sorted.data(), (size_t)n, &d)) return rc;
     } else {
-        if (int rc = upload(ctx, values, (size_t)n, &d)) return rc;
+        if (int rc = upload_into(ctx, ctx->d_z[run][stream], values, (size_t)n, &d)) return rc;
     }
     DevRun &r = ctx->runs[run];
     if (stream == 0) { r.z = d; r.n_z = n; } else { r.z1 = d; r.n_z1 = n; }

@@ -706,3 +706,29 @@ def test_range_bins_split_by_cross_section_knots(M, O):
         assert np.array_equal(cc[k], om.cell_counts(th, z, xs)), k
         assert np.array_equal(counts[k], om.raw_tof(th, z, xs, density=False)), k
         assert rel(float(lp[k]), float(om.lnprob(th, np.ones(2048), z, xs))) <= RTOL
+
+
+def test_rebinding_draws_and_observables_reuses_device_memory(M, O):
+    """Refreshing the draws every step must not grow device memory."""
+    import torch
+    cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE)
+    om = O.sweep_model()
+    rs = np.random.RandomState(0)
+    th = np.array([[1050.0, 0.1], [1060.0, 0.11]])
+    with M.TofModel(cfg) as m:
+        m.set_observables(np.ones(2048))
+        m.set_draws(rs.standard_normal(1024))
+        m.lnprob_batch(th)
+        torch.cuda.synchronize()
+        free0 = torch.cuda.mem_get_info()[0]
+        last = None
+        for _ in range(200):
+            z = rs.standard_normal(1024)
+            m.set_draws(z)
+            m.set_observables(np.ones(2048) * 2)
+            last = (z, m.lnprob_batch(th))
+        torch.cuda.synchronize()
+        assert free0 - torch.cuda.mem_get_info()[0] < (8 << 20)
+    z, got = last
+    for k in range(2):
+        assert rel(float(got[k]), float(om.lnprob(th[k], np.ones(2048) * 2, z))) <= RTOL

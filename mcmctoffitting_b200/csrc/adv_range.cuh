@@ -25,13 +25,19 @@ constexpr int RANGE_STREAM_MIN = 8192;  // draws per walker from which the warp-
 constexpr int RANGE_SPLIT = 6;      // long runs: pieces per warp when a tile has few (row, interval) tasks
 constexpr int SIMULT_ULUT = 256;   // same for the 10-row simultaneous fit (fewer lookups per tile)
 
+// bytes of the per-tile lookup region; after phase 1 it holds the reciprocal deuteron speeds ([E] doubles)
+__host__ __device__ inline size_t range_ulut_bytes(int E) {
+    const size_t a = (size_t)RANGE_ULUT * 2, b = (size_t)E * 8;
+    return ((a > b ? a : b) + 15) / 16 * 16;
+}
+
 // hcap: cells of the (possibly banded) histogram; rcap: staged T2 records
 __host__ __device__ inline size_t range_smem_bytes(int X, int E, int T, int hcap, int rcap, int P, int n_taps, int lut_n,
                                                    int rng_n) {
     size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
     region_a = (region_a + 15) / 16 * 16;
     size_t d = (size_t)hcap + (size_t)rcap * (P + 3) + E + n_taps + 40 + X /* per-row offsets */;
-    return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16 + RANGE_ULUT * 2 + (((size_t)X * 8 + 15) / 16) * 16 +
+    return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16 + range_ulut_bytes(E) + (((size_t)X * 8 + 15) / 16) * 16 +
            (size_t)rng_n * 8 + (((size_t)rng_n * 2 + 15) / 16) * 16 + 16;
 }
 
@@ -76,6 +82,61 @@ __device__ __forceinline__ double t1_eval(double E0, const DevModel &m) {
     return acc;
 }
 
+// Four consecutive samples of one (row, interval) run: acc += dt*q(dt) with dt = u0[d] + off and
+// q = a1 + a2 dt + ... + aP dt^(P-1) (the a0 term is added once per run as n*a0).  Sample k counts only if k < r.
+// Written in PTX so that the tile pointer stays a 32-bit shared address in a register and the accumulate is a
+// predicated DFMA: 1 LDS + 1 DADD + P DFMA per sample.
+template <int P>
+__device__ __forceinline__ void poly_trip4(double &acc, unsigned addr, int r, double off, const double (&a)[P + 1]) {
+    static_assert(P == 7, "poly_trip4 is written for degree-7 records");
+    asm("{\n\t"
+        ".reg .pred p0, p1, p2, p3;\n\t"
+        ".reg .f64 t0, t1, t2, t3, q0, q1, q2, q3;\n\t"
+        "ld.shared.f64 t0, [%1];\n\t"
+        "ld.shared.f64 t1, [%1+8];\n\t"
+        "ld.shared.f64 t2, [%1+16];\n\t"
+        "ld.shared.f64 t3, [%1+24];\n\t"
+        "setp.gt.s32 p0, %2, 0;\n\t"
+        "setp.gt.s32 p1, %2, 1;\n\t"
+        "setp.gt.s32 p2, %2, 2;\n\t"
+        "setp.gt.s32 p3, %2, 3;\n\t"
+        "add.rn.f64 t0, t0, %3;\n\t"
+        "add.rn.f64 t1, t1, %3;\n\t"
+        "add.rn.f64 t2, t2, %3;\n\t"
+        "add.rn.f64 t3, t3, %3;\n\t"
+        "fma.rn.f64 q0, %10, t0, %9;\n\t"
+        "fma.rn.f64 q1, %10, t1, %9;\n\t"
+        "fma.rn.f64 q2, %10, t2, %9;\n\t"
+        "fma.rn.f64 q3, %10, t3, %9;\n\t"
+        "fma.rn.f64 q0, q0, t0, %8;\n\t"
+        "fma.rn.f64 q1, q1, t1, %8;\n\t"
+        "fma.rn.f64 q2, q2, t2, %8;\n\t"
+        "fma.rn.f64 q3, q3, t3, %8;\n\t"
+        "fma.rn.f64 q0, q0, t0, %7;\n\t"
+        "fma.rn.f64 q1, q1, t1, %7;\n\t"
+        "fma.rn.f64 q2, q2, t2, %7;\n\t"
+        "fma.rn.f64 q3, q3, t3, %7;\n\t"
+        "fma.rn.f64 q0, q0, t0, %6;\n\t"
+        "fma.rn.f64 q1, q1, t1, %6;\n\t"
+        "fma.rn.f64 q2, q2, t2, %6;\n\t"
+        "fma.rn.f64 q3, q3, t3, %6;\n\t"
+        "fma.rn.f64 q0, q0, t0, %5;\n\t"
+        "fma.rn.f64 q1, q1, t1, %5;\n\t"
+        "fma.rn.f64 q2, q2, t2, %5;\n\t"
+        "fma.rn.f64 q3, q3, t3, %5;\n\t"
+        "fma.rn.f64 q0, q0, t0, %4;\n\t"
+        "fma.rn.f64 q1, q1, t1, %4;\n\t"
+        "fma.rn.f64 q2, q2, t2, %4;\n\t"
+        "fma.rn.f64 q3, q3, t3, %4;\n\t"
+        "@p0 fma.rn.f64 %0, q0, t0, %0;\n\t"
+        "@p1 fma.rn.f64 %0, q1, t1, %0;\n\t"
+        "@p2 fma.rn.f64 %0, q2, t2, %0;\n\t"
+        "@p3 fma.rn.f64 %0, q3, t3, %0;\n\t"
+        "}"
+        : "+d"(acc)
+        : "r"(addr), "r"(r), "d"(off), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]));
+}
+
 // Phase 1 for one tile of sorted u0 values (shared memory): add the cross-section weights of every (draw, row)
 // sample to the (x,E) histogram H.  Called by all threads of the CTA (contains barriers).
 template <int NT, int P>
@@ -110,7 +171,11 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
     }
     if (v_hi <= v_lo) return;                        // uniform: no usable draw in this tile
     const double tu_min = u0[v_lo], tu_max = u0[v_hi - 1];
-    const double tu_inv = (tu_max > tu_min) ? (double)n_ulut / (tu_max - tu_min) : 0.0;
+    // The draw-range searches start from a lookup cell taken a hair low (tu_bias cells) so that only a forward walk is
+    // needed; that is sound while tu_bias * cell width (>= 1.5e-11 cm) dwarfs the rounding of v (< 1e-12 cm for
+    // u < 1000 cm).  Narrower tiles (degenerate spread) are walked from their first draw.
+    constexpr double tu_bias = 1.0 / 65536.0;
+    const double tu_inv = (tu_max - tu_min > 1e-6 * (double)n_ulut) ? (double)n_ulut / (tu_max - tu_min) : 0.0;
     // per-tile lookup: ulut[c] = first draw with u0 >= tu_min + c*cell
     for (int c = tid; c < n_ulut; c += NT) {
         const double x = tu_min + (double)c * ((tu_max - tu_min) / (double)n_ulut);
@@ -162,14 +227,16 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
     const int nA = n_iv * Gf, nB = R ? (n_iv + per_b - 1) / per_b : 0;
     // One (row, interval) cell for this lane; with nch > 1 the lane takes piece `piece` of the run and the pieces
     // are combined with atomics (long runs: tiles of a big draw set cover few intervals).
+    // `right` of the last (closed) interval: v > u_max  <=>  v >= nextafter(u_max)
+    const double umax_next = __longlong_as_double(__double_as_longlong(umax) + 1);
+    const unsigned u0_s32 = (unsigned)__cvta_generic_to_shared(u0);
     auto do_cell = [&](int row, int j, bool active, int piece, int nch) {
         active = active && j >= band_lo && j <= band_hi;
         j = j < band_lo ? band_lo : (j > band_hi ? band_hi : j);
         const double2 *rj = reinterpret_cast<const double2 *>(rec + (j - jbase) * RW);
         const double2 hd = rj[0];
         const double left = j ? rec[(j - 1 - jbase) * RW] : 0.0;
-        const bool last = (j == M - 1);
-        const double right = last ? umax : hd.x;
+        const double right = (j == M - 1) ? umax_next : hd.x;
         const int bin = __double2loint(hd.y);
         double a[P + 1];
 #pragma unroll
@@ -178,39 +245,42 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
             a[k] = c2.x;
             a[k + 1] = c2.y;
         }
-        if (!active) return;
-        const double delta = sdelta[row];
-        // first draw with v >= left
-        int c = (int)((left - delta - tu_min) * tu_inv);
-        c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
-        int lb = ulut[c];
-        while (lb > v_lo && __dadd_rn(u0[lb - 1], delta) >= left) --lb;
-        while (lb < v_hi && !(__dadd_rn(u0[lb], delta) >= left)) ++lb;
-        // first draw beyond the interval: v >= right (v > u_max for the last interval, which is closed)
-        c = (int)((right - delta - tu_min) * tu_inv);
-        c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
-        int ub = ulut[c];
-        if (last) {
-            while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) > right) --ub;
-            while (ub < v_hi && !(__dadd_rn(u0[ub], delta) > right)) ++ub;
-        } else {
-            while (ub > v_lo && __dadd_rn(u0[ub - 1], delta) >= right) --ub;
+        int lb = 0, n = 0;
+        double off = 0.0;
+        if (active) {
+            const double delta = sdelta[row];
+            off = delta - left;
+            // first draw with v >= left.  The lookup cell is taken a hair low (tu_bias cells), so the cell's first
+            // draw can only be at or before the answer: one forward walk, no backward fix-up.
+            int c = (int)fma(left - delta - tu_min, tu_inv, -tu_bias);
+            c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
+            lb = ulut[c];
+            while (lb < v_hi && !(__dadd_rn(u0[lb], delta) >= left)) ++lb;
+            // first draw beyond the interval: v >= right
+            c = (int)fma(right - delta - tu_min, tu_inv, -tu_bias);
+            c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
+            int ub = ulut[c];
+            ub = ub < lb ? lb : ub;
             while (ub < v_hi && !(__dadd_rn(u0[ub], delta) >= right)) ++ub;
+            if (nch > 1) {
+                const int len = (ub - lb + nch - 1) / nch;
+                lb += piece * len;
+                ub = (lb + len < ub) ? lb + len : ub;
+            }
+            n = ub > lb ? ub - lb : 0;
         }
-        if (nch > 1) {
-            const int len = (ub - lb + nch - 1) / nch;
-            lb += piece * len;
-            ub = (lb + len < ub) ? lb + len : ub;
-        }
-        if (ub <= lb) return;
+        // sum_d poly(dt_d) = n*a0 + sum_d dt_d*q(dt_d): all lanes run to the longest run of the warp, four samples
+        // per trip, lanes past their own run predicated off (no divergent loop, no remainder loops).  A finished lane
+        // reads u0[0..3] instead (always inside the tile buffer) and discards the result.
+        const int nmax = __reduce_max_sync(FULL, n);
+        const unsigned p32 = u0_s32 + (unsigned)lb * 8u;
         double acc = 0.0;
-        for (int d = lb; d < ub; ++d) {
-            const double dt = __dadd_rn(u0[d], delta) - left;
-            double wgt = a[P];
-#pragma unroll
-            for (int k = P - 1; k >= 0; --k) wgt = fma(wgt, dt, a[k]);
-            acc += wgt;
+        for (int i = 0; i < nmax; i += 4) {
+            const int r = n - i;
+            poly_trip4<P>(acc, r > 0 ? p32 + (unsigned)i * 8u : u0_s32, r, off, a);
         }
+        if (n == 0) return;
+        acc = fma((double)n, a[0], acc);
         const int col = bin - (hlo ? hlo[row] : 0);
         if ((unsigned)col >= (unsigned)hstride) return;       // cannot happen: the band has an interval of slack
         double *cell = H + (size_t)row * hstride + col;
@@ -264,7 +334,13 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
 template <int NT, int P>
 __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(const DevModel m, const DevRun run, const double *__restrict__ theta,
                                                        long long n_walkers, ModelOut out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_sym[];
+    // The base of dynamic shared memory is made opaque (but still known to be shared): the compiler otherwise
+    // re-derives it from the symbol (S2UR CgaCtaId + 4 uniform ops) at every use inside the hot loops instead of
+    // keeping it in a register.
+    unsigned char *smem_raw = smem_sym;
+    asm volatile("" : "+l"(smem_raw));
+    __builtin_assume(__isShared(smem_raw));
     constexpr int RW = P + 3;
     const int T = run.tof_bins, X = m.x_bins, EB = m.e_bins, M = m.rng_n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -287,7 +363,8 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     double *sdelta = scratch + 40;                                      // [X] sgn*(x_i - x_start)
     unsigned short *lut = reinterpret_cast<unsigned short *>(sdelta + X);
     unsigned short *ulut = lut + ((m.rng_lut_n + 7) / 8) * 8;           // [RANGE_ULUT]
-    int *srow = reinterpret_cast<int *>(ulut + RANGE_ULUT);             // [X]
+    int *srow = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(ulut) + range_ulut_bytes(EB));   // [X]
+    double *rvd = reinterpret_cast<double *>(ulut);                      // [EB] 1/svd, aliases ulut (phases 2-3 only)
     int *hlo_s = srow + X;                                              // [X] first E-bin of each row (banded launch)
     double *sbrk = reinterpret_cast<double *>(hlo_s + X + (X & 1));     // [M] interval ends
     unsigned short *sbin = reinterpret_cast<unsigned short *>(sbrk + M);  // [M] E-bin of each interval
@@ -379,12 +456,8 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
         }
         for (int i = tid; i < (j_hi_all - jbase + 1) * RW; i += NT) rec[i] = recf[(size_t)jbase * RW + i];
     }
-    // ---- per walker: zero the cell histogram, deuteron speeds ------------------------------------------------
+    // ---- per walker: zero the cell histogram ------------------------------------------------------------------
     for (int i = tid; i < X * hstride; i += NT) H[i] = 0.0;
-    for (int j = tid; j < EB; j += NT) {
-        const double eff = __ddiv_rn(__dadd_rn(e0, m.e_centers[j]), 2.0);   // adv:151
-        svd[j] = speed_of(m.c, eff, m.m_d);
-    }
 
     // ---- phase 1: (x,E) histogram of cross-section weights through the range tables ---------------------
     int bin_lo_all = EB, bin_hi_all = -1;                  // E-bins any draw of any tile can have touched (uniform)
@@ -491,6 +564,12 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
 
     // ---- phase 2: normalise (adv:143) ---------------------------------------------------------------------
     for (int i = tid; i < T; i += NT) tofc[i] = 0u;        // u0 is dead now
+    for (int j = tid; j < EB; j += NT) {                   // deuteron speeds and their reciprocals (the lookup is dead too)
+        const double eff = __ddiv_rn(__dadd_rn(e0, m.e_centers[j]), 2.0);   // adv:151
+        const double v = speed_of(m.c, eff, m.m_d);
+        svd[j] = v;
+        rvd[j] = __ddiv_rn(1.0, v);
+    }
     const double de = (m.e_max - m.e_min) / (double)EB;
     const double dx = (m.x_max - m.x_min) / (double)X;
     // banded launch: every row holds `hstride` bins from hlo[row]; full-size launch: only bins bin_lo_all..bin_hi_all
@@ -507,6 +586,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     const double t_step = (run.tof_max - run.tof_min) / (double)T;
     const double t_scale = (double)T / (run.tof_max - run.tof_min);
     const double nsamp = (double)m.n_samples;
+    const double rS = __ddiv_rn(1.0, S);                    // IEEE quotients below come from this reciprocal (div_by_recip)
     if (out.cells) {                                        // debug output: every cell, zeros included
         for (int idx = tid; idx < X * EB; idx += NT) {
             const double cnt = rint(__dmul_rn(__ddiv_rn(H[idx], S), nsamp));
@@ -522,10 +602,10 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
             if (j >= EB) break;
             const double h = Hr[jb];
             if (h != 0.0 && S > 0.0) {
-                const double cnt = rint(__dmul_rn(__ddiv_rn(h, S), nsamp));
+                const double cnt = rint(__dmul_rn(div_by_recip(h, S, rS), nsamp));
                 if (cnt > 0.0) {
-                    const double tof_d = __ddiv_rn(xi, svd[j]);
-                    const double tof_n = __ddiv_rn(di, __ldg(m.neutron_speed + j));
+                    const double tof_d = div_by_recip(xi, svd[j], rvd[j]);
+                    const double tof_n = div_by_recip(di, __ldg(m.neutron_speed + j), __ldg(m.neutron_rspeed + j));
                     const int b = np_bin(__dadd_rn(tof_d, tof_n), T, run.tof_min, run.tof_max, t_step, t_scale);
                     if (b >= 0) atomicAdd(tofc + b, (unsigned int)cnt);
                 }

@@ -23,7 +23,7 @@ struct DevModel {
     double c, m_d, m_n, m_he3, q_ddn, cell_length, simple_neutron_base;
     double bethe_A[TOF_MAX_MATERIALS], bethe_B[TOF_MAX_MATERIALS];
     double prior_lo[TOF_MAX_DIM], prior_hi[TOF_MAX_DIM];
-    const double *x_centers, *e_centers, *neutron_speed, *xs_breaks, *xs_coefs, *taps, *zd_times, *zd_weights;
+    const double *x_centers, *e_centers, *neutron_speed, *neutron_rspeed /* 1/neutron_speed */, *xs_breaks, *xs_coefs, *taps, *zd_times, *zd_weights;
     const unsigned char *xs_lut;
     int xs_lut_n;
     double xs_lut_lo, xs_lut_inv;
@@ -140,6 +140,18 @@ __device__ __forceinline__ double bethe(double E, const double *A, const double 
 // ---- flight time: utilities.py:64-73 in the reference's operation order ----------------------------
 __device__ __forceinline__ double speed_of(double c, double energy, double mass) {
     return __dmul_rn(c, __dsqrt_rn(__ddiv_rn(__dmul_rn(2.0, energy), mass)));
+}
+
+// a / b correctly rounded (== __ddiv_rn(a, b)) given y = RN(1/b): product, then two Markstein corrections
+// (residual by FMA is exact once q is within an ulp; Markstein 1990).  Five FP64 instructions, no branch -- used where
+// many quotients share a divisor (cell / S, distance / speed_j).  b = 0 or non-finite gives NaN instead of inf; the
+// callers drop both (np_bin).
+__device__ __forceinline__ double div_by_recip(double a, double b, double y) {
+    double q = __dmul_rn(a, y);
+    double r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-b, q, a);
+    return __fma_rn(r, y, q);
 }
 
 // ---- Philox4x32-10 counter-based generator (Salmon et al. 2011) ------------------------------------

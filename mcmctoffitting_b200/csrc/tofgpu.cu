@@ -373,6 +373,11 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         TRY(upload(ctx, cfg->x_centers, cfg->x_bins, &m.x_centers));
         TRY(upload(ctx, cfg->e_centers, cfg->e_bins, &m.e_centers));
         TRY(upload(ctx, cfg->neutron_speed, cfg->e_bins, &m.neutron_speed));
+        {
+            std::vector<double> rs(cfg->e_bins);
+            for (int j = 0; j < cfg->e_bins; ++j) rs[j] = 1.0 / cfg->neutron_speed[j];   // correctly rounded (div_by_recip)
+            TRY(upload(ctx, rs.data(), cfg->e_bins, &m.neutron_rspeed));
+        }
         TRY(upload(ctx, cfg->xs_breaks, cfg->n_xs, &m.xs_breaks));
         TRY(upload(ctx, cfg->xs_coefs, (size_t)(cfg->n_xs - 1) * 4, &m.xs_coefs));
         TRY(upload(ctx, cfg->taps, cfg->n_taps, &m.taps));

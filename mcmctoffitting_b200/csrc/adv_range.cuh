@@ -22,6 +22,7 @@ namespace tof {
 constexpr int RANGE_TILE = 1024;   // draws staged in shared memory at a time
 constexpr int RANGE_ULUT = 1024;   // cells of the per-tile draw-index lookup table
 constexpr int RANGE_STREAM_MIN = 8192;  // draws per walker from which the warp-private streaming walk is used
+constexpr int RANGE_PAIR = 4;       // consecutive intervals per lane in a type-A task (fewer when tasks are scarce)
 constexpr int RANGE_SPLIT = 6;      // long runs: pieces per warp when a tile has few (row, interval) tasks
 constexpr int SIMULT_ULUT = 256;   // same for the 10-row simultaneous fit (fewer lookups per tile)
 
@@ -176,18 +177,18 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
     // u < 1000 cm).  Narrower tiles (degenerate spread) are walked from their first draw.
     constexpr double tu_bias = 1.0 / 65536.0;
     const double tu_inv = (tu_max - tu_min > 1e-6 * (double)n_ulut) ? (double)n_ulut / (tu_max - tu_min) : 0.0;
-    // per-tile lookup: ulut[c] = first draw with u0 >= tu_min + c*cell
-    for (int c = tid; c < n_ulut; c += NT) {
-        const double x = tu_min + (double)c * ((tu_max - tu_min) / (double)n_ulut);
-        int lo = v_lo, hi = v_hi;
-        for (int it = 0; it < nsteps; ++it) {
-            const int mid = (lo + hi) >> 1;
-            const bool ge = u0[mid < nt ? mid : nt - 1] >= x;
-            const bool go = lo < hi;
-            hi = (go && ge) ? mid : hi;
-            lo = (go && !ge) ? mid + 1 : lo;
+    // per-tile lookup: ulut[c] = first draw whose cell (uniform in u between the tile's extremes) is >= c.  The draws
+    // are sorted, so draw d owns the cells after its predecessor's up to its own: a scatter, no searches.  (A narrow
+    // tile, tu_inv == 0, only ever looks at cell 0.)
+    for (int d = v_lo + tid; d < v_hi; d += NT) {
+        int c1 = (int)((u0[d] - tu_min) * tu_inv);
+        c1 = c1 > n_ulut - 1 ? n_ulut - 1 : c1;
+        int c0 = -1;
+        if (d > v_lo) {
+            c0 = (int)((u0[d - 1] - tu_min) * tu_inv);
+            c0 = c0 > n_ulut - 1 ? n_ulut - 1 : c0;
         }
-        ulut[c] = (unsigned short)lo;
+        for (int c = c0 + 1; c <= c1; ++c) ulut[c] = (unsigned short)d;
     }
     // per-row interval of the tile's median draw: rows are processed along the trajectory (interval j = k + shift(row)),
     // so that the 32 lanes of a task look at the same slice of the draw distribution and have runs of similar length
@@ -230,62 +231,75 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
     // `right` of the last (closed) interval: v > u_max  <=>  v >= nextafter(u_max)
     const double umax_next = __longlong_as_double(__double_as_longlong(umax) + 1);
     const unsigned u0_s32 = (unsigned)__cvta_generic_to_shared(u0);
-    auto do_cell = [&](int row, int j, bool active, int piece, int nch) {
-        active = active && j >= band_lo && j <= band_hi;
-        j = j < band_lo ? band_lo : (j > band_hi ? band_hi : j);
-        const double2 *rj = reinterpret_cast<const double2 *>(rec + (j - jbase) * RW);
-        const double2 hd = rj[0];
-        const double left = j ? rec[(j - 1 - jbase) * RW] : 0.0;
-        const double right = (j == M - 1) ? umax_next : hd.x;
-        const int bin = __double2loint(hd.y);
-        double a[P + 1];
+    // `ncell` consecutive intervals j0, j0+1, .. of one row: the end of one run is the start of the next, so every
+    // further cell costs one search instead of two.
+    auto do_cell = [&](int row, int j0, bool row_ok, int piece, int nch, int ncell) {
+        const double delta = sdelta[row];
+        int carry = -1;                                  // first draw beyond the previous interval of this lane
+        for (int q = 0; q < ncell; ++q) {
+            int j = j0 + q;
+            const bool active = row_ok && j >= band_lo && j <= band_hi;
+            j = j < band_lo ? band_lo : (j > band_hi ? band_hi : j);
+            const double2 *rj = reinterpret_cast<const double2 *>(rec + (j - jbase) * RW);
+            const double2 hd = rj[0];
+            const double left = j ? rec[(j - 1 - jbase) * RW] : 0.0;
+            const double right = (j == M - 1) ? umax_next : hd.x;
+            const int bin = __double2loint(hd.y);
+            double a[P + 1];
 #pragma unroll
-        for (int k = 0; k <= P; k += 2) {
-            const double2 c2 = rj[1 + (k >> 1)];
-            a[k] = c2.x;
-            a[k + 1] = c2.y;
-        }
-        int lb = 0, n = 0;
-        double off = 0.0;
-        if (active) {
-            const double delta = sdelta[row];
-            off = delta - left;
-            // first draw with v >= left.  The lookup cell is taken a hair low (tu_bias cells), so the cell's first
-            // draw can only be at or before the answer: one forward walk, no backward fix-up.
-            int c = (int)fma(left - delta - tu_min, tu_inv, -tu_bias);
-            c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
-            lb = ulut[c];
-            while (lb < v_hi && !(__dadd_rn(u0[lb], delta) >= left)) ++lb;
-            // first draw beyond the interval: v >= right
-            c = (int)fma(right - delta - tu_min, tu_inv, -tu_bias);
-            c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
-            int ub = ulut[c];
-            ub = ub < lb ? lb : ub;
-            while (ub < v_hi && !(__dadd_rn(u0[ub], delta) >= right)) ++ub;
-            if (nch > 1) {
-                const int len = (ub - lb + nch - 1) / nch;
-                lb += piece * len;
-                ub = (lb + len < ub) ? lb + len : ub;
+            for (int k = 0; k <= P; k += 2) {
+                const double2 c2 = rj[1 + (k >> 1)];
+                a[k] = c2.x;
+                a[k + 1] = c2.y;
             }
-            n = ub > lb ? ub - lb : 0;
+            int lb = 0, n = 0;
+            double off = 0.0;
+            if (active) {
+                off = delta - left;
+                // first draw with v >= left.  The lookup cell is taken a hair low (tu_bias cells), so the cell's
+                // first draw can only be at or before the answer: one forward walk, no backward fix-up.
+                if (carry >= 0) {
+                    lb = carry;
+                } else {
+                    int c = (int)fma(left - delta - tu_min, tu_inv, -tu_bias);
+                    c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
+                    lb = ulut[c];
+                    while (lb < v_hi && !(__dadd_rn(u0[lb], delta) >= left)) ++lb;
+                }
+                // first draw beyond the interval: v >= right
+                int c = (int)fma(right - delta - tu_min, tu_inv, -tu_bias);
+                c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
+                int ub = ulut[c];
+                ub = ub < lb ? lb : ub;
+                while (ub < v_hi && !(__dadd_rn(u0[ub], delta) >= right)) ++ub;
+                carry = ub;
+                if (nch > 1) {
+                    const int len = (ub - lb + nch - 1) / nch;
+                    lb += piece * len;
+                    ub = (lb + len < ub) ? lb + len : ub;
+                }
+                n = ub > lb ? ub - lb : 0;
+            } else {
+                carry = -1;
+            }
+            // sum_d poly(dt_d) = n*a0 + sum_d dt_d*q(dt_d): all lanes run to the longest run of the warp, four
+            // samples per trip, lanes past their own run predicated off (no divergent loop, no remainder loops).
+            // A finished lane reads u0[0..3] instead (always inside the tile buffer) and discards the result.
+            const int nmax = __reduce_max_sync(FULL, n);
+            const unsigned p32 = u0_s32 + (unsigned)lb * 8u;
+            double acc = 0.0;
+            for (int i = 0; i < nmax; i += 4) {
+                const int r = n - i;
+                poly_trip4<P>(acc, r > 0 ? p32 + (unsigned)i * 8u : u0_s32, r, off, a);
+            }
+            if (n == 0) continue;
+            acc = fma((double)n, a[0], acc);
+            const int col = bin - (hlo ? hlo[row] : 0);
+            if ((unsigned)col >= (unsigned)hstride) continue;     // cannot happen: the band has an interval of slack
+            double *cell = H + (size_t)row * hstride + col;
+            if (nch > 1 || __double2hiint(hd.y) < 0) atomicAdd(cell, acc);   // shared cell: pieces / bin split over intervals
+            else *cell += acc;
         }
-        // sum_d poly(dt_d) = n*a0 + sum_d dt_d*q(dt_d): all lanes run to the longest run of the warp, four samples
-        // per trip, lanes past their own run predicated off (no divergent loop, no remainder loops).  A finished lane
-        // reads u0[0..3] instead (always inside the tile buffer) and discards the result.
-        const int nmax = __reduce_max_sync(FULL, n);
-        const unsigned p32 = u0_s32 + (unsigned)lb * 8u;
-        double acc = 0.0;
-        for (int i = 0; i < nmax; i += 4) {
-            const int r = n - i;
-            poly_trip4<P>(acc, r > 0 ? p32 + (unsigned)i * 8u : u0_s32, r, off, a);
-        }
-        if (n == 0) return;
-        acc = fma((double)n, a[0], acc);
-        const int col = bin - (hlo ? hlo[row] : 0);
-        if ((unsigned)col >= (unsigned)hstride) return;       // cannot happen: the band has an interval of slack
-        double *cell = H + (size_t)row * hstride + col;
-        if (nch > 1 || __double2hiint(hd.y) < 0) atomicAdd(cell, acc);   // shared cell: pieces / bin split over intervals
-        else *cell += acc;
     };
     const int GfD = Gf > 0 ? Gf : 1;
     const int n_tasks = nA + nB;
@@ -296,13 +310,18 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
         nch = nch > 64 ? 64 : nch;
     }
     if (nch == 1) {
-        // (jj, g) of type-A task `task` without a division in the loop
+        // type-A tasks take up to RANGE_PAIR consecutive intervals per lane (measured: 1 -> 2 +3 %, 2 -> 4 +1 %).  Static striding over the tasks (a shared work
+        // counter with heaviest-first order was measured slower); (jj, g) of a type-A task without a division in the
+        // loop
+        const int pair = nA >= 8 * NW ? RANGE_PAIR : (nA >= 4 * NW ? 2 : 1);
+        const int n_pr = (n_iv + pair - 1) / pair;
+        const int nA2 = n_pr * Gf;
         int a_jj = warp / GfD, a_g = warp - a_jj * GfD;
         const int step_j = NW / GfD, step_g = NW - step_j * GfD;
-        for (int task = warp; task < n_tasks; task += NW) {
-            if (task < nA) {
+        for (int task = warp; task < nA2 + nB; task += NW) {
+            if (task < nA2) {
                 const int row = (a_g << 5) + lane;
-                do_cell(row, k_lo + a_jj + (srow[row] - s_ref), true, 0, 1);
+                do_cell(row, k_lo + a_jj * pair + (srow[row] - s_ref), true, 0, 1, pair);
                 a_jj += step_j;
                 a_g += step_g;
                 if (a_g >= GfD) {
@@ -312,7 +331,7 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
             } else {
                 const int isub = lane / R;
                 const int row = (Gf << 5) + (lane - isub * R);
-                do_cell(row, k_lo + (task - nA) * per_b + isub + (srow[row] - s_ref), isub < per_b, 0, 1);
+                do_cell(row, k_lo + (task - nA2) * per_b + isub + (srow[row] - s_ref), isub < per_b, 0, 1, 1);
             }
         }
     } else {
@@ -321,11 +340,11 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
             if (task < nA) {
                 const int jj = task / GfD;
                 const int row = ((task - jj * GfD) << 5) + lane;
-                do_cell(row, k_lo + jj + (srow[row] - s_ref), true, piece, nch);
+                do_cell(row, k_lo + jj + (srow[row] - s_ref), true, piece, nch, 1);
             } else {
                 const int isub = lane / R;
                 const int row = (Gf << 5) + (lane - isub * R);
-                do_cell(row, k_lo + (task - nA) * per_b + isub + (srow[row] - s_ref), isub < per_b, piece, nch);
+                do_cell(row, k_lo + (task - nA) * per_b + isub + (srow[row] - s_ref), isub < per_b, piece, nch, 1);
             }
         }
     }

@@ -229,7 +229,10 @@ def run_gpu_arm(args):
 
     om, z, obs, thetas = workload(O)
     ode = {"rk4": M.config.ODE_RK4, "range": M.config.ODE_RANGE}[args.ode]
-    cfg = M.config.sweep(ode_mode=ode)
+    f32 = args.precision == "fp32"
+    if f32 and ode != M.config.ODE_RANGE:
+        raise SystemExit("--precision fp32 needs --ode range")
+    cfg = M.config.sweep(ode_mode=ode, precision=M.config.PRECISION_FP32 if f32 else M.config.PRECISION_FP64)
     flop_per_eval = FLOP_PER_EVAL_RANGE if ode == M.config.ODE_RANGE else FLOP_PER_EVAL_RK4
     fn = M.make_lnprob(cfg, obs, z, device=local_rank)
     model = fn.model
@@ -298,6 +301,38 @@ def run_gpu_arm(args):
 
     finite_frac = float(torch.isfinite(lp).double().mean().item())
 
+    # ---- optional FP32 sample stage, reported beside the FP64 headline (N = 1, range formulation) ----------
+    fp32_mode = None
+    if world == 1 and not f32 and ode == M.config.ODE_RANGE and not args.no_fp32:
+        fn32 = M.make_lnprob(M.config.sweep(ode_mode=ode, precision=M.config.PRECISION_FP32), obs, z, device=local_rank)
+        m32 = fn32.model
+        half_n = N_WALKERS // 2
+        th_dev = torch.from_numpy(thetas).to(device)
+        out32 = torch.empty(N_WALKERS, dtype=torch.float64, device=device)
+        out64 = torch.empty(N_WALKERS, dtype=torch.float64, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        for h in (0, 1):
+            model.lnprob_batch_device(th_dev[h * half_n:].data_ptr(), half_n, out64[h * half_n:].data_ptr(), stream)
+        m32.set_timing(True)
+        ms32 = []
+        for i in range(3 + max(1, min(args.steps, 5))):
+            flush.zero_()
+            for h in (0, 1):
+                m32.lnprob_batch_device(th_dev[h * half_n:].data_ptr(), half_n, out32[h * half_n:].data_ptr(), stream)
+                torch.cuda.synchronize()
+                if i >= 3:
+                    ms32.append(m32.last_kernel_ms())
+        both = torch.isfinite(out32) & torch.isfinite(out64)
+        dev32 = ((out32[both] - out64[both]).abs() / out64[both].abs())
+        fp32_mode = {
+            "value": half_n / (statistics.mean(ms32) * 1e-3), "unit": "evals/s", "kernel_ms": statistics.mean(ms32),
+            "what": "precision=PRECISION_FP32: phase-1 sample arithmetic in FP32, reductions and later stages in FP64; "
+                    "kernel time of one half-ensemble call (device-resident)",
+            "max_rel_dev_vs_fp64": float(dev32.max().item()), "tolerance": 1e-4,
+            "finiteness_agreement": float((torch.isfinite(out32) == torch.isfinite(out64)).double().mean().item()),
+        }
+        m32.close()
+
     if rank == 0:
         fp64_peak = model.measure_fp64_peak()
         peaks = {}
@@ -337,7 +372,8 @@ def run_gpu_arm(args):
         line = {
             "metric": "walker lnprob evals/sec (adv TOF model)", "value": value, "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 samples / f64 reductions" if f32 else "f64", "data": "synthetic",
             "config": {"workload": "adv TOF model sweep: %d walkers x %d TOF bins x %d MC draws" % (N_WALKERS, N_TOF_BINS, N_DRAWS),
                        "step": "one ensemble MCMC step = 2 red/blue half-steps = %d lnprob evaluations" % N_WALKERS,
                        "parallelism": "walkers sharded over %d rank(s); all_gather of the updated half per half-step" % world,
@@ -345,7 +381,7 @@ def run_gpu_arm(args):
                                else "rk4 x%d per x-interval" % cfg.ode_substeps), "threads_per_cta": model.stats()["threads"],
                        "l2": "flushed between timed steps (256 MiB memset outside the event bracket)",
                        "finite_lnprob_fraction": finite_frac},
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "fp32_mode": fp32_mode,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": N_WALKERS * 2 * 8,
                     "d2h_bytes_per_step": N_WALKERS * 8},
             "gpu_launches": launches_timed, "clocks": clock_info,
@@ -366,6 +402,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--ode", choices=["range", "rk4"], default="range", help="stopping-stage formulation of the CUDA path")
+    ap.add_argument("--precision", choices=["fp64", "fp32"], default="fp64",
+                    help="fp64 (default, the reference's arithmetic) or the optional FP32 sample stage as the measured arm")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the secondary FP32-mode measurement of the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

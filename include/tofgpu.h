@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TOF_ABI_VERSION 1
+#define TOF_ABI_VERSION 2
 
 #define TOF_MAX_DIM 16       /* parameters per walker (reference max: 9, simultFit.py:444-448) */
 #define TOF_MAX_RUNS 8       /* simultaneous standoff runs (reference max: 5, simultFit.py:127-131) */
@@ -47,6 +47,15 @@ typedef enum tof_ode_mode {
     TOF_ODE_RK4 = 0,   /* classical RK4, ode_substeps per x-interval (the oracle's scheme)      */
     TOF_ODE_RANGE = 1  /* range-energy table of the autonomous Bethe ODE staged in shared memory */
 } tof_ode_mode;
+
+/* arithmetic of the Monte-Carlo sample stage (BASELINE.json north_star: 1e-9 in FP64, 1e-4 in an optional FP32 mode) */
+typedef enum tof_precision {
+    TOF_PRECISION_FP64 = 0, /* everything in FP64: integer stages bit-exact, lnprob <= 1e-9 relative               */
+    TOF_PRECISION_FP32 = 1  /* adv/intermediate model with TOF_ODE_RANGE: per-sample arithmetic (energy-loss lookup
+                             * offsets, interval search, cross-section weight) in FP32, every reduction and every
+                             * stage after the (x,E) histogram in FP64; lnprob <= 1e-4 relative.  Draw sets of >= 8192
+                             * per walker are run by the FP64 kernels. */
+} tof_precision;
 
 /* spectrum stages returned by tof_model_batch */
 typedef enum tof_stage {
@@ -133,6 +142,7 @@ typedef struct tof_config {
     const double *stop_coefs;   /* [x_bins][stop_n-1][4] power basis, highest order first, about the left node */
     const double *attenuation;  /* [x_bins] exp(-x/20 cm) (initialization.py:35-40) */
     const double *taps2;        /* [n_taps2] np.convolve(pdf, taps2, 'full')[:T] (csi_oneBD.py:519) */
+    int32_t precision;          /* tof_precision; 0 = FP64 (the reference computes in FP64 throughout) */
 } tof_config;
 
 typedef struct tof_ctx tof_ctx;
@@ -205,6 +215,7 @@ typedef struct tof_stats {
     int32_t band_ctas_per_sm; /* range kernel, banded launch (512 threads): resident CTAs per SM; 0 = disabled */
     int32_t band_cells;       /* ... cell-histogram capacity of the banded launch */
     int64_t band_queued_last; /* ... walkers of the most recent call that needed the full-size launch */
+    int32_t fp32_active;      /* 1 when the FP32 sample stage is what the model kernel runs (see tof_precision) */
 } tof_stats;
 int tof_get_stats(const tof_ctx *ctx, tof_stats *out);
 

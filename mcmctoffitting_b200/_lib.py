@@ -8,7 +8,7 @@ import re
 from . import build as _build
 
 MAX_DIM, MAX_RUNS, MAX_MATERIALS = 16, 8, 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _dp = C.POINTER(C.c_double)
 
@@ -38,6 +38,7 @@ class TofConfig(C.Structure):
         ("rng_lut", C.POINTER(C.c_uint16)),
         ("stop_n", C.c_int32), ("n_taps2", C.c_int32), ("stop_lo", C.c_double), ("stop_step", C.c_double),
         ("beam_energy", C.c_double), ("stop_coefs", _dp), ("attenuation", _dp), ("taps2", _dp),
+        ("precision", C.c_int32),
     ]
 
 
@@ -45,7 +46,7 @@ class TofStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("evaluations", C.c_int64), ("nan_results", C.c_int64),
                 ("sm_count", C.c_int32), ("smem_bytes", C.c_int32), ("threads", C.c_int32),
                 ("ctas_per_sm", C.c_int32), ("band_ctas_per_sm", C.c_int32), ("band_cells", C.c_int32),
-                ("band_queued_last", C.c_int64)]
+                ("band_queued_last", C.c_int64), ("fp32_active", C.c_int32)]
 
 
 class TofError(RuntimeError):

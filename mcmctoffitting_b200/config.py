@@ -170,6 +170,7 @@ def zero_degree_tables(e_n: np.ndarray, n_segments: int = 10) -> Tuple[np.ndarra
 # ---- model configurations --------------------------------------------------------------------------
 KIND_SIMPLE, KIND_ADV, KIND_SIMULT, KIND_ONEBD = 1, 2, 3, 4
 ODE_RK4, ODE_RANGE = 0, 1
+PRECISION_FP64, PRECISION_FP32 = 0, 1     # tof_precision (include/tofgpu.h)
 
 
 @dataclass(frozen=True)
@@ -194,6 +195,7 @@ class ModelConfig:
     ode_mode: int = ODE_RK4
     ode_substeps: int = 1
     ode_from_zero: bool = False
+    precision: int = PRECISION_FP64   # PRECISION_FP32: optional single-precision sample stage (adv/intermediate + ODE_RANGE)
     zero_deg_half_length_in_path: bool = True   # adv adds zeroDegLength/2 (adv:154), simultFit does not (290-291)
     n_zero_deg: int = 0
     nan_to_neginf: bool = False
@@ -292,6 +294,10 @@ class ModelConfig:
                 raise ValueError("standoffs / tof_ranges / tof_bins must have one entry per run")
         if len(self.prior) != self.ndim:
             raise ValueError("prior needs one (lo, hi) pair per parameter")
+        if self.precision not in (PRECISION_FP64, PRECISION_FP32):
+            raise ValueError("precision must be PRECISION_FP64 or PRECISION_FP32")
+        if self.precision == PRECISION_FP32 and not (self.kind == KIND_ADV and self.ode_mode == ODE_RANGE):
+            raise ValueError("PRECISION_FP32 is built for the adv/intermediate model with ode_mode=ODE_RANGE only")
 
 
 def simple(n_draws: int = 1000000) -> ModelConfig:

@@ -1,5 +1,7 @@
 // adv / intermediate model, range-table formulation (TOF_ODE_RANGE).
 #pragma once
+#include <type_traits>
+
 #include "tof_common.cuh"
 #include "adv_rk4.cuh"
 
@@ -24,6 +26,8 @@ constexpr int RANGE_ULUT = 1024;   // cells of the per-tile draw-index lookup ta
 constexpr int RANGE_STREAM_MIN = 8192;  // draws per walker from which the warp-private streaming walk is used
 constexpr int RANGE_PAIR = 4;       // consecutive intervals per lane in a type-A task (fewer when tasks are scarce)
 constexpr int RANGE_SPLIT = 6;      // long runs: pieces per warp when a tile has few (row, interval) tasks
+constexpr int RANGE_PF = 3;         // FP32 mode: degree of the per-interval weight polynomial (float records)
+constexpr int RANGE_RWF = 8;        // FP32 mode: floats per record = c0..c3, E-bin, shared-cell flag, c0 as a double
 constexpr int SIMULT_ULUT = 256;   // same for the 10-row simultaneous fit (fewer lookups per tile)
 
 // bytes of the per-tile lookup region; after phase 1 it holds the reciprocal deuteron speeds ([E] doubles)
@@ -32,12 +36,18 @@ __host__ __device__ inline size_t range_ulut_bytes(int E) {
     return ((a > b ? a : b) + 15) / 16 * 16;
 }
 
+// doubles reserved for the staged T2 records: FP64 records, or (FP32 mode) float records followed by the float tile
+__host__ __device__ inline size_t range_rec_doubles(int rcap, int P) {
+    const size_t a = (size_t)rcap * (P + 3), b = (size_t)rcap * (RANGE_RWF / 2) + RANGE_TILE / 2;
+    return a > b ? a : b;
+}
+
 // hcap: cells of the (possibly banded) histogram; rcap: staged T2 records
 __host__ __device__ inline size_t range_smem_bytes(int X, int E, int T, int hcap, int rcap, int P, int n_taps, int lut_n,
                                                    int rng_n) {
     size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
     region_a = (region_a + 15) / 16 * 16;
-    size_t d = (size_t)hcap + (size_t)rcap * (P + 3) + E + n_taps + 40 + X /* per-row offsets */;
+    size_t d = (size_t)hcap + range_rec_doubles(rcap, P) + E + n_taps + 40 + X /* per-row offsets */;
     return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16 + range_ulut_bytes(E) + (((size_t)X * 8 + 15) / 16) * 16 +
            (size_t)rng_n * 8 + (((size_t)rng_n * 2 + 15) / 16) * 16 + 16;
 }
@@ -138,9 +148,52 @@ __device__ __forceinline__ void poly_trip4(double &acc, unsigned addr, int r, do
         : "r"(addr), "r"(r), "d"(off), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]));
 }
 
+// ================================================================================================
+// FP32 mode (tof_config.precision = TOF_PRECISION_FP32): the per-sample arithmetic of phase 1 in single precision
+// ================================================================================================
+// Which draws fall into which (row, interval) cell is decided exactly as in FP64 mode (same searches on the FP64
+// tile), so the two modes bin every sample identically.  The cross-section weight of a sample is evaluated in single
+// precision: a second copy of the tile holds u0 - center as floats (center = u of the walker's mean energy: a few cm
+// at most), dt = u0f - (float)(left - delta - center), and a degree-3 polynomial from float records fitted to the
+// degree-7 ones at tof_create (fit + rounding <= 1e-7 relative).  A cell's sum is n*c0 in FP64 plus the float sum of
+// the dt-dependent part; everything after phase 1 (normalisation, np.rint, flight times, density, timing response,
+// likelihood) is the FP64 code.  Contract: 1e-4 relative on lnprob (BASELINE.json north_star).
+__device__ __forceinline__ void poly_trip4_f32(float &acc, unsigned addr, int r, float thr, float c1, float c2, float c3) {
+    asm("{\n\t"
+        ".reg .pred p0, p1, p2, p3;\n\t"
+        ".reg .f32 t0, t1, t2, t3, q0, q1, q2, q3;\n\t"
+        "ld.shared.f32 t0, [%1];\n\t"
+        "ld.shared.f32 t1, [%1+4];\n\t"
+        "ld.shared.f32 t2, [%1+8];\n\t"
+        "ld.shared.f32 t3, [%1+12];\n\t"
+        "setp.gt.s32 p0, %2, 0;\n\t"
+        "setp.gt.s32 p1, %2, 1;\n\t"
+        "setp.gt.s32 p2, %2, 2;\n\t"
+        "setp.gt.s32 p3, %2, 3;\n\t"
+        "sub.rn.f32 t0, t0, %3;\n\t"
+        "sub.rn.f32 t1, t1, %3;\n\t"
+        "sub.rn.f32 t2, t2, %3;\n\t"
+        "sub.rn.f32 t3, t3, %3;\n\t"
+        "fma.rn.f32 q0, %6, t0, %5;\n\t"
+        "fma.rn.f32 q1, %6, t1, %5;\n\t"
+        "fma.rn.f32 q2, %6, t2, %5;\n\t"
+        "fma.rn.f32 q3, %6, t3, %5;\n\t"
+        "fma.rn.f32 q0, q0, t0, %4;\n\t"
+        "fma.rn.f32 q1, q1, t1, %4;\n\t"
+        "fma.rn.f32 q2, q2, t2, %4;\n\t"
+        "fma.rn.f32 q3, q3, t3, %4;\n\t"
+        "@p0 fma.rn.f32 %0, q0, t0, %0;\n\t"
+        "@p1 fma.rn.f32 %0, q1, t1, %0;\n\t"
+        "@p2 fma.rn.f32 %0, q2, t2, %0;\n\t"
+        "@p3 fma.rn.f32 %0, q3, t3, %0;\n\t"
+        "}"
+        : "+f"(acc)
+        : "r"(addr), "r"(r), "f"(thr), "f"(c1), "f"(c2), "f"(c3));
+}
+
 // Phase 1 for one tile of sorted u0 values (shared memory): add the cross-section weights of every (draw, row)
 // sample to the (x,E) histogram H.  Called by all threads of the CTA (contains barriers).
-template <int NT, int P>
+template <int NT, int P, bool F32 = false>
 // `brk`: the ends of all T2 intervals (shared memory) for interval searches; `rec`: the shared-memory copy of records
 // jbase.. used by the tasks; H has `hstride` bins per row; row i starts at E-bin hlo[i] (banded layout; hlo == nullptr:
 // every row starts at bin 0).
@@ -148,8 +201,10 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
                                                       const unsigned short *lut, unsigned short *ulut, int n_ulut,
                                                       const double *sdelta, int *srow, double *H, int hstride, const int *hlo,
                                                       int X, int M, double umax, double lut_inv, int lut_n, int &bin_lo_all,
-                                                      int &bin_hi_all) {
+                                                      int &bin_hi_all, const float *u0f = nullptr, double center = 0.0) {
+    // F32: `rec` points at float records (RANGE_RWF floats each), `u0f` is the float tile (u0 - center)
     constexpr int RW = P + 3;
+    const float *recf = reinterpret_cast<const float *>(rec);
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nsteps = 32 - __clz(nt);                 // binary-search iterations for [0, nt]
@@ -212,8 +267,13 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
     if (!(vmax >= 0.0) || vmin > umax) return;         // uniform
     const int band_lo = range_interval(vmin > 0.0 ? vmin : 0.0, brk, lut, lut_inv, lut_n, M);
     const int band_hi = range_interval(vmax < umax ? vmax : umax, brk, lut, lut_inv, lut_n, M);
-    bin_lo_all = min(bin_lo_all, __double2loint(rec[(band_lo - jbase) * RW + 1]));
-    bin_hi_all = max(bin_hi_all, __double2loint(rec[(band_hi - jbase) * RW + 1]));
+    if (F32) {
+        bin_lo_all = min(bin_lo_all, __float_as_int(recf[(band_lo - jbase) * RANGE_RWF + 4]));
+        bin_hi_all = max(bin_hi_all, __float_as_int(recf[(band_hi - jbase) * RANGE_RWF + 4]));
+    } else {
+        bin_lo_all = min(bin_lo_all, __double2loint(rec[(band_lo - jbase) * RW + 1]));
+        bin_hi_all = max(bin_hi_all, __double2loint(rec[(band_hi - jbase) * RW + 1]));
+    }
     // One task = 32 (row, interval) cells.  Type A: one T2 interval x 32 consecutive rows (lane = row; all
     // lanes use the same polynomial).  Type B, for the X % 32 leftover rows: R rows x (32/R) consecutive
     // intervals.  A lane's draws are the contiguous range [lb, ub) found through the per-tile lookup.
@@ -231,26 +291,47 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
     // `right` of the last (closed) interval: v > u_max  <=>  v >= nextafter(u_max)
     const double umax_next = __longlong_as_double(__double_as_longlong(umax) + 1);
     const unsigned u0_s32 = (unsigned)__cvta_generic_to_shared(u0);
+    const unsigned u0f_s32 = F32 ? (unsigned)__cvta_generic_to_shared(u0f) : 0u;
     // `ncell` consecutive intervals j0, j0+1, .. of one row: the end of one run is the start of the next, so every
     // further cell costs one search instead of two.
-    auto do_cell = [&](int row, int j0, bool row_ok, int piece, int nch, int ncell) {
+    auto do_cell = [&](int row, int j0, bool row_ok, int piece, int nch, auto ncell_c) {
+        constexpr int ncell = decltype(ncell_c)::value;
         const double delta = sdelta[row];
         int carry = -1;                                  // first draw beyond the previous interval of this lane
         for (int q = 0; q < ncell; ++q) {
             int j = j0 + q;
             const bool active = row_ok && j >= band_lo && j <= band_hi;
             j = j < band_lo ? band_lo : (j > band_hi ? band_hi : j);
-            const double2 *rj = reinterpret_cast<const double2 *>(rec + (j - jbase) * RW);
-            const double2 hd = rj[0];
-            const double left = j ? rec[(j - 1 - jbase) * RW] : 0.0;
-            const double right = (j == M - 1) ? umax_next : hd.x;
-            const int bin = __double2loint(hd.y);
-            double a[P + 1];
+            double left, right;
+            int bin;
+            bool shared_cell;
+            double a[F32 ? 1 : P + 1];                     // FP64: a0..aP; FP32: a0 only (FP64 copy in the float record)
+            float cf1 = 0.0f, cf2 = 0.0f, cf3 = 0.0f;
+            if (F32) {
+                const float *rj = recf + (j - jbase) * RANGE_RWF;
+                const float4 c4 = *reinterpret_cast<const float4 *>(rj);
+                const int2 hb = *reinterpret_cast<const int2 *>(rj + 4);
+                left = j ? brk[j - 1] : 0.0;              // brk[j] = break that ends interval j (+inf for the last)
+                right = (j == M - 1) ? umax_next : brk[j];
+                a[0] = *reinterpret_cast<const double *>(rj + 6);
+                cf1 = c4.y;
+                cf2 = c4.z;
+                cf3 = c4.w;
+                bin = hb.x;
+                shared_cell = hb.y != 0;
+            } else {
+                const double2 *rj = reinterpret_cast<const double2 *>(rec + (j - jbase) * RW);
+                const double2 hd = rj[0];
+                left = j ? rec[(j - 1 - jbase) * RW] : 0.0;
+                right = (j == M - 1) ? umax_next : hd.x;
+                bin = __double2loint(hd.y);
+                shared_cell = __double2hiint(hd.y) < 0;
 #pragma unroll
-            for (int k = 0; k <= P; k += 2) {
-                const double2 c2 = rj[1 + (k >> 1)];
-                a[k] = c2.x;
-                a[k + 1] = c2.y;
+                for (int k = 0; k <= P; k += 2) {
+                    const double2 c2 = rj[1 + (k >> 1)];
+                    a[k] = c2.x;
+                    a[F32 ? 0 : k + 1] = c2.y;
+                }
             }
             int lb = 0, n = 0;
             double off = 0.0;
@@ -286,23 +367,36 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
             // samples per trip, lanes past their own run predicated off (no divergent loop, no remainder loops).
             // A finished lane reads u0[0..3] instead (always inside the tile buffer) and discards the result.
             const int nmax = __reduce_max_sync(FULL, n);
-            const unsigned p32 = u0_s32 + (unsigned)lb * 8u;
             double acc = 0.0;
-            for (int i = 0; i < nmax; i += 4) {
-                const int r = n - i;
-                poly_trip4<P>(acc, r > 0 ? p32 + (unsigned)i * 8u : u0_s32, r, off, a);
+            if constexpr (F32) {
+                // dt in single precision from the float tile; the n*a0 term stays in FP64
+                const float thr = (float)(left - delta - center);
+                const unsigned p32 = u0f_s32 + (unsigned)lb * 4u;
+                float accf = 0.0f;
+                for (int i = 0; i < nmax; i += 4) {
+                    const int r = n - i;
+                    poly_trip4_f32(accf, r > 0 ? p32 + (unsigned)i * 4u : u0f_s32, r, thr, cf1, cf2, cf3);
+                }
+                acc = (double)accf;
+            } else {
+                const unsigned p32 = u0_s32 + (unsigned)lb * 8u;
+                for (int i = 0; i < nmax; i += 4) {
+                    const int r = n - i;
+                    if constexpr (!F32) poly_trip4<P>(acc, r > 0 ? p32 + (unsigned)i * 8u : u0_s32, r, off, a);
+                }
             }
             if (n == 0) continue;
             acc = fma((double)n, a[0], acc);
             const int col = bin - (hlo ? hlo[row] : 0);
             if ((unsigned)col >= (unsigned)hstride) continue;     // cannot happen: the band has an interval of slack
             double *cell = H + (size_t)row * hstride + col;
-            if (nch > 1 || __double2hiint(hd.y) < 0) atomicAdd(cell, acc);   // shared cell: pieces / bin split over intervals
+            if (nch > 1 || shared_cell) atomicAdd(cell, acc);    // shared cell: pieces / bin split over intervals
             else *cell += acc;
         }
     };
     const int GfD = Gf > 0 ? Gf : 1;
     const int n_tasks = nA + nB;
+    constexpr std::integral_constant<int, 1> one_c{};
     // few tasks (a tile of a big draw set spans few intervals): split every run so that all warps have work
     int nch = 1;
     if (n_tasks < 2 * NW) {
@@ -313,44 +407,48 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
         // type-A tasks take up to RANGE_PAIR consecutive intervals per lane (measured: 1 -> 2 +3 %, 2 -> 4 +1 %).  Static striding over the tasks (a shared work
         // counter with heaviest-first order was measured slower); (jj, g) of a type-A task without a division in the
         // loop
-        const int pair = nA >= 8 * NW ? RANGE_PAIR : (nA >= 4 * NW ? 2 : 1);
-        const int n_pr = (n_iv + pair - 1) / pair;
-        const int nA2 = n_pr * Gf;
-        int a_jj = warp / GfD, a_g = warp - a_jj * GfD;
-        const int step_j = NW / GfD, step_g = NW - step_j * GfD;
-        for (int task = warp; task < nA2 + nB; task += NW) {
-            if (task < nA2) {
-                const int row = (a_g << 5) + lane;
-                do_cell(row, k_lo + a_jj * pair + (srow[row] - s_ref), true, 0, 1, pair);
-                a_jj += step_j;
-                a_g += step_g;
-                if (a_g >= GfD) {
-                    a_g -= GfD;
-                    ++a_jj;
+        auto run_tasks = [&](auto pair_c) {
+            constexpr int pair = decltype(pair_c)::value;
+            const int n_pr = (n_iv + pair - 1) / pair;
+            const int nA2 = n_pr * Gf;
+            int a_jj = warp / GfD, a_g = warp - a_jj * GfD;
+            const int step_j = NW / GfD, step_g = NW - step_j * GfD;
+            for (int task = warp; task < nA2 + nB; task += NW) {
+                if (task < nA2) {
+                    const int row = (a_g << 5) + lane;
+                    do_cell(row, k_lo + a_jj * pair + (srow[row] - s_ref), true, 0, 1, pair_c);
+                    a_jj += step_j;
+                    a_g += step_g;
+                    if (a_g >= GfD) {
+                        a_g -= GfD;
+                        ++a_jj;
+                    }
+                } else {
+                    const int isub = lane / R;
+                    const int row = (Gf << 5) + (lane - isub * R);
+                    do_cell(row, k_lo + (task - nA2) * per_b + isub + (srow[row] - s_ref), isub < per_b, 0, 1, one_c);
                 }
-            } else {
-                const int isub = lane / R;
-                const int row = (Gf << 5) + (lane - isub * R);
-                do_cell(row, k_lo + (task - nA2) * per_b + isub + (srow[row] - s_ref), isub < per_b, 0, 1, 1);
             }
-        }
+        };
+        if (nA >= 6 * NW) run_tasks(std::integral_constant<int, RANGE_PAIR>{});   // enough tasks left for every warp
+        else run_tasks(one_c);
     } else {
         for (int t2 = warp; t2 < n_tasks * nch; t2 += NW) {
             const int task = t2 / nch, piece = t2 - task * nch;
             if (task < nA) {
                 const int jj = task / GfD;
                 const int row = ((task - jj * GfD) << 5) + lane;
-                do_cell(row, k_lo + jj + (srow[row] - s_ref), true, piece, nch, 1);
+                do_cell(row, k_lo + jj + (srow[row] - s_ref), true, piece, nch, one_c);
             } else {
                 const int isub = lane / R;
                 const int row = (Gf << 5) + (lane - isub * R);
-                do_cell(row, k_lo + (task - nA) * per_b + isub + (srow[row] - s_ref), isub < per_b, piece, nch, 1);
+                do_cell(row, k_lo + (task - nA) * per_b + isub + (srow[row] - s_ref), isub < per_b, piece, nch, one_c);
             }
         }
     }
 }
 
-template <int NT, int P>
+template <int NT, int P, bool F32 = false>
 __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(const DevModel m, const DevRun run, const double *__restrict__ theta,
                                                        long long n_walkers, ModelOut out) {
     extern __shared__ __align__(16) unsigned char smem_sym[];
@@ -376,7 +474,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     unsigned int *tofc = reinterpret_cast<unsigned int *>(pa);
     double *u0 = reinterpret_cast<double *>(pa);                       // aliases tofc (phase 1 only)
     double *rec = reinterpret_cast<double *>(pa + region_a);
-    double *svd = rec + (size_t)out.rcap * RW;
+    double *svd = rec + range_rec_doubles(out.rcap, P);
     double *staps = svd + EB;
     double *scratch = staps + m.n_taps;
     double *sdelta = scratch + 40;                                      // [X] sgn*(x_i - x_start)
@@ -390,8 +488,13 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     __shared__ int s_band[3];                                           // widest row, first / last interval of the walker
 
     // ---- walker-independent tables: staged once per CTA (persistent CTAs loop over walkers) ------------------
-    if (!banded)
-        for (int i = tid; i < M * RW; i += NT) rec[i] = m.rng_rec[i];
+    float *rec_f = reinterpret_cast<float *>(rec);        // FP32 mode: float records live in the same region
+    if (!banded) {
+        if (F32)
+            for (int i = tid; i < M * RANGE_RWF; i += NT) rec_f[i] = m.rng_rec_f32[i];
+        else
+            for (int i = tid; i < M * RW; i += NT) rec[i] = m.rng_rec[i];
+    }
     const double *recf = m.rng_rec;                        // full table in global memory
     for (int j = tid; j < M; j += NT) {
         sbrk[j] = recf[(size_t)j * RW];
@@ -473,14 +576,17 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
             if (tid == 0 && split == 0) out.queue_out[atomicAdd(out.queue_count, 1ull)] = (int)w;
             continue;
         }
-        for (int i = tid; i < (j_hi_all - jbase + 1) * RW; i += NT) rec[i] = recf[(size_t)jbase * RW + i];
+        if (F32)
+            for (int i = tid; i < (j_hi_all - jbase + 1) * RANGE_RWF; i += NT) rec_f[i] = m.rng_rec_f32[(size_t)jbase * RANGE_RWF + i];
+        else
+            for (int i = tid; i < (j_hi_all - jbase + 1) * RW; i += NT) rec[i] = recf[(size_t)jbase * RW + i];
     }
     // ---- per walker: zero the cell histogram ------------------------------------------------------------------
     for (int i = tid; i < X * hstride; i += NT) H[i] = 0.0;
 
     // ---- phase 1: (x,E) histogram of cross-section weights through the range tables ---------------------
     int bin_lo_all = EB, bin_hi_all = -1;                  // E-bins any draw of any tile can have touched (uniform)
-    if (m.n_draws >= RANGE_STREAM_MIN) {
+    if (!F32 && m.n_draws >= RANGE_STREAM_MIN) {           // (FP32 contexts with big draw sets are run by the FP64 kernels)
         // Big draw sets: the sorted draws of one interval are hundreds of consecutive values, so a lane that walks
         // draws in order changes interval rarely.  Warp-private streaming, no barriers: a warp takes 128 consecutive
         // draws (4 per lane, T1 evaluated once, kept in registers and broadcast by shuffle) and, for every group of
@@ -549,6 +655,21 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
         for (long long tile = 0; tile < m.n_draws; tile += RANGE_TILE) {
             const int nt = (int)((m.n_draws - tile < RANGE_TILE) ? (m.n_draws - tile) : RANGE_TILE);
             __syncthreads();                               // previous tile fully consumed / staging done
+            if (F32) {
+                // FP64 tile for the searches + float copy relative to u(mean energy) for the weights
+                float *u0f = rec_f + (size_t)out.rcap * RANGE_RWF;
+                double center = t1_eval(e0, m);
+                center = (center > -CUDART_INF && center < CUDART_INF) ? center : 0.0;
+                for (int d = tid; d < nt; d += NT) {
+                    const double u = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 - (tile + d) : tile + d)))), m);
+                    u0[d] = u;
+                    u0f[d] = (float)(u - center);
+                }
+                __syncthreads();
+                range_accumulate_tile<NT, P, true>(u0, nt, sbrk, rec, jbase, lut, ulut, RANGE_ULUT, sdelta, srow, H, hstride, hlo,
+                                                   X, M, umax, m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all, u0f, center);
+                continue;
+            }
             for (int d = tid; d < nt; d += NT)
                 u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 - (tile + d) : tile + d)))), m);
             __syncthreads();

@@ -30,6 +30,7 @@ struct DevModel {
     // range-energy tables (TOF_ODE_RANGE), see range_tables.py
     const double *t1_coefs;        // [t1_n][8]
     const double *rng_rec;         // [rng_n][P+3]: next break, bin, a0..aP
+    const float *rng_rec_f32;      // FP32 mode: [rng_n][8] floats: c0..c3, bin, shared-cell flag, c0 as a double (adv_range.cuh)
     const unsigned short *rng_lut; // [rng_lut_n]
     int t1_q, t1_key_lo, t1_n, rng_degree, rng_n, rng_lut_n;
     double rng_sign, rng_u_max, rng_lut_inv, e_tab_lo, e_tab_hi;

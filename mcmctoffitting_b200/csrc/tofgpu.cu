@@ -38,8 +38,9 @@ struct tof_ctx {
     int adv_nt = 1024, adv_dpt = 1;
     size_t adv_smem = 0;
     int rng_nt = 1024;
+    bool f32 = false;        // FP32 sample stage active (tof_config.precision, tiled draw sets only)
     // banded launch of the range kernel: 512 threads, 2 CTAs/SM
-    int band_hcap = 0, band_rcap = 0, band_ctas = 0;
+    int band_hcap = 0, band_rcap = 0, band_ctas = 0, band_nt = 512;
     size_t band_smem = 0;
     bool band_enabled = false;
     size_t simult_smem = 0, onebd_smem = 0;
@@ -113,11 +114,20 @@ AdvKernel adv_variant(int nt, int dpt, int nmat) {
     return nullptr;
 }
 
-AdvKernel range_variant(int nt, int degree) {
+AdvKernel range_variant_f32(int nt, int degree) {
+    if (nt == 1024 && degree == 7) return adv_range_kernel<1024, 7, true>;
+    if (nt == 512 && degree == 7) return adv_range_kernel<512, 7, true>;
+    return nullptr;
+}
+
+AdvKernel range_variant(int nt, int degree, bool f32 = false) {
+    if (f32) return range_variant_f32(nt, degree);
     if (nt == 1024 && degree == 7) return adv_range_kernel<1024, 7>;
     if (nt == 800 && degree == 7) return adv_range_kernel<800, 7>;
     if (nt == 640 && degree == 7) return adv_range_kernel<640, 7>;
     if (nt == 512 && degree == 7) return adv_range_kernel<512, 7>;
+    if (nt == 448 && degree == 7) return adv_range_kernel<448, 7>;
+    if (nt == 384 && degree == 7) return adv_range_kernel<384, 7>;
     return nullptr;
 }
 
@@ -145,7 +155,7 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
         if (c.ode_mode == TOF_ODE_RANGE) {
             // persistent CTAs: one per resident slot, walkers handed out through global counters.
             // d_work = {banded work counter, full-size work counter, queue length}
-            AdvKernel kfull = range_variant(ctx->rng_nt, c.rng_degree);
+            AdvKernel kfull = range_variant(ctx->rng_nt, c.rng_degree, ctx->f32);
             int rc = ensure(ctx, ctx->d_work, 3 * sizeof(unsigned long long));
             if (rc) return rc;
             CU(ctx, cudaMemsetAsync(ctx->d_work.p, 0, 3 * sizeof(unsigned long long), st));
@@ -186,9 +196,9 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 ob.rcap = ctx->band_rcap;
                 ob.queue_out = static_cast<int *>(ctx->d_queue.p);
                 ob.queue_count = cnt + 2;
-                AdvKernel kband = range_variant(512, c.rng_degree);
+                AdvKernel kband = range_variant(ctx->band_nt, c.rng_degree, ctx->f32);
                 const long long slots_band = (long long)ctx->stats.sm_count * std::max(ctx->band_ctas, 1);
-                kband<<<(unsigned)std::min<long long>(n_work, slots_band), 512, ctx->band_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, ob);
+                kband<<<(unsigned)std::min<long long>(n_work, slots_band), ctx->band_nt, ctx->band_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, ob);
                 // 2) full-size launch over the queue (exits at once when it is empty)
                 out.work = cnt + 1;
                 out.queue_in = static_cast<const int *>(ctx->d_queue.p);
@@ -418,6 +428,14 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
     }
 
     const bool use_range = cfg->ode_mode == TOF_ODE_RANGE && (cfg->model == TOF_MODEL_ADV || cfg->model == TOF_MODEL_SIMULT);
+    if (cfg->precision != TOF_PRECISION_FP64 && cfg->precision != TOF_PRECISION_FP32) {
+        ctx->err = "precision must be TOF_PRECISION_FP64 or TOF_PRECISION_FP32";
+        return bail(TOF_ERR_INVALID);
+    }
+    if (cfg->precision == TOF_PRECISION_FP32 && !(cfg->model == TOF_MODEL_ADV && cfg->ode_mode == TOF_ODE_RANGE)) {
+        ctx->err = "TOF_PRECISION_FP32 is built for the adv/intermediate model with TOF_ODE_RANGE only";
+        return bail(TOF_ERR_INVALID);
+    }
     if (use_range) {
         if (!cfg->t1_coefs || !cfg->rng_breaks || !cfg->rng_bins || !cfg->rng_coefs || !cfg->rng_lut || cfg->rng_n < 1 ||
             cfg->t1_n < 1 || cfg->rng_lut_n < 1 || !(cfg->rng_u_max > 0.0)) {
@@ -451,6 +469,60 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
             for (int k = 0; k <= P; ++k) rec[(size_t)j * RW + 2 + k] = cfg->rng_coefs[(size_t)j * (P + 1) + k];
         }
         TRY(upload(ctx, rec.data(), rec.size(), &m.rng_rec));
+        if (cfg->precision == TOF_PRECISION_FP32) {
+            // float records: degree-3 interpolant of the degree-7 weight polynomial at the Chebyshev nodes of the
+            // interval, monomials in dt; the fit is checked against the FP64 polynomial and refused if it is not
+            // single-precision accurate (very wide E-bins)
+            std::vector<float> recf((size_t)Mi * RANGE_RWF, 0.0f);
+            double worst = 0.0;
+            for (int j = 0; j < Mi; ++j) {
+                const double *a = cfg->rng_coefs + (size_t)j * (P + 1);
+                const double w = ((j + 1 < Mi) ? cfg->rng_breaks[j + 1] : cfg->rng_u_max) - cfg->rng_breaks[j];
+                auto p7 = [&](double d) { double v = a[P]; for (int k = P - 1; k >= 0; --k) v = v * d + a[k]; return v; };
+                constexpr int N = RANGE_PF + 1;
+                long double A[N][N + 1];
+                for (int k = 0; k < N; ++k) {
+                    const long double sk = 0.5L * (1.0L - cosl((2 * k + 1) * 3.14159265358979323846264338327950288L / (2 * N)));
+                    long double pw = 1.0L;
+                    for (int c = 0; c < N; ++c) { A[k][c] = pw; pw *= sk; }          // monomials in s = dt / w
+                    A[k][N] = (long double)p7((double)(sk * w));
+                }
+                for (int c = 0; c < N; ++c) {                                          // Gaussian elimination, partial pivoting
+                    int piv = c;
+                    for (int r = c + 1; r < N; ++r) if (fabsl(A[r][c]) > fabsl(A[piv][c])) piv = r;
+                    for (int q = 0; q <= N; ++q) std::swap(A[c][q], A[piv][q]);
+                    for (int r = 0; r < N; ++r) {
+                        if (r == c) continue;
+                        const long double f = A[r][c] / A[c][c];
+                        for (int q = c; q <= N; ++q) A[r][q] -= f * A[c][q];
+                    }
+                }
+                float cf[N];
+                long double wp = 1.0L;
+                for (int c = 0; c < N; ++c) { cf[c] = (float)(A[c][N] / A[c][c] / wp); wp *= w; }
+                for (int t = 0; t <= 32; ++t) {
+                    const double d = w * t / 32.0;
+                    double v = cf[N - 1];
+                    for (int k = N - 2; k >= 0; --k) v = v * d + (double)cf[k];
+                    const double ref = p7(d);
+                    if (ref != 0.0) worst = std::max(worst, std::fabs(v / ref - 1.0));
+                }
+                float *r = recf.data() + (size_t)j * RANGE_RWF;
+                for (int c = 0; c < N; ++c) r[c] = cf[c];
+                const int32_t bin = cfg->rng_bins[j];
+                const int32_t shared = ((j > 0 && cfg->rng_bins[j - 1] == bin) || (j + 1 < Mi && cfg->rng_bins[j + 1] == bin)) ? 1 : 0;
+                std::memcpy(r + 4, &bin, 4);
+                std::memcpy(r + 5, &shared, 4);
+                const double c0 = (double)(A[0][N] / A[0][0]);      // constant term in FP64 (n*c0 is added in FP64)
+                std::memcpy(r + 6, &c0, 8);
+            }
+            if (!(worst <= 3e-7)) {
+                ctx->err = "TOF_PRECISION_FP32: the degree-3 weight polynomials miss single precision on this E binning (max rel. error " +
+                           std::to_string(worst) + "); use TOF_PRECISION_FP64";
+                return bail(TOF_ERR_CAPACITY);
+            }
+            TRY(upload(ctx, recf.data(), recf.size(), &m.rng_rec_f32));
+        }
         TRY(upload(ctx, cfg->t1_coefs, (size_t)cfg->t1_n * 8, &m.t1_coefs));
         TRY(upload(ctx, cfg->rng_lut, (size_t)cfg->rng_lut_n, &m.rng_lut));
         m.t1_q = cfg->t1_q; m.t1_key_lo = cfg->t1_key_lo; m.t1_n = cfg->t1_n; m.rng_degree = P; m.rng_n = Mi;
@@ -471,7 +543,10 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
                        std::to_string(ctx->max_smem_optin);
             return bail(TOF_ERR_CAPACITY);
         }
-        AdvKernel k = range_variant(ctx->rng_nt, P);
+        ctx->f32 = cfg->precision == TOF_PRECISION_FP32 && m.n_draws < RANGE_STREAM_MIN;   // big draw sets: FP64 streaming walk
+        ctx->stats.fp32_active = ctx->f32 ? 1 : 0;
+        if (ctx->f32 && !range_variant(ctx->rng_nt, P, true)) { ctx->err = "TOF_PRECISION_FP32 runs with 512 or 1024 threads"; return bail(TOF_ERR_INVALID); }
+        AdvKernel k = range_variant(ctx->rng_nt, P, ctx->f32);
         CUC(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->adv_smem));
         CUC(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int occ = 0;
@@ -483,7 +558,13 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         {
             const char *env = std::getenv("TOFGPU_RANGE_BANDED");
             const bool want = !(env && std::atoi(env) == 0);
-            AdvKernel kband = range_variant(512, P);
+            if (const char *v = std::getenv("TOFGPU_BAND_THREADS")) {      // tuning knob: 384, 448 or 512
+                const int nt = std::atoi(v);
+                if (nt > 512 || !range_variant(nt, P)) { ctx->err = "TOFGPU_BAND_THREADS must be 384, 448 or 512"; return bail(TOF_ERR_INVALID); }
+                ctx->band_nt = nt;
+            }
+            if (ctx->f32 && ctx->band_nt != 512) { ctx->err = "TOF_PRECISION_FP32 runs the banded launch with 512 threads"; return bail(TOF_ERR_INVALID); }
+            AdvKernel kband = range_variant(ctx->band_nt, P, ctx->f32);
             const int per_cta = (int)prop.sharedMemPerBlockOptin / 2 - 2048;   // two CTAs + the per-CTA reservation
             const int rcap = std::min(Mi, 128);
             const size_t fixed = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], 0, rcap, P, cfg->n_taps, cfg->rng_lut_n, Mi);
@@ -497,7 +578,7 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
                 CUC(cudaFuncSetAttribute(kband, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->band_smem));
                 CUC(cudaFuncSetAttribute(kband, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 int occb = 0;
-                CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, kband, 512, ctx->band_smem));
+                CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, kband, ctx->band_nt, ctx->band_smem));
                 ctx->band_ctas = occb;
                 ctx->band_enabled = occb >= 2;
             }

@@ -44,6 +44,7 @@ class TofModel:
         c.model = config.kind
         c.device = self.device
         c.ode_mode = config.ode_mode
+        c.precision = config.precision
         c.ode_substeps = config.ode_substeps
         c.ode_from_zero = int(config.ode_from_zero)
         c.prior_strict = int(config.prior_strict)

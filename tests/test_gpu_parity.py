@@ -732,3 +732,78 @@ def test_rebinding_draws_and_observables_reuses_device_memory(M, O):
     z, got = last
     for k in range(2):
         assert rel(float(got[k]), float(om.lnprob(th[k], np.ones(2048) * 2, z))) <= RTOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# optional FP32 mode (BASELINE.json north_star: 1e-4 relative on the log-likelihood)
+# ---------------------------------------------------------------------------------------------------
+RTOL_FP32 = 1e-4
+
+
+def test_fp32_mode_sweep_shape_within_1e4(M, O):
+    """precision=PRECISION_FP32 at the benchmark shape: banded and full-size launches, against the FP64 kernels on
+    4096 walkers and against the oracle on a handful."""
+    kw = dict(ode_mode=M.config.ODE_RANGE)
+    om = O.sweep_model(ode_scheme="exact")
+    xs = O.DDNXS()
+    z = np.random.RandomState(20260101).standard_normal(1024)
+    obs = np.rint(1e5 * om.model_pdf([1050, 0.10], np.random.RandomState(7).standard_normal(1024)))
+    rs = np.random.RandomState(1)
+    thetas = np.array([1050, 0.10]) + np.array([10, 1e-2]) * rs.standard_normal((4096, 2))
+    thetas[-64:, 1] = rs.uniform(0.15, 0.45, 64)          # wide spreads: overflow queue / full-size launch
+    thetas[-64:, 0] = rs.uniform(1010, 1400, 64)
+    with M.TofModel(M.config.sweep(**kw)) as m64, M.TofModel(M.config.sweep(precision=M.config.PRECISION_FP32, **kw)) as m32:
+        for m in (m64, m32):
+            m.set_observables(obs)
+            m.set_draws(z)
+        lp64, lp32 = m64.lnprob_batch(thetas), m32.lnprob_batch(thetas)
+        assert m32.stats()["fp32_active"] == 1 and m64.stats()["fp32_active"] == 0
+        assert m32.stats()["band_queued_last"] > 0          # both launches took part
+        c64 = m64.model_batch(thetas[:16], stage="counts")
+        c32 = m32.model_batch(thetas[:16], stage="counts")
+    both = np.isfinite(lp64) & np.isfinite(lp32)
+    # a count that flips in an otherwise empty observed bin turns a finite value into -inf or back: rare
+    assert np.mean(np.isfinite(lp64) == np.isfinite(lp32)) >= 0.995
+    assert both.sum() > 500
+    dev = np.abs(lp32[both] - lp64[both]) / np.abs(lp64[both])
+    assert dev.max() <= RTOL_FP32, dev.max()
+    # integer TOF spectra: both modes bin every sample identically, so only np.rint flips can differ
+    for a, b in zip(c64, c32):
+        assert np.abs(a - b).sum() <= 4, np.abs(a - b).sum()
+    for k in np.flatnonzero(both)[:6]:
+        want = om.lnprob(thetas[k], obs, z, xs)
+        assert rel(float(lp32[k]), float(want)) <= RTOL_FP32, k
+
+
+def test_fp32_mode_adv_config_as_written(M, O):
+    """adv script as written (I = 19.2: energies RISE along the cell), 4096 draws in 4 tiles, 50 TOF bins."""
+    kw = dict(n_samples=4096, n_ev_per_loop=4096, mean_excitation=19.2, ode_mode=M.config.ODE_RANGE)
+    om = O.adv_model(0, n_samples=4096, n_ev_per_loop=4096, mean_excitation=19.2, ode_scheme="exact")
+    xs = O.DDNXS()
+    z = np.random.RandomState(8).standard_normal(4096)
+    obs = np.rint(5e4 * om.model_pdf([1050, .10], np.random.RandomState(7).standard_normal(4096)))
+    rs = np.random.RandomState(3)
+    thetas = np.column_stack([rs.uniform(1030, 1075, 200), rs.uniform(0.08, 0.12, 200)])
+    with M.TofModel(M.config.adv(0, precision=M.config.PRECISION_FP32, **kw)) as m32, M.TofModel(M.config.adv(0, **kw)) as m64:
+        for m in (m64, m32):
+            m.set_observables(obs)
+            m.set_draws(z)
+        lp64, lp32 = m64.lnprob_batch(thetas), m32.lnprob_batch(thetas)
+        assert m32.stats()["fp32_active"] == 1
+    both = np.isfinite(lp64) & np.isfinite(lp32)
+    assert both.sum() >= 150 and np.mean(np.isfinite(lp64) == np.isfinite(lp32)) >= 0.98
+    dev = np.abs(lp32[both] - lp64[both]) / np.abs(lp64[both])
+    assert dev.max() <= RTOL_FP32, dev.max()
+    k = int(np.flatnonzero(both)[0])
+    assert rel(float(lp32[k]), float(om.lnprob(thetas[k], obs, z, xs))) <= RTOL_FP32
+
+
+def test_fp32_mode_is_refused_where_it_is_not_built(M):
+    with pytest.raises(ValueError):
+        M.TofModel(M.config.sweep(ode_mode=M.config.ODE_RK4, precision=M.config.PRECISION_FP32))
+    with pytest.raises(ValueError):
+        M.TofModel(M.config.simult(precision=M.config.PRECISION_FP32, ode_mode=M.config.ODE_RANGE))
+    # big draw sets: the context is accepted and served by the FP64 streaming kernels
+    with M.TofModel(M.config.adv(0, n_samples=16384, n_ev_per_loop=16384, mean_excitation=19.2e-3,
+                                 ode_mode=M.config.ODE_RANGE, precision=M.config.PRECISION_FP32)) as m:
+        assert m.stats()["fp32_active"] == 0

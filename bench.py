@@ -348,9 +348,9 @@ def run_gpu_arm(args):
             "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE model call at this size (131072 walkers: the banded
             # launch <512,7> plus the full-size launch <1024,7> over its overflow queue), from the ncu --set full capture
-            # summarised in profiles/r1_range_adv_kernel_bench_size_ncu_summary.txt; algorithmic bytes are evals * 24
-            "traffic": (3113472 * evals_per_launch // 131072) if ode == M.config.ODE_RANGE else None,
-            "traffic_source": "profiles/r1_range_adv_kernel_bench_size_ncu_summary.txt (scaled by walkers per launch)",
+            # summarised in profiles/r1_range_fp64_ncu_summary.txt; algorithmic bytes are evals * 24
+            "traffic": (3536384 * evals_per_launch // 131072) if ode == M.config.ODE_RANGE else None,
+            "traffic_source": "profiles/r1_range_fp64_ncu_summary.txt (dram read + write of both launches, scaled by walkers per launch)",
             "kernel": ("adv_range_kernel<512,7> (banded, 2 CTAs/SM) + adv_range_kernel<1024,7> (overflow queue)"
                        if ode == M.config.ODE_RANGE else "adv_lnprob_kernel"),
             "kernel_ms": k_ms, "evals_per_launch": evals_per_launch,

@@ -412,6 +412,41 @@ def test_gpu_sampler_runs_and_respects_the_prior(M, O):
     fn.model.close()
 
 
+def test_gpu_chain_equals_the_cpu_chain_from_the_same_seed(M, O):
+    """BASELINE.json north_star: 'chains from a fixed seed must agree'.  The proposal stream is counter-based and
+    the GPU log-likelihood agrees with the oracle to ~1e-13, so the whole chain -- positions, log-probabilities and
+    acceptance counts -- is reproduced by the numpy sampler driving the oracle, not just its moments."""
+    from mcmctoffitting_b200.ensemble import EnsembleSampler
+    from oracle.stretch_oracle import NumpyBackend
+    # RK4 kernel against the RK4 oracle (the same scheme step for step; the closed-form oracle is too slow to drive a
+    # chain), 50 TOF bins and ~2000 observed counts so that about half of the proposals are accepted
+    kw = dict(n_samples=1024, n_ev_per_loop=1024, mean_excitation=19.2e-3)
+    cfg = M.config.adv(0, **kw)
+    om = O.adv_model(0, **kw)
+    xs = O.DDNXS()
+    z = np.random.RandomState(8).standard_normal(1024)
+    obs = np.rint(2e3 * om.model_pdf([1050, 0.10], np.random.RandomState(7).standard_normal(1024)))
+    k, steps = 24, 12
+    p0 = np.array([1050, 0.10]) + np.array([10, 1e-2]) * np.random.RandomState(5).standard_normal((k, 2))
+
+    def cpu_lnprob(pos):
+        return np.array([om.lnprob(th, obs, z, xs) for th in pos])
+
+    fn = M.make_lnprob(cfg, obs, z)
+    gpu = EnsembleSampler(k, 2, fn, seed=99)
+    cpu = EnsembleSampler(k, 2, backend=NumpyBackend(cpu_lnprob), seed=99)
+    pg, lg, _ = gpu.run_mcmc(p0, steps)
+    pc, lc, _ = cpu.run_mcmc(p0, steps)
+    fn.model.close()
+    assert gpu.chain.shape == cpu.chain.shape == (k, steps, 2)
+    np.testing.assert_allclose(gpu.chain, cpu.chain, rtol=1e-12, atol=0)
+    fin = np.isfinite(cpu.lnprobability)
+    assert np.array_equal(fin, np.isfinite(gpu.lnprobability))
+    np.testing.assert_allclose(gpu.lnprobability[fin], cpu.lnprobability[fin], rtol=RTOL)
+    assert np.array_equal(gpu.naccepted.cpu().numpy(), cpu.naccepted.numpy())
+    assert k * steps // 4 < int(gpu.naccepted.sum()) < k * steps    # the chain moved, and not every proposal was taken
+
+
 # ---------------------------------------------------------------------------------------------------
 # simultaneous multi-standoff fit (config 4): tests/simultFit.py
 # ---------------------------------------------------------------------------------------------------

@@ -160,7 +160,7 @@ def run_reference_arm(args):
 class ClockSampler(threading.Thread):
     """Polls SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.05):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -255,7 +255,8 @@ def run_gpu_arm(args):
     launches_warm = model.stats()["kernel_launches"]
 
     clocks = ClockSampler(local_rank)
-    clocks.start()
+    if rank == 0:                          # NVML polling takes driver locks: one poller per box is enough
+        clocks.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     model.set_timing(True)

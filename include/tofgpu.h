@@ -185,6 +185,11 @@ int tof_model_batch(tof_ctx *ctx, const double *theta, int64_t n, int run, int s
 /* Integer (x, E) cell counts drawHist2d (adv:146; simultFit.py:283): counts[n][x_bins][e_bins]. */
 int tof_cell_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run, int64_t *counts);
 
+/* Unweighted (x, E) histogram of the stopped deuteron energies of the LAST loop, [n][x_bins][e_bins]: the
+ * `eD_atEachX` rows that utilities/ppcTools.py:140-157 collects for posterior-predictive checks (its leading row
+ * of zeros omitted).  Built for TOF_MODEL_SIMULT with TOF_ODE_RK4 (the model ppcTools re-runs). */
+int tof_deuteron_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run, int64_t *counts);
+
 /* ---- ensemble driver: emcee 2.x EnsembleSampler stretch move (a = 2), red/blue halves -------- */
 
 /* Propose for a half-ensemble (DEVICE buffers, async on stream):

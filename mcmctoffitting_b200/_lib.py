@@ -71,6 +71,7 @@ SIGNATURES = {
     "tof_lnprob_batch_device": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),
     "tof_model_batch": (C.c_int, [_vp, _dp, C.c_int64, C.c_int, C.c_int, _dp]),
     "tof_cell_counts_batch": (C.c_int, [_vp, _dp, C.c_int64, C.c_int, C.POINTER(C.c_int64)]),
+    "tof_deuteron_counts_batch": (C.c_int, [_vp, _dp, C.c_int64, C.c_int, C.POINTER(C.c_int64)]),
     "tof_stretch_propose": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_double, C.c_uint64,
                                       C.c_int64, C.c_int, _vp, _vp, _vp]),
     "tof_stretch_accept": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_uint64, C.c_int64,

@@ -27,6 +27,11 @@ __device__ __forceinline__ void simult_tail(const DevModel &m, const DevRun &run
                                             bool exhausted) {
     const int T = run.tof_bins, X = m.x_bins, EB = m.e_bins, CELLS = X * EB;
     const int tid = threadIdx.x;
+    if (out.unweighted) {                                   // raw per-cell counts of the last loop, nothing else
+        if (out.cells)
+            for (int c = tid; c < CELLS; c += NT) out.cells[(size_t)w * CELLS + c] = (long long)H[c];
+        return;
+    }
     // ---- normalise, quantise (simultFit.py:279-283) --------------------------------------------------------
     const double de = (m.e_max - m.e_min) / (double)EB, dx = (m.x_max - m.x_min) / (double)X;
     double part = 0.0;
@@ -181,7 +186,11 @@ __global__ void __launch_bounds__(NT) simult_run_kernel(const DevModel m, const 
                             x_prev = sx[i];
                         }
                         const int b = np_bin(E, EB, m.e_min, m.e_max, e_step, e_scale);       // simultFit.py:264
-                        if (b >= 0) atomicAdd(Hmine + i * EB + b, xs_eval(E, xs));           // simultFit.py:263
+                        if (out.unweighted) {                                                 // ppcTools.py:151-154 eD_atEachX
+                            if (b >= 0 && loop == m.n_loops - 1) atomicAdd(Hmine + i * EB + b, 1.0);
+                        } else if (b >= 0) {
+                            atomicAdd(Hmine + i * EB + b, xs_eval(E, xs));                    // simultFit.py:263
+                        }
                     }
                 }
             }

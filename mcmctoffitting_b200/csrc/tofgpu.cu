@@ -812,6 +812,28 @@ int tof_cell_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run,
     return TOF_OK;
 }
 
+int tof_deuteron_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run, int64_t *counts) {
+    if (!ctx || (n > 0 && (!theta || !counts))) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    if (int rc = check_run(ctx, run)) return rc;
+    if (ctx->cfg.model != TOF_MODEL_SIMULT || ctx->cfg.ode_mode != TOF_ODE_RK4)
+        return fail(ctx, TOF_ERR_INVALID, "deuteron counts are built for TOF_MODEL_SIMULT with TOF_ODE_RK4");
+    if (n <= 0) return n == 0 ? TOF_OK : fail(ctx, TOF_ERR_INVALID, "n < 0");
+    if (int rc = ready(ctx, false)) return rc;
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t cells = (size_t)ctx->cfg.x_bins * ctx->cfg.e_bins;
+    const size_t tb = (size_t)n * ctx->cfg.ndim * sizeof(double), cb = (size_t)n * cells * sizeof(long long);
+    if (int rc = ensure(ctx, ctx->d_theta, tb)) return rc;
+    if (int rc = ensure(ctx, ctx->d_cells, cb)) return rc;
+    CU(ctx, cudaMemcpyAsync(ctx->d_theta.p, theta, tb, cudaMemcpyHostToDevice, ctx->stream));
+    ModelOut o{};
+    o.cells = static_cast<long long *>(ctx->d_cells.p);
+    o.unweighted = 1;
+    if (int rc = launch_model(ctx, static_cast<const double *>(ctx->d_theta.p), n, run, o, ctx->stream)) return rc;
+    CU(ctx, cudaMemcpyAsync(counts, ctx->d_cells.p, cb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return TOF_OK;
+}
+
 int tof_stretch_propose(tof_ctx *ctx, const double *d_s, int64_t n, int64_t walker0, const double *d_comp, int64_t n_comp,
                         double a, uint64_t seed, int64_t step, int half, double *d_q, double *d_log_zz, void *stream) {
     if (!ctx || !d_s || !d_comp || !d_q || !d_log_zz) return fail(ctx, TOF_ERR_INVALID, "null argument");

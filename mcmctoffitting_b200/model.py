@@ -201,6 +201,15 @@ class TofModel:
                                                     out.ctypes.data_as(C.POINTER(C.c_int64))))
         return out
 
+    def deuteron_counts(self, thetas, run: int = 0) -> np.ndarray:
+        """Unweighted per-x histograms of the stopped deuteron energies of the last loop, ``[n, X, E]`` -- the
+        ``eD_atEachX`` rows of utilities/ppcTools.py:140-157 (simult model, ODE_RK4)."""
+        t = self._thetas(thetas)
+        out = np.empty((t.shape[0], self.config.x_bins, self.config.e_bins), dtype=np.int64)
+        self._check(self._lib.tof_deuteron_counts_batch(self._ctx, _dptr(t), t.shape[0], run,
+                                                        out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
     # -- sampler kernels (device pointers) ------------------------------------------------------------
     def stretch_propose(self, s_ptr, n, walker0, comp_ptr, n_comp, a, seed, step, half, q_ptr, logzz_ptr, stream=0):
         self._check(self._lib.tof_stretch_propose(self._ctx, C.c_void_p(s_ptr), n, walker0, C.c_void_p(comp_ptr), n_comp,

@@ -4,7 +4,8 @@
 a chain and re-runs ``generateModelData`` for each of them, run by run -- minutes of CPU per hundred samples.
 Here the same thing is two batched GPU calls per run: the TOF spectra (``tof_model_batch``) and the integer
 (x, E) cell counts (``tof_cell_counts_batch``), whose rows are the reference's ``eN_atEachX`` neutron spectra
-(ppcTools.py:170-180).  The unweighted deuteron-energy histograms (``eD_atEachX``) are not produced.
+(ppcTools.py:170-180); :func:`deuteron_spectra` gives the unweighted deuteron-energy histograms (``eD_atEachX``,
+ppcTools.py:151-157) and :func:`sdef_sia_cumulative` the MCNP source card of ppcTools.py:397-422.
 """
 from __future__ import annotations
 
@@ -37,3 +38,28 @@ def generate_ppc(model: TofModel, thetas: np.ndarray) -> Tuple[List[np.ndarray],
 def ppc_bands(spectra: np.ndarray, quantiles=(0.16, 0.5, 0.84)) -> np.ndarray:
     """Per-bin quantile bands of a stack of PPC spectra ``[n, T]`` (what the PPC plots draw)."""
     return np.quantile(spectra, quantiles, axis=0)
+
+
+def deuteron_spectra(model: TofModel, thetas: np.ndarray) -> List[np.ndarray]:
+    """Per run ``[n, X, E]`` unweighted histograms of the stopped deuteron energies (last loop only, as the
+    reference keeps them: ppcTools.py:141, 151-157).  Needs the simult model with ``ode_mode=ODE_RK4``."""
+    thetas = np.ascontiguousarray(thetas, dtype=np.float64)
+    return [model.deuteron_counts(thetas, run=run) for run in range(model.config.n_runs)]
+
+
+def neutron_spectrum(cell_counts: np.ndarray) -> np.ndarray:
+    """ppcTools.py:406-412: the neutron spectra of the FIRST run of every posterior sample, summed along the cell
+    and over the samples.  ``cell_counts``: ``[n, X, E]`` of run 0 (the rows are ``eN_atEachX``)."""
+    return np.asarray(cell_counts).sum(axis=(0, 1)).astype(np.float64)
+
+
+def sdef_sia_cumulative(cell_counts: np.ndarray, e_n_centers: np.ndarray, dist_number: int = 100) -> dict:
+    """MCNP SDEF ``SI A`` / ``SP`` cards for the neutron distribution marginalised over the cell length
+    (ppcTools.makeSDEF_sia_cumulative, ppcTools.py:397-422): energies in MeV with three decimals, counts as
+    integers.  ``e_n_centers`` = ``getDDneutronEnergy(eD_binCenters)`` in keV (ppcTools.py:81)."""
+    spec = neutron_spectrum(cell_counts)
+    if len(spec) != len(e_n_centers):
+        raise ValueError("one neutron energy per E-bin is needed")
+    energies = "".join(" %.3f" % (e / 1000) for e in e_n_centers)
+    weights = "".join(" %.0f" % c for c in spec)
+    return {"si": "si%d a%s" % (dist_number, energies), "sp": "sp%d%s" % (dist_number, weights)}

@@ -518,6 +518,39 @@ def test_simult_vs_oracle(M, O, ode):
     fn.model.close()
 
 
+def test_ppc_deuteron_spectra_and_sdef_card(M, O):
+    """the unweighted deuteron spectra ppcTools keeps (eD_atEachX, last loop only,
+    ppcTools.py:141-157) bit-exact against the oracle, the neutron spectra (cell-count rows) and the SDEF card."""
+    from mcmctoffitting_b200 import ppc
+    cfg = M.config.simult(n_samples=3000, n_ev_per_loop=1000)             # 3 loops: only the last one is kept
+    om = O.SimultModel(n_samples=3000, n_ev_per_loop=1000)
+    z_main, z_extra = _simult_tables(O, cfg, 77)
+    td = O.TableDraws(z_main, z_extra)
+    thetas = np.array([[1878.4, 850, 170, 0.5, 3e4, 2e4, 2e4, 4e4, 4e4],
+                       [1825.0, 1000, 300, 1.2, 3e4, 2e4, 2e4, 4e4, 4e4]])       # the second one redraws ~20 %
+    fn = M.make_lnprob(cfg, [np.ones(t) for t in cfg.tof_bins], [z.ravel() for z in z_main], extra_draws=z_extra)
+    spectra = ppc.deuteron_spectra(fn.model, thetas)
+    assert len(spectra) == 5 and spectra[0].shape == (2, 10, 50)
+    for k, th in enumerate(thetas):
+        for r in (0, 3):
+            td.reset()
+            want = om.deuteron_counts(list(th[:4]) + [th[4 + r]], r, td)
+            assert np.array_equal(spectra[r][k], want), (k, r)
+            assert want.sum() <= 10 * 1000 and want.sum() > 5000           # one loop's draws at 10 x positions
+    _, cells = ppc.generate_ppc(fn.model, thetas)
+    e_n = M.config.dd_neutron_energy(cfg.e_centers())
+    card = ppc.sdef_sia_cumulative(cells[0], e_n)
+    assert [int(v) for v in card["sp"].split()[1:]] == list(cells[0].sum(axis=(0, 1)))
+    assert card["si"].split()[2] == "%.3f" % (e_n[0] / 1000)
+    # the range-table context refuses the request loudly instead of answering with another scheme
+    fr = M.make_lnprob(M.config.simult(n_samples=3000, n_ev_per_loop=1000, ode_mode=M.config.ODE_RANGE),
+                       [np.ones(t) for t in cfg.tof_bins], [z.ravel() for z in z_main], extra_draws=z_extra)
+    with pytest.raises(Exception):
+        fr.model.deuteron_counts(thetas)
+    fr.model.close()
+    fn.model.close()
+
+
 def test_simult_reference_goldens(M, O, golden, pf):
     """Seed-pinned lnprob values produced by the reference's own simultFit functions (scipy dopri5 there)."""
     g = golden["simult"]

@@ -208,3 +208,32 @@ def test_tof_data_file_round_trip(tmp_path):
     if ref_loader.available():
         ref_mod = ref_loader.load_utilities().utilities
         assert np.array_equal(ref_mod.readMultiStandoffTOFdata(path, nRuns=5), data)
+
+
+def test_sdef_card_matches_the_reference_writer():
+    """ppc.sdef_sia_cumulative against ppcTools.makeSDEF_sia_cumulative (utilities/ppcTools.py:397-422) itself, run as
+    an unbound method on a stand-in that carries the three attributes it reads."""
+    import sys
+    import types
+    from unittest import mock
+    from oracle import ref_loader
+    from mcmctoffitting_b200 import ppc
+    rs = np.random.RandomState(4)
+    n, X, E = 7, 10, 50
+    cells = rs.poisson(30.0, size=(n, X, E)).astype(np.int64)
+    e_n = np.linspace(2900.0, 4400.0, E) + rs.uniform(0, 1, E)
+    got = ppc.sdef_sia_cumulative(cells, e_n, dist_number=100)
+    assert got["si"].startswith("si100 a ") and got["sp"].startswith("sp100 ")
+    assert len(got["si"].split()) == E + 2 and len(got["sp"].split()) == E + 1
+    assert [int(v) for v in got["sp"].split()[1:]] == list(cells.sum(axis=(0, 1)))
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    if ref_loader.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, ref_loader.REFERENCE_ROOT)
+    stubs = {k: mock.MagicMock(name=k) for k in ("matplotlib", "matplotlib.pyplot", "corner")}
+    with mock.patch.dict(sys.modules, stubs):
+        import utilities.ppcTools as ref_ppc
+    stand_in = types.SimpleNamespace(tofData=[0], eD_bins=E, eN_binCenters=e_n,
+                                     neutronSpectra=[[cells[k].astype(float)] for k in range(n)])   # [sample][run][x, E]
+    want = ref_ppc.ppcTools.makeSDEF_sia_cumulative(stand_in, 100)
+    assert got == {"si": want["si"], "sp": want["sp"]}

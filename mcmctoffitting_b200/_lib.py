@@ -98,6 +98,11 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     if _LIB is not None:
         return _LIB
     path = _build.LIB_PATH
+    override = os.environ.get("TOFGPU_LIB")            # e.g. the checked build (build.py --checked); same ABI, same kernels
+    if override:
+        if not os.path.exists(override):
+            raise RuntimeError("TOFGPU_LIB=%s does not exist" % override)
+        path = override
     if not os.path.exists(path):
         if not build_if_missing:
             raise RuntimeError("libtofgpu.so is not built; run `python -m mcmctoffitting_b200.build`")

@@ -36,6 +36,21 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+CHECKED_LIB_PATH = os.path.join(PKG_DIR, "libtofgpu_checked.so")
+
+
+def build_checked(verbose: bool = False) -> str:
+    """Same sources with -DTOF_CHECKED: every shared-memory index of the range kernels is asserted on the device
+    (tof_device.cuh).  Not shipped; load it with TOFGPU_LIB=<path> to run the parity suite against it."""
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-DTOF_CHECKED"] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", CHECKED_LIB_PATH]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or proc.returncode != 0:
+        sys.stderr.write(proc.stdout)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed for the checked build")
+    return CHECKED_LIB_PATH
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu -> libtofgpu.so.  Returns the library path."""
     if not force and not is_stale():
@@ -53,4 +68,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    if "--checked" in sys.argv:
+        print(build_checked(verbose=True))
+    else:
+        print(build_library(force="--force" in sys.argv, verbose=True))

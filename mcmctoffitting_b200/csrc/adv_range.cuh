@@ -243,6 +243,7 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
             c0 = (int)((u0[d - 1] - tu_min) * tu_inv);
             c0 = c0 > n_ulut - 1 ? n_ulut - 1 : c0;
         }
+        TOF_CHECK(c1 >= 0 && c1 < n_ulut && c0 >= -1 && c0 <= c1);
         for (int c = c0 + 1; c <= c1; ++c) ulut[c] = (unsigned short)d;
     }
     // per-row interval of the tile's median draw: rows are processed along the trajectory (interval j = k + shift(row)),
@@ -267,6 +268,7 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
     if (!(vmax >= 0.0) || vmin > umax) return;         // uniform
     const int band_lo = range_interval(vmin > 0.0 ? vmin : 0.0, brk, lut, lut_inv, lut_n, M);
     const int band_hi = range_interval(vmax < umax ? vmax : umax, brk, lut, lut_inv, lut_n, M);
+    TOF_CHECK(band_lo >= jbase && band_lo <= band_hi && band_hi < M);
     if (F32) {
         bin_lo_all = min(bin_lo_all, __float_as_int(recf[(band_lo - jbase) * RANGE_RWF + 4]));
         bin_hi_all = max(bin_hi_all, __float_as_int(recf[(band_hi - jbase) * RANGE_RWF + 4]));
@@ -302,6 +304,7 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
             int j = j0 + q;
             const bool active = row_ok && j >= band_lo && j <= band_hi;
             j = j < band_lo ? band_lo : (j > band_hi ? band_hi : j);
+            TOF_CHECK(j - jbase >= 0 && (j == 0 || j - 1 - jbase >= 0 || F32));   // staged records cover the band
             double left, right;
             int bin;
             bool shared_cell;
@@ -354,6 +357,7 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
                 ub = ub < lb ? lb : ub;
                 while (ub < v_hi && !(__dadd_rn(u0[ub], delta) >= right)) ++ub;
                 carry = ub;
+                TOF_CHECK(lb >= v_lo && lb <= ub && ub <= v_hi && v_hi <= nt);
                 if (nch > 1) {
                     const int len = (ub - lb + nch - 1) / nch;
                     lb += piece * len;
@@ -388,6 +392,7 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
             if (n == 0) continue;
             acc = fma((double)n, a[0], acc);
             const int col = bin - (hlo ? hlo[row] : 0);
+            TOF_CHECK((unsigned)col < (unsigned)hstride && row >= 0 && row < X);
             if ((unsigned)col >= (unsigned)hstride) continue;     // cannot happen: the band has an interval of slack
             double *cell = H + (size_t)row * hstride + col;
             if (nch > 1 || shared_cell) atomicAdd(cell, acc);    // shared cell: pieces / bin split over intervals
@@ -576,10 +581,12 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
             if (tid == 0 && split == 0) out.queue_out[atomicAdd(out.queue_count, 1ull)] = (int)w;
             continue;
         }
-        if (F32)
+        TOF_CHECK(j_hi_all - jbase + 1 <= out.rcap && j_hi_all < M && jbase >= 0 && X * hstride <= out.hcap);
+        if (F32) {
             for (int i = tid; i < (j_hi_all - jbase + 1) * RANGE_RWF; i += NT) rec_f[i] = m.rng_rec_f32[(size_t)jbase * RANGE_RWF + i];
-        else
+        } else {
             for (int i = tid; i < (j_hi_all - jbase + 1) * RW; i += NT) rec[i] = recf[(size_t)jbase * RW + i];
+        }
     }
     // ---- per walker: zero the cell histogram ------------------------------------------------------------------
     for (int i = tid; i < X * hstride; i += NT) H[i] = 0.0;
@@ -747,6 +754,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
                     const double tof_d = div_by_recip(xi, svd[j], rvd[j]);
                     const double tof_n = div_by_recip(di, __ldg(m.neutron_speed + j), __ldg(m.neutron_rspeed + j));
                     const int b = np_bin(__dadd_rn(tof_d, tof_n), T, run.tof_min, run.tof_max, t_step, t_scale);
+                    TOF_CHECK(b < T && j < EB);
                     if (b >= 0) atomicAdd(tofc + b, (unsigned int)cnt);
                 }
             }

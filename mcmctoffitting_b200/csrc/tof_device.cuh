@@ -10,6 +10,24 @@
 
 #include "../../include/tofgpu.h"
 
+// Checked build (python -m mcmctoffitting_b200.build --checked -> libtofgpu_checked.so): every shared-memory index
+// the range kernels compute is asserted; a violation prints its site and traps (the call then fails with a CUDA
+// error).  compute-sanitizer is not available on the GPU pool, so this is how out-of-bounds indexing is hunted:
+// the parity suite is run once against the checked library (profiles/).  Compiled out of the shipped library.
+#ifdef TOF_CHECKED
+#include <cstdio>
+#define TOF_CHECK(cond)                                                                                     \
+    do {                                                                                                    \
+        if (!(cond)) {                                                                                      \
+            printf("TOF_CHECK failed: %s at %s:%d (block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+                   (int)threadIdx.x);                                                                       \
+            __trap();                                                                                       \
+        }                                                                                                   \
+    } while (0)
+#else
+#define TOF_CHECK(cond) ((void)0)
+#endif
+
 namespace tof {
 
 constexpr unsigned FULL = 0xffffffffu;

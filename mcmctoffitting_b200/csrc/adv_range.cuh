@@ -16,8 +16,9 @@ namespace tof {
 // (range_tables.py).  The library keeps the draws sorted, so for a fixed row the samples of one interval are a
 // contiguous range of draws.  Three phase-1 strategies share the tables:
 //   * tiles (n_draws < RANGE_STREAM_MIN): 1024 draws staged in shared memory, a per-tile lookup from u to draw
-//     index, tasks of 32 (row, interval) cells with lane = row -- every cell is summed by exactly one lane, no
-//     atomics, fixed order (range_accumulate_tile);
+//     index, tasks of 32 lanes x up to RANGE_PAIR consecutive (row, interval) cells with lane = row -- every cell is
+//     summed by exactly one lane, no atomics, fixed order; the polynomial loop is warp-uniform and predicated
+//     (range_accumulate_tile, poly_trip4).  Optional FP32 weights: see "FP32 mode" below;
 //   * pieces: when a tile spans few intervals each run is split over several lanes (atomics on the cell);
 //   * streaming (big draw sets): warp-private walk over 128 draws at a time, values broadcast by shuffle.
 // The cell histogram is either full (X*E doubles, 1 CTA/SM) or banded per row (2 CTAs/SM), see adv_range_kernel.

@@ -208,6 +208,17 @@ int tof_stretch_accept(tof_ctx *ctx, double *d_s, double *d_lnprob, int64_t n, i
                        const double *d_q, const double *d_new_lnprob, const double *d_log_zz,
                        uint64_t seed, int64_t step, int half, int64_t *d_n_accept, void *stream);
 
+/* n_steps whole ensemble steps (both red/blue half-steps each: propose -> lnprob -> accept) for an ensemble that lives
+ * on this GPU, enqueued on `stream` without returning to the host in between -- what emcee's
+ * EnsembleSampler.sample(p0, iterations=n_steps) loop does (adv:311-317; simultFit.py:733-740) for the kwargs bound
+ * with tof_set_observables / tof_set_draws.  d_pos [n_walkers][ndim] and d_lnprob [n_walkers] are DEVICE buffers
+ * updated in place (d_lnprob must hold the log-probabilities of d_pos on entry, e.g. from tof_lnprob_batch_device);
+ * first half = walkers [0, n/2), like emcee.  Randomness as in tof_stretch_propose with step = step0 + s, so the
+ * chain equals the one produced half-step by half-step (and by any sharding).  d_n_accept [n_walkers] may be NULL.
+ * emcee's own constructor checks apply: n_walkers even and >= 2*ndim. */
+int tof_ensemble_step(tof_ctx *ctx, double *d_pos, double *d_lnprob, int64_t n_walkers, int64_t n_steps, double a,
+                      uint64_t seed, int64_t step0, int64_t *d_n_accept, void *stream);
+
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 typedef struct tof_stats {
     int64_t kernel_launches; /* kernels launched by this context since creation */

@@ -76,6 +76,7 @@ SIGNATURES = {
                                       C.c_int64, C.c_int, _vp, _vp, _vp]),
     "tof_stretch_accept": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_uint64, C.c_int64,
                                      C.c_int, _vp, _vp]),
+    "tof_ensemble_step": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double, C.c_uint64, C.c_int64, _vp, _vp]),
     "tof_get_stats": (C.c_int, [_vp, C.POINTER(TofStats)]),
     "tof_set_timing": (C.c_int, [_vp, C.c_int]),
     "tof_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),

@@ -27,7 +27,7 @@ struct tof_ctx {
     DevModel dm{};
     DevRun runs[TOF_MAX_RUNS]{};
     std::vector<void *> owned;  // device allocations freed in tof_destroy
-    DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial, d_work, d_queue, d_split, d_tickets;
+    DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial, d_work, d_queue, d_split, d_tickets, d_ens;
     // rebindable inputs: reused across tof_set_draws / tof_set_observables calls (no growth when draws are refreshed)
     DeviceBuf d_z[TOF_MAX_RUNS][2], d_obs[TOF_MAX_RUNS], d_obs_idx[TOF_MAX_RUNS], d_obs_val[TOF_MAX_RUNS];
     cudaStream_t stream = nullptr;
@@ -856,6 +856,41 @@ int tof_stretch_accept(tof_ctx *ctx, double *d_s, double *d_lnprob, int64_t n, i
         d_s, d_lnprob, n, walker0, d_q, d_new_lnprob, d_log_zz, ctx->cfg.ndim, seed, step, half,
         reinterpret_cast<long long *>(d_n_accept));
     ctx->stats.kernel_launches += 1;
+    CU(ctx, cudaGetLastError());
+    return TOF_OK;
+}
+
+int tof_ensemble_step(tof_ctx *ctx, double *d_pos, double *d_lnprob, int64_t n_walkers, int64_t n_steps, double a,
+                      uint64_t seed, int64_t step0, int64_t *d_n_accept, void *stream) {
+    if (!ctx || !d_pos || !d_lnprob) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    const int ndim = ctx->cfg.ndim;
+    if (n_walkers < 2 || (n_walkers & 1)) return fail(ctx, TOF_ERR_INVALID, "The number of walkers must be even.");
+    if (n_walkers < 2 * (int64_t)ndim)
+        return fail(ctx, TOF_ERR_INVALID, "The number of walkers needs to be more than twice the dimension of your parameter space.");
+    if (n_steps < 0 || !(a > 1.0)) return fail(ctx, TOF_ERR_INVALID, "bad stretch-move arguments");
+    if (int rc = ready(ctx, true)) return rc;
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long h = n_walkers / 2;
+    // scratch of one half-step: proposals q[h][ndim], log_zz[h], new_lnprob[h]
+    if (int rc = ensure(ctx, ctx->d_ens, (size_t)h * (ndim + 2) * sizeof(double))) return rc;
+    double *q = static_cast<double *>(ctx->d_ens.p), *log_zz = q + (size_t)h * ndim, *new_lp = log_zz + h;
+    const unsigned grid = (unsigned)((h + 255) / 256);
+    for (int64_t s = 0; s < n_steps; ++s) {
+        for (int half = 0; half < 2; ++half) {
+            double *sl = d_pos + (size_t)half * h * ndim;                 // the half that moves ...
+            const double *comp = d_pos + (size_t)(1 - half) * h * ndim;   // ... against the complementary half
+            double *lp = d_lnprob + (size_t)half * h;
+            const long long walker0 = half * h;
+            stretch_propose_kernel<<<grid, 256, 0, st>>>(sl, h, walker0, comp, h, ndim, a, seed, step0 + s, half, q, log_zz);
+            ModelOut o{};
+            o.lnprob = new_lp;
+            if (int rc = launch_model(ctx, q, h, 0, o, st)) return rc;
+            stretch_accept_kernel<<<grid, 256, 0, st>>>(sl, lp, h, walker0, q, new_lp, log_zz, ndim, seed, step0 + s, half,
+                                                        reinterpret_cast<long long *>(d_n_accept ? d_n_accept + walker0 : nullptr));
+            ctx->stats.kernel_launches += 2;
+        }
+    }
     CU(ctx, cudaGetLastError());
     return TOF_OK;
 }

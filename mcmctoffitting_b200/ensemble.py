@@ -54,6 +54,11 @@ class CudaBackend:
         self.model.stretch_accept(s.data_ptr(), lp.data_ptr(), s.shape[0], walker0, q.data_ptr(), new_lp.data_ptr(),
                                   log_zz.data_ptr(), seed, step, half, n_accept.data_ptr(), self._stream())
 
+    def ensemble_step(self, pos, lp, steps, a, seed, step0, n_accept):
+        """Whole steps for an unsharded ensemble in one library call (no per-half-step host work)."""
+        self.model.ensemble_step(pos.data_ptr(), lp.data_ptr(), pos.shape[0], steps, a, seed, step0, n_accept.data_ptr(),
+                                 self._stream())
+
 
 class EnsembleSampler:
     """emcee-2.x-shaped sampler over a sharded walker ensemble.
@@ -176,6 +181,12 @@ class EnsembleSampler:
 
     # -- device-resident stepping for throughput runs (no per-step host copies) ------------------------------
     def run_device(self, pos: torch.Tensor, lp: torch.Tensor, steps: int) -> None:
+        if self.world == 1 and hasattr(self.backend, "ensemble_step") and pos.is_contiguous() and lp.is_contiguous():
+            # the whole loop inside the library: same kernels, same counters, same chain
+            self.backend.ensemble_step(pos, lp, int(steps), self.a, self.seed, self._step, self.naccepted)
+            self._step += int(steps)
+            self.iterations += int(steps)
+            return
         for _ in range(int(steps)):
             self._half_step(pos, lp, 0)
             self._half_step(pos, lp, 1)

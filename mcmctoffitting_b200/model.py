@@ -223,6 +223,12 @@ class TofModel:
                                                  step, half, C.c_void_p(naccept_ptr), C.c_void_p(stream)))
 
     # -- diagnostics ----------------------------------------------------------------------------------
+    def ensemble_step(self, pos_ptr, lnprob_ptr, n_walkers, n_steps, a, seed, step0, naccept_ptr=0, stream=0) -> None:
+        """``n_steps`` whole stretch-move steps of an ensemble resident on this GPU, enqueued without host round trips
+        (tof_ensemble_step)."""
+        self._check(self._lib.tof_ensemble_step(self._ctx, C.c_void_p(pos_ptr), C.c_void_p(lnprob_ptr), n_walkers, n_steps,
+                                                a, seed, step0, C.c_void_p(naccept_ptr), C.c_void_p(stream)))
+
     def stats(self) -> dict:
         s = _lib.TofStats()
         self._check(self._lib.tof_get_stats(self._ctx, C.byref(s)))

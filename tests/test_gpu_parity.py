@@ -412,6 +412,41 @@ def test_gpu_sampler_runs_and_respects_the_prior(M, O):
     fn.model.close()
 
 
+def test_ensemble_step_entry_point_equals_the_half_step_driver(M, O):
+    """tof_ensemble_step (whole steps inside the library, no host round trips) against the per-half-step driver that
+    the sharded sampler uses: same kernels and counters, so positions, log-probabilities and acceptance counts are
+    identical.  Also emcee's constructor checks, which the entry point repeats."""
+    import torch
+    from mcmctoffitting_b200.ensemble import EnsembleSampler
+    kw = dict(n_samples=1024, n_ev_per_loop=1024, mean_excitation=19.2e-3, ode_mode=M.config.ODE_RANGE)
+    cfg = M.config.adv(0, **kw)
+    om = O.adv_model(0, n_samples=1024, n_ev_per_loop=1024, mean_excitation=19.2e-3)
+    z = np.random.RandomState(8).standard_normal(1024)
+    obs = np.rint(2e3 * om.model_pdf([1050, 0.10], np.random.RandomState(7).standard_normal(1024)))
+    k, steps = 48, 9
+    p0 = np.array([1050, 0.10]) + np.array([10, 1e-2]) * np.random.RandomState(5).standard_normal((k, 2))
+    fn = M.make_lnprob(cfg, obs, z)
+    a = EnsembleSampler(k, 2, fn, seed=31)
+    pa, la, _ = a.run_mcmc(p0, steps)                                   # half-step by half-step (ensemble._half_step)
+    b = EnsembleSampler(k, 2, fn, seed=31, store_chain=False)
+    dev = torch.device("cuda", 0)
+    pos = torch.from_numpy(p0).to(dev)
+    lp = b.initial_lnprob(pos)
+    launches0 = fn.model.stats()["kernel_launches"]
+    b.run_device(pos, lp, 4)                                            # tof_ensemble_step, in two calls: the step
+    b.run_device(pos, lp, steps - 4)                                    # counter carries over
+    torch.cuda.synchronize()
+    assert fn.model.stats()["kernel_launches"] - launches0 >= steps * 2 * 3
+    assert np.array_equal(pos.cpu().numpy(), pa) and np.array_equal(lp.cpu().numpy(), la)
+    assert np.array_equal(b.naccepted.cpu().numpy(), a.naccepted.cpu().numpy()) and int(b.naccepted.sum()) > 0
+    assert b.iterations == steps
+    with pytest.raises(Exception, match="even"):
+        fn.model.ensemble_step(pos.data_ptr(), lp.data_ptr(), 47, 1, 2.0, 0, 0)
+    with pytest.raises(Exception, match="twice the dimension"):
+        fn.model.ensemble_step(pos.data_ptr(), lp.data_ptr(), 2, 1, 2.0, 0, 0)
+    fn.model.close()
+
+
 def test_gpu_chain_equals_the_cpu_chain_from_the_same_seed(M, O):
     """BASELINE.json north_star: 'chains from a fixed seed must agree'.  The proposal stream is counter-based and
     the GPU log-likelihood agrees with the oracle to ~1e-13, so the whole chain -- positions, log-probabilities and

@@ -223,7 +223,8 @@ int tof_ensemble_step(tof_ctx *ctx, double *d_pos, double *d_lnprob, int64_t n_w
 typedef struct tof_stats {
     int64_t kernel_launches; /* kernels launched by this context since creation */
     int64_t evaluations;     /* walker lnprob evaluations issued */
-    int64_t nan_results;     /* reserved (always 0 in this version) */
+    int64_t nan_results;     /* walkers inside the prior whose log-probability came out NaN since creation (returned as
+                              * NaN, or as -inf when nan_to_neginf is set: the case simultFit.py:463-468 prints a dump for) */
     int32_t sm_count;
     int32_t smem_bytes;      /* dynamic shared memory of the main model kernel */
     int32_t threads;         /* threads per CTA of the main model kernel */

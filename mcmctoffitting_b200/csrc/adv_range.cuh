@@ -820,6 +820,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     if (tid == 0 && out.lnprob) {
         double r = degenerate ? CUDART_NAN : lp;
         if (!inside) r = -CUDART_INF;
+        if (r != r && out.nan_count) atomicAdd(out.nan_count, 1ull);
         if (m.nan_to_neginf && r != r) r = -CUDART_INF;
         out.lnprob[w] = r;
     }

@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(NT) simple_finish_kernel(const DevModel m, con
     if (tid == 0 && out.lnprob) {
         double r = (total_i == 0) ? CUDART_NAN : lp;
         if (!inside) r = -CUDART_INF;
+        if (r != r && out.nan_count) atomicAdd(out.nan_count, 1ull);
         if (m.nan_to_neginf && r != r) r = -CUDART_INF;
         out.lnprob[w] = r;
     }

@@ -357,7 +357,8 @@ __global__ void __launch_bounds__(NT, 4) simult_range_kernel(const DevModel m, c
 
 // lnprob = lnprior + sum of the per-run log-likelihoods in run order (simultFit.py:412-420, 444-469).
 __global__ void simult_finish_kernel(const DevModel m, const double *__restrict__ theta, long long n_walkers,
-                                     const double *__restrict__ partial, double *__restrict__ lnprob) {
+                                     const double *__restrict__ partial, double *__restrict__ lnprob,
+                                     unsigned long long *nan_count) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_walkers) return;
     bool inside = true;
@@ -370,6 +371,7 @@ __global__ void simult_finish_kernel(const DevModel m, const double *__restrict_
     if (inside) {
         r = 0.0;
         for (int k = 0; k < m.n_runs; ++k) r += partial[w * m.n_runs + k];
+        if (r != r && nan_count) atomicAdd(nan_count, 1ull);                               // the dump the reference prints, as a counter
         if (m.nan_to_neginf && r != r) r = -CUDART_INF;                                    // simultFit.py:463-468
     }
     lnprob[w] = r;

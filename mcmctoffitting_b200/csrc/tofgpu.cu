@@ -27,7 +27,7 @@ struct tof_ctx {
     DevModel dm{};
     DevRun runs[TOF_MAX_RUNS]{};
     std::vector<void *> owned;  // device allocations freed in tof_destroy
-    DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial, d_work, d_queue, d_split, d_tickets, d_ens;
+    DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial, d_work, d_queue, d_split, d_tickets, d_ens, d_nan;
     // rebindable inputs: reused across tof_set_draws / tof_set_observables calls (no growth when draws are refreshed)
     DeviceBuf d_z[TOF_MAX_RUNS][2], d_obs[TOF_MAX_RUNS], d_obs_idx[TOF_MAX_RUNS], d_obs_val[TOF_MAX_RUNS];
     cudaStream_t stream = nullptr;
@@ -150,6 +150,13 @@ int ready(tof_ctx *ctx, bool need_obs) {
 int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, ModelOut out, cudaStream_t st) {
     if (n <= 0) return TOF_OK;
     const tof_config &c = ctx->cfg;
+    if (out.lnprob && !out.spectra && !out.cells) {          // production calls count NaN results (tof_get_stats)
+        if (!ctx->d_nan.p) {
+            if (int rc = ensure(ctx, ctx->d_nan, sizeof(unsigned long long))) return rc;
+            CU(ctx, cudaMemsetAsync(ctx->d_nan.p, 0, sizeof(unsigned long long), st));
+        }
+        out.nan_count = static_cast<unsigned long long *>(ctx->d_nan.p);
+    }
     if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev0, st));
     if (c.model == TOF_MODEL_ADV) {
         if (c.ode_mode == TOF_ODE_RANGE) {
@@ -242,7 +249,7 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
             ModelOut po{};
             po.lnprob = static_cast<double *>(ctx->d_partial.p);
             onebd_run_kernel<256><<<(unsigned)(n * c.n_runs), 256, ctx->onebd_smem, st>>>(ctx->dm, rs, d_theta, n, po, -1);
-            simult_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->dm, d_theta, n, po.lnprob, out.lnprob);
+            simult_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->dm, d_theta, n, po.lnprob, out.lnprob, out.nan_count);
             ctx->stats.kernel_launches += 2;
         }
     } else if (c.model == TOF_MODEL_SIMULT) {
@@ -261,7 +268,7 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
             po.lnprob = static_cast<double *>(ctx->d_partial.p);
             if (rng) simult_range_kernel<256, 7><<<(unsigned)(n * c.n_runs), 256, ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, po, -1);
             else simult_run_kernel<256><<<(unsigned)(n * c.n_runs), 256, ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, po, -1);
-            simult_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->dm, d_theta, n, po.lnprob, out.lnprob);
+            simult_finish_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->dm, d_theta, n, po.lnprob, out.lnprob, out.nan_count);
             ctx->stats.kernel_launches += 2;
         }
     } else {
@@ -901,6 +908,11 @@ int tof_get_stats(const tof_ctx *ctx, tof_stats *out) {
     out->band_ctas_per_sm = ctx->band_enabled ? ctx->band_ctas : 0;
     out->band_cells = ctx->band_enabled ? ctx->band_hcap : 0;
     out->band_queued_last = 0;
+    if (ctx->d_nan.p) {
+        unsigned long long nn = 0;
+        cudaSetDevice(ctx->cfg.device);
+        if (cudaMemcpy(&nn, ctx->d_nan.p, sizeof(nn), cudaMemcpyDeviceToHost) == cudaSuccess) out->nan_results = (int64_t)nn;
+    }
     if (ctx->band_enabled && ctx->d_work.p) {
         unsigned long long q = 0;
         cudaSetDevice(ctx->cfg.device);

@@ -613,8 +613,13 @@ def test_simult_exhausted_replacement_stream_is_neg_inf(M, O):
     z_main, z_extra = _simult_tables(O, cfg, 5, extra_per_run=3)      # far too few replacement draws
     obs = [np.ones(n) for n in cfg.tof_bins]
     fn = M.make_lnprob(cfg, obs, [z.ravel() for z in z_main], extra_draws=z_extra)
+    assert fn.model.stats()["nan_results"] == 0
     got = fn.batch([[1825.0, 1000, 300, 1.2, 3e4, 2e4, 2e4, 4e4, 4e4]])
     assert got[0] == -np.inf                                             # NaN -> -inf (simultFit.py:463-468)
+    # ... and counted: the reference prints a dump for this case, the library keeps a counter (tof_stats.nan_results)
+    assert fn.model.stats()["nan_results"] == 1
+    fn.batch([[1825.0, 1000, 300, 1.2, 3e4, 2e4, 2e4, 4e4, 4e4], [1800.0, 1000, 300, 1.2, 3e4, 2e4, 2e4, 4e4, 4e4]])
+    assert fn.model.stats()["nan_results"] == 2                          # the second walker is outside the prior: not a NaN
     fn.model.close()
 
 

@@ -179,6 +179,34 @@ class EnsembleSampler:
             pass
         return out
 
+    # -- checkpoint / resume -------------------------------------------------------------------------------
+    def save_checkpoint(self, path: str, pos, lnprob) -> None:
+        """Binary state for an exact resume (the reference only has its append-only text chain, adv:314-317, and
+        hands burn-in over to the main chain in memory, adv:337-339): positions and log-probabilities at full
+        precision, the counter of the proposal generator, the seed, acceptance counters and the stored chain."""
+        if self.rank != 0:
+            return
+        np.savez(path, pos=np.asarray(pos, dtype=np.float64), lnprob=np.asarray(lnprob, dtype=np.float64),
+                 rstate=np.int64(self._step), seed=np.int64(self.seed), a=np.float64(self.a),
+                 naccepted=self.naccepted.cpu().numpy(), iterations=np.int64(self.iterations),
+                 chain=self.chain, lnprobability=self.lnprobability)
+
+    def load_checkpoint(self, path: str):
+        """Restore what :meth:`save_checkpoint` wrote; returns ``(pos, lnprob, rstate)`` ready for
+        ``sample(pos, lnprob0=lnprob, rstate0=rstate)``.  The continued chain equals the uninterrupted one."""
+        with np.load(path if str(path).endswith(".npz") else str(path) + ".npz") as f:
+            pos, lnprob = f["pos"], f["lnprob"]
+            if pos.shape != (self.k, self.dim):
+                raise ValueError("checkpoint holds %s positions, sampler expects %s" % (pos.shape, (self.k, self.dim)))
+            if int(f["seed"]) != self.seed or float(f["a"]) != self.a:
+                raise ValueError("checkpoint was written with seed=%d a=%g" % (int(f["seed"]), float(f["a"])))
+            self._step = int(f["rstate"])
+            self.iterations = int(f["iterations"])
+            self.naccepted = torch.from_numpy(f["naccepted"].copy()).to(self.device)
+            self._chain = [c.copy() for c in np.moveaxis(f["chain"], 1, 0)]
+            self._lnprob = [c.copy() for c in np.moveaxis(f["lnprobability"], 1, 0)]
+            return pos.copy(), lnprob.copy(), self._step
+
     # -- device-resident stepping for throughput runs (no per-step host copies) ------------------------------
     def run_device(self, pos: torch.Tensor, lp: torch.Tensor, steps: int) -> None:
         if self.world == 1 and hasattr(self.backend, "ensemble_step") and pos.is_contiguous() and lp.is_contiguous():

@@ -134,3 +134,26 @@ def test_chain_file_is_readable_by_the_reference_reader(tmp_path):
     chain, probs, p2, w2, s2 = read_chain(path)
     assert (n_params, n_walkers, n_steps) == (p2, w2, s2) == (dim, k, steps)
     assert np.array_equal(chain_ref, chain) and np.array_equal(probs_ref, probs)
+
+
+def test_checkpoint_resume_continues_the_same_chain(tmp_path):
+    """Binary checkpoint: stop after 7 of 15 steps, resume in a fresh sampler, same chain."""
+    k, dim = 32, 3
+    p0 = MU + 0.1 * np.random.RandomState(6).standard_normal((k, dim))
+    full = EnsembleSampler(k, dim, backend=NumpyBackend(gauss_lnprob), seed=11)
+    pos_full, lp_full, _ = full.run_mcmc(p0, 15)
+    first = EnsembleSampler(k, dim, backend=NumpyBackend(gauss_lnprob), seed=11)
+    pos7, lp7, state7 = first.run_mcmc(p0, 7)
+    ck = str(tmp_path / "state.npz")
+    first.save_checkpoint(ck, pos7, lp7)
+    second = EnsembleSampler(k, dim, backend=NumpyBackend(gauss_lnprob), seed=11)
+    pos, lp, rstate = second.load_checkpoint(ck)
+    assert rstate == state7 == 7 and np.array_equal(pos, pos7) and np.array_equal(lp, lp7)
+    pos_res, lp_res, state = second.run_mcmc(pos, 8, rstate0=rstate, lnprob0=lp)
+    assert state == 15 and np.array_equal(pos_res, pos_full) and np.array_equal(lp_res, lp_full)
+    assert np.array_equal(second.chain, full.chain) and np.array_equal(second.lnprobability, full.lnprobability)
+    assert np.array_equal(second.naccepted.numpy(), full.naccepted.numpy()) and second.iterations == 15
+    with pytest.raises(ValueError):
+        EnsembleSampler(k, dim, backend=NumpyBackend(gauss_lnprob), seed=12).load_checkpoint(ck)
+    with pytest.raises(ValueError):
+        EnsembleSampler(k + 2, dim, backend=NumpyBackend(gauss_lnprob), seed=11).load_checkpoint(ck)

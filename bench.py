@@ -302,6 +302,21 @@ def run_gpu_arm(args):
 
     finite_frac = float(torch.isfinite(lp).double().mean().item())
 
+    # ---- per-stage breakdown from the library's own stage timing (separate instrumented kernels, outside the
+    # timed region): share of CTA cycles per stage over one ensemble step --------------------------------------
+    stage_profile = None
+    if rank == 0 and not f32 and ode == M.config.ODE_RANGE and not args.no_stage_profile:
+        model.set_stage_timing(True)
+        th_prof = torch.from_numpy(thetas).to(device)
+        out_prof = torch.empty(N_WALKERS // 2, dtype=torch.float64, device=device)
+        per = N_WALKERS // 2 // world
+        model.lnprob_batch_device(th_prof.data_ptr(), per, out_prof.data_ptr(), torch.cuda.current_stream(device).cuda_stream)
+        torch.cuda.synchronize()
+        stage_profile = model.stage_profile()
+        stage_profile["what"] = ("tof_set_stage_timing: SM clock cycles per stage summed over CTAs, one call of %d walkers, "
+                                 "instrumented instantiation of the same kernel" % per)
+        model.set_stage_timing(False)
+
     # ---- optional FP32 sample stage, reported beside the FP64 headline (N = 1, range formulation) ----------
     fp32_mode = None
     if world == 1 and not f32 and ode == M.config.ODE_RANGE and not args.no_fp32:
@@ -382,7 +397,7 @@ def run_gpu_arm(args):
                                else "rk4 x%d per x-interval" % cfg.ode_substeps), "threads_per_cta": model.stats()["threads"],
                        "l2": "flushed between timed steps (256 MiB memset outside the event bracket)",
                        "finite_lnprob_fraction": finite_frac},
-            "roofline": roofline, "cpu_baseline": cpu, "fp32_mode": fp32_mode,
+            "roofline": roofline, "cpu_baseline": cpu, "fp32_mode": fp32_mode, "stage_profile": stage_profile,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": N_WALKERS * 2 * 8,
                     "d2h_bytes_per_step": N_WALKERS * 8},
             "gpu_launches": launches_timed, "clocks": clock_info,
@@ -406,6 +421,7 @@ def main():
     ap.add_argument("--precision", choices=["fp64", "fp32"], default="fp64",
                     help="fp64 (default, the reference's arithmetic) or the optional FP32 sample stage as the measured arm")
     ap.add_argument("--no-fp32", action="store_true", help="skip the secondary FP32-mode measurement of the default run")
+    ap.add_argument("--no-stage-profile", action="store_true", help="skip the per-stage cycle breakdown (tof_set_stage_timing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -241,6 +241,20 @@ int tof_get_stats(const tof_ctx *ctx, tof_stats *out);
 int tof_set_timing(tof_ctx *ctx, int enabled);
 int tof_last_kernel_ms(tof_ctx *ctx, float *ms);
 
+/* Per-stage timing of the shipped adv/intermediate kernel (TOF_ODE_RANGE): while enabled, every CTA charges its SM
+ * clock cycles to the stage that just ended (thread 0, between barriers).  tof_get_stage_cycles returns the sums since
+ * the last call and resets them: cycles[k] for the TOF_N_STAGES stages below, then the number of walkers processed.
+ *   0 setup      work fetch, prior, per-row E-band, record staging, histogram reset
+ *   1 histogram  energy-loss lookup per draw, draw-index lookup, (row, interval) cell sums      adv:128-138
+ *   2 normalise  sum(H * dE * dx)                                                                adv:143
+ *   3 scatter    np.rint counts, flight time of every non-empty cell, TOF histogram             adv:146-159
+ *   4 likelihood density, timing response at the observed bins, sum(obs * log)                  adv:160-181
+ * Off by default (one predicated branch per stage); this is the profiling hook the reference lacks
+ * (testStoppingApproximation.py:5-6 "really we should actually profile the sampling"). */
+#define TOF_N_STAGES 5
+int tof_set_stage_timing(tof_ctx *ctx, int enabled);
+int tof_get_stage_cycles(tof_ctx *ctx, uint64_t cycles[TOF_N_STAGES + 1]);
+
 /* Peak FP64 FMA rate of the device measured with a register-resident DFMA loop (TFLOP/s):
  * the roofline denominator for this FP64-pipe-bound path. */
 int tof_measure_fp64_peak(tof_ctx *ctx, double *tflops);

@@ -79,6 +79,8 @@ SIGNATURES = {
     "tof_ensemble_step": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double, C.c_uint64, C.c_int64, _vp, _vp]),
     "tof_get_stats": (C.c_int, [_vp, C.POINTER(TofStats)]),
     "tof_set_timing": (C.c_int, [_vp, C.c_int]),
+    "tof_set_stage_timing": (C.c_int, [_vp, C.c_int]),
+    "tof_get_stage_cycles": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "tof_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "tof_measure_fp64_peak": (C.c_int, [_vp, C.POINTER(C.c_double)]),
 }

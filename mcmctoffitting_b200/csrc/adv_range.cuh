@@ -454,7 +454,7 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
     }
 }
 
-template <int NT, int P, bool F32 = false>
+template <int NT, int P, bool F32 = false, bool PROF = false>
 __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(const DevModel m, const DevRun run, const double *__restrict__ theta,
                                                        long long n_walkers, ModelOut out) {
     extern __shared__ __align__(16) unsigned char smem_sym[];
@@ -512,6 +512,19 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     const double x_start = m.ode_from_zero ? 0.0 : m.x_centers[0];
     for (int i = tid; i < X; i += NT) sdelta[i] = sgn * (m.x_centers[i] - x_start);
     __shared__ long long s_next;
+    // stage timing (tof_set_stage_timing; PROF instantiations only, the shipped kernels carry none of this): thread 0
+    // charges the SM clock between stage boundaries to the stage that ends there -- it leaves a barrier when the CTA
+    // does, so this is CTA time per stage, summed over CTAs
+    long long t_mark = PROF ? clock64() : 0;
+    auto stage_done = [&](int k) {
+        if constexpr (PROF) {
+            if (tid == 0) {
+                const long long t = clock64();
+                atomicAdd(out.stage_cycles + k, (unsigned long long)(t - t_mark));
+                t_mark = t;
+            }
+        }
+    };
     for (long long iter = 0;; ++iter) {
     __syncthreads();                                       // the previous walker is done with shared memory
     if (tid == 0)
@@ -592,6 +605,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     // ---- per walker: zero the cell histogram ------------------------------------------------------------------
     for (int i = tid; i < X * hstride; i += NT) H[i] = 0.0;
 
+    stage_done(0);                                         // work fetch, prior, band, record staging, histogram reset
     // ---- phase 1: (x,E) histogram of cross-section weights through the range tables ---------------------
     int bin_lo_all = EB, bin_hi_all = -1;                  // E-bins any draw of any tile can have touched (uniform)
     if (!F32 && m.n_draws >= RANGE_STREAM_MIN) {           // (FP32 contexts with big draw sets are run by the FP64 kernels)
@@ -686,6 +700,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
         }
     }
     __syncthreads();
+    stage_done(1);                                         // phase 1: T1, lookup, (row, interval) tasks
 
     if (NS > 1) {
         // partial histogram -> L2-resident scratch; the CTA that arrives last adds the NS partials in split order
@@ -729,6 +744,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
         for (int jb = lane; jb < nbw; jb += 32) part += __dmul_rn(__dmul_rn(Hr[jb], de), dx);
     }
     const double S = block_sum<double>(part, scratch);     // includes the barrier that publishes tofc = 0
+    stage_done(2);                                         // normalisation sum (+ split merge when several CTAs share a walker)
 
     // ---- phase 3: quantise (adv:146) and scatter every non-empty cell to its flight time (adv:149-158) ----
     const double t_step = (run.tof_max - run.tof_min) / (double)T;
@@ -762,6 +778,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
         }
     }
     __syncthreads();
+    stage_done(3);                                         // quantise + scatter to flight times
 
     // ---- phase 4: density (np.histogram density=True) into the (now free) H region -------------------------
     long long cpart = 0;
@@ -824,6 +841,8 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
         if (m.nan_to_neginf && r != r) r = -CUDART_INF;
         out.lnprob[w] = r;
     }
+    stage_done(4);                                         // density, timing response, likelihood
+    if (PROF && tid == 0) atomicAdd(out.stage_cycles + TOF_N_STAGES, 1ull);
     }   // persistent walker loop
 }
 

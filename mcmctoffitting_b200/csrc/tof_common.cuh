@@ -11,6 +11,7 @@ struct ModelOut {
     long long *cells;     // optional [n][X][E] integer cell counts
     int stage;
     int unweighted;       // simult RK4 kernel: cells = unweighted (x,E) histogram of the LAST loop (ppcTools.py:151-157)
+    unsigned long long *stage_cycles; // optional [TOF_N_STAGES + 1]: SM clock cycles per stage summed over CTAs, then walkers (adv range kernel)
     unsigned long long *nan_count;   // optional: walkers inside the prior whose log-probability came out NaN (diagnostics)
     unsigned long long *work;  // optional global work counter (persistent CTAs take walkers dynamically)
     // range kernel, banded launch: capacity of the cell histogram (cells) and of the staged T2 records

@@ -27,12 +27,12 @@ struct tof_ctx {
     DevModel dm{};
     DevRun runs[TOF_MAX_RUNS]{};
     std::vector<void *> owned;  // device allocations freed in tof_destroy
-    DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial, d_work, d_queue, d_split, d_tickets, d_ens, d_nan;
+    DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial, d_work, d_queue, d_split, d_tickets, d_ens, d_nan, d_stage;
     // rebindable inputs: reused across tof_set_draws / tof_set_observables calls (no growth when draws are refreshed)
     DeviceBuf d_z[TOF_MAX_RUNS][2], d_obs[TOF_MAX_RUNS], d_obs_idx[TOF_MAX_RUNS], d_obs_val[TOF_MAX_RUNS];
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool timing = false, timed = false;
+    bool timing = false, timed = false, stage_timing = false;
     std::string err;
     tof_stats stats{};
     int adv_nt = 1024, adv_dpt = 1;
@@ -120,7 +120,14 @@ AdvKernel range_variant_f32(int nt, int degree) {
     return nullptr;
 }
 
-AdvKernel range_variant(int nt, int degree, bool f32 = false) {
+AdvKernel range_variant_prof(int nt, int degree) {          // stage-timing instantiations (tof_set_stage_timing)
+    if (nt == 1024 && degree == 7) return adv_range_kernel<1024, 7, false, true>;
+    if (nt == 512 && degree == 7) return adv_range_kernel<512, 7, false, true>;
+    return nullptr;
+}
+
+AdvKernel range_variant(int nt, int degree, bool f32 = false, bool prof = false) {
+    if (prof) return range_variant_prof(nt, degree);
     if (f32) return range_variant_f32(nt, degree);
     if (nt == 1024 && degree == 7) return adv_range_kernel<1024, 7>;
     if (nt == 800 && degree == 7) return adv_range_kernel<800, 7>;
@@ -157,12 +164,14 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
         }
         out.nan_count = static_cast<unsigned long long *>(ctx->d_nan.p);
     }
+    if (ctx->stage_timing && ctx->d_stage.p) out.stage_cycles = static_cast<unsigned long long *>(ctx->d_stage.p);
     if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev0, st));
     if (c.model == TOF_MODEL_ADV) {
         if (c.ode_mode == TOF_ODE_RANGE) {
             // persistent CTAs: one per resident slot, walkers handed out through global counters.
             // d_work = {banded work counter, full-size work counter, queue length}
-            AdvKernel kfull = range_variant(ctx->rng_nt, c.rng_degree, ctx->f32);
+            const bool prof = out.stage_cycles != nullptr;
+            AdvKernel kfull = range_variant(ctx->rng_nt, c.rng_degree, ctx->f32, prof);
             int rc = ensure(ctx, ctx->d_work, 3 * sizeof(unsigned long long));
             if (rc) return rc;
             CU(ctx, cudaMemsetAsync(ctx->d_work.p, 0, 3 * sizeof(unsigned long long), st));
@@ -203,7 +212,7 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 ob.rcap = ctx->band_rcap;
                 ob.queue_out = static_cast<int *>(ctx->d_queue.p);
                 ob.queue_count = cnt + 2;
-                AdvKernel kband = range_variant(ctx->band_nt, c.rng_degree, ctx->f32);
+                AdvKernel kband = range_variant(ctx->band_nt, c.rng_degree, ctx->f32, prof);
                 const long long slots_band = (long long)ctx->stats.sm_count * std::max(ctx->band_ctas, 1);
                 kband<<<(unsigned)std::min<long long>(n_work, slots_band), ctx->band_nt, ctx->band_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, ob);
                 // 2) full-size launch over the queue (exits at once when it is empty)
@@ -919,6 +928,36 @@ int tof_get_stats(const tof_ctx *ctx, tof_stats *out) {
         if (cudaMemcpy(&q, static_cast<unsigned long long *>(ctx->d_work.p) + 2, sizeof(q), cudaMemcpyDeviceToHost) == cudaSuccess)
             out->band_queued_last = (int64_t)q;
     }
+    return TOF_OK;
+}
+
+int tof_set_stage_timing(tof_ctx *ctx, int enabled) {
+    if (!ctx) return TOF_ERR_INVALID;
+    if (enabled && !(ctx->cfg.model == TOF_MODEL_ADV && ctx->cfg.ode_mode == TOF_ODE_RANGE))
+        return fail(ctx, TOF_ERR_INVALID, "stage timing is built into the adv/intermediate TOF_ODE_RANGE kernel only");
+    if (enabled && (ctx->f32 || !range_variant_prof(ctx->rng_nt, ctx->cfg.rng_degree) || !range_variant_prof(ctx->band_nt, ctx->cfg.rng_degree)))
+        return fail(ctx, TOF_ERR_INVALID, "stage timing needs an FP64 context with the default 512/1024-thread launches");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    if (enabled) {      // the instrumented instantiations need the same shared-memory opt-in as the shipped ones
+        CU(ctx, cudaFuncSetAttribute(range_variant_prof(ctx->rng_nt, ctx->cfg.rng_degree), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->adv_smem));
+        if (ctx->band_enabled)
+            CU(ctx, cudaFuncSetAttribute(range_variant_prof(ctx->band_nt, ctx->cfg.rng_degree), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->band_smem));
+    }
+    if (enabled && !ctx->d_stage.p) {
+        if (int rc = ensure(ctx, ctx->d_stage, (TOF_N_STAGES + 1) * sizeof(unsigned long long))) return rc;
+        CU(ctx, cudaMemset(ctx->d_stage.p, 0, (TOF_N_STAGES + 1) * sizeof(unsigned long long)));
+    }
+    ctx->stage_timing = enabled != 0;
+    return TOF_OK;
+}
+
+int tof_get_stage_cycles(tof_ctx *ctx, uint64_t cycles[TOF_N_STAGES + 1]) {
+    if (!ctx || !cycles) return TOF_ERR_INVALID;
+    if (!ctx->d_stage.p) return fail(ctx, TOF_ERR_STATE, "stage timing was never enabled");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    CU(ctx, cudaDeviceSynchronize());
+    CU(ctx, cudaMemcpy(cycles, ctx->d_stage.p, (TOF_N_STAGES + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CU(ctx, cudaMemset(ctx->d_stage.p, 0, (TOF_N_STAGES + 1) * sizeof(unsigned long long)));
     return TOF_OK;
 }
 

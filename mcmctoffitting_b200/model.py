@@ -234,6 +234,20 @@ class TofModel:
         self._check(self._lib.tof_get_stats(self._ctx, C.byref(s)))
         return {k: getattr(s, k) for k, _ in s._fields_}
 
+    STAGES = ("setup", "histogram", "normalise", "scatter", "likelihood")
+
+    def set_stage_timing(self, enabled: bool) -> None:
+        """Per-stage SM-cycle accounting inside the adv/intermediate range kernel (tof_set_stage_timing)."""
+        self._check(self._lib.tof_set_stage_timing(self._ctx, int(enabled)))
+
+    def stage_profile(self) -> dict:
+        """Cycles per stage since the last call (and reset): ``{"cycles": {...}, "share": {...}, "walkers": n}``."""
+        buf = (C.c_uint64 * (len(self.STAGES) + 1))()
+        self._check(self._lib.tof_get_stage_cycles(self._ctx, buf))
+        cyc = {k: int(buf[i]) for i, k in enumerate(self.STAGES)}
+        tot = max(sum(cyc.values()), 1)
+        return {"cycles": cyc, "share": {k: v / tot for k, v in cyc.items()}, "walkers": int(buf[len(self.STAGES)])}
+
     def set_timing(self, enabled: bool) -> None:
         self._check(self._lib.tof_set_timing(self._ctx, int(enabled)))
 

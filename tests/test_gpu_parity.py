@@ -915,3 +915,33 @@ def test_fp32_mode_is_refused_where_it_is_not_built(M):
     with M.TofModel(M.config.adv(0, n_samples=16384, n_ev_per_loop=16384, mean_excitation=19.2e-3,
                                  ode_mode=M.config.ODE_RANGE, precision=M.config.PRECISION_FP32)) as m:
         assert m.stats()["fp32_active"] == 0
+
+
+def test_stage_timing_accounts_for_every_walker_and_changes_nothing(M, O):
+    """tof_set_stage_timing: the instrumented instantiation returns the same log-probabilities, counts every walker
+    once and charges most cycles to the (x,E) histogram stage; refused where it is not built."""
+    cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE)
+    om = O.sweep_model()
+    z = np.random.RandomState(20260101).standard_normal(1024)
+    obs = np.rint(1e5 * om.model_pdf([1050, 0.10], np.random.RandomState(7).standard_normal(1024)))
+    rs = np.random.RandomState(1)
+    thetas = np.array([1050, 0.10]) + np.array([10, 1e-2]) * rs.standard_normal((3000, 2))
+    thetas[-40:, 1] = rs.uniform(0.2, 0.45, 40)                      # some for the full-size launch
+    thetas[7] = [900.0, 0.1]                                         # outside the prior: not a processed walker
+    with M.TofModel(cfg) as m:
+        m.set_observables(obs)
+        m.set_draws(z)
+        plain = m.lnprob_batch(thetas)
+        m.set_stage_timing(True)
+        timed = m.lnprob_batch(thetas)
+        prof = m.stage_profile()
+        m.set_stage_timing(False)
+        again = m.lnprob_batch(thetas)
+    assert np.array_equal(plain, timed, equal_nan=True) and np.array_equal(plain, again, equal_nan=True)
+    assert prof["walkers"] == len(thetas) - 1
+    assert set(prof["share"]) == {"setup", "histogram", "normalise", "scatter", "likelihood"}
+    assert abs(sum(prof["share"].values()) - 1.0) < 1e-12 and prof["share"]["histogram"] > 0.4
+    assert all(v > 0 for v in prof["cycles"].values())
+    with pytest.raises(Exception):
+        with M.TofModel(M.config.sweep(ode_mode=M.config.ODE_RK4)) as m2:
+            m2.set_stage_timing(True)

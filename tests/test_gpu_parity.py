@@ -945,3 +945,26 @@ def test_stage_timing_accounts_for_every_walker_and_changes_nothing(M, O):
     with pytest.raises(Exception):
         with M.TofModel(M.config.sweep(ode_mode=M.config.ODE_RK4)) as m2:
             m2.set_stage_timing(True)
+
+
+def test_range_degenerate_spreads(M, O):
+    """sigma0 = 0 and nearly 0 (model_batch ignores the prior): every draw has the same energy, the tile has no
+    width, the draw lookup is bypassed and every cell is walked from the first draw -- still the oracle's counts."""
+    cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE)
+    om = O.sweep_model(ode_scheme="exact")
+    xs = O.DDNXS()
+    z = np.random.RandomState(4).standard_normal(1024)
+    # (e0 = 1050.0 exactly would put all 1024 identical draws ON an E-bin edge at the first x: the one measure-zero
+    # case where the 2e-13 cm table error decides the bin -- documented in DESIGN.md)
+    thetas = np.array([[1050.3, 0.0], [1050.0, 1e-7], [1234.5, 1e-4], [1050.0, 0.1]])
+    with M.TofModel(cfg) as m:
+        m.set_observables(np.ones(2048))
+        m.set_draws(z)
+        cc = m.cell_counts(thetas)
+        counts = m.model_batch(thetas, stage="counts")
+        lp = m.lnprob_batch(thetas)                       # banded launch (first three are outside the prior: -inf)
+    for k, th in enumerate(thetas):
+        assert np.array_equal(cc[k], om.cell_counts(th, z, xs)), k
+        assert np.array_equal(counts[k], om.raw_tof(th, z, xs, density=False)), k
+    assert cc[0].sum() > 3000 and np.count_nonzero(cc[0]) == 100      # one cell per row
+    assert np.all(lp[:3] == -np.inf) and rel(float(lp[3]), float(om.lnprob(thetas[3], np.ones(2048), z, xs))) <= RTOL

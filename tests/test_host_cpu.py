@@ -2,6 +2,7 @@
 match the oracle / reference KATs, the range tables reproduce the oracle's integer cell counts, and
 the pool adapter behaves like emcee's pool seam.  No GPU compute here."""
 import ctypes
+import os
 import warnings
 
 import numpy as np
@@ -237,3 +238,64 @@ def test_sdef_card_matches_the_reference_writer():
                                      neutronSpectra=[[cells[k].astype(float)] for k in range(n)])   # [sample][run][x, E]
     want = ref_ppc.ppcTools.makeSDEF_sia_cumulative(stand_in, 100)
     assert got == {"si": want["si"], "sp": want["sp"]}
+
+
+@pytest.mark.parametrize("name", ["sweep", "adv", "intermediate", "wide_bins"])
+def test_fp32_weight_records_reach_single_precision(name):
+    """The FP32 mode's degree-3 weight polynomials (fitted in tof_create at the Chebyshev nodes of every T2 interval
+    from the degree-7 ones) restated in numpy: <= 1e-7 on the shipped binnings, and clearly worse on a binning the
+    library is expected to refuse (its own threshold is 3e-7)."""
+    cfg = {"sweep": lambda: C.sweep(), "adv": lambda: C.adv(0), "intermediate": lambda: C.intermediate(0),
+           "wide_bins": lambda: C.sweep(e_bins=12)}[name]()                       # 200-keV bins
+    tab = R.build_cached(cfg)
+    br, co = np.asarray(tab.breaks), np.asarray(tab.coefs)
+    worst = 0.0
+    k = np.arange(4)
+    for j in range(len(br) - 1):
+        w = br[j + 1] - br[j]
+        nodes = 0.5 * (1.0 - np.cos((2 * k + 1) * np.pi / 8.0))                   # in s = dt / w
+        p7 = np.polynomial.polynomial.polyval(nodes * w, co[j])
+        b = np.linalg.solve(np.vander(nodes, 4, increasing=True), p7)
+        c32 = (b / w ** k).astype(np.float32).astype(np.float64)
+        d = np.linspace(0.0, w, 33)
+        ref = np.polynomial.polynomial.polyval(d, co[j])
+        worst = max(worst, float(np.max(np.abs(np.polynomial.polynomial.polyval(d, c32) / ref - 1.0))))
+    if name == "wide_bins":
+        assert worst > 3e-7, worst
+    else:
+        assert worst <= 1e-7, worst
+
+
+def test_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference on the host cores: one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "evals/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("walker lnprob evals/sec") and line["value"] > 0 and line["dtype"] == "f64"
+    assert "262144 walkers" in line["config"]["workload"] and line["vs_baseline"] is None
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "evaluations" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # ranks other than 0 do no work under torchrun
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         stdout=subprocess.PIPE, text=True, timeout=120, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_gpu_arm_refuses_to_run_without_a_device():
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, cwd=root)
+    assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)

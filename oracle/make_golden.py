@@ -132,6 +132,34 @@ def adv(excitation, label):
             "cases": cases, "spectra": spectra}
 
 
+def intermediate(excitation, label, run=3):
+    """tests/intermediateTOFmodel.py (BASELINE config 2) through its own functions: `-run 3` = far standoff, 70 TOF
+    bins on (190, 260); E grid 150 bins on 200-1700 keV, rho = 8.37e-5 (intermediate:55-97); test-sized loops."""
+    ns = ref_loader.load("intermediateTOFmodel", argv=["-run", str(run)])
+    ref = ref_loader.load_utilities()
+    n_ev = 1000
+    ns["nEvPerLoop"] = n_ev
+    ns["data_x"] = np.repeat(ns["x_binCenters"], n_ev)
+    model = ref.ionStopping.ionStopping.simpleBethe([1, 2, 8.37e-5, 1, excitation])
+    ns["stoppingModel"] = model
+    standoff = ns["standoff"][run]
+    np.random.seed(17)
+    raw = ns["generateModelData"]([900, .12], standoff, ns["ddnXSinstance"], model.dEdx, 4000, True)
+    obs = np.rint(ns["beamTiming"].applySpreading(raw) * 2e4)
+    cases = []
+    for seed, theta, nd in [(18, [900, .12], 4000), (19, [880, .10], 4000), (20, [950, .15], 2000), (21, [1199, .169], 3000)]:
+        np.random.seed(seed)
+        val = ns["lnlike"](theta, obs, nDraws=nd)
+        np.random.seed(seed)
+        cnt = ns["generateModelData"](theta, standoff, ns["ddnXSinstance"], model.dEdx, nd, False)
+        cases.append({"seed": seed, "theta": theta, "nDraws": nd, "kind": "lnlike", "value": f(val), "counts": fl(cnt)})
+    np.random.seed(22)
+    outside = ns["lnprob"]([700.0, .1], obs)                       # outside the prior box (intermediate:185-189)
+    return {"label": label, "run": run, "mean_excitation": excitation, "n_ev_per_loop": n_ev, "obs": fl(obs),
+            "cases": cases, "lnprob_outside_prior": f(outside),
+            "tof_bins": int(ns["tof_nBins"]), "tof_range": [f(v) for v in ns["tof_range"]]}
+
+
 def sweep():
     """adv model at the benchmark shape: 1024 draws, 2048 TOF bins on [128,256)."""
     ns = ref_loader.load("advIntermediateTOFmodel")
@@ -198,6 +226,8 @@ def main():
         "simple": simple(),
         "adv_as_written": adv(19.2, "I=19.2 keV as written (adv:94)"),
         "adv_physical": adv(19.2e-3, "I=19.2e-3 keV (physical)"),
+        "intermediate_as_written": intermediate(19.2, "intermediateTOFmodel.py -run 3, I=19.2 keV as written (intermediate:94)"),
+        "intermediate_physical": intermediate(19.2e-3, "intermediateTOFmodel.py -run 3, I=19.2e-3 keV (physical)"),
         "sweep": sweep(),
         "simult": simult(full="--quick" not in sys.argv),
         "onebd": onebd(),

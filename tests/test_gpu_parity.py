@@ -196,6 +196,36 @@ def test_intermediate_model_vs_oracle(M, O):
         assert np.array_equal(cc[k], om.cell_counts(th, z, xs))
 
 
+@pytest.mark.parametrize("ode", ["rk4", "range"])
+@pytest.mark.parametrize("key", ["intermediate_as_written", "intermediate_physical"])
+def test_intermediate_reference_goldens(M, O, golden, pf, key, ode):
+    """BASELINE config 2: values produced by tests/intermediateTOFmodel.py's own lnlike / generateModelData."""
+    g = golden[key]
+    obs = parse_floats(g["obs"])
+    mode = M.config.ODE_RANGE if ode == "range" else M.config.ODE_RK4
+    n_ok = 0
+    for c in g["cases"]:
+        cfg = M.config.intermediate(g["run"], n_samples=c["nDraws"], n_ev_per_loop=g["n_ev_per_loop"],
+                                    mean_excitation=g["mean_excitation"], ode_mode=mode)
+        z = np.random.RandomState(c["seed"]).standard_normal(cfg.n_draws)
+        with M.TofModel(cfg) as m:
+            m.set_observables(obs)
+            m.set_draws(z)
+            got = float(m.lnprob_batch([c["theta"]])[0])
+            counts = m.model_batch([c["theta"]], stage="counts")[0]
+        want = pf(c["value"])
+        assert rel(got, want) <= 1e-4, (c["theta"], got, want)       # at most one LSODA-tolerance count flip
+        if rel(got, want) <= RTOL:
+            n_ok += 1
+            assert np.array_equal(counts, parse_floats(c["counts"])), c["theta"]
+    assert n_ok >= len(g["cases"]) - 1, n_ok
+    cfg = M.config.intermediate(g["run"], n_samples=1000, n_ev_per_loop=1000, mean_excitation=g["mean_excitation"], ode_mode=mode)
+    with M.TofModel(cfg) as m:
+        m.set_observables(obs)
+        m.set_draws(np.zeros(1000))
+        assert m.lnprob_batch([[700.0, .1]])[0] == pf(g["lnprob_outside_prior"]) == -np.inf
+
+
 def test_simple_model_goldens(M, O, golden, pf):
     g = golden["simple"]
     obs = np.array(g["obs"], dtype=np.float64)

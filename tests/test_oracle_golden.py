@@ -99,6 +99,31 @@ def test_adv_model_goldens(golden, pf, key):
         np.testing.assert_allclose(m.raw_tof(s["theta"], z, xs, density=True), parse_floats(s["pdf"]), rtol=1e-14)
 
 
+@pytest.mark.parametrize("key", ["intermediate_as_written", "intermediate_physical"])
+def test_intermediate_model_goldens(golden, pf, key):
+    """BASELINE config 2 through tests/intermediateTOFmodel.py's own functions (-run 3: far standoff, 70 TOF bins;
+    150 E-bins on 200-1700 keV, rho = 8.37e-5): log-likelihoods and integer TOF spectra."""
+    g = golden[key]
+    obs = parse_floats(g["obs"])
+    xs = O.DDNXS()
+    exact = 0
+    for c in g["cases"]:
+        nd = c["nDraws"]
+        m = O.intermediate_model(g["run"], mean_excitation=g["mean_excitation"], n_ev_per_loop=g["n_ev_per_loop"], n_samples=nd)
+        assert (m.tof_bins, [m.tof_min, m.tof_max]) == (g["tof_bins"], g["tof_range"])
+        z = np.random.RandomState(c["seed"]).standard_normal(m.n_loops * m.n_ev_per_loop)
+        got = m.lnlike(c["theta"], obs, z, xs)
+        want = pf(c["value"])
+        assert rel(got, want) <= 1e-4, (c["theta"], got, want)      # one LSODA-tolerance count flip at most
+        same = rel(got, want) <= 1e-12
+        exact += same
+        if same:
+            assert np.array_equal(m.raw_tof(c["theta"], z, xs, density=False), parse_floats(c["counts"]))
+    assert exact >= len(g["cases"]) - 1
+    m = O.intermediate_model(g["run"], mean_excitation=g["mean_excitation"], n_ev_per_loop=1000, n_samples=1000)
+    assert m.lnprob([700.0, .1], obs, np.zeros(1000), xs) == pf(g["lnprob_outside_prior"]) == -np.inf
+
+
 @pytest.mark.slow
 @pytest.mark.parametrize("key", ["adv_as_written", "adv_physical"])
 def test_adv_model_default_ndraws(golden, pf, key):

@@ -231,6 +231,7 @@ def main():
         "sweep": sweep(),
         "simult": simult(full="--quick" not in sys.argv),
         "onebd": onebd(),
+        "ppc": ppc(),
     }
     path = os.path.join(ROOT, "tests", "golden", "reference_golden.json")
     with open(path, "w") as fh:
@@ -238,6 +239,40 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+
+
+def ppc():
+    """utilities/ppcTools.py: the reference's own ppcTools class (its 20 x 100 grid, 1000 tracks per loop, 2 loops)
+    fed with a throw-away chain file; generateModelData -> (TOF spectrum, eN_atEachX, eD_atEachX), seeded."""
+    import tempfile
+    from unittest import mock
+    from mcmctoffitting_b200.ensemble import write_chain_step
+    sys.path.insert(0, ref_loader.REFERENCE_ROOT)
+    stubs = {k: mock.MagicMock(name=k) for k in ("matplotlib", "matplotlib.pyplot", "corner")}
+    shim = ref_loader._LinspaceShim()
+    with mock.patch.dict(sys.modules, stubs):
+        import utilities.ppcTools as ref_ppc
+        path = os.path.join(tempfile.mkdtemp(), "chain.dat")
+        rs = np.random.RandomState(0)
+        for _ in range(3):
+            write_chain_step(path, rs.standard_normal((18, 9)), rs.standard_normal(18))
+        np.linspace = shim
+        try:
+            pt = ref_ppc.ppcTools(path, 1000, nBins_eD=100, nBins_x=20, nRuns=4)
+        finally:
+            np.linspace = shim._orig
+    out = {"x_bins": 20, "e_bins": 100, "n_ev_per_loop": 1000, "n_samples": 2000, "cases": []}
+    for seed, run, params in [(5, 0, [1878.4, 850, 170, 0.5, 3e4]), (6, 3, [1825.0, 1000, 300, 1.2, 4e4])]:
+        np.random.seed(seed)
+        tof, eN, eD = pt.generateModelData(params, pt.standoffs[run], pt.tof_range[run], pt.tofRunBins[run], pt.ddnXSinstance,
+                                           pt.stoppingModel.dEdx, pt.beamTiming, 2000, True)
+        out["cases"].append({"seed": seed, "run": run, "params": params, "tof": fl(tof),
+                             "eN_atEachX": [[int(v) for v in r] for r in eN[1:]],      # without the leading row of zeros
+                             "eD_atEachX": [[int(v) for v in r] for r in eD[1:]]})
+    cells = np.array([c["eN_atEachX"] for c in out["cases"][:1]], dtype=float)
+    pt.tofData, pt.neutronSpectra = [0], [[cells[0]]]
+    out["sdef_case0"] = pt.makeSDEF_sia_cumulative(100)
+    return out
 
 
 def onebd():

@@ -616,6 +616,27 @@ def test_ppc_deuteron_spectra_and_sdef_card(M, O):
     fn.model.close()
 
 
+def test_ppc_reference_goldens(M, O, golden):
+    """The reference's ppcTools class (its own 20 x 100 grid) against the CUDA path: TOF spectrum, neutron spectra
+    per x (cell counts) and the unweighted deuteron spectra, from the draws the class consumed."""
+    g = golden["ppc"]
+    kw = dict(n_samples=g["n_samples"], n_ev_per_loop=g["n_ev_per_loop"])
+    om = O.SimultModel(x_bins=g["x_bins"], eD_bins=g["e_bins"], **kw)
+    cfg = M.config.simult(x_bins=g["x_bins"], e_bins=g["e_bins"], **kw)
+    for c in g["cases"]:
+        r = c["run"]
+        rec = _Recorder(O.GlobalStateDraws(np.random.RandomState(c["seed"])), 5)
+        om.cell_counts(c["params"], r, rec)                              # records the draws the reference consumed
+        z_main = [np.concatenate(rec.rec_main[r]) if k == r else np.zeros(cfg.n_draws) for k in range(5)]
+        z_extra = [np.concatenate(rec.rec_extra[r]) if (k == r and rec.rec_extra[r]) else np.zeros(0) for k in range(5)]
+        theta = np.array([c["params"][:4] + [c["params"][4]] * 5])
+        fn = M.make_lnprob(cfg, [np.ones(t) for t in cfg.tof_bins], z_main, extra_draws=z_extra)
+        assert np.array_equal(fn.model.cell_counts(theta, run=r)[0], np.array(c["eN_atEachX"]))
+        assert np.array_equal(fn.model.deuteron_counts(theta, run=r)[0], np.array(c["eD_atEachX"]))
+        np.testing.assert_allclose(fn.model.model_batch(theta, run=r, stage="spread")[0], parse_floats(c["tof"]), rtol=1e-11)
+        fn.model.close()
+
+
 def test_simult_reference_goldens(M, O, golden, pf):
     """Seed-pinned lnprob values produced by the reference's own simultFit functions (scipy dopri5 there)."""
     g = golden["simult"]

@@ -248,3 +248,19 @@ def test_onebd_goldens(golden, pf):
             ev, _ = m.model(p, r, z_all[-1], rs.poisson(p[4], m.tof_bins[r]), xs, tab)
             total.append(m.bin_loglike(ev, obs[r]))
         assert rel(float(np.sum(total)), pf(c["lnprob"])) <= 1e-13
+
+
+def test_ppc_goldens_from_the_reference_class(golden):
+    """utilities/ppcTools.py's own class (20 x 100 grid, dopri5): its TOF spectrum, the neutron spectra per x
+    (eN_atEachX = rows of the integer cell counts) and the unweighted deuteron spectra of the last loop (eD_atEachX)."""
+    g = golden["ppc"]
+    om = O.SimultModel(x_bins=g["x_bins"], eD_bins=g["e_bins"], n_samples=g["n_samples"], n_ev_per_loop=g["n_ev_per_loop"])
+    for c in g["cases"]:
+        draws = lambda: O.GlobalStateDraws(np.random.RandomState(c["seed"]))      # noqa: E731
+        counts, _ = om.cell_counts(c["params"], c["run"], draws())
+        assert np.array_equal(counts, np.array(c["eN_atEachX"]))
+        assert np.array_equal(om.deuteron_counts(c["params"], c["run"], draws()), np.array(c["eD_atEachX"]))
+        np.testing.assert_allclose(om.model(c["params"], c["run"], draws(), None, True), parse_floats(c["tof"]), rtol=1e-13)
+    from mcmctoffitting_b200 import ppc
+    card = ppc.sdef_sia_cumulative(np.array([g["cases"][0]["eN_atEachX"]]), O.getDDneutronEnergy(om.eD_binCenters))
+    assert card == g["sdef_case0"]

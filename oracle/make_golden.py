@@ -232,6 +232,7 @@ def main():
         "simult": simult(full="--quick" not in sys.argv),
         "onebd": onebd(),
         "ppc": ppc(),
+        "templates": templates(),
     }
     path = os.path.join(ROOT, "tests", "golden", "reference_golden.json")
     with open(path, "w") as fh:
@@ -272,6 +273,26 @@ def ppc():
     cells = np.array([c["eN_atEachX"] for c in out["cases"][:1]], dtype=float)
     pt.tofData, pt.neutronSpectra = [0], [[cells[0]]]
     out["sdef_case0"] = pt.makeSDEF_sia_cumulative(100)
+    return out
+
+
+def templates():
+    """tests/devShapeTemplates.py:195-268 through its own functions: TOF templates of three of the 32 energy slices
+    at two standoffs (uniform initial energies per slice; 150 x 100 grid, rho = 8.565e-5, I = 19.2e-3), test-sized
+    loops, and buildModelTOF on them."""
+    ns = ref_loader.load("devShapeTemplates")
+    n_ev = 1000
+    ns["nEvPerLoop"] = n_ev
+    ns["data_x"] = np.repeat(ns["x_binCenters"], n_ev)
+    bounds = ns["templateEnergyBounds"]
+    out = {"bounds": fl(bounds), "n_ev_per_loop": n_ev, "n_samples": 2000, "cases": []}
+    for seed, run, k in [(40, 0, 0), (41, 0, 13), (42, 3, 31), (43, 3, 20)]:
+        np.random.seed(seed)
+        t = ns["generateModelData"]((bounds[k], bounds[k + 1]), ns["standoffs"][run], ns["tofRunBins"][run], ns["tof_range"][run],
+                                    ns["ddnXSinstance"], ns["stoppingModel"].dEdx, 2000, True)
+        out["cases"].append({"seed": seed, "run": run, "slice": k, "template": fl(t)})
+    tpl = [np.array(c["template"]) for c in out["cases"][:2]]
+    out["buildModelTOF_2_3_5"] = fl(ns["buildModelTOF"]([2.0, 3.0, 5.0], tpl))
     return out
 
 

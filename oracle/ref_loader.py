@@ -31,6 +31,7 @@ PREFIX_LINES = {
     "advIntermediateTOFmodel": 204,  # advIntermediateTOFmodel.py:191-199 is lnprob
     "simultFit": 518,               # simultFit.py:444-469 is lnprob, data read at 521
     "csi_oneBD": 700,
+    "devShapeTemplates": 268,       # generateModelData 195-244, template bounds 246-253, buildModelTOF 256-268
 }
 
 

@@ -790,6 +790,22 @@ def test_template_precomputation(M, O):
     np.testing.assert_allclose(M.templates.build_model_tof(coeffs, tpl), 2.0 * tpl.sum(axis=0), rtol=1e-14)
 
 
+@pytest.mark.parametrize("ode", ["rk4", "range"])
+def test_template_reference_goldens(M, golden, ode):
+    """Templates produced by tests/devShapeTemplates.py's own generateModelData (195-244), two standoffs."""
+    g = golden["templates"]
+    bounds = parse_floats(g["bounds"])
+    mode = M.config.ODE_RANGE if ode == "range" else M.config.ODE_RK4
+    for c in g["cases"]:
+        cfg = M.config.intermediate(c["run"], n_samples=g["n_samples"], n_ev_per_loop=g["n_ev_per_loop"],
+                                    materials=((1, 2, 8.565e-5, 19.2e-3),), ode_mode=mode)   # devShapeTemplates.py:98-107
+        u = np.random.RandomState(c["seed"]).random_sample(cfg.n_draws)
+        with M.TofModel(cfg) as m:
+            tpl = M.templates.build_templates(m, bounds, u)
+        assert tpl.shape == (32, cfg.tof_bins[0])
+        np.testing.assert_allclose(tpl[c["slice"]], parse_floats(c["template"]), rtol=1e-11, atol=1e-300)
+
+
 def test_api_edge_cases(M):
     cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE)
     with M.TofModel(cfg) as m:

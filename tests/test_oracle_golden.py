@@ -264,3 +264,21 @@ def test_ppc_goldens_from_the_reference_class(golden):
     from mcmctoffitting_b200 import ppc
     card = ppc.sdef_sia_cumulative(np.array([g["cases"][0]["eN_atEachX"]]), O.getDDneutronEnergy(om.eD_binCenters))
     assert card == g["sdef_case0"]
+
+
+def test_template_goldens_from_the_reference_script(golden):
+    """tests/devShapeTemplates.py:195-268: the script's own templates (uniform initial energies per slice) are the
+    adv pipeline with sigma0 = (e1 - e0)/e0 and uniform numbers in place of the normals (mcmctoffitting_b200.templates)."""
+    from mcmctoffitting_b200 import templates as T
+    g = golden["templates"]
+    bounds = parse_floats(g["bounds"])
+    thetas = T.template_thetas(bounds)
+    xs = O.DDNXS()
+    for c in g["cases"]:
+        om = O.intermediate_model(c["run"], rho=8.565e-5, mean_excitation=19.2e-3, n_samples=g["n_samples"],
+                                  n_ev_per_loop=g["n_ev_per_loop"])
+        u = np.random.RandomState(c["seed"]).random_sample(g["n_samples"])          # np.random.uniform per loop, in order
+        got = om.model_pdf(list(thetas[c["slice"]]), u, xs)                          # density + applySpreading
+        assert np.array_equal(got, parse_floats(c["template"])), (c["run"], c["slice"])
+    tpl = [parse_floats(c["template"]) for c in g["cases"][:2]]
+    np.testing.assert_allclose(T.build_model_tof([2.0, 3.0, 5.0], tpl), parse_floats(g["buildModelTOF_2_3_5"]), rtol=1e-15)

@@ -157,3 +157,40 @@ def test_checkpoint_resume_continues_the_same_chain(tmp_path):
         EnsembleSampler(k, dim, backend=NumpyBackend(gauss_lnprob), seed=12).load_checkpoint(ck)
     with pytest.raises(ValueError):
         EnsembleSampler(k + 2, dim, backend=NumpyBackend(gauss_lnprob), seed=11).load_checkpoint(ck)
+
+
+def test_chain_file_reader_agrees_with_the_reference_on_awkward_numbers(tmp_path):
+    """Property check of the text chain format over shapes and magnitudes numpy prints differently: scientific
+    notation, wrapped rows (ndim up to 16), negative values, -inf log-probabilities.  Where the reference tree is
+    present, its own readChainFromFile (utilities.py:432-500) must parse the file identically."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from oracle import ref_loader
+    uu = ref_loader.load_utilities().utilities if ref_loader.available() else None
+    counter = [0]
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(k=st.integers(2, 7), dim=st.integers(1, 16), steps=st.integers(1, 4), scale=st.sampled_from([1e-6, 1.0, 1e3, 1e7]),
+           seed=st.integers(0, 10 ** 6), neg_inf=st.booleans())
+    def run(k, dim, steps, scale, seed, neg_inf):
+        rs = np.random.RandomState(seed)
+        counter[0] += 1
+        path = str(tmp_path / ("chain_%d.dat" % counter[0]))
+        want_c, want_p = [], []
+        for _ in range(steps):
+            pos = rs.standard_normal((k, dim)) * scale
+            lp = rs.standard_normal(k) * 1e4
+            if neg_inf:
+                lp[0] = -np.inf
+            write_chain_step(path, pos, lp)
+            want_c.append(pos)
+            want_p.append(lp)
+        chain, probs, n_params, n_walkers, n_steps = read_chain(path)
+        assert (n_params, n_walkers, n_steps) == (dim, k, steps)
+        np.testing.assert_allclose(chain, np.array(want_c), rtol=2e-7, atol=scale * 1e-8)   # numpy prints 8 digits
+        np.testing.assert_allclose(probs, np.array(want_p), rtol=1e-12)
+        if uu is not None and dim > 1:        # (the reference reader infers the walker count from rows of > 1 parameter)
+            c_ref, p_ref, np_ref, nw_ref, ns_ref = uu.readChainFromFile(path)
+            assert (np_ref, nw_ref, ns_ref) == (dim, k, steps)
+            assert np.array_equal(c_ref, chain) and np.array_equal(p_ref, probs)
+
+    run()

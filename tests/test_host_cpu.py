@@ -299,3 +299,71 @@ def test_gpu_arm_refuses_to_run_without_a_device():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"],
                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, cwd=root)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_draw_lookup_never_starts_beyond_the_answer():
+    """The range kernel's draw-range search (adv_range.cuh, do_cell) starts from a per-tile lookup cell taken a hair low
+    (tu_bias cells) and only walks forward.  That is sound only if the lookup never starts beyond the first draw with
+    fl(u0 + delta) >= left.  The device arithmetic restated in numpy (FP64, the lookup built by the same scatter rule),
+    on sorted tiles of many shapes, with thresholds placed exactly ON draw values as the adversarial case."""
+    n_ulut, bias = 1024, 1.0 / 65536.0
+    rs = np.random.RandomState(123)
+    worst_walk, total_walk, n_cases = 0, 0, 0
+    for trial in range(300):
+        nt = int(rs.choice([37, 256, 1000, 1024]))
+        centre = rs.uniform(0.5, 60.0)
+        width = 10.0 ** rs.uniform(-2.5, 1.0)                     # tile widths from 3e-3 cm to 10 cm
+        kind = trial % 3
+        if kind == 0:
+            u0 = centre + width * rs.standard_normal(nt)
+        elif kind == 1:
+            u0 = centre + width * rs.standard_t(2.5, nt)          # heavy tails: long empty stretches of lookup cells
+        else:
+            u0 = centre + width * np.round(rs.standard_normal(nt), 1)   # many exact duplicates
+        u0 = np.sort(u0)
+        tu_min, tu_max = u0[0], u0[-1]
+        tu_inv = n_ulut / (tu_max - tu_min) if tu_max - tu_min > 1e-6 * n_ulut else 0.0
+        cell = np.minimum(((u0 - tu_min) * tu_inv).astype(np.int64), n_ulut - 1)
+        ulut = np.searchsorted(cell, np.arange(n_ulut), side="left")   # first draw whose cell is >= c (the scatter)
+        for delta in rs.uniform(-3.0, 3.0, 4):
+            v = u0 + delta                                         # fl(u0 + delta), as the kernel compares it
+            lefts = np.concatenate([v[rs.randint(0, nt, 40)],      # thresholds ON sample values
+                                    np.nextafter(v[rs.randint(0, nt, 20)], np.inf),
+                                    rs.uniform(v[0] - 1.0, v[-1] + 1.0, 40)])
+            for left in lefts:
+                true_lb = int(np.searchsorted(v, left, side="left"))          # first draw with v >= left
+                x = (left - delta) - tu_min
+                c = int(np.float64(np.longdouble(x) * np.longdouble(tu_inv) - np.longdouble(bias)))   # fma, truncated
+                c = min(max(c, 0), n_ulut - 1)
+                start = int(ulut[c]) if c < len(ulut) else nt
+                assert start <= true_lb, (trial, nt, width, delta, left, start, true_lb)
+                worst_walk = max(worst_walk, true_lb - start)
+                total_walk += true_lb - start
+                n_cases += 1
+    assert n_cases == 300 * 4 * 100
+    assert total_walk / n_cases < 3.0                              # the walk stays short on average
+
+
+def test_div_by_recip_restated_is_correctly_rounded():
+    """tof_device.cuh div_by_recip: a*y with y = RN(1/b), then two FMA corrections, equals IEEE a/b.  Restated with
+    exact rational arithmetic (Fraction -> float conversion rounds to nearest), including mantissas next to 1 and 2."""
+    from fractions import Fraction as F
+    import struct
+    rs = np.random.RandomState(5)
+
+    def fma(a, b, c):
+        return float(F(a) * F(b) + F(c))
+
+    def div_by_recip(a, b, y):
+        q = a * y
+        q = fma(fma(-b, q, a), y, q)
+        return fma(fma(-b, q, a), y, q)
+
+    cases = [(rs.uniform(0, 3), rs.uniform(0.1, 30)) for _ in range(4000)]
+    cases += [(10.0 ** rs.uniform(-3, 5), 10.0 ** rs.uniform(-3, 7)) for _ in range(4000)]
+    for _ in range(4000):
+        a = struct.unpack("d", struct.pack("Q", (1023 << 52) | int(rs.randint(0, 256))))[0] * float(rs.choice([1, 3, 5]))
+        b = struct.unpack("d", struct.pack("Q", (1023 << 52) | ((1 << 52) - 1 - int(rs.randint(0, 256)))))[0]
+        cases.append((a, b))
+    for a, b in cases:
+        assert div_by_recip(a, b, 1.0 / b) == a / b, (a, b)

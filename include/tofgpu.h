@@ -219,6 +219,16 @@ int tof_stretch_accept(tof_ctx *ctx, double *d_s, double *d_lnprob, int64_t n, i
 int tof_ensemble_step(tof_ctx *ctx, double *d_pos, double *d_lnprob, int64_t n_walkers, int64_t n_steps, double a,
                       uint64_t seed, int64_t step0, int64_t *d_n_accept, void *stream);
 
+/* One red/blue half-step for the slice of the ensemble THIS GPU owns, on the packed state the sharded driver keeps:
+ * d_state [n_walkers][ndim + 1] = positions followed by the log-probability of each walker (so that one all-gather of
+ * the rows a rank owns refreshes both on every replica).  Rows [half*h + own0, half*h + own0 + n_own)
+ * (h = n_walkers/2) are proposed against the whole complementary half, evaluated and accepted in place; every other
+ * row is only read.  Randomness as in tof_stretch_propose (keyed by the global walker index), so the chain is the one
+ * tof_ensemble_step produces on a single GPU.  The caller then all-gathers rows [half*h, (half+1)*h) over its ranks
+ * (emcee's EnsembleSampler.sample loop, adv:311-317, with walkers sharded instead of pool.map'ed). */
+int tof_ensemble_half_step(tof_ctx *ctx, double *d_state, int64_t n_walkers, int half, int64_t own0, int64_t n_own, double a,
+                           uint64_t seed, int64_t step, int64_t *d_n_accept, void *stream);
+
 /* ---- diagnostics ----------------------------------------------------------------------------- */
 typedef struct tof_stats {
     int64_t kernel_launches; /* kernels launched by this context since creation */

@@ -77,6 +77,8 @@ SIGNATURES = {
     "tof_stretch_accept": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_uint64, C.c_int64,
                                      C.c_int, _vp, _vp]),
     "tof_ensemble_step": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_double, C.c_uint64, C.c_int64, _vp, _vp]),
+    "tof_ensemble_half_step": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_double, C.c_uint64, C.c_int64,
+                                         _vp, _vp]),
     "tof_get_stats": (C.c_int, [_vp, C.POINTER(TofStats)]),
     "tof_set_timing": (C.c_int, [_vp, C.c_int]),
     "tof_set_stage_timing": (C.c_int, [_vp, C.c_int]),

@@ -292,6 +292,13 @@ class ModelConfig:
                 raise ValueError("x bin centres are not aligned with their bins")
             if len(self.standoffs) != self.n_runs or len(self.tof_ranges) != self.n_runs:
                 raise ValueError("standoffs / tof_ranges / tof_bins must have one entry per run")
+        if self.kind == KIND_ADV and self.ode_mode == ODE_RANGE:
+            # tof_create refuses these with TOF_ERR_CAPACITY (the range kernel reuses the cell histogram as the
+            # density buffer and keeps E-bin indices in 16 bits); fail here with the same wording
+            if self.tof_bins[0] > self.x_bins * self.e_bins:
+                raise ValueError("ODE_RANGE needs tof_bins <= x_bins*e_bins; use ode_mode=ODE_RK4")
+            if self.e_bins > 65535:
+                raise ValueError("ODE_RANGE keeps E-bin indices in 16 bits: e_bins must be <= 65535")
         if len(self.prior) != self.ndim:
             raise ValueError("prior needs one (lo, hi) pair per parameter")
         if self.precision not in (PRECISION_FP64, PRECISION_FP32):

@@ -8,8 +8,10 @@ namespace tof {
 // ensemble stretch move (emcee 2.x EnsembleSampler._propose_stretch, restated from Goodman & Weare)
 // ================================================================================================
 // counter layout: ctr_lo = global walker index, ctr_hi = step*4 + half*2 + kind (kind 0 propose, 1 accept)
+// `ld_s` / `ld_c`: doubles between consecutive rows of s / comp (ndim for plain position arrays, ndim + 1 for the
+// packed [positions, lnprob] state the sharded driver keeps so that ONE all-gather refreshes both)
 __global__ void stretch_propose_kernel(const double *__restrict__ s, long long n, long long walker0,
-                                       const double *__restrict__ comp, long long n_comp, int ndim, double a,
+                                       const double *__restrict__ comp, long long n_comp, int ndim, int ld_s, int ld_c, double a,
                                        unsigned long long seed, long long step, int half, double *__restrict__ q,
                                        double *__restrict__ log_zz) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -20,23 +22,23 @@ __global__ void stretch_propose_kernel(const double *__restrict__ s, long long n
     long long j = (long long)(rng.u1() * (double)n_comp);
     if (j >= n_comp) j = n_comp - 1;
     for (int p = 0; p < ndim; ++p) {
-        const double c = comp[j * ndim + p];
-        q[i * ndim + p] = c - zz * (c - s[i * ndim + p]);
+        const double c = comp[j * ld_c + p];
+        q[i * ndim + p] = c - zz * (c - s[i * ld_s + p]);
     }
     log_zz[i] = (double)(ndim - 1) * log(zz);
 }
 
 __global__ void stretch_accept_kernel(double *__restrict__ s, double *__restrict__ lnprob, long long n, long long walker0,
                                       const double *__restrict__ q, const double *__restrict__ new_lnprob,
-                                      const double *__restrict__ log_zz, int ndim, unsigned long long seed, long long step,
-                                      int half, long long *__restrict__ n_accept) {
+                                      const double *__restrict__ log_zz, int ndim, int ld_s, int ld_lp, unsigned long long seed,
+                                      long long step, int half, long long *__restrict__ n_accept) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Philox rng(seed, (uint64_t)(walker0 + i), (uint64_t)step * 4ull + (uint64_t)half * 2ull + 1ull);
-    const double lnpdiff = log_zz[i] + new_lnprob[i] - lnprob[i];
+    const double lnpdiff = log_zz[i] + new_lnprob[i] - lnprob[i * ld_lp];
     if (lnpdiff > log(rng.u0())) {  // NaN and -inf proposals compare false: rejected
-        for (int p = 0; p < ndim; ++p) s[i * ndim + p] = q[i * ndim + p];
-        lnprob[i] = new_lnprob[i];
+        for (int p = 0; p < ndim; ++p) s[i * ld_s + p] = q[i * ndim + p];
+        lnprob[i * ld_lp] = new_lnprob[i];
         if (n_accept) n_accept[i] += 1;
     }
 }

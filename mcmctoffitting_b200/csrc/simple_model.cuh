@@ -7,14 +7,14 @@ namespace tof {
 // ================================================================================================
 // simple model: tests/simpleTOFmodel.py:57-120  (every sample is histogrammed directly)
 // ================================================================================================
-// grid = (chunks, walkers).  counts[n][T] (u64, zeroed by the caller) accumulate across chunks.
+// grid = (walkers, chunks).  counts[n][T] (u64, zeroed by the caller) accumulate across chunks.
 template <int NT>
 __global__ void __launch_bounds__(NT) simple_hist_kernel(const DevModel m, const DevRun run, const double *__restrict__ theta,
                                                          long long n_walkers, unsigned long long *__restrict__ counts,
                                                          int ignore_prior) {
     __shared__ unsigned int sh[1024];
     const int T = run.tof_bins;
-    const long long w = blockIdx.y;
+    const long long w = blockIdx.x;
     const int tid = threadIdx.x;
     const double e0 = theta[w * 3 + 0], e1 = theta[w * 3 + 1], sigma = theta[w * 3 + 2];
     bool inside = true;
@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(NT) simple_hist_kernel(const DevModel m, const
     const double k_dm = __dsub_rn(m.m_he3, m.m_d);
     const double k_q = __dmul_rn(m.q_ddn, m.m_he3);
 
-    const long long per = (m.n_draws + gridDim.x - 1) / gridDim.x;
-    const long long lo = (long long)blockIdx.x * per;
+    const long long per = (m.n_draws + gridDim.y - 1) / gridDim.y;
+    const long long lo = (long long)blockIdx.y * per;
     const long long hi = (lo + per < m.n_draws) ? lo + per : m.n_draws;
     for (long long d = lo + tid; d < hi; d += NT) {
         const double x = __dmul_rn(m.cell_length, __ldg(run.z1 + d));                       // simple:62

@@ -32,6 +32,11 @@ struct tof_ctx {
     DeviceBuf d_z[TOF_MAX_RUNS][2], d_obs[TOF_MAX_RUNS], d_obs_idx[TOF_MAX_RUNS], d_obs_val[TOF_MAX_RUNS];
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // recorded after every model launch on the launching stream: rebinding inputs and reading counters wait for
+    // THIS event only (no device-wide synchronisation: other contexts / ranks of the process keep running)
+    cudaEvent_t ev_busy = nullptr;
+    bool busy = false;
+    unsigned long long *h_counters = nullptr;   // pinned staging for tof_get_stats: {nan results, queued walkers}
     bool timing = false, timed = false, stage_timing = false;
     std::string err;
     tof_stats stats{};
@@ -79,9 +84,13 @@ int ensure(tof_ctx *ctx, DeviceBuf &b, size_t bytes);
 template <typename T>
 int upload_into(tof_ctx *ctx, DeviceBuf &b, const T *host, size_t count, const T **dev) {
     if (int rc = ensure(ctx, b, std::max<size_t>(count, 1) * sizeof(T))) return rc;
-    // make sure no kernel of this context still reads the previous contents
-    CU(ctx, cudaDeviceSynchronize());
-    if (count) CU(ctx, cudaMemcpy(b.p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    // make sure no kernel of this context still reads the previous contents: wait for the context's last model
+    // launch (whatever stream it went to), not for the device
+    if (ctx->busy) CU(ctx, cudaEventSynchronize(ctx->ev_busy));
+    if (count) {
+        CU(ctx, cudaMemcpyAsync(b.p, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));       // `host` may be a temporary of the caller
+    }
     *dev = static_cast<const T *>(b.p);
     return TOF_OK;
 }
@@ -185,7 +194,18 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
             if (!debug && ctx->dm.n_draws >= RANGE_STREAM_MIN) {
                 const long long slots = (long long)ctx->stats.sm_count * (ctx->band_enabled ? std::max(ctx->band_ctas, 1) : 1);
                 const long long chunks = (ctx->dm.n_draws + 128LL * 16 - 1) / (128LL * 16);   // >= one 128-draw chunk per warp
-                long long S = std::min<long long>(std::min<long long>(slots / n, 16), chunks);
+                // pick the split that minimises the number of rounds of the persistent grid per unit of work,
+                // rounds(S)/S with rounds = ceil(n*S/slots), plus a small charge for merging S partial histograms
+                // (256 walkers on 296 slots: S = 1 leaves 40 slots idle for a whole walker; S = 15 fills 13 rounds)
+                long long S = 1;
+                if (n < 2 * slots) {
+                    double best = 1e300;
+                    for (long long s = 1; s <= std::min<long long>(16, chunks); ++s) {
+                        const double rounds = (double)((n * s + slots - 1) / slots);
+                        const double cost = rounds / (double)s + (s > 1 ? 0.02 + 0.004 * (double)s : 0.0);
+                        if (cost < best - 1e-12) { best = cost; S = s; }
+                    }
+                }
                 if (S > 1) {
                     const size_t stride = (size_t)c.x_bins * c.e_bins;
                     rc = ensure(ctx, ctx->d_split, (size_t)n * S * stride * sizeof(double));
@@ -238,7 +258,8 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
         // enough chunks to fill the machine ~4x over, but at least ~4096 draws per CTA
         long long chunks = std::max<long long>(1, std::min<long long>((ctx->stats.sm_count * 8 + n - 1) / n,
                                                                        (ctx->dm.n_draws + 4095) / 4096));
-        dim3 grid((unsigned)chunks, (unsigned)n);
+        chunks = std::min<long long>(chunks, 65535);
+        dim3 grid((unsigned)n, (unsigned)chunks);          // walkers on grid.x: no 65535 limit on the batch
         simple_hist_kernel<256><<<grid, 256, 0, st>>>(ctx->dm, ctx->runs[0], d_theta, n,
                                                       static_cast<unsigned long long *>(ctx->d_counts.p),
                                                       out.spectra != nullptr);
@@ -288,6 +309,13 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
         ctx->timed = true;
     }
     CU(ctx, cudaGetLastError());
+    {   // (not while `st` is being captured into a CUDA graph: a captured event cannot be waited on from the host)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap == cudaStreamCaptureStatusNone) {
+            CU(ctx, cudaEventRecord(ctx->ev_busy, st));
+            ctx->busy = true;
+        }
+    }
     ctx->stats.evaluations += n;
     return TOF_OK;
 }
@@ -370,6 +398,8 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CUC(cudaEventCreate(&ctx->ev0));
     CUC(cudaEventCreate(&ctx->ev1));
+    CUC(cudaEventCreateWithFlags(&ctx->ev_busy, cudaEventDisableTiming));
+    CUC(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_counters), 2 * sizeof(unsigned long long)));
     ctx->stats.sm_count = prop.multiProcessorCount;
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
 
@@ -547,6 +577,16 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
     }
     if (cfg->model == TOF_MODEL_ADV && use_range) {
         const int P = cfg->rng_degree, Mi = cfg->rng_n;
+        // the range kernel reuses the (x,E) cell histogram as the density buffer (T doubles) and keeps E-bins and
+        // interval indices in 16-bit tables: refuse what does not fit instead of overrunning shared memory
+        if ((long long)cfg->tof_bins[0] > (long long)cfg->x_bins * cfg->e_bins) {
+            ctx->err = "TOF_ODE_RANGE needs tof_bins <= x_bins*e_bins (the density reuses the cell histogram); use TOF_ODE_RK4";
+            return bail(TOF_ERR_CAPACITY);
+        }
+        if (cfg->e_bins > 65535 || Mi > 65535 || cfg->rng_lut_n > 65535) {
+            ctx->err = "TOF_ODE_RANGE keeps E-bins and table intervals in 16 bits: e_bins, rng_n and rng_lut_n must be <= 65535";
+            return bail(TOF_ERR_CAPACITY);
+        }
         if (const char *v = std::getenv("TOFGPU_RANGE_THREADS")) {
             const int nt = std::atoi(v);
             if (!range_variant(nt, P)) { ctx->err = "TOFGPU_RANGE_THREADS must be 512, 640, 800 or 1024"; return bail(TOF_ERR_INVALID); }
@@ -689,13 +729,17 @@ void tof_destroy(tof_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     for (void *p : ctx->owned) cudaFree(p);
-    for (DeviceBuf *b : {&ctx->d_theta, &ctx->d_out, &ctx->d_spectra, &ctx->d_cells, &ctx->d_counts, &ctx->d_partial, &ctx->d_work, &ctx->d_queue, &ctx->d_split, &ctx->d_tickets})
+    if (ctx->busy && ctx->ev_busy) cudaEventSynchronize(ctx->ev_busy);
+    for (DeviceBuf *b : {&ctx->d_theta, &ctx->d_out, &ctx->d_spectra, &ctx->d_cells, &ctx->d_counts, &ctx->d_partial, &ctx->d_work,
+                         &ctx->d_queue, &ctx->d_split, &ctx->d_tickets, &ctx->d_ens, &ctx->d_nan, &ctx->d_stage})
         if (b->p) cudaFree(b->p);
     for (int r = 0; r < TOF_MAX_RUNS; ++r)
         for (DeviceBuf *b : {&ctx->d_z[r][0], &ctx->d_z[r][1], &ctx->d_obs[r], &ctx->d_obs_idx[r], &ctx->d_obs_val[r]})
             if (b->p) cudaFree(b->p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -741,7 +785,7 @@ int tof_set_draws(tof_ctx *ctx, int run, int stream, const double *values, int64
         std::vector<double> sorted(values, values + n);
         const long long per = ctx->cfg.n_ev_per_loop;
         for (long long l = 0; l < ctx->cfg.n_loops; ++l)
-            std::sort(sorted.begin() + l * per, sorted.begin() + (l + 1) * per, [](double a, double b) { return a > b; });
+            std::sort(sorted.begin() + l * per, sorted.begin() + (l + 1) * per, [](double a, double b) { return a > b || (b != b && a == a); });   // NaNs last: a strict weak order
         if (int rc = upload_into(ctx, ctx->d_z[run][stream], sorted.data(), (size_t)n, &d)) return rc;
     } else if (stream == 0 && ctx->cfg.ode_mode == TOF_ODE_RANGE && ctx->cfg.model == TOF_MODEL_ADV) {
         // the model is a symmetric function of the draws; the range kernel walks them in ascending order
@@ -856,7 +900,7 @@ int tof_stretch_propose(tof_ctx *ctx, const double *d_s, int64_t n, int64_t walk
     if (n <= 0 || n_comp <= 0 || !(a > 1.0)) return fail(ctx, TOF_ERR_INVALID, "bad stretch-move arguments");
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     stretch_propose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        d_s, n, walker0, d_comp, n_comp, ctx->cfg.ndim, a, seed, step, half, d_q, d_log_zz);
+        d_s, n, walker0, d_comp, n_comp, ctx->cfg.ndim, ctx->cfg.ndim, ctx->cfg.ndim, a, seed, step, half, d_q, d_log_zz);
     ctx->stats.kernel_launches += 1;
     CU(ctx, cudaGetLastError());
     return TOF_OK;
@@ -869,7 +913,7 @@ int tof_stretch_accept(tof_ctx *ctx, double *d_s, double *d_lnprob, int64_t n, i
     if (n <= 0) return fail(ctx, TOF_ERR_INVALID, "n <= 0");
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     stretch_accept_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        d_s, d_lnprob, n, walker0, d_q, d_new_lnprob, d_log_zz, ctx->cfg.ndim, seed, step, half,
+        d_s, d_lnprob, n, walker0, d_q, d_new_lnprob, d_log_zz, ctx->cfg.ndim, ctx->cfg.ndim, 1, seed, step, half,
         reinterpret_cast<long long *>(d_n_accept));
     ctx->stats.kernel_launches += 1;
     CU(ctx, cudaGetLastError());
@@ -898,15 +942,44 @@ int tof_ensemble_step(tof_ctx *ctx, double *d_pos, double *d_lnprob, int64_t n_w
             const double *comp = d_pos + (size_t)(1 - half) * h * ndim;   // ... against the complementary half
             double *lp = d_lnprob + (size_t)half * h;
             const long long walker0 = half * h;
-            stretch_propose_kernel<<<grid, 256, 0, st>>>(sl, h, walker0, comp, h, ndim, a, seed, step0 + s, half, q, log_zz);
+            stretch_propose_kernel<<<grid, 256, 0, st>>>(sl, h, walker0, comp, h, ndim, ndim, ndim, a, seed, step0 + s, half, q, log_zz);
             ModelOut o{};
             o.lnprob = new_lp;
             if (int rc = launch_model(ctx, q, h, 0, o, st)) return rc;
-            stretch_accept_kernel<<<grid, 256, 0, st>>>(sl, lp, h, walker0, q, new_lp, log_zz, ndim, seed, step0 + s, half,
+            stretch_accept_kernel<<<grid, 256, 0, st>>>(sl, lp, h, walker0, q, new_lp, log_zz, ndim, ndim, 1, seed, step0 + s, half,
                                                         reinterpret_cast<long long *>(d_n_accept ? d_n_accept + walker0 : nullptr));
             ctx->stats.kernel_launches += 2;
         }
     }
+    CU(ctx, cudaGetLastError());
+    return TOF_OK;
+}
+
+int tof_ensemble_half_step(tof_ctx *ctx, double *d_state, int64_t n_walkers, int half, int64_t own0, int64_t n_own, double a,
+                           uint64_t seed, int64_t step, int64_t *d_n_accept, void *stream) {
+    if (!ctx || !d_state) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    const int ndim = ctx->cfg.ndim, ld = ndim + 1;
+    if (n_walkers < 2 || (n_walkers & 1)) return fail(ctx, TOF_ERR_INVALID, "The number of walkers must be even.");
+    const long long h = n_walkers / 2;
+    if (half < 0 || half > 1 || own0 < 0 || n_own < 0 || own0 + n_own > h || !(a > 1.0))
+        return fail(ctx, TOF_ERR_INVALID, "bad half-step arguments");
+    if (n_own == 0) return TOF_OK;
+    if (int rc = ready(ctx, true)) return rc;
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (int rc = ensure(ctx, ctx->d_ens, (size_t)n_own * (ndim + 2) * sizeof(double))) return rc;
+    double *q = static_cast<double *>(ctx->d_ens.p), *log_zz = q + (size_t)n_own * ndim, *new_lp = log_zz + n_own;
+    const long long walker0 = (long long)half * h + own0;
+    double *sl = d_state + (size_t)walker0 * ld;                            // own rows of the half that moves
+    const double *comp = d_state + (size_t)(1 - half) * h * ld;              // the whole complementary half
+    const unsigned grid = (unsigned)((n_own + 255) / 256);
+    stretch_propose_kernel<<<grid, 256, 0, st>>>(sl, n_own, walker0, comp, h, ndim, ld, ld, a, seed, step, half, q, log_zz);
+    ModelOut o{};
+    o.lnprob = new_lp;
+    if (int rc = launch_model(ctx, q, n_own, 0, o, st)) return rc;
+    stretch_accept_kernel<<<grid, 256, 0, st>>>(sl, sl + ndim, n_own, walker0, q, new_lp, log_zz, ndim, ld, ld, seed, step, half,
+                                                reinterpret_cast<long long *>(d_n_accept ? d_n_accept + walker0 : nullptr));
+    ctx->stats.kernel_launches += 2;
     CU(ctx, cudaGetLastError());
     return TOF_OK;
 }
@@ -917,16 +990,23 @@ int tof_get_stats(const tof_ctx *ctx, tof_stats *out) {
     out->band_ctas_per_sm = ctx->band_enabled ? ctx->band_ctas : 0;
     out->band_cells = ctx->band_enabled ? ctx->band_hcap : 0;
     out->band_queued_last = 0;
-    if (ctx->d_nan.p) {
-        unsigned long long nn = 0;
+    // counters are read on the context's own stream, ordered after its last model launch (ev_busy): the host waits for
+    // that launch only -- no device-wide or legacy-stream synchronisation
+    const bool want_nan = ctx->d_nan.p != nullptr, want_q = ctx->band_enabled && ctx->d_work.p != nullptr;
+    if ((want_nan || want_q) && ctx->h_counters) {
         cudaSetDevice(ctx->cfg.device);
-        if (cudaMemcpy(&nn, ctx->d_nan.p, sizeof(nn), cudaMemcpyDeviceToHost) == cudaSuccess) out->nan_results = (int64_t)nn;
-    }
-    if (ctx->band_enabled && ctx->d_work.p) {
-        unsigned long long q = 0;
-        cudaSetDevice(ctx->cfg.device);
-        if (cudaMemcpy(&q, static_cast<unsigned long long *>(ctx->d_work.p) + 2, sizeof(q), cudaMemcpyDeviceToHost) == cudaSuccess)
-            out->band_queued_last = (int64_t)q;
+        bool ok = true;
+        if (ctx->busy) ok = cudaStreamWaitEvent(ctx->stream, ctx->ev_busy, 0) == cudaSuccess;
+        ctx->h_counters[0] = ctx->h_counters[1] = 0ull;
+        if (ok && want_nan)
+            ok = cudaMemcpyAsync(ctx->h_counters + 0, ctx->d_nan.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess;
+        if (ok && want_q)
+            ok = cudaMemcpyAsync(ctx->h_counters + 1, static_cast<unsigned long long *>(ctx->d_work.p) + 2, sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess;
+        if (ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess) {
+            if (want_nan) out->nan_results = (int64_t)ctx->h_counters[0];
+            if (want_q) out->band_queued_last = (int64_t)ctx->h_counters[1];
+        }
     }
     return TOF_OK;
 }
@@ -955,7 +1035,7 @@ int tof_get_stage_cycles(tof_ctx *ctx, uint64_t cycles[TOF_N_STAGES + 1]) {
     if (!ctx || !cycles) return TOF_ERR_INVALID;
     if (!ctx->d_stage.p) return fail(ctx, TOF_ERR_STATE, "stage timing was never enabled");
     CU(ctx, cudaSetDevice(ctx->cfg.device));
-    CU(ctx, cudaDeviceSynchronize());
+    if (ctx->busy) CU(ctx, cudaEventSynchronize(ctx->ev_busy));
     CU(ctx, cudaMemcpy(cycles, ctx->d_stage.p, (TOF_N_STAGES + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     CU(ctx, cudaMemset(ctx->d_stage.p, 0, (TOF_N_STAGES + 1) * sizeof(unsigned long long)));
     return TOF_OK;

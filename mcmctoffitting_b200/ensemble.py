@@ -16,6 +16,7 @@ depend on ``G``.
 """
 from __future__ import annotations
 
+import os
 from typing import Iterator, Optional, Tuple
 
 import numpy as np
@@ -59,6 +60,12 @@ class CudaBackend:
         self.model.ensemble_step(pos.data_ptr(), lp.data_ptr(), pos.shape[0], steps, a, seed, step0, n_accept.data_ptr(),
                                  self._stream())
 
+    def half_step_packed(self, state, half, own0, n_own, a, seed, step, n_accept):
+        """Propose -> lnprob -> accept for the rows this rank owns, in place on the packed ``[k, dim+1]`` state
+        (tof_ensemble_half_step): one library call, no temporaries on the Python side."""
+        self.model.ensemble_half_step(state.data_ptr(), state.shape[0], half, own0, n_own, a, seed, step, n_accept.data_ptr(),
+                                      self._stream())
+
 
 class EnsembleSampler:
     """emcee-2.x-shaped sampler over a sharded walker ensemble.
@@ -66,6 +73,11 @@ class EnsembleSampler:
     Parameters mirror ``emcee.EnsembleSampler(nwalkers, dim, lnpostfn, a=2.0)``; ``lnpostfn`` is a
     :class:`~mcmctoffitting_b200.lnprob.TofLnProb` (or any object exposing ``.model``), or a backend
     is injected directly (tests run the sharding logic on CPU/gloo with a numpy backend).
+
+    State layout: one ``[k, dim+1]`` float64 tensor per rank -- the positions of every walker followed by its
+    log-probability.  A rank updates only the rows it owns; after each half-step ONE in-place all-gather of the
+    half's ``[h, dim+1]`` slab (each rank contributes its ``[h/G, dim+1]`` rows) refreshes positions and
+    log-probabilities on every replica.
     """
 
     def __init__(self, nwalkers: int, dim: int, lnpostfn=None, a: float = 2.0, seed: int = 0, backend=None,
@@ -85,6 +97,8 @@ class EnsembleSampler:
         if self.h % self.world != 0:
             raise ValueError("half-ensemble size %d must divide evenly over %d ranks" % (self.h, self.world))
         self.n_own = self.h // self.world
+        # NCCL gathers in place (sendbuff == recvbuff + rank*count); other backends get a private copy of the input
+        self._inplace_gather = self.distributed and dist.get_backend(group) == "nccl"
         self.store_chain = store_chain
         self.reset()
         self._step = 0
@@ -93,7 +107,8 @@ class EnsembleSampler:
     def reset(self) -> None:
         self._chain = []
         self._lnprob = []
-        self.naccepted = torch.zeros(self.k, dtype=torch.int64, device=self.device)
+        # every rank counts the acceptances of the rows it owns; the other rows are filled in by _gather_naccepted
+        self._nacc = torch.zeros(self.k, dtype=torch.int64, device=self.device)
         self.iterations = 0
 
     @property
@@ -114,27 +129,56 @@ class EnsembleSampler:
         c = self.chain
         return c.reshape(-1, self.dim)
 
+    def _own(self, half: int) -> slice:
+        lo = half * self.h + self.rank * self.n_own
+        return slice(lo, lo + self.n_own)
+
+    def _gather_rows(self, full: torch.Tensor, half: int) -> None:
+        """All-gather the rows of one half: every rank contributes the rows it owns."""
+        lo = half * self.h
+        slab, mine = full[lo:lo + self.h], full[self._own(half)]
+        dist.all_gather_into_tensor(slab, mine if self._inplace_gather else mine.clone(), group=self.group)
+
+    @property
+    def naccepted(self) -> torch.Tensor:
+        """Per-walker acceptance counts of the WHOLE ensemble.  With several ranks this is a collective (every rank
+        must read it): each rank only counts for the walkers it owns."""
+        if self.world > 1:
+            for half in (0, 1):
+                self._gather_rows(self._nacc, half)
+        return self._nacc
+
+    @naccepted.setter
+    def naccepted(self, value: torch.Tensor) -> None:
+        self._nacc = value
+
     @property
     def acceptance_fraction(self) -> np.ndarray:
+        """emcee's ``acceptance_fraction`` (collective when sharded, see :attr:`naccepted`)."""
         return self.naccepted.cpu().numpy() / max(self.iterations, 1)
 
-    # -- one red/blue half-step on device tensors ----------------------------------------------------------
-    def _half_step(self, pos: torch.Tensor, lp: torch.Tensor, half: int) -> None:
-        h, n, g = self.h, self.n_own, self.rank
-        lo = half * h
-        own = slice(lo + g * n, lo + (g + 1) * n)
-        comp = pos[(1 - half) * h:(2 - half) * h]
-        s, lps = pos[own], lp[own]
-        walker0 = lo + g * n
-        q, log_zz = self.backend.propose(s, walker0, comp, self.a, self.seed, self._step, half)
-        new_lp = self.backend.lnprob(q)
-        self.backend.accept(s, lps, walker0, q, new_lp, log_zz, self.seed, self._step, half, self.naccepted[own])
+    # -- packed state ----------------------------------------------------------------------------------
+    def pack_state(self, pos, lnprob) -> torch.Tensor:
+        """``[k, dim+1]`` device tensor: positions, then the log-probability of each walker."""
+        st = torch.empty((self.k, self.dim + 1), dtype=torch.float64, device=self.device)
+        st[:, :self.dim] = self._as_device(pos, (self.k, self.dim))
+        st[:, self.dim] = self._as_device(lnprob, (self.k,))
+        return st
+
+    # -- one red/blue half-step on the packed state --------------------------------------------------------
+    def _half_step(self, state: torch.Tensor, half: int) -> None:
+        h, n, g, d = self.h, self.n_own, self.rank, self.dim
+        if hasattr(self.backend, "half_step_packed"):
+            self.backend.half_step_packed(state, half, g * n, n, self.a, self.seed, self._step, self._nacc)
+        else:
+            own = self._own(half)
+            comp = state[(1 - half) * h:(2 - half) * h, :d]
+            s, lps = state[own, :d], state[own, d]
+            q, log_zz = self.backend.propose(s, own.start, comp, self.a, self.seed, self._step, half)
+            new_lp = self.backend.lnprob(q)
+            self.backend.accept(s, lps, own.start, q, new_lp, log_zz, self.seed, self._step, half, self._nacc[own])
         if self.world > 1:
-            packed = torch.cat([s, lps.unsqueeze(1)], dim=1).contiguous()           # [n, dim+1]
-            gathered = torch.empty((h, self.dim + 1), dtype=pos.dtype, device=pos.device)
-            dist.all_gather_into_tensor(gathered, packed, group=self.group)
-            pos[lo:lo + h] = gathered[:, :self.dim]
-            lp[lo:lo + h] = gathered[:, self.dim]
+            self._gather_rows(state, half)             # positions AND log-probabilities, one collective, in place
 
     def _as_device(self, a, shape) -> torch.Tensor:
         t = torch.as_tensor(np.asarray(a, dtype=np.float64) if not torch.is_tensor(a) else a, dtype=torch.float64)
@@ -162,12 +206,14 @@ class EnsembleSampler:
         lp = self._as_device(lnprob0, (self.k,)) if lnprob0 is not None else self.initial_lnprob(pos)
         if bool(torch.isnan(lp).any()):
             raise ValueError("The initial lnprob was NaN.")                         # emcee raises the same
+        state = self.pack_state(pos, lp)
         for _ in range(int(iterations)):
-            self._half_step(pos, lp, 0)
-            self._half_step(pos, lp, 1)
+            self._half_step(state, 0)
+            self._half_step(state, 1)
             self._step += 1
             self.iterations += 1
-            p_host, lp_host = pos.cpu().numpy(), lp.cpu().numpy()
+            host = state.cpu().numpy()
+            p_host, lp_host = np.ascontiguousarray(host[:, :self.dim]), np.ascontiguousarray(host[:, self.dim])
             if store:
                 self._chain.append(p_host.copy())
                 self._lnprob.append(lp_host.copy())
@@ -183,17 +229,26 @@ class EnsembleSampler:
     def save_checkpoint(self, path: str, pos, lnprob) -> None:
         """Binary state for an exact resume (the reference only has its append-only text chain, adv:314-317, and
         hands burn-in over to the main chain in memory, adv:337-339): positions and log-probabilities at full
-        precision, the counter of the proposal generator, the seed, acceptance counters and the stored chain."""
-        if self.rank != 0:
-            return
-        np.savez(path, pos=np.asarray(pos, dtype=np.float64), lnprob=np.asarray(lnprob, dtype=np.float64),
-                 rstate=np.int64(self._step), seed=np.int64(self.seed), a=np.float64(self.a),
-                 naccepted=self.naccepted.cpu().numpy(), iterations=np.int64(self.iterations),
-                 chain=self.chain, lnprobability=self.lnprobability)
+        precision, the counter of the proposal generator, the seed, acceptance counters and the stored chain.
+        Collective when sharded: every rank calls it (the acceptance counters are gathered), rank 0 writes to a
+        temporary file and renames it over ``path`` (a crash mid-write leaves the previous checkpoint intact), and
+        all ranks leave together so that a following :meth:`load_checkpoint` sees the finished file."""
+        nacc = self.naccepted.cpu().numpy()                       # collective gather when world > 1
+        if self.rank == 0:
+            final = path if str(path).endswith(".npz") else str(path) + ".npz"
+            tmp = final + ".tmp.npz"
+            np.savez(tmp, pos=np.asarray(pos, dtype=np.float64), lnprob=np.asarray(lnprob, dtype=np.float64),
+                     rstate=np.int64(self._step), seed=np.int64(self.seed), a=np.float64(self.a),
+                     naccepted=nacc, iterations=np.int64(self.iterations),
+                     chain=self.chain, lnprobability=self.lnprobability)
+            os.replace(tmp, final)
+        if self.world > 1:
+            dist.barrier(group=self.group)
 
     def load_checkpoint(self, path: str):
         """Restore what :meth:`save_checkpoint` wrote; returns ``(pos, lnprob, rstate)`` ready for
-        ``sample(pos, lnprob0=lnprob, rstate0=rstate)``.  The continued chain equals the uninterrupted one."""
+        ``sample(pos, lnprob0=lnprob, rstate0=rstate)``.  The continued chain equals the uninterrupted one.  Every
+        rank loads the full acceptance counters and keeps counting for the rows it owns."""
         with np.load(path if str(path).endswith(".npz") else str(path) + ".npz") as f:
             pos, lnprob = f["pos"], f["lnprob"]
             if pos.shape != (self.k, self.dim):
@@ -202,24 +257,33 @@ class EnsembleSampler:
                 raise ValueError("checkpoint was written with seed=%d a=%g" % (int(f["seed"]), float(f["a"])))
             self._step = int(f["rstate"])
             self.iterations = int(f["iterations"])
-            self.naccepted = torch.from_numpy(f["naccepted"].copy()).to(self.device)
+            self._nacc = torch.from_numpy(f["naccepted"].copy()).to(self.device)
             self._chain = [c.copy() for c in np.moveaxis(f["chain"], 1, 0)]
             self._lnprob = [c.copy() for c in np.moveaxis(f["lnprobability"], 1, 0)]
             return pos.copy(), lnprob.copy(), self._step
 
     # -- device-resident stepping for throughput runs (no per-step host copies) ------------------------------
+    def run_state(self, state: torch.Tensor, steps: int) -> None:
+        """``steps`` whole steps on a packed state (see :meth:`pack_state`), in place, nothing copied to the host:
+        per half-step one library call (propose -> lnprob -> accept for the own rows) and, when sharded, one
+        in-place all-gather."""
+        for _ in range(int(steps)):
+            self._half_step(state, 0)
+            self._half_step(state, 1)
+            self._step += 1
+            self.iterations += 1
+
     def run_device(self, pos: torch.Tensor, lp: torch.Tensor, steps: int) -> None:
         if self.world == 1 and hasattr(self.backend, "ensemble_step") and pos.is_contiguous() and lp.is_contiguous():
             # the whole loop inside the library: same kernels, same counters, same chain
-            self.backend.ensemble_step(pos, lp, int(steps), self.a, self.seed, self._step, self.naccepted)
+            self.backend.ensemble_step(pos, lp, int(steps), self.a, self.seed, self._step, self._nacc)
             self._step += int(steps)
             self.iterations += int(steps)
             return
-        for _ in range(int(steps)):
-            self._half_step(pos, lp, 0)
-            self._half_step(pos, lp, 1)
-            self._step += 1
-            self.iterations += 1
+        state = self.pack_state(pos, lp)
+        self.run_state(state, steps)
+        pos.copy_(state[:, :self.dim])
+        lp.copy_(state[:, self.dim])
 
 
 # ---- chain files in the reference's text format (adv:314-317; simultFit.py:737-740) -----------------------

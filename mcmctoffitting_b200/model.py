@@ -229,6 +229,11 @@ class TofModel:
         self._check(self._lib.tof_ensemble_step(self._ctx, C.c_void_p(pos_ptr), C.c_void_p(lnprob_ptr), n_walkers, n_steps,
                                                 a, seed, step0, C.c_void_p(naccept_ptr), C.c_void_p(stream)))
 
+    def ensemble_half_step(self, state_ptr, n_walkers, half, own0, n_own, a, seed, step, naccept_ptr=0, stream=0) -> None:
+        """One half-step for the rows this GPU owns of the packed ``[n_walkers, ndim+1]`` state (tof_ensemble_half_step)."""
+        self._check(self._lib.tof_ensemble_half_step(self._ctx, C.c_void_p(state_ptr), n_walkers, half, own0, n_own, a, seed,
+                                                     step, C.c_void_p(naccept_ptr), C.c_void_p(stream)))
+
     def stats(self) -> dict:
         s = _lib.TofStats()
         self._check(self._lib.tof_get_stats(self._ctx, C.byref(s)))

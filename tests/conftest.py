@@ -34,5 +34,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden2():
+    """Round-2 reference goldens (oracle/make_golden.py --r2)."""
+    with open(os.path.join(ROOT, "tests", "golden", "reference_golden_r2.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.fixture(scope="session")
 def pf():
     return _pf

@@ -81,42 +81,57 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, k, dim, steps, p0, out_q):
+def _worker(rank, world, port, k, dim, steps, p0, out_q, ckdir):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         s = EnsembleSampler(k, dim, backend=NumpyBackend(gauss_lnprob), seed=7)
         assert s.world == world and s.n_own == k // 2 // world
-        pos, lp, _ = s.run_mcmc(p0, steps)
-        out_q.put((rank, pos, lp, s.naccepted.numpy().copy()))
+        pos, lp, state = s.run_mcmc(p0, steps)
+        af = s.acceptance_fraction                         # collective: the owners' counters are gathered
+        # sharded checkpoint: every rank calls save (counters gathered, rank 0 writes atomically, barrier), then
+        # every rank resumes from the file and continues the chain
+        ck = os.path.join(ckdir, "sharded_state.npz")
+        s.save_checkpoint(ck, pos, lp)
+        s2 = EnsembleSampler(k, dim, backend=NumpyBackend(gauss_lnprob), seed=7)
+        pos_l, lp_l, rstate = s2.load_checkpoint(ck)
+        pos2, lp2, _ = s2.run_mcmc(pos_l, 5, rstate0=rstate, lnprob0=lp_l)
+        out_q.put((rank, pos, lp, s.naccepted.numpy().copy(), af, pos2, lp2, s2.naccepted.numpy().copy(), s2.iterations))
         dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-def test_sharded_sampler_over_gloo_matches_single_process():
+def test_sharded_sampler_over_gloo_matches_single_process(tmp_path):
     k, dim, steps = 64, 3, 25
     p0 = MU + 0.1 * np.random.RandomState(3).standard_normal((k, dim))
     ref = EnsembleSampler(k, dim, backend=NumpyBackend(gauss_lnprob), seed=7)
-    pos1, lp1, _ = ref.run_mcmc(p0, steps)
+    pos1, lp1, state1 = ref.run_mcmc(p0, steps)
+    af1 = ref.acceptance_fraction
+    nacc1 = ref.naccepted.numpy().copy()
+    pos1b, lp1b, _ = ref.run_mcmc(pos1, 5, rstate0=state1, lnprob0=lp1)      # the uninterrupted chain, 5 steps on
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, k, dim, steps, p0, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, k, dim, steps, p0, q, str(tmp_path))) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in range(2)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, pos2, lp2, nacc in results:
+    for rank, pos2, lp2, nacc, af, pos_r, lp_r, nacc_r, iters_r in results:
         # chains do not depend on the number of ranks: counter-based RNG keyed by the global walker index
         assert np.array_equal(pos2, pos1), rank
         assert np.array_equal(lp2, lp1), rank
-    # acceptance counters are per-owner: summed over ranks they equal the single-process counters
-    total = sum(r[3] for r in results)
-    assert np.array_equal(total, ref.naccepted.numpy())
+        # every rank reports the acceptance counters of the WHOLE ensemble (gathered from the owners), equal to
+        # the single-process ones
+        assert np.array_equal(nacc, nacc1), rank
+        assert np.array_equal(af, af1), rank
+        # resume from the sharded checkpoint: same chain and the same counters as the uninterrupted single process
+        assert np.array_equal(pos_r, pos1b) and np.array_equal(lp_r, lp1b), rank
+        assert np.array_equal(nacc_r, ref.naccepted.numpy()) and iters_r == steps + 5, rank
 
 
 def test_chain_file_is_readable_by_the_reference_reader(tmp_path):

@@ -37,20 +37,30 @@ def O():
     return tof_oracle
 
 
-def _adv_pair(M, O, n_draws, excitation, **kw):
-    cfg = M.config.adv(0, n_samples=n_draws, n_ev_per_loop=min(n_draws, 1024), mean_excitation=excitation, **kw)
+ODE_MODES = ["rk4", "range"]      # "range" = the shipped range-table kernel (bench.py, smoke())
+
+
+def _ode(M, ode):
+    return {"rk4": M.config.ODE_RK4, "range": M.config.ODE_RANGE}[ode]
+
+
+def _adv_pair(M, O, n_draws, excitation, ode="rk4", **kw):
+    cfg = M.config.adv(0, n_samples=n_draws, n_ev_per_loop=min(n_draws, 1024), mean_excitation=excitation,
+                       ode_mode=_ode(M, ode), **kw)
     om = O.adv_model(0, n_samples=n_draws, n_ev_per_loop=min(n_draws, 1024), mean_excitation=excitation)
     return cfg, om
 
 
+@pytest.mark.parametrize("ode", ODE_MODES)
 @pytest.mark.parametrize("key", ["adv_as_written", "adv_physical"])
-def test_adv_reference_goldens(M, O, golden, pf, key):
-    """lnlike values produced by the reference's own functions (seeded), small draw counts."""
+def test_adv_reference_goldens(M, O, golden, pf, key, ode):
+    """lnlike values produced by the reference's own functions (seeded): 1024-4096 draws (tiles) and the script's
+    default nDraws (97 x 1024 = 99 328 draws: the streaming path of the range kernel)."""
     g = golden[key]
     obs = parse_floats(g["obs"])
     for c in g["cases"]:
         nd = c["nDraws"]
-        cfg, om = _adv_pair(M, O, nd, g["mean_excitation"])
+        cfg, om = _adv_pair(M, O, nd, g["mean_excitation"], ode)
         z = np.random.RandomState(c["seed"]).standard_normal(cfg.n_draws)
         with M.TofModel(cfg) as m:
             m.set_observables(obs)
@@ -61,11 +71,12 @@ def test_adv_reference_goldens(M, O, golden, pf, key):
         assert rel(got, want) <= tol, (c, got)
 
 
+@pytest.mark.parametrize("ode", ODE_MODES)
 @pytest.mark.parametrize("key", ["adv_as_written", "adv_physical"])
-def test_adv_spectra_bit_exact(M, O, golden, key):
+def test_adv_spectra_bit_exact(M, O, golden, key, ode):
     g = golden[key]
     for s in g["spectra"]:
-        cfg, om = _adv_pair(M, O, 1024, g["mean_excitation"])
+        cfg, om = _adv_pair(M, O, 1024, g["mean_excitation"], ode)
         z = np.random.RandomState(s["seed"]).standard_normal(1024)
         with M.TofModel(cfg) as m:
             m.set_draws(z)
@@ -78,13 +89,20 @@ def test_adv_spectra_bit_exact(M, O, golden, key):
                                    rtol=1e-13, atol=1e-300)
 
 
+@pytest.mark.parametrize("ode", ODE_MODES)
 @pytest.mark.parametrize("excitation", [19.2, 19.2e-3])
-def test_adv_cell_counts_vs_oracle(M, O, excitation):
+def test_adv_cell_counts_vs_oracle(M, O, excitation, ode):
     """drawHist2d (adv:146) for a spread of walkers, including wide sigma0 with E0 <= 0 draws."""
-    cfg, om = _adv_pair(M, O, 2048, excitation)
+    cfg, om = _adv_pair(M, O, 2048, excitation, ode)
     rs = np.random.RandomState(5)
     z = rs.standard_normal(cfg.n_draws)
     thetas = np.array([[1050, .10], [1500, .05], [2000, .3], [1200, .45], [2590, .02], [1001, .49]])
+    if ode == "range":
+        # draws that start at a few keV (sigma0 * |z_min| ~ 1) are where the oracle's fixed-step RK4 itself is not
+        # accurate; the range kernel is checked on those against the closed-form oracle in
+        # test_range_cell_counts_vs_oracle.  Here: every walker whose lowest draw stays above ~10 % of e0.
+        thetas = thetas[thetas[:, 1] * (-z.min()) < 0.9]
+        assert len(thetas) >= 3
     xs = O.DDNXS()
     with M.TofModel(cfg) as m:
         m.set_draws(z)
@@ -96,9 +114,10 @@ def test_adv_cell_counts_vs_oracle(M, O, excitation):
     assert mismatched == 0
 
 
-def test_sweep_shape_reference_goldens(M, O, golden, pf):
+@pytest.mark.parametrize("ode", ODE_MODES)
+def test_sweep_shape_reference_goldens(M, O, golden, pf, ode):
     g = golden["sweep"]
-    cfg = M.config.sweep()
+    cfg = M.config.sweep(ode_mode=_ode(M, ode))
     obs = np.zeros(2048)
     obs[g["obs_nonzero_idx"]] = parse_floats(g["obs_nonzero_val"])
     z = np.random.RandomState(g["draw_seed"]).standard_normal(1024)
@@ -128,8 +147,30 @@ def test_sweep_shape_reference_goldens(M, O, golden, pf):
     assert n_bad <= 1, n_bad
 
 
-def test_sweep_vs_oracle_many_walkers(M, O):
-    cfg = M.config.sweep()
+@pytest.mark.parametrize("ode", ODE_MODES)
+def test_sweep_finite_reference_goldens(M, golden2, pf, ode):
+    """Benchmark shape, observables most walkers can explain: 23 of the 24 reference log-likelihoods are finite
+    (tests/golden/reference_golden_r2.json, made by oracle/make_golden.py --r2 from adv:115-181)."""
+    g = golden2["sweep_finite"]
+    cfg = M.config.sweep(ode_mode=_ode(M, ode))
+    obs = np.zeros(2048)
+    obs[g["obs_nonzero_idx"]] = parse_floats(g["obs_nonzero_val"])
+    z = np.random.RandomState(g["draw_seed"]).standard_normal(1024)
+    thetas = np.array(g["thetas"])
+    with M.TofModel(cfg) as m:
+        m.set_observables(obs)
+        m.set_draws(z)
+        got = m.lnprob_batch(thetas)
+    want = np.array([pf(v) for v in g["lnlike"]])
+    assert np.isfinite(want).sum() >= 16
+    assert np.array_equal(np.isfinite(got), np.isfinite(want))
+    bad = [k for k in range(len(want)) if rel(float(got[k]), float(want[k])) > RTOL]
+    assert len(bad) <= 1, (bad, got[bad], want[bad])      # at most one LSODA-tolerance flip among 24
+
+
+@pytest.mark.parametrize("ode", ODE_MODES)
+def test_sweep_vs_oracle_many_walkers(M, O, ode):
+    cfg = M.config.sweep(ode_mode=_ode(M, ode))
     om = O.sweep_model()
     z = np.random.RandomState(20260101).standard_normal(1024)
     zstar = np.random.RandomState(7).standard_normal(1024)
@@ -313,33 +354,6 @@ def test_range_cell_counts_vs_oracle(M, O, excitation):
         assert np.count_nonzero(got[k] != want) == 0, (k, th)
 
 
-def test_range_sweep_reference_goldens(M, O, golden, pf):
-    g = golden["sweep"]
-    cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE)
-    obs = np.zeros(2048)
-    obs[g["obs_nonzero_idx"]] = parse_floats(g["obs_nonzero_val"])
-    z = np.random.RandomState(g["draw_seed"]).standard_normal(1024)
-    thetas = np.array(g["thetas"])
-    with M.TofModel(cfg) as m:
-        m.set_observables(obs)
-        m.set_draws(z)
-        got = m.lnprob_batch(thetas)
-        counts = m.model_batch(thetas, stage="counts")
-        pdf0 = m.model_batch(thetas[:1], stage="spread")[0]
-    want = np.array([pf(v) for v in g["lnlike"]])
-    bad = [k for k in range(len(want)) if rel(float(got[k]), float(want[k])) > RTOL]
-    assert len(bad) <= 1, (bad, got[bad], want[bad])
-    n_bad = 0
-    for k, c in enumerate(g["counts"]):
-        want_c = np.zeros(2048)
-        want_c[c["idx"]] = c["val"]
-        n_bad += int(not np.array_equal(counts[k], want_c))
-    assert n_bad <= 1, n_bad
-    want0 = np.zeros(2048)
-    want0[g["pdf0_nonzero_idx"]] = parse_floats(g["pdf0_nonzero_val"])
-    np.testing.assert_allclose(pdf0, want0, rtol=1e-12, atol=0)
-
-
 @pytest.mark.parametrize("excitation", [19.2, 19.2e-3])
 def test_range_vs_rk4_kernels_many_walkers(M, O, excitation):
     """The two CUDA formulations on 2048 walkers spread over the whole prior box: integer TOF spectra
@@ -384,6 +398,95 @@ def test_range_multiple_tiles_and_loops(M, O):
     for k, th in enumerate(thetas):
         assert np.array_equal(cc[k], om.cell_counts(th, z, xs)), k
         assert rel(float(got[k]), float(om.lnprob(th, obs, z, xs))) <= RTOL, (k, got[k])
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configurations at their FULL draw counts ("full-size configs are not parity-checked")
+# ---------------------------------------------------------------------------------------------------
+_FULL_CACHE = {}
+
+
+def _full_size_oracle(O, name):
+    """Oracle side of a full-size config, computed once per session (the GPU box's host cores; C2 takes ~2 min):
+    real observables generated by the oracle at the script's guess, then per walker the integer TOF spectrum
+    (adv:159, density=False) and the log-probability built from it exactly as adv:160-181 does."""
+    if name in _FULL_CACHE:
+        return _FULL_CACHE[name]
+    xs = O.DDNXS()
+    if name == "C3":       # tests/advIntermediateTOFmodel.py: nSamples = nEvPerLoop = 1e5 (adv:76), -run 0
+        om = O.adv_model(0, mean_excitation=19.2e-3, n_samples=100000, n_ev_per_loop=100000, ode_substeps=2)
+        star, scale = [1050.0, 0.10], 5e4
+        thetas = np.array([[1050, .10], [1040, .11], [1100, .05], [1500, .20], [2400, .03]])
+        seeds = (301, 302)
+    else:                  # C2, tests/intermediateTOFmodel.py: nSamples 1e6 in loops of 1e4 (intermediate:76,126), -run 3
+        om = O.intermediate_model(3, mean_excitation=19.2e-3, n_samples=1000000, n_ev_per_loop=10000, ode_substeps=2)
+        star, scale = [900.0, 0.15], 2e4
+        thetas = np.array([[900, .15], [910, .14], [800, .05], [1100, .16]])
+        seeds = (201, 202)
+    nd = om.n_loops * om.n_ev_per_loop
+    z = np.random.RandomState(seeds[0]).standard_normal(nd)
+    obs = np.rint(scale * om.model_pdf(star, np.random.RandomState(seeds[1]).standard_normal(nd), xs))
+    counts, lps = [], []
+    edges = np.linspace(om.tof_min, om.tof_max, om.tof_bins + 1)
+    for th in thetas:
+        c = om.raw_tof(list(th), z, xs, density=False)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            pdf = c / np.diff(edges) / c.sum()                                  # np.histogram(density=True)
+        ev = O.apply_spreading(pdf, np.asarray(om.taps))
+        lps.append(float(O.shape_loglike(ev, obs)) if np.isfinite(om.lnprior(th)) else -np.inf)
+        counts.append(c)
+    _FULL_CACHE[name] = (z, obs, thetas, counts, lps)
+    return _FULL_CACHE[name]
+
+
+@pytest.mark.parametrize("ode", ODE_MODES)
+@pytest.mark.parametrize("name", ["C3", "C2"])
+def test_full_size_adv_and_intermediate_configs(M, O, name, ode):
+    """C3 (adv, 1e5 draws in one loop) and C2 (intermediate, 1e6 draws in 100 loops) at the scripts' own draw counts:
+    integer TOF spectra bit-exact and lnprob to 1e-9 against the oracle, for both CUDA formulations."""
+    z, obs, thetas, counts, lps = _full_size_oracle(O, name)
+    if name == "C3":
+        cfg = M.config.adv(0, mean_excitation=19.2e-3, ode_mode=_ode(M, ode), ode_substeps=2)
+    else:
+        cfg = M.config.intermediate(3, mean_excitation=19.2e-3, ode_mode=_ode(M, ode), ode_substeps=2)
+    assert cfg.n_draws == len(z) and cfg.n_samples == len(z)
+    with M.TofModel(cfg) as m:
+        m.set_observables(obs)
+        m.set_draws(z)
+        got = m.lnprob_batch(thetas)
+        got_counts = m.model_batch(thetas, stage="counts")
+    assert np.isfinite(lps).sum() >= 2
+    for k in range(len(thetas)):
+        assert np.array_equal(got_counts[k], counts[k]), (name, ode, k, int(np.abs(got_counts[k] - counts[k]).sum()))
+        assert rel(float(got[k]), lps[k]) <= RTOL, (name, ode, k, got[k], lps[k])
+
+
+@pytest.mark.parametrize("ode", ODE_MODES)
+def test_full_size_simult_config(M, O, golden, ode):
+    """C4 (simultFit.py: 5 runs x 200 000 draws in loops of 50 000) on 4 walkers around the script's guess, against
+    the oracle on the same explicit draws; observables are the reference's own (the seed-pinned golden's)."""
+    g = golden["simult"]
+    c = [c for c in g["cases"] if c["n_draws"] == 200000][0]
+    obs = [parse_floats(o) for o in c["obs"]]
+    th0 = np.array(g["theta"])
+    thetas = np.array([th0, th0 * [1.002, 1.01, 0.97, 1.03, 1, 1, 1, 1, 1], th0 * [0.999, 0.98, 1.05, 0.95, 1.1, .9, 1, 1, 1.2],
+                       th0 * [1.0, 1.0, 1.0, 1.0, 0.5, 2.0, 1, 1, 1]])
+    cfg = M.config.simult(ode_mode=_ode(M, ode))
+    assert cfg.n_samples == 200000 and cfg.n_ev_per_loop == 50000 and cfg.n_loops == 4          # simultFit.py:178,239
+    # both kernels against the RK4 x4 oracle (its closed-form twin takes 3 minutes per evaluation at this size and
+    # gives the identical value for the golden theta)
+    om = O.SimultModel()
+    z_main, z_extra = _simult_tables(O, cfg, 4242)
+    xs = O.DDNXS()
+    want = []
+    for th in thetas:
+        want.append(float(om.lnprob(list(th), obs, O.TableDraws(z_main, z_extra), xs)))
+    fn = M.make_lnprob(cfg, obs, [z.ravel() for z in z_main], extra_draws=z_extra)
+    got = fn.batch(thetas)
+    fn.model.close()
+    assert np.isfinite(want).sum() >= 3
+    for k in range(len(thetas)):
+        assert rel(float(got[k]), want[k]) <= RTOL, (ode, k, got[k], want[k])
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -641,9 +744,7 @@ def test_simult_reference_goldens(M, O, golden, pf):
     """Seed-pinned lnprob values produced by the reference's own simultFit functions (scipy dopri5 there)."""
     g = golden["simult"]
     th = g["theta"]
-    for c in g["cases"]:
-        if c["n_draws"] > 10000:
-            continue
+    for c in g["cases"]:                       # 3500, 4000 and the script's own 200 000 draws (config 4 at full size)
         om = O.SimultModel(n_samples=c["n_draws"], n_ev_per_loop=c["n_ev_per_loop"])
         obs = [parse_floats(o) for o in c["obs"]]
         rec = _Recorder(O.GlobalStateDraws(np.random.RandomState(c["seed_eval"])), 5)

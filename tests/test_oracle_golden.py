@@ -159,6 +159,24 @@ def test_sweep_shape_goldens(golden, pf):
     np.testing.assert_allclose(pdf0, want0, rtol=1e-13, atol=0)
 
 
+def test_sweep_finite_goldens(golden2, pf):
+    """Benchmark shape with observables most walkers can explain (23 of 24 finite in the reference itself)."""
+    g = golden2["sweep_finite"]
+    m = O.sweep_model()
+    obs = np.zeros(2048)
+    obs[g["obs_nonzero_idx"]] = parse_floats(g["obs_nonzero_val"])
+    z = np.random.RandomState(g["draw_seed"]).standard_normal(1024)
+    xs = O.DDNXS()
+    want = [pf(v) for v in g["lnlike"]]
+    assert sum(math.isfinite(v) for v in want) >= 16
+    n_ok = 0
+    for th, w in zip(g["thetas"], want):
+        got = m.lnlike(th, obs, z, xs)
+        assert math.isfinite(got) == math.isfinite(w)
+        n_ok += int(got == w or rel(got, w) <= 1e-12)
+    assert n_ok >= len(want) - 1           # at most one LSODA-tolerance count flip among 24
+
+
 def test_simult_goldens_small(golden, pf):
     g = golden["simult"]
     for c in g["cases"]:

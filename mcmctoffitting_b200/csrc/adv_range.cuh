@@ -43,14 +43,33 @@ __host__ __device__ inline size_t range_rec_doubles(int rcap, int P) {
     return a > b ? a : b;
 }
 
-// hcap: cells of the (possibly banded) histogram; rcap: staged T2 records
-__host__ __device__ inline size_t range_smem_bytes(int X, int E, int T, int hcap, int rcap, int P, int n_taps, int lut_n,
-                                                   int rng_n) {
+// hcap: cells of the (possibly banded) histogram; rcap: staged T2 records.  Regions, in order:
+//   H [hcap] f64 | region A: draw tile u0 [RANGE_TILE] f64, later the TOF counters [T] u32 | staged T2 records |
+//   deuteron speeds [E] | taps | 40 doubles of reduction scratch | delta [X] | interval lookup (u16) | per-tile draw
+//   lookup (u16; later 1/speed [E]) | srow [X] int | hlo [X] int | interval ends [M] f64 | E-bin of each interval [M] u16
+inline RangeLayout range_layout(int X, int E, int T, int hcap, int rcap, int P, int n_taps, int lut_n, int rng_n) {
+    RangeLayout L;
     size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
     region_a = (region_a + 15) / 16 * 16;
-    size_t d = (size_t)hcap + range_rec_doubles(rcap, P) + E + n_taps + 40 + X /* per-row offsets */;
-    return d * 8 + region_a + (((size_t)lut_n * 2 + 15) / 16) * 16 + range_ulut_bytes(E) + (((size_t)X * 8 + 15) / 16) * 16 +
-           (size_t)rng_n * 8 + (((size_t)rng_n * 2 + 15) / 16) * 16 + 16;
+    size_t o = (size_t)hcap * 8;
+    L.pa = (unsigned)o;        o += region_a;
+    L.rec = (unsigned)o;       o += range_rec_doubles(rcap, P) * 8;
+    L.svd = (unsigned)o;       o += (size_t)E * 8;
+    L.staps = (unsigned)o;     o += (size_t)n_taps * 8;
+    L.scratch = (unsigned)o;   o += 40 * 8;
+    L.sdelta = (unsigned)o;    o += (size_t)X * 8;
+    L.lut = (unsigned)o;       o += (size_t)((lut_n + 7) / 8) * 8 * 2;
+    L.ulut = (unsigned)o;      o += range_ulut_bytes(E);
+    L.srow = (unsigned)o;      o += (size_t)X * 4;
+    L.hlo = (unsigned)o;       o += (size_t)(X + (X & 1)) * 4;
+    L.sbrk = (unsigned)o;      o += (size_t)rng_n * 8;
+    L.sbin = (unsigned)o;      o += (((size_t)rng_n * 2 + 15) / 16) * 16;
+    L.total = (unsigned)(o + 16);
+    return L;
+}
+
+inline size_t range_smem_bytes(int X, int E, int T, int hcap, int rcap, int P, int n_taps, int lut_n, int rng_n) {
+    return range_layout(X, E, T, hcap, rcap, P, n_taps, lut_n, rng_n).total;
 }
 
 
@@ -454,6 +473,350 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
     }
 }
 
+// ================================================================================================
+// Phase 1, planned form (FP64, a single tile of sorted draws, one T2 interval per E-bin)
+// ================================================================================================
+// The general routine above finds a cell's draws and sums its polynomial in one loop; with the search state, the
+// record and the polynomial all live at once the compiler runs out of registers at 64 per thread (spills, the four
+// Horner chains of a trip serialised).  When every E-bin is exactly one T2 interval (interval j == bin j: no
+// cross-section knot falls inside a bin) and the walker's draws are one tile, the two jobs separate cleanly and the
+// cell histogram itself carries the hand-over:
+//   plan     lane = interval, consecutive lanes = consecutive intervals of one row.  Lane finds the first draw at or
+//            beyond the left edge of its interval (per-tile lookup + short forward walk); the neighbour's answer is
+//            the end of its run (shuffle).  (first draw, count) is written INTO the cell's 8-byte slot of H.
+//   execute  lane = row, 32 rows of one trajectory-aligned interval offset (runs of similar length).  Lane reads its
+//            slot, loads the polynomial, sums its run -- four samples per trip, warp-uniform trip count, the four
+//            Horner chains interleaved -- and overwrites the slot with the sum.
+// Every cell is planned by one lane and summed by one lane: no atomics, fixed summation order, same membership rule
+// (RN(u0 + delta) >= edge) as the general routine, so both produce the same cells from the same draws.
+template <int P>
+__device__ __forceinline__ void poly_run4(double &acc, unsigned addr, int r, double off, const double (&a)[P + 1]) {
+    static_assert(P == 7, "poly_run4 is written for degree-7 records");
+    // Samples past the lane's run (k >= r) keep t = 0 and add q(0)*0 = 0: the loads are predicated, the arithmetic is
+    // not -- no select after the Horner chains.
+    asm("{\n\t"
+        ".reg .pred p0, p1, p2, p3;\n\t"
+        ".reg .f64 t0, t1, t2, t3, q0, q1, q2, q3;\n\t"
+        "setp.gt.s32 p0, %2, 0;\n\t"
+        "setp.gt.s32 p1, %2, 1;\n\t"
+        "setp.gt.s32 p2, %2, 2;\n\t"
+        "setp.gt.s32 p3, %2, 3;\n\t"
+        "mov.f64 t0, 0d0000000000000000;\n\t"
+        "mov.f64 t1, 0d0000000000000000;\n\t"
+        "mov.f64 t2, 0d0000000000000000;\n\t"
+        "mov.f64 t3, 0d0000000000000000;\n\t"
+        "@p0 ld.shared.f64 t0, [%1];\n\t"
+        "@p1 ld.shared.f64 t1, [%1+8];\n\t"
+        "@p2 ld.shared.f64 t2, [%1+16];\n\t"
+        "@p3 ld.shared.f64 t3, [%1+24];\n\t"
+        "@p0 add.rn.f64 t0, t0, %3;\n\t"
+        "@p1 add.rn.f64 t1, t1, %3;\n\t"
+        "@p2 add.rn.f64 t2, t2, %3;\n\t"
+        "@p3 add.rn.f64 t3, t3, %3;\n\t"
+        "fma.rn.f64 q0, %10, t0, %9;\n\t"
+        "fma.rn.f64 q1, %10, t1, %9;\n\t"
+        "fma.rn.f64 q2, %10, t2, %9;\n\t"
+        "fma.rn.f64 q3, %10, t3, %9;\n\t"
+        "fma.rn.f64 q0, q0, t0, %8;\n\t"
+        "fma.rn.f64 q1, q1, t1, %8;\n\t"
+        "fma.rn.f64 q2, q2, t2, %8;\n\t"
+        "fma.rn.f64 q3, q3, t3, %8;\n\t"
+        "fma.rn.f64 q0, q0, t0, %7;\n\t"
+        "fma.rn.f64 q1, q1, t1, %7;\n\t"
+        "fma.rn.f64 q2, q2, t2, %7;\n\t"
+        "fma.rn.f64 q3, q3, t3, %7;\n\t"
+        "fma.rn.f64 q0, q0, t0, %6;\n\t"
+        "fma.rn.f64 q1, q1, t1, %6;\n\t"
+        "fma.rn.f64 q2, q2, t2, %6;\n\t"
+        "fma.rn.f64 q3, q3, t3, %6;\n\t"
+        "fma.rn.f64 q0, q0, t0, %5;\n\t"
+        "fma.rn.f64 q1, q1, t1, %5;\n\t"
+        "fma.rn.f64 q2, q2, t2, %5;\n\t"
+        "fma.rn.f64 q3, q3, t3, %5;\n\t"
+        "fma.rn.f64 q0, q0, t0, %4;\n\t"
+        "fma.rn.f64 q1, q1, t1, %4;\n\t"
+        "fma.rn.f64 q2, q2, t2, %4;\n\t"
+        "fma.rn.f64 q3, q3, t3, %4;\n\t"
+        "fma.rn.f64 %0, q0, t0, %0;\n\t"
+        "fma.rn.f64 %0, q1, t1, %0;\n\t"
+        "fma.rn.f64 %0, q2, t2, %0;\n\t"
+        "fma.rn.f64 %0, q3, t3, %0;\n\t"
+        "}"
+        : "+d"(acc)
+        : "r"(addr), "r"(r), "d"(off), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]));
+}
+
+// Four samples, all of them inside the lane's run: no predicates at all.
+template <int P>
+__device__ __forceinline__ void poly_full4(double &acc, unsigned addr, double off, const double (&a)[P + 1]) {
+    static_assert(P == 7, "poly_full4 is written for degree-7 records");
+    asm("{\n\t"
+        ".reg .f64 t0, t1, t2, t3, q0, q1, q2, q3;\n\t"
+        "ld.shared.f64 t0, [%1];\n\t"
+        "ld.shared.f64 t1, [%1+8];\n\t"
+        "ld.shared.f64 t2, [%1+16];\n\t"
+        "ld.shared.f64 t3, [%1+24];\n\t"
+        "add.rn.f64 t0, t0, %2;\n\t"
+        "add.rn.f64 t1, t1, %2;\n\t"
+        "add.rn.f64 t2, t2, %2;\n\t"
+        "add.rn.f64 t3, t3, %2;\n\t"
+        "fma.rn.f64 q0, %9, t0, %8;\n\t"
+        "fma.rn.f64 q1, %9, t1, %8;\n\t"
+        "fma.rn.f64 q2, %9, t2, %8;\n\t"
+        "fma.rn.f64 q3, %9, t3, %8;\n\t"
+        "fma.rn.f64 q0, q0, t0, %7;\n\t"
+        "fma.rn.f64 q1, q1, t1, %7;\n\t"
+        "fma.rn.f64 q2, q2, t2, %7;\n\t"
+        "fma.rn.f64 q3, q3, t3, %7;\n\t"
+        "fma.rn.f64 q0, q0, t0, %6;\n\t"
+        "fma.rn.f64 q1, q1, t1, %6;\n\t"
+        "fma.rn.f64 q2, q2, t2, %6;\n\t"
+        "fma.rn.f64 q3, q3, t3, %6;\n\t"
+        "fma.rn.f64 q0, q0, t0, %5;\n\t"
+        "fma.rn.f64 q1, q1, t1, %5;\n\t"
+        "fma.rn.f64 q2, q2, t2, %5;\n\t"
+        "fma.rn.f64 q3, q3, t3, %5;\n\t"
+        "fma.rn.f64 q0, q0, t0, %4;\n\t"
+        "fma.rn.f64 q1, q1, t1, %4;\n\t"
+        "fma.rn.f64 q2, q2, t2, %4;\n\t"
+        "fma.rn.f64 q3, q3, t3, %4;\n\t"
+        "fma.rn.f64 q0, q0, t0, %3;\n\t"
+        "fma.rn.f64 q1, q1, t1, %3;\n\t"
+        "fma.rn.f64 q2, q2, t2, %3;\n\t"
+        "fma.rn.f64 q3, q3, t3, %3;\n\t"
+        "fma.rn.f64 %0, q0, t0, %0;\n\t"
+        "fma.rn.f64 %0, q1, t1, %0;\n\t"
+        "fma.rn.f64 %0, q2, t2, %0;\n\t"
+        "fma.rn.f64 %0, q3, t3, %0;\n\t"
+        "}"
+        : "+d"(acc)
+        : "r"(addr), "d"(off), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]));
+}
+
+// Execute half of the planned form (see range_tile_planned below): a function of its own so that the polynomial
+// loop is register-allocated without the planner's state.  `hlo` is never null here (all zeros for the full-size
+// launch).  Work split: a warp keeps ONE group of 32 rows for the whole tile (row-dependent values are loaded once)
+// and walks the interval offsets of that group with a stride; the X % 32 leftover rows get a warp of their own that
+// packs R rows x (32/R) interval offsets per visit.
+template <int NT, int P>
+__device__ __noinline__ void range_exec_cells(const double *u0, const double *brk, const double *rec, int jbase,
+                                              const double *sdelta, const int *srow, double *H, int hstride, const int *hlo,
+                                              int X, int band_lo, int band_hi) {
+    __builtin_assume(__isShared(u0));
+    __builtin_assume(__isShared(brk));
+    __builtin_assume(__isShared(rec));
+    __builtin_assume(__isShared(sdelta));
+    __builtin_assume(__isShared(srow));
+    __builtin_assume(__isShared(H));
+    __builtin_assume(__isShared(hlo));
+    constexpr int RW = P + 3;
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int Gf = X >> 5, R = X & 31;
+    const int s_ref = srow[0];
+    const int s_b = srow[X - 1] - s_ref;               // the shift is monotone in the row index
+    const int s_min = s_b < 0 ? s_b : 0, s_max = s_b < 0 ? 0 : s_b;
+    const int k_lo = band_lo - s_max;
+    const int n_iv = (band_hi - s_min) - k_lo + 1;
+    const int per_b = R ? 32 / R : 1;
+    const int nB = R ? (n_iv + per_b - 1) / per_b : 0;
+    const unsigned u0_s32 = (unsigned)__cvta_generic_to_shared(u0);
+    // warps for the leftover rows: in proportion to their share of the visits, at least one when there are any
+    int wB = 0;
+    if (R) {
+        wB = Gf ? (NW * nB + (n_iv * Gf + nB) / 2) / (n_iv * Gf + nB) : NW;
+        wB = wB < 1 ? 1 : (wB > NW - 1 && Gf ? NW - 1 : wB);
+    }
+    const int wA = NW - wB;                            // warps that own a full group of 32 rows
+    // one (row, interval) cell of this lane: sum its run and overwrite the slot
+    auto cell = [&](int j, bool ok, double delta, double *Hrow /* row base minus its first E-bin */, int row_lo) {
+        const int col = j - row_lo;
+        const bool active = ok && j >= band_lo && j <= band_hi && (unsigned)col < (unsigned)hstride;
+        int lb = 0, n = 0;
+        if (active) {
+            const long long dn = *reinterpret_cast<const long long *>(Hrow + j);   // 0.0 (untouched) reads as n == 0
+            lb = (int)(unsigned)dn;
+            n = (int)(dn >> 32);
+        }
+        const int nmax = __reduce_max_sync(FULL, n);
+        if (nmax == 0) return;                         // uniform
+        const int nmin = __reduce_min_sync(FULL, n);
+        double a[P + 1];
+        double off = 0.0;
+        const double *rj = rec + (n > 0 ? (j - jbase) * RW + 2 : 2);
+        if (n > 0) {
+            TOF_CHECK(j - jbase >= 0 && lb >= 0);
+            const double2 *r2 = reinterpret_cast<const double2 *>(rj);
+            a[1] = r2[0].y;
+#pragma unroll
+            for (int k = 2; k <= P; k += 2) {
+                const double2 c2 = r2[k >> 1];
+                a[k] = c2.x;
+                a[k + 1] = c2.y;
+            }
+            off = delta - (j ? brk[j - 1] : 0.0);
+        } else {
+#pragma unroll
+            for (int k = 1; k <= P; ++k) a[k] = 0.0;
+        }
+        a[0] = 0.0;                                    // the constant term is added once per run, after the loop
+        double acc = 0.0;
+        unsigned addr = u0_s32 + (unsigned)lb * 8u;
+        const int tfull = nmin >> 2;                   // trips in which every lane still has four samples
+#pragma unroll 1
+        for (int t = tfull; t > 0; --t) {
+            poly_full4<P>(acc, addr, off, a);
+            addr += 32u;
+        }
+        int rem = n - (tfull << 2);
+#pragma unroll 1
+        for (int t = ((nmax + 3) >> 2) - tfull; t > 0; --t) {
+            poly_run4<P>(acc, addr, rem, off, a);
+            addr += 32u;
+            rem -= 4;
+        }
+        if (n > 0) Hrow[j] = fma((double)n, rj[0], acc);
+    };
+    if (warp < wA) {
+        if (Gf <= wA) {                                // the usual case: this warp keeps one group of rows
+            const int g = warp % Gf, idx = warp / Gf;
+            const int cnt = (wA - g + Gf - 1) / Gf;    // warps sharing group g
+            const int row = (g << 5) + lane;
+            const int row_lo = hlo[row];
+            const double delta = sdelta[row];
+            double *Hrow = H + (size_t)row * hstride - row_lo;
+            const int jrow = k_lo + (srow[row] - s_ref);
+            for (int jj = idx; jj < n_iv; jj += cnt) cell(jrow + jj, true, delta, Hrow, row_lo);
+        } else {                                       // more groups than warps: stride over (offset, group) pairs
+            for (int task = warp; task < n_iv * Gf; task += wA) {
+                const int jj = task / Gf;
+                const int row = ((task - jj * Gf) << 5) + lane;
+                const int row_lo = hlo[row];
+                cell(k_lo + jj + (srow[row] - s_ref), true, sdelta[row], H + (size_t)row * hstride - row_lo, row_lo);
+            }
+        }
+    } else {
+        const int isub = lane / R;
+        const int row = (Gf << 5) + (lane - isub * R);
+        const int row_lo = hlo[row];
+        const double delta = sdelta[row];
+        double *Hrow = H + (size_t)row * hstride - row_lo;
+        const int jrow = k_lo + isub + (srow[row] - s_ref);
+        for (int tb = warp - wA; tb < nB; tb += wB) cell(jrow + tb * per_b, isub < per_b, delta, Hrow, row_lo);
+    }
+}
+
+// Called by all threads of the CTA (contains barriers).  H must be zero where no draw can land (the kernel clears it
+// per walker); `rec` holds the staged records jbase.. (coefficients at +2 doubles), `brk` the ends of all intervals.
+// __noinline__ on purpose: the call is a register-allocation firewall.  Inlined into the kernel, the routine competes
+// with the kernel's own live state for 64 registers and ptxas serialises the Horner chains; as a function it is
+// allocated on its own (the caller's live registers are saved once per tile).
+template <int NT, int P>
+__device__ __noinline__ void range_tile_planned(const double *u0, int nt, const double *brk, const double *rec, int jbase,
+                                                   const unsigned short *lut, unsigned short *ulut, int n_ulut,
+                                                   const double *sdelta, int *srow, double *H, int hstride, const int *hlo,
+                                                   int X, int M, double umax, double lut_inv, int lut_n, int &bin_lo_all,
+                                                   int &bin_hi_all) {
+    // every pointer is a shared-memory address (the call boundary hides that from the compiler: without the hints it
+    // emits generic LD.E / ST.E instead of LDS / STS)
+    __builtin_assume(__isShared(u0));
+    __builtin_assume(__isShared(brk));
+    __builtin_assume(__isShared(rec));
+    __builtin_assume(__isShared(lut));
+    __builtin_assume(__isShared(ulut));
+    __builtin_assume(__isShared(sdelta));
+    __builtin_assume(__isShared(srow));
+    __builtin_assume(__isShared(H));
+    __builtin_assume(__isShared(hlo));
+    constexpr int RW = P + 3;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nsteps = 32 - __clz(nt);
+    int v_lo = 0, v_hi = nt;                          // finite part of the sorted tile: -inf first, +inf last
+    {
+        int lo = 0, hi = nt, lo2 = 0, hi2 = nt;
+        for (int it = 0; it < nsteps; ++it) {
+            const int mid = (lo + hi) >> 1, mid2 = (lo2 + hi2) >> 1;
+            const bool ge = u0[mid < nt ? mid : nt - 1] > -CUDART_INF;
+            const bool gt = u0[mid2 < nt ? mid2 : nt - 1] >= CUDART_INF;
+            const bool go = lo < hi, go2 = lo2 < hi2;
+            hi = (go && ge) ? mid : hi;
+            lo = (go && !ge) ? mid + 1 : lo;
+            hi2 = (go2 && gt) ? mid2 : hi2;
+            lo2 = (go2 && !gt) ? mid2 + 1 : lo2;
+        }
+        v_lo = lo;
+        v_hi = lo2;
+    }
+    if (v_hi <= v_lo) return;                         // uniform: no usable draw
+    const double tu_min = u0[v_lo], tu_max = u0[v_hi - 1];
+    constexpr double tu_bias = 1.0 / 65536.0;         // lookup cell taken a hair low: forward walks only (see above)
+    const double tu_inv = (tu_max - tu_min > 1e-6 * (double)n_ulut) ? (double)n_ulut / (tu_max - tu_min) : 0.0;
+    for (int d = v_lo + tid; d < v_hi; d += NT) {     // ulut[c] = first draw whose lookup cell is >= c (scatter)
+        int c1 = (int)((u0[d] - tu_min) * tu_inv);
+        c1 = c1 > n_ulut - 1 ? n_ulut - 1 : c1;
+        int c0 = -1;
+        if (d > v_lo) {
+            c0 = (int)((u0[d - 1] - tu_min) * tu_inv);
+            c0 = c0 > n_ulut - 1 ? n_ulut - 1 : c0;
+        }
+        TOF_CHECK(c1 >= 0 && c1 < n_ulut && c0 >= -1 && c0 <= c1);
+        for (int c = c0 + 1; c <= c1; ++c) ulut[c] = (unsigned short)d;
+    }
+    {                                                 // trajectory alignment: interval of the median draw per row
+        const double u_med = u0[(v_lo + v_hi) >> 1];
+        for (int i = tid; i < X; i += NT) {
+            double vm = __dadd_rn(u_med, sdelta[i]);
+            vm = vm < 0.0 ? 0.0 : (vm > umax ? umax : vm);
+            srow[i] = range_interval(vm, brk, lut, lut_inv, lut_n, M);
+        }
+    }
+    double dmin = sdelta[0], dmax = sdelta[0];
+    {
+        const double dl = sdelta[X - 1];
+        dmin = dl < dmin ? dl : dmin;
+        dmax = dl > dmax ? dl : dmax;
+    }
+    const double vmin = __dadd_rn(tu_min, dmin), vmax = __dadd_rn(tu_max, dmax);
+    __syncthreads();
+    if (!(vmax >= 0.0) || vmin > umax) return;        // uniform
+    const int band_lo = range_interval(vmin > 0.0 ? vmin : 0.0, brk, lut, lut_inv, lut_n, M);
+    const int band_hi = range_interval(vmax < umax ? vmax : umax, brk, lut, lut_inv, lut_n, M);
+    TOF_CHECK(band_lo >= jbase && band_lo <= band_hi && band_hi < M);
+    bin_lo_all = min(bin_lo_all, band_lo);            // interval j == E-bin j on this path
+    bin_hi_all = max(bin_hi_all, band_hi);
+    const double umax_next = __longlong_as_double(__double_as_longlong(umax) + 1);
+
+    // ---- plan: (first draw, count) of every cell into its slot of H ------------------------------------------
+    for (int row = warp; row < X; row += NW) {
+        const double delta = sdelta[row];
+        const int row_lo = hlo[row];
+        int ja = row_lo > band_lo ? row_lo : band_lo;
+        int jb = row_lo + hstride - 1;
+        jb = jb < band_hi ? jb : band_hi;
+        long long *Hrow = reinterpret_cast<long long *>(H + (size_t)row * hstride) - row_lo;
+        for (int j0 = ja; j0 <= jb; j0 += 31) {       // lanes 0..30 own a cell each, lane 31 supplies the last edge
+            int j = j0 + lane;
+            j = j <= jb + 1 ? j : jb + 1;
+            // left edge of interval j (the right edge of the last, closed, interval is nextafter(u_max))
+            const double edge = (j == 0) ? 0.0 : (j >= M ? umax_next : brk[j - 1]);
+            int c = (int)fma(edge - delta - tu_min, tu_inv, -tu_bias);
+            c = c < 0 ? 0 : (c > n_ulut - 1 ? n_ulut - 1 : c);
+            int d = ulut[c];
+            while (d < v_hi && !(__dadd_rn(u0[d], delta) >= edge)) ++d;
+            const int d_next = __shfl_down_sync(FULL, d, 1);
+            const int n = d_next - d;
+            TOF_CHECK(d >= v_lo && d <= v_hi && (lane == 31 || n >= 0));
+            if (lane < 31 && j0 + lane <= jb && n > 0) {
+                TOF_CHECK(j - row_lo >= 0 && j - row_lo < hstride && j - jbase >= 0);
+                Hrow[j] = (long long)(unsigned)d | ((long long)n << 32);
+            }
+        }
+    }
+    __syncthreads();
+    range_exec_cells<NT, P>(u0, brk, rec, jbase, sdelta, srow, H, hstride, hlo, X, band_lo, band_hi);
+}
+
 template <int NT, int P, bool F32 = false, bool PROF = false>
 __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(const DevModel m, const DevRun run, const double *__restrict__ theta,
                                                        long long n_walkers, ModelOut out) {
@@ -474,23 +837,21 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     // for the full-size launch
     const bool banded = out.hcap < X * EB;
     double *H = reinterpret_cast<double *>(smem_raw);
-    size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
-    region_a = (region_a + 15) / 16 * 16;
-    unsigned char *pa = reinterpret_cast<unsigned char *>(H + (size_t)out.hcap);
+    unsigned char *pa = smem_raw + out.lay.pa;
     unsigned int *tofc = reinterpret_cast<unsigned int *>(pa);
     double *u0 = reinterpret_cast<double *>(pa);                       // aliases tofc (phase 1 only)
-    double *rec = reinterpret_cast<double *>(pa + region_a);
-    double *svd = rec + range_rec_doubles(out.rcap, P);
-    double *staps = svd + EB;
-    double *scratch = staps + m.n_taps;
-    double *sdelta = scratch + 40;                                      // [X] sgn*(x_i - x_start)
-    unsigned short *lut = reinterpret_cast<unsigned short *>(sdelta + X);
-    unsigned short *ulut = lut + ((m.rng_lut_n + 7) / 8) * 8;           // [RANGE_ULUT]
-    int *srow = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(ulut) + range_ulut_bytes(EB));   // [X]
+    double *rec = reinterpret_cast<double *>(smem_raw + out.lay.rec);
+    double *svd = reinterpret_cast<double *>(smem_raw + out.lay.svd);
+    double *staps = reinterpret_cast<double *>(smem_raw + out.lay.staps);
+    double *scratch = reinterpret_cast<double *>(smem_raw + out.lay.scratch);
+    double *sdelta = reinterpret_cast<double *>(smem_raw + out.lay.sdelta);   // [X] sgn*(x_i - x_start)
+    unsigned short *lut = reinterpret_cast<unsigned short *>(smem_raw + out.lay.lut);
+    unsigned short *ulut = reinterpret_cast<unsigned short *>(smem_raw + out.lay.ulut);   // [RANGE_ULUT]
+    int *srow = reinterpret_cast<int *>(smem_raw + out.lay.srow);       // [X]
     double *rvd = reinterpret_cast<double *>(ulut);                      // [EB] 1/svd, aliases ulut (phases 2-3 only)
-    int *hlo_s = srow + X;                                              // [X] first E-bin of each row (banded launch)
-    double *sbrk = reinterpret_cast<double *>(hlo_s + X + (X & 1));     // [M] interval ends
-    unsigned short *sbin = reinterpret_cast<unsigned short *>(sbrk + M);  // [M] E-bin of each interval
+    int *hlo_s = reinterpret_cast<int *>(smem_raw + out.lay.hlo);       // [X] first E-bin of each row (banded launch)
+    double *sbrk = reinterpret_cast<double *>(smem_raw + out.lay.sbrk); // [M] interval ends
+    unsigned short *sbin = reinterpret_cast<unsigned short *>(smem_raw + out.lay.sbin);  // [M] E-bin of each interval
     __shared__ int s_band[3];                                           // widest row, first / last interval of the walker
 
     // ---- walker-independent tables: staged once per CTA (persistent CTAs loop over walkers) ------------------
@@ -511,6 +872,8 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
     const double sgn = m.rng_sign, umax = m.rng_u_max;
     const double x_start = m.ode_from_zero ? 0.0 : m.x_centers[0];
     for (int i = tid; i < X; i += NT) sdelta[i] = sgn * (m.x_centers[i] - x_start);
+    if (!banded)
+        for (int i = tid; i < X; i += NT) hlo_s[i] = 0;      // full-size launch: every row starts at E-bin 0
     __shared__ long long s_next;
     // stage timing (tof_set_stage_timing; PROF instantiations only, the shipped kernels carry none of this): thread 0
     // charges the SM clock between stage boundaries to the stage that ends there -- it leaves a barrier when the CTA
@@ -695,8 +1058,12 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
             for (int d = tid; d < nt; d += NT)
                 u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 - (tile + d) : tile + d)))), m);
             __syncthreads();
-            range_accumulate_tile<NT, P>(u0, nt, sbrk, rec, jbase, lut, ulut, RANGE_ULUT, sdelta, srow, H, hstride, hlo, X, M,
-                                         umax, m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all);
+            if (m.rng_identity && m.n_draws <= RANGE_TILE)      // one tile, one interval per E-bin: plan / execute
+                range_tile_planned<NT, P>(u0, nt, sbrk, rec, jbase, lut, ulut, RANGE_ULUT, sdelta, srow, H, hstride, hlo_s, X, M,
+                                          umax, m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all);
+            else
+                range_accumulate_tile<NT, P>(u0, nt, sbrk, rec, jbase, lut, ulut, RANGE_ULUT, sdelta, srow, H, hstride, hlo, X, M,
+                                             umax, m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all);
         }
     }
     __syncthreads();

@@ -4,6 +4,14 @@
 
 namespace tof {
 
+// Byte offsets of the range kernel's regions inside dynamic shared memory, computed once on the host
+// (range_layout, adv_range.cuh) and passed with the launch: inside the kernel every region pointer is "base + one
+// constant-bank word" -- cheap to re-materialise under register pressure, where the arithmetic that derives the
+// offsets from (T, E, X, hcap, rcap, ...) was being re-executed inside the hot loops (11 % of all instructions).
+struct RangeLayout {
+    unsigned pa, rec, svd, staps, scratch, sdelta, lut, ulut, srow, hlo, sbrk, sbin, total;
+};
+
 // Outputs requested from a model kernel.  Production: only `lnprob`.
 struct ModelOut {
     double *lnprob;       // [n] (adv/simple) or [n][n_runs] partials (simult)
@@ -16,6 +24,7 @@ struct ModelOut {
     unsigned long long *work;  // optional global work counter (persistent CTAs take walkers dynamically)
     // range kernel, banded launch: capacity of the cell histogram (cells) and of the staged T2 records
     int hcap, rcap;
+    RangeLayout lay;                 // shared-memory layout of this launch (range kernel)
     int *queue_out;                  // walkers that do not fit the banded layout ...
     unsigned long long *queue_count; // ... and how many
     const int *queue_in;             // full-size launch: process queue_in[0 .. *queue_count)

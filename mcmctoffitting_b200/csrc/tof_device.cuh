@@ -51,6 +51,7 @@ struct DevModel {
     const float *rng_rec_f32;      // FP32 mode: [rng_n][8] floats: c0..c3, bin, shared-cell flag, c0 as a double (adv_range.cuh)
     const unsigned short *rng_lut; // [rng_lut_n]
     int t1_q, t1_key_lo, t1_n, rng_degree, rng_n, rng_lut_n;
+    int rng_identity;              // 1: T2 interval j is exactly E-bin j (no cross-section knot inside a bin)
     double rng_sign, rng_u_max, rng_lut_inv, e_tab_lo, e_tab_hi;
     // oneBD: spline stopping table, attenuation, causal transit taps
     const double *stop_coefs, *attenuation, *taps2;

@@ -48,6 +48,7 @@ struct tof_ctx {
     int band_hcap = 0, band_rcap = 0, band_ctas = 0, band_nt = 512;
     size_t band_smem = 0;
     bool band_enabled = false;
+    RangeLayout lay_full{}, lay_band{};   // shared-memory layouts of the two launches (host-computed offsets)
     size_t simult_smem = 0, onebd_smem = 0;
     int max_smem_optin = 0;
     bool have_obs[TOF_MAX_RUNS]{};
@@ -189,6 +190,7 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
             const bool debug = out.spectra != nullptr || out.cells != nullptr;
             out.hcap = c.x_bins * c.e_bins;
             out.rcap = c.rng_n;
+            out.lay = ctx->lay_full;
             // few walkers and a big (streamed) draw set: several CTAs per walker
             out.n_split = 1;
             if (!debug && ctx->dm.n_draws >= RANGE_STREAM_MIN) {
@@ -230,6 +232,7 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 ob.work = cnt + 0;
                 ob.hcap = ctx->band_hcap;
                 ob.rcap = ctx->band_rcap;
+                ob.lay = ctx->lay_band;
                 ob.queue_out = static_cast<int *>(ctx->d_queue.p);
                 ob.queue_count = cnt + 2;
                 AdvKernel kband = range_variant(ctx->band_nt, c.rng_degree, ctx->f32, prof);
@@ -571,6 +574,12 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         }
         TRY(upload(ctx, cfg->t1_coefs, (size_t)cfg->t1_n * 8, &m.t1_coefs));
         TRY(upload(ctx, cfg->rng_lut, (size_t)cfg->rng_lut_n, &m.rng_lut));
+        {
+            bool ident = Mi == cfg->e_bins;
+            for (int j = 0; ident && j < Mi; ++j) ident = cfg->rng_bins[j] == j;
+            if (const char *v = std::getenv("TOFGPU_RANGE_PLANNED")) ident = ident && std::atoi(v) != 0;   // tuning / A-B knob
+            m.rng_identity = ident ? 1 : 0;
+        }
         m.t1_q = cfg->t1_q; m.t1_key_lo = cfg->t1_key_lo; m.t1_n = cfg->t1_n; m.rng_degree = P; m.rng_n = Mi;
         m.rng_lut_n = cfg->rng_lut_n; m.rng_sign = cfg->rng_sign; m.rng_u_max = cfg->rng_u_max;
         m.rng_lut_inv = (double)cfg->rng_lut_n / cfg->rng_u_max; m.e_tab_lo = cfg->e_tab_lo; m.e_tab_hi = cfg->e_tab_hi;
@@ -592,8 +601,9 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
             if (!range_variant(nt, P)) { ctx->err = "TOFGPU_RANGE_THREADS must be 512, 640, 800 or 1024"; return bail(TOF_ERR_INVALID); }
             ctx->rng_nt = nt;
         }
-        ctx->adv_smem = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], cfg->x_bins * cfg->e_bins, Mi, P, cfg->n_taps,
-                                         cfg->rng_lut_n, Mi);
+        ctx->lay_full = range_layout(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], cfg->x_bins * cfg->e_bins, Mi, P, cfg->n_taps,
+                                     cfg->rng_lut_n, Mi);
+        ctx->adv_smem = ctx->lay_full.total;
         if ((int)ctx->adv_smem > ctx->max_smem_optin) {
             ctx->err = "range kernel needs " + std::to_string(ctx->adv_smem) + " B of shared memory per CTA; device offers " +
                        std::to_string(ctx->max_smem_optin);
@@ -629,8 +639,9 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
             if (want && kband && hcap >= (long long)cfg->x_bins * 8 && hcap >= cfg->tof_bins[0]) {
                 ctx->band_hcap = (int)hcap;
                 ctx->band_rcap = rcap;
-                ctx->band_smem = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], (int)hcap, rcap, P, cfg->n_taps,
-                                                  cfg->rng_lut_n, Mi);
+                ctx->lay_band = range_layout(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], (int)hcap, rcap, P, cfg->n_taps,
+                                             cfg->rng_lut_n, Mi);
+                ctx->band_smem = ctx->lay_band.total;
                 CUC(cudaFuncSetAttribute(kband, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->band_smem));
                 CUC(cudaFuncSetAttribute(kband, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 int occb = 0;

@@ -711,8 +711,11 @@ __device__ __noinline__ void range_exec_cells(const double *u0, const double *br
 // __noinline__ on purpose: the call is a register-allocation firewall.  Inlined into the kernel, the routine competes
 // with the kernel's own live state for 64 registers and ptxas serialises the Horner chains; as a function it is
 // allocated on its own (the caller's live registers are saved once per tile).
-template <int NT, int P>
-__device__ __noinline__ void range_tile_planned(const double *u0, int nt, const double *brk, const double *rec, int jbase,
+// EXEC = false: plan only; the caller runs range_exec_cells itself with the band returned in bin_lo_all / bin_hi_all
+// (returns false when the tile has nothing to execute).  A callee is register-allocated in what its callers leave
+// free, so the hot loop wants to be called from the leanest frame available (adv_planned_kernel calls it directly).
+template <int NT, int P, bool EXEC = true>
+__device__ __noinline__ bool range_tile_planned(const double *u0, int nt, const double *brk, const double *rec, int jbase,
                                                    const unsigned short *lut, unsigned short *ulut, int n_ulut,
                                                    const double *sdelta, int *srow, double *H, int hstride, const int *hlo,
                                                    int X, int M, double umax, double lut_inv, int lut_n, int &bin_lo_all,
@@ -748,7 +751,7 @@ __device__ __noinline__ void range_tile_planned(const double *u0, int nt, const 
         v_lo = lo;
         v_hi = lo2;
     }
-    if (v_hi <= v_lo) return;                         // uniform: no usable draw
+    if (v_hi <= v_lo) return false;                   // uniform: no usable draw
     const double tu_min = u0[v_lo], tu_max = u0[v_hi - 1];
     constexpr double tu_bias = 1.0 / 65536.0;         // lookup cell taken a hair low: forward walks only (see above)
     const double tu_inv = (tu_max - tu_min > 1e-6 * (double)n_ulut) ? (double)n_ulut / (tu_max - tu_min) : 0.0;
@@ -779,7 +782,7 @@ __device__ __noinline__ void range_tile_planned(const double *u0, int nt, const 
     }
     const double vmin = __dadd_rn(tu_min, dmin), vmax = __dadd_rn(tu_max, dmax);
     __syncthreads();
-    if (!(vmax >= 0.0) || vmin > umax) return;        // uniform
+    if (!(vmax >= 0.0) || vmin > umax) return false;  // uniform
     const int band_lo = range_interval(vmin > 0.0 ? vmin : 0.0, brk, lut, lut_inv, lut_n, M);
     const int band_hi = range_interval(vmax < umax ? vmax : umax, brk, lut, lut_inv, lut_n, M);
     TOF_CHECK(band_lo >= jbase && band_lo <= band_hi && band_hi < M);
@@ -814,7 +817,8 @@ __device__ __noinline__ void range_tile_planned(const double *u0, int nt, const 
         }
     }
     __syncthreads();
-    range_exec_cells<NT, P>(u0, brk, rec, jbase, sdelta, srow, H, hstride, hlo, X, band_lo, band_hi);
+    if constexpr (EXEC) range_exec_cells<NT, P>(u0, brk, rec, jbase, sdelta, srow, H, hstride, hlo, X, band_lo, band_hi);
+    return true;
 }
 
 template <int NT, int P, bool F32 = false, bool PROF = false>

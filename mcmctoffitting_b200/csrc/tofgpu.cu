@@ -48,6 +48,7 @@ struct tof_ctx {
     int band_hcap = 0, band_rcap = 0, band_ctas = 0, band_nt = 512;
     size_t band_smem = 0;
     bool band_enabled = false;
+    bool planned = false;    // banded launch runs adv_planned_kernel (FP64, <= one tile of draws, interval == E-bin)
     RangeLayout lay_full{}, lay_band{};   // shared-memory layouts of the two launches (host-computed offsets)
     size_t simult_smem = 0, onebd_smem = 0;
     int max_smem_optin = 0;
@@ -236,6 +237,8 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 ob.queue_out = static_cast<int *>(ctx->d_queue.p);
                 ob.queue_count = cnt + 2;
                 AdvKernel kband = range_variant(ctx->band_nt, c.rng_degree, ctx->f32, prof);
+                // many walkers x one tile of draws, one interval per E-bin: the lean cut of the same kernel
+                if (ctx->planned && out.n_split == 1) kband = prof ? adv_planned_kernel<512, 7, true> : adv_planned_kernel<512, 7, false>;
                 const long long slots_band = (long long)ctx->stats.sm_count * std::max(ctx->band_ctas, 1);
                 kband<<<(unsigned)std::min<long long>(n_work, slots_band), ctx->band_nt, ctx->band_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, ob);
                 // 2) full-size launch over the queue (exits at once when it is empty)
@@ -648,6 +651,14 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
                 CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, kband, ctx->band_nt, ctx->band_smem));
                 ctx->band_ctas = occb;
                 ctx->band_enabled = occb >= 2;
+                if (ctx->band_enabled && !ctx->f32 && ctx->band_nt == 512 && P == 7 && m.rng_identity && m.n_draws <= RANGE_TILE) {
+                    AdvKernel kp = adv_planned_kernel<512, 7, false>;
+                    CUC(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->band_smem));
+                    CUC(cudaFuncSetAttribute(kp, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                    int occp = 0;
+                    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, kp, 512, ctx->band_smem));
+                    ctx->planned = occp >= 2;
+                }
             }
         }
     } else if (cfg->model == TOF_MODEL_ADV) {
@@ -1033,6 +1044,10 @@ int tof_set_stage_timing(tof_ctx *ctx, int enabled) {
         CU(ctx, cudaFuncSetAttribute(range_variant_prof(ctx->rng_nt, ctx->cfg.rng_degree), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->adv_smem));
         if (ctx->band_enabled)
             CU(ctx, cudaFuncSetAttribute(range_variant_prof(ctx->band_nt, ctx->cfg.rng_degree), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->band_smem));
+        if (ctx->planned) {
+            AdvKernel kp = adv_planned_kernel<512, 7, true>;
+            CU(ctx, cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->band_smem));
+        }
     }
     if (enabled && !ctx->d_stage.p) {
         if (int rc = ensure(ctx, ctx->d_stage, (TOF_N_STAGES + 1) * sizeof(unsigned long long))) return rc;

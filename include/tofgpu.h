@@ -40,7 +40,8 @@ typedef enum tof_model_kind {
     TOF_MODEL_SIMPLE = 1, /* tests/simpleTOFmodel.py:57-120 (and mpiTOFmodel.py:40-128)        */
     TOF_MODEL_ADV = 2,    /* tests/advIntermediateTOFmodel.py:115-199 = intermediateTOFmodel.py */
     TOF_MODEL_SIMULT = 3, /* tests/simultFit.py:223-300, 380-469                                */
-    TOF_MODEL_ONEBD = 4   /* tests/csi_oneBD.py:415-521, 543-649 (production "one-BD" model)        */
+    TOF_MODEL_ONEBD = 4   /* tests/csi_oneBD.py:415-521, 543-649 (production "one-BD" model); with n_zero_deg = 10
+                           * and tau = 4 transit taps: its posterior-predictive twin, utilities/ppcTools_oneBD.py:185-268 */
 } tof_model_kind;
 
 typedef enum tof_ode_mode {
@@ -187,7 +188,8 @@ int tof_cell_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run,
 
 /* Unweighted (x, E) histogram of the stopped deuteron energies of the LAST loop, [n][x_bins][e_bins]: the
  * `eD_atEachX` rows that utilities/ppcTools.py:140-157 collects for posterior-predictive checks (its leading row
- * of zeros omitted).  Built for TOF_MODEL_SIMULT with TOF_ODE_RK4 (the model ppcTools re-runs). */
+ * of zeros omitted).  Built for TOF_MODEL_SIMULT with TOF_ODE_RK4 (the model ppcTools re-runs) and for
+ * TOF_MODEL_ONEBD (utilities/ppcTools_oneBD.py:214, 223-224). */
 int tof_deuteron_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run, int64_t *counts);
 
 /* ---- ensemble driver: emcee 2.x EnsembleSampler stretch move (a = 2), red/blue halves -------- */

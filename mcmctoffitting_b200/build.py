@@ -10,7 +10,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libtofgpu.so")
 SOURCES = ["tofgpu.cu"]
-HEADERS = ["tof_device.cuh", "tof_kernels.cuh", "tof_common.cuh", "adv_rk4.cuh", "adv_range.cuh", "adv_planned.cuh", "simple_model.cuh",
+HEADERS = ["tof_device.cuh", "tof_kernels.cuh", "tof_common.cuh", "adv_rk4.cuh", "adv_range.cuh", "adv_planned.cuh", "adv_zrank.cuh", "simple_model.cuh",
            "simult_model.cuh", "onebd_model.cuh", "sampler.cuh", os.path.join("..", "..", "include", "tofgpu.h")]
 
 NVCC_FLAGS = [

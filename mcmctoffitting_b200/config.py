@@ -404,3 +404,15 @@ def onebd(n_samples: int = 200000, n_ev_per_loop: int = 10000, **overrides) -> M
               beam_energy=2490.0, stop_grid=(100, 2400, 100), attenuation_length=20.0, taps2=tuple(taps2))
     kw.update(overrides)
     return ModelConfig(**kw)
+
+
+def onebd_ppc(n_samples: int = 50000, n_ev_per_loop: int = 10000, **overrides) -> ModelConfig:
+    """utilities/ppcTools_oneBD.py: the posterior-predictive twin of the oneBD model.  Same pipeline as
+    :func:`onebd` on the grid ``initialize_oneBD`` sets up today (20 x-bins, 400 E-bins; initialization.py:12-33),
+    plus the 10 zero-degree sub-times per cell (ppcTools_oneBD.py:246-248) and a causal transit convolution with
+    tau = 4 bins (ppcTools_oneBD.py:87-88; csi_oneBD.py:407-408 uses 2).  nSamples 5e4, nEvPerLoop 1e4 (78-79)."""
+    zc = np.linspace(0, 24, 7, True)
+    taps2 = np.exp(-zc / 4.) / np.sum(np.exp(-zc / 4.))                                                     # ppcTools_oneBD.py:87-88
+    kw = dict(name="onebd_ppc", x_bins=20, e_bins=400, n_zero_deg=10, taps2=tuple(taps2))
+    kw.update(overrides)
+    return onebd(n_samples=n_samples, n_ev_per_loop=n_ev_per_loop, **kw)

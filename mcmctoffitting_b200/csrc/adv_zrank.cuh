@@ -1,0 +1,559 @@
+// adv / intermediate model, range-table formulation: the shipped kernel for "many walkers, one tile of draws each".
+//
+// Same model, tables and arithmetic as adv_range_kernel / adv_planned_kernel (adv_range.cuh, adv_planned.cuh): a
+// (draw, row) sample is v = u0_d + delta_i, the cell (row, E-bin j) sums the degree-7 weight polynomial of interval j
+// over the contiguous run of sorted draws whose v lies in [brk[j-1], brk[j]), membership decided by the same compare
+// RN(u0[d] + delta) >= edge.  What is new is how a run is FOUND and what happens after it is summed:
+//
+//  * rank hints instead of a per-walker plan.  "First draw with u(E0_d) + delta_i >= U_j" is "first draw with
+//    E0_d >= Theta[i][j]", Theta[i][j] = u^-1(U_j - delta_i) -- the initial energy that reaches row i with the lower
+//    edge energy of E-bin j.  Theta does not depend on the walker; and because E0_d = e0 + spread * z_d with the SAME
+//    sorted normals z_d for every walker, the rank of a threshold is a lookup in a walker-independent table over z
+//    (built once per draw set: zlut[c] = first draw with z >= z_lo + c/z_inv).  One float FMA turns Theta into the
+//    lookup cell (per-walker constants a = z_inv/spread, b), taken a quarter cell low so that the exact answer is
+//    reached by a short forward walk with the usual compare.  The hint only has to be low and close; the membership
+//    rule is untouched, so the cells are the ones adv_range_kernel / adv_planned_kernel produce, bit for bit.
+//    This removes the per-walker lookup build, the plan pass (18 % of the instructions of adv_planned_kernel), its
+//    barrier and the slot hand-over through the histogram.
+//  * the normalisation sum S = sum(H * dE * dx) (adv:143) is accumulated by the lane that produces a cell (no second
+//    pass over the histogram), and every cell of a row's window is written, zero or not (no histogram reset).
+//  * scatter (adv:146-159): rint(H/S * N) and the TOF bin of a cell are first formed from reciprocals (two products);
+//    unless the value sits within 1e-6 of a rounding / bin boundary that IS the correctly rounded reference result,
+//    otherwise the cell takes the exact path (div_by_recip quotients + numpy's edge rule) -- same integers always.
+//  * the density (np.histogram density=True) is only evaluated at the bins the timing response of a non-zero observed
+//    bin reads.
+//  * walkers whose E-band does not fit the banded histogram (sigma0 >~ 0.2) no longer wait for a second, full-size
+//    launch at 1 CTA/SM: the same CTA keeps their cell sums in an L2-resident scratch histogram (WIDE instantiation
+//    of the same phase functions) -- one launch per call, no serial tail.
+//
+// Used for: FP64, n_draws <= RANGE_TILE, one T2 interval per E-bin (rng_identity), production output (lnprob only).
+#pragma once
+#include "adv_planned.cuh"
+#ifdef TOF_ZR_DEBUG
+#include <cstdio>
+#endif
+
+namespace tof {
+
+constexpr int ZR_LUT = 4096;             // cells of the draw-rank lookup over z (entries: ZR_LUT + 1)
+constexpr float ZR_BIAS = 0.25f;         // cells the hint is lowered by (float rounding of the hint << 0.25 cell)
+constexpr double ZR_MIN_SPREAD = 2.0;    // keV; below this (and for reversed / degenerate spreads) hints are off
+
+// Byte offsets of the regions of adv_zrank_kernel's dynamic shared memory (host-computed).  Order:
+//   H [hcap] f64 (later the density [T]) | draw tile u0 [RANGE_TILE] f64, later the TOF counters [T] u32 |
+//   staged T2 records [rcap][P+3] f64, later deuteron speeds and reciprocals [2][E] | taps | 40 doubles of scratch |
+//   delta [X] | srow [X] int | hlo [X] int | interval ends [M] f64
+inline RangeLayout zrank_layout(int X, int E, int T, int hcap, int rcap, int P, int n_taps, int rng_n) {
+    RangeLayout L{};
+    size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
+    region_a = (region_a + 15) / 16 * 16;
+    size_t rec_b = (size_t)rcap * (P + 3) * 8;
+    rec_b = rec_b > (size_t)2 * E * 8 ? rec_b : (size_t)2 * E * 8;
+    size_t o = (size_t)hcap * 8;
+    L.pa = (unsigned)o;        o += region_a;
+    L.rec = (unsigned)o;
+    L.svd = (unsigned)o;                          // aliases the records (dead after the cell sums)
+    L.ulut = (unsigned)(o + (size_t)E * 8);       // 1/speed [E]
+    o += (rec_b + 15) / 16 * 16;
+    L.staps = (unsigned)o;     o += (size_t)n_taps * 8;
+    L.scratch = (unsigned)o;   o += 40 * 8;
+    L.sdelta = (unsigned)o;    o += (size_t)X * 8;
+    L.srow = (unsigned)o;      o += (size_t)X * 4;
+    L.hlo = (unsigned)o;       o += (size_t)(X + (X & 1)) * 4;
+    L.sbrk = (unsigned)o;      o += (size_t)rng_n * 8;
+    L.lut = L.sbin = 0;
+    L.total = (unsigned)(o + 16);
+    return L;
+}
+
+// per-walker scalars handed from phase to phase (static shared memory)
+struct ZrFrame {
+    long long next;          // work item fetched by thread 0
+    long long w;             // walker index
+    double e0;
+    int hstride, jbase;
+    int band[3];             // widest row window, first / last interval of the walker
+    int wide;                // 1: cell sums live in the CTA's global scratch histogram, records are read from global
+    float hint_a, hint_b;    // lookup cell of a threshold energy: Theta * a + b
+    long long t_mark;        // stage timing (PROF)
+};
+
+__device__ __forceinline__ float ldg_stream_f32(const float *p) {   // read-only, do not allocate in L1
+    float v;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// Work fetch, prior, per-row E-window, record staging, energy-loss lookup of the draws (adv:128-129), hint constants.
+// Returns PLANNED_DONE / PLANNED_SKIP (outside the prior: -inf written) / PLANNED_RUN.  Uniform; ends with a barrier.
+template <int NT, int P, bool PROF>
+__device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const double *__restrict__ theta, long long n_walkers,
+                                     const ModelOut *op, unsigned char *smem_raw, ZrFrame *f) {
+    __builtin_assume(__isShared(smem_raw));
+    __builtin_assume(__isShared(f));
+    const DevModel &m = *mp;
+    const DevRun &run = *rp;
+    const ModelOut &out = *op;
+    constexpr int RW = P + 3;
+    const int tid = threadIdx.x;
+    const int X = m.x_bins, M = m.rng_n, T = run.tof_bins;
+    double *u0 = reinterpret_cast<double *>(smem_raw + out.lay.pa);
+    double *rec = reinterpret_cast<double *>(smem_raw + out.lay.rec);
+    const double *sdelta = reinterpret_cast<const double *>(smem_raw + out.lay.sdelta);
+    int *srow = reinterpret_cast<int *>(smem_raw + out.lay.srow);
+    int *hlo_s = reinterpret_cast<int *>(smem_raw + out.lay.hlo);
+    const double *sbrk = reinterpret_cast<const double *>(smem_raw + out.lay.sbrk);
+    __syncthreads();                                       // the previous walker is done with shared memory
+    if (tid == 0) {
+        f->next = (long long)atomicAdd(out.work, 1ull);
+        f->band[0] = 0;
+        f->band[1] = M;
+        f->band[2] = -1;
+    }
+    __syncthreads();
+    const long long w = f->next;
+    if (w >= n_walkers) return PLANNED_DONE;
+    const double e0 = theta[w * m.ndim + 0];
+    const double sigma0 = theta[w * m.ndim + 1];
+    bool inside = true;
+    for (int p = 0; p < m.ndim; ++p) {
+        const double v = theta[w * m.ndim + p];
+        inside = inside && (m.prior_strict ? (m.prior_lo[p] < v && v < m.prior_hi[p])
+                                           : !(v < m.prior_lo[p] || v > m.prior_hi[p]));
+    }
+    if (!inside) {                                         // adv:191-195: the model is never evaluated outside the prior
+        if (tid == 0) out.lnprob[w] = -CUDART_INF;
+        return PLANNED_SKIP;
+    }
+    const double spread = __dmul_rn(sigma0, e0);          // adv:128
+    const bool rev = spread < 0.0;                         // draws are sorted ascending: E0 ascends unless the spread is negative
+    const double umax = m.rng_u_max;
+    const int nt = (int)m.n_draws;                         // one tile
+    // E-bins the walker can touch: the draws are sorted, first and last give the extremes
+    const double u_lo = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? nt - 1 : 0)))), m);
+    const double u_hi = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? 0 : nt - 1)))), m);
+    const double u_med = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (nt >> 1)))), m);
+    // every row has its own window of E-bins: [u_lo + delta_i, u_hi + delta_i], one interval of slack on both sides
+    // (T1 is only monotone up to its 2e-13 cm fit error); interval j == E-bin j on this path.  srow: interval of the
+    // median draw -- rows are processed along the trajectory so that the lanes of a warp have runs of similar length.
+    for (int i = tid; i < X; i += NT) {
+        const double dl = sdelta[i];
+        double vmin = (u_lo > -CUDART_INF ? u_lo : 0.0) + dl;   // -inf draws: the lowest in-range v is 0
+        double vmax = u_hi + dl;
+        vmin = vmin > 0.0 ? vmin : 0.0;
+        vmax = vmax < umax ? vmax : umax;
+        int j_lo = 0, j_hi = 0;
+        if (vmax >= vmin) {                               // otherwise this row gets nothing: any window will do
+            j_lo = range_interval(vmin, sbrk, m.rng_lut, m.rng_lut_inv, m.rng_lut_n, M);
+            j_hi = range_interval(vmax, sbrk, m.rng_lut, m.rng_lut_inv, m.rng_lut_n, M);
+            j_lo = j_lo > 0 ? j_lo - 1 : 0;
+            j_hi = j_hi < M - 1 ? j_hi + 1 : M - 1;
+            atomicMin(&f->band[1], j_lo);
+            atomicMax(&f->band[2], j_hi);
+        }
+        hlo_s[i] = j_lo;
+        atomicMax(&f->band[0], j_hi - j_lo + 1);
+        double vm = __dadd_rn(u_med, dl);
+        vm = vm < 0.0 ? 0.0 : (vm > umax ? umax : vm);    // NaN (median draw outside the table) -> any interval
+        srow[i] = (vm == vm) ? range_interval(vm, sbrk, m.rng_lut, m.rng_lut_inv, m.rng_lut_n, M) : 0;
+    }
+    __syncthreads();
+    const int hstride = f->band[0];
+    const int j_lo_all = f->band[2] >= 0 ? f->band[1] : 0, j_hi_all = f->band[2] >= 0 ? f->band[2] : 0;
+    const int jbase = j_lo_all > 0 ? j_lo_all - 1 : 0;
+    const bool fits = (long long)X * hstride <= out.hcap && (j_hi_all - jbase + 1) <= out.rcap;
+    TOF_CHECK(T <= out.hcap && hstride <= M);
+    if (fits) {
+        const double *recg = m.rng_rec;
+        for (int i = tid; i < (j_hi_all - jbase + 1) * RW; i += NT) rec[i] = recg[(size_t)jbase * RW + i];
+    }
+    for (int d = tid; d < nt; d += NT)
+        u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? nt - 1 - d : d)))), m);
+    if (tid == 0) {
+        f->w = w;
+        f->e0 = e0;
+        f->hstride = hstride;
+        f->jbase = fits ? jbase : 0;
+        f->wide = fits ? 0 : 1;
+        if (f->band[2] < 0) {                             // no row can be reached: nothing to visit
+            f->band[1] = 0;
+            f->band[2] = -1;
+        }
+        // rank hint of a threshold energy Th: cell = ((Th - e0)/spread - z_lo) * z_inv - bias
+        float ha = 0.0f, hb = 0.0f;
+        if (spread >= ZR_MIN_SPREAD && spread < 1e30 && run.zlut != nullptr) {
+            const double inv = 1.0 / spread;
+            ha = (float)(run.zlut_inv * inv);
+            hb = (float)((-e0 * inv - run.zlut_lo) * run.zlut_inv - (double)ZR_BIAS);
+        }
+        f->hint_a = ha;
+        f->hint_b = hb;
+        if (!fits && out.queue_count) atomicAdd(out.queue_count, 1ull);   // statistics: walkers kept in the scratch histogram
+    }
+    __syncthreads();
+    return PLANNED_RUN;
+}
+
+// The (x,E) histogram of cross-section weights (adv:128-138) for one walker, lane = row, one (row, interval) cell per
+// lane and visit.  Returns this thread's share of sum(H * dE * dx) (adv:143).  WIDE: H and rec are global pointers.
+// Work split as in range_exec_cells: a warp keeps ONE group of 32 rows and walks the trajectory-aligned interval
+// offsets of that group with a stride; the X % 32 leftover rows get warps of their own that pack R rows x (32/R)
+// offsets per visit.
+template <int NT, int P, bool WIDE>
+__device__ __noinline__ double zr_exec(const DevModel *mp, const DevRun *rp, const ModelOut *op, unsigned char *smem_raw,
+                                       const ZrFrame *f, double *Hglobal) {
+    __builtin_assume(__isShared(smem_raw));
+    __builtin_assume(__isShared(f));
+    const DevModel &m = *mp;
+    constexpr int RW = P + 3;
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int X = m.x_bins, M = m.rng_n;
+    const double *u0 = reinterpret_cast<const double *>(smem_raw + op->lay.pa);
+    const double *brk = reinterpret_cast<const double *>(smem_raw + op->lay.sbrk);
+    const double *sdelta = reinterpret_cast<const double *>(smem_raw + op->lay.sdelta);
+    const int *srow = reinterpret_cast<const int *>(smem_raw + op->lay.srow);
+    const int *hlo = reinterpret_cast<const int *>(smem_raw + op->lay.hlo);
+    double *H = WIDE ? Hglobal : reinterpret_cast<double *>(smem_raw);
+    const double *rec = WIDE ? m.rng_rec : reinterpret_cast<const double *>(smem_raw + op->lay.rec);
+    const int hstride = f->hstride, jbase = f->jbase;
+    const int j_lo_all = f->band[1], j_hi_all = f->band[2];
+    const float ha = f->hint_a, hb = f->hint_b;
+    const int nt = (int)m.n_draws;
+    const float *theta_t = m.rank_theta;
+    const int tstride = m.rank_stride;
+    const unsigned short *__restrict__ zlut = rp->zlut;
+    const double umax_next = __longlong_as_double(__double_as_longlong(m.rng_u_max) + 1);
+    const double de = (m.e_max - m.e_min) / (double)m.e_bins;
+    const double dx = (m.x_max - m.x_min) / (double)X;
+    double part = 0.0;
+    if (j_hi_all < j_lo_all) return part;                  // uniform: no row can be reached
+    const int Gf = X >> 5, R = X & 31;
+    const int s_ref = srow[0];
+    const int s_b = srow[X - 1] - s_ref;                   // the shift is monotone in the row index
+    const int s_min = s_b < 0 ? s_b : 0, s_max = s_b < 0 ? 0 : s_b;
+    const int k_lo = j_lo_all - s_max;
+    const int n_iv = (j_hi_all - s_min) - k_lo + 1;
+    const int per_b = R ? 32 / R : 1;
+    const int nB = R ? (n_iv + per_b - 1) / per_b : 0;
+    const unsigned u0_s32 = (unsigned)__cvta_generic_to_shared(u0);
+    int wB = 0;                                            // warps for the leftover rows, in proportion to their visits
+    if (R) {
+        wB = Gf ? (NW * nB + (n_iv * Gf + nB) / 2) / (n_iv * Gf + nB) : NW;
+        wB = wB < 1 ? 1 : (wB > NW - 1 && Gf ? NW - 1 : wB);
+    }
+    const int wA = NW - wB;
+#ifdef TOF_ZR_DEBUG
+    if (f->w == 0 && lane == 8) printf("exec warp=%d wide=%d Gf=%d R=%d wA=%d wB=%d n_iv=%d k_lo=%d s_ref=%d s_b=%d hstride=%d jlo=%d jhi=%d hlo[40]=%d srow[40]=%d\n", warp, (int)WIDE, Gf, R, wA, wB, n_iv, k_lo, s_ref, s_b, hstride, j_lo_all, j_hi_all, hlo[40], srow[40]);
+#endif
+    auto cell = [&](int j, bool ok, double delta, double *Hrow /* row base minus its first E-bin */, int row_lo, int row) {
+        const int col = j - row_lo;
+        const bool active = ok && (unsigned)col < (unsigned)hstride && j >= j_lo_all && j <= j_hi_all;
+        int d0 = 0, n = 0;
+        double left = 0.0;
+#ifdef TOF_ZR_DEBUG
+        if (f->w == 0 && row == 40) printf("  visit row=%d j=%d ok=%d col=%d active=%d\n", row, j, (int)ok, col, (int)active);
+#endif
+        if (active) {
+            // rank hints: first draw whose initial energy reaches the lower / upper edge of E-bin j at this row
+            const float th0 = ldg_stream_f32(theta_t + (size_t)j * tstride + row);
+            const float th1 = ldg_stream_f32(theta_t + (size_t)(j + 1) * tstride + row);
+            int c0 = __float2int_rz(fmaf(th0, ha, hb)), c1 = __float2int_rz(fmaf(th1, ha, hb));
+            c0 = c0 < 0 ? 0 : (c0 > ZR_LUT ? ZR_LUT : c0);
+            c1 = c1 < 0 ? 0 : (c1 > ZR_LUT ? ZR_LUT : c1);
+            d0 = __ldg(zlut + c0);
+            int d1 = __ldg(zlut + c1);
+            left = j ? brk[j - 1] : 0.0;                   // brk[j] = break that ends interval j
+            const double right = (j == M - 1) ? umax_next : brk[j];   // last interval is closed: v > u_max <=> v >= next(u_max)
+            // the hints are low by construction: forward walks with the membership compare of the other range kernels
+            while (d0 < nt && !(__dadd_rn(u0[d0], delta) >= left)) ++d0;
+            d1 = d1 < d0 ? d0 : d1;
+            while (d1 < nt && !(__dadd_rn(u0[d1], delta) >= right)) ++d1;
+            n = d1 - d0;
+#ifdef TOF_ZR_DEBUG
+            if (f->w < 2 && row == 40 && (j & 7) == 0) printf("  cell w=%lld row=%d j=%d th0=%g th1=%g c0=%d c1=%d d0=%d d1=%d left=%g right=%g u0[d0]=%g delta=%g\n", f->w, row, j, (double)th0, (double)th1, c0, c1, d0, d1, left, right, d0 < nt ? u0[d0] : -1.0, delta);
+#endif
+            TOF_CHECK(d0 >= 0 && d1 <= nt && n >= 0 && (WIDE || j - jbase >= 0));
+        }
+        const int nmax = __reduce_max_sync(FULL, n);
+        if (nmax == 0) {                                   // uniform
+            if (active) Hrow[j] = 0.0;
+            return;
+        }
+        const int nmin = __reduce_min_sync(FULL, n);
+        // idle lanes read the first record (valid memory, finite numbers) and multiply it by t = 0
+        const double *rj = rec + (active ? (j - jbase) * RW + 2 : 2);
+        double a[P + 1];
+        {
+            const double2 *r2 = reinterpret_cast<const double2 *>(rj);
+            a[1] = r2[0].y;
+#pragma unroll
+            for (int k = 2; k <= P; k += 2) {
+                const double2 c2 = r2[k >> 1];
+                a[k] = c2.x;
+                a[k + 1] = c2.y;
+            }
+        }
+        a[0] = 0.0;                                        // the constant term is added once per run, after the loop
+        const double off = delta - left;
+        double acc = 0.0;
+        unsigned addr = u0_s32 + (unsigned)d0 * 8u;
+        const int tfull = nmin >> 2;                       // trips in which every lane still has four samples
+#pragma unroll 1
+        for (int t = tfull; t > 0; --t) {
+            poly_full4<P>(acc, addr, off, a);
+            addr += 32u;
+        }
+        int rem = n - (tfull << 2);
+#pragma unroll 1
+        for (int t = ((nmax + 3) >> 2) - tfull; t > 0; --t) {
+            poly_run4<P>(acc, addr, rem, off, a);
+            addr += 32u;
+            rem -= 4;
+        }
+        if (active) {
+            const double val = fma((double)n, rj[0], acc);
+            Hrow[j] = val;
+            part += __dmul_rn(__dmul_rn(val, de), dx);     // adv:143
+        }
+    };
+    if (warp < wA) {
+        if (Gf <= wA) {                                    // the usual case: this warp keeps one group of rows
+            const int g = warp % Gf, idx = warp / Gf;
+            const int cnt = (wA - g + Gf - 1) / Gf;        // warps sharing group g
+            const int row = (g << 5) + lane;
+            const int row_lo = hlo[row];
+            const double delta = sdelta[row];
+            double *Hrow = H + (size_t)row * hstride - row_lo;
+            const int jrow = k_lo + (srow[row] - s_ref);
+            for (int jj = idx; jj < n_iv; jj += cnt) cell(jrow + jj, true, delta, Hrow, row_lo, row);
+        } else {                                           // more groups than warps: stride over (offset, group) pairs
+            for (int task = warp; task < n_iv * Gf; task += wA) {
+                const int jj = task / Gf;
+                const int row = ((task - jj * Gf) << 5) + lane;
+                const int row_lo = hlo[row];
+                cell(k_lo + jj + (srow[row] - s_ref), true, sdelta[row], H + (size_t)row * hstride - row_lo, row_lo, row);
+            }
+        }
+    } else {
+        const int isub = lane / R;
+        const int row = (Gf << 5) + (lane - isub * R);
+        const int row_lo = hlo[row];
+        const double delta = sdelta[row];
+        double *Hrow = H + (size_t)row * hstride - row_lo;
+        const int jrow = k_lo + isub + (srow[row] - s_ref);
+        for (int tb = warp - wA; tb < nB; tb += wB) cell(jrow + tb * per_b, isub < per_b, delta, Hrow, row_lo, row);
+    }
+    return part;
+}
+
+// Normalise (adv:143), np.rint + flight-time scatter (adv:146-159), density, timing response at the observed bins and
+// log-likelihood (adv:160-181).  Same integers and the same floating-point results as adv_range_kernel's phases 2-5
+// given the same cell sums; `part` is this thread's share of the normalisation sum.
+template <int NT, int P, bool PROF, bool WIDE>
+__device__ __noinline__ void zr_finish(const DevModel *mp, const DevRun *rp, const ModelOut *op, unsigned char *smem_raw,
+                                       ZrFrame *f, double *Hglobal, double part) {
+    __builtin_assume(__isShared(smem_raw));
+    __builtin_assume(__isShared(f));
+    const DevModel &m = *mp;
+    const DevRun &run = *rp;
+    const ModelOut &out = *op;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int X = m.x_bins, T = run.tof_bins;
+    const double *H = WIDE ? Hglobal : reinterpret_cast<const double *>(smem_raw);
+    unsigned int *tofc = reinterpret_cast<unsigned int *>(smem_raw + out.lay.pa);
+    double *svd = reinterpret_cast<double *>(smem_raw + out.lay.svd);     // [E] deuteron speeds (records are dead now)
+    double *rvd = reinterpret_cast<double *>(smem_raw + out.lay.ulut);    // [E] their reciprocals
+    const double *staps = reinterpret_cast<const double *>(smem_raw + out.lay.staps);
+    double *scratch = reinterpret_cast<double *>(smem_raw + out.lay.scratch);
+    const int *hlo = reinterpret_cast<const int *>(smem_raw + out.lay.hlo);
+    const long long w = f->w;
+    const double e0 = f->e0;
+    const int hstride = f->hstride;
+    const int j_lo_all = f->band[1], j_hi_all = f->band[2];
+
+    // ---- phase 2: normalise (adv:143); the products were formed where the cells were summed -----------------
+    // (the caller's barrier after the cell sums: every warp is done with the draw tile and the records)
+    for (int i = tid; i < T; i += NT) tofc[i] = 0u;
+    for (int j = j_lo_all + tid; j <= j_hi_all; j += NT) { // deuteron speeds of the E-bins in reach, and reciprocals
+        const double eff = __ddiv_rn(__dadd_rn(e0, m.e_centers[j]), 2.0);   // adv:151
+        const double v = speed_of(m.c, eff, m.m_d);
+        svd[j] = v;
+        rvd[j] = __ddiv_rn(1.0, v);
+    }
+    const double S = block_sum<double>(part, scratch);     // includes the barrier that publishes tofc = 0 and the speeds
+    if (PROF && tid == 0) {
+        const long long t = clock64();
+        atomicAdd(out.stage_cycles + 2, (unsigned long long)(t - f->t_mark));
+        f->t_mark = t;
+    }
+
+    // ---- phase 3: quantise (adv:146) and scatter every non-empty cell to its flight time (adv:149-158) ----
+    const double t_step = (run.tof_max - run.tof_min) / (double)T;
+    const double t_scale = (double)T / (run.tof_max - run.tof_min);
+    const double nsamp = (double)m.n_samples;
+    const double rS = __ddiv_rn(1.0, S);                    // IEEE quotients below come from this reciprocal (div_by_recip)
+    if (S > 0.0 && S < CUDART_INF) {
+        constexpr double MAGIC = 6755399441055744.0;        // 2^52 + 2^51: x + MAGIC - MAGIC = rint(x), low word = (int)rint(x)
+        constexpr double SURE = 0.499999;                   // farther than 1e-6 from a rounding boundary
+        const double k1 = __dmul_rn(rS, nsamp);
+        const double q_off = __dmul_rn(-run.tof_min, t_scale) - 0.5;
+        for (int row = warp; row < X; row += NW) {
+            const double xi = __ldg(m.x_centers + row), di = __ldg(run.neutron_dist + row);
+            const int row_lo = hlo[row];
+            const double *Hr = H + (size_t)row * hstride;
+            int jb_hi = j_hi_all - row_lo + 1;              // cells beyond the walker's last interval were never written
+            jb_hi = jb_hi < hstride ? jb_hi : hstride;
+            for (int jb = lane + (row_lo < j_lo_all ? j_lo_all - row_lo : 0); jb < jb_hi; jb += 32) {
+                const int j = row_lo + jb;
+                const double h = Hr[jb];
+                if (h != 0.0) {
+                    // cnt = rint(RN(RN(h/S) * N)) (adv:146).  Fast: c = h * RN(rS*N) is within 2 ulp of the product the
+                    // reference rounds; if it is not within 1e-6 of a half-integer both round to the same integer.
+                    const double c = __dmul_rn(h, k1);
+                    const double cm = __dadd_rn(c, MAGIC);
+                    double cnt = __dsub_rn(cm, MAGIC);
+                    if (!(fabs(__dsub_rn(c, cnt)) < SURE && c < 1e9))
+                        cnt = rint(__dmul_rn(div_by_recip(h, S, rS), nsamp));
+                    if (cnt > 0.0) {
+                        // TOF bin (adv:149-159).  Fast: t = (tof - tof_min) * T/(max - min) - 1/2 from reciprocals; if t
+                        // is not within 1e-6 of a half-integer, rint(t) is numpy's bin (its edges are within 1e-12 bins
+                        // of the uniform grid); otherwise the exact quotients and numpy's edge rule decide.
+                        const double rvn = __ldg(m.neutron_rspeed + j);
+                        const double tof = fma(xi, rvd[j], __dmul_rn(di, rvn));
+                        const double t = fma(tof, t_scale, q_off);
+                        const double tm = __dadd_rn(t, MAGIC);
+                        int b = __double2loint(tm);
+                        if (!(fabs(__dsub_rn(t, __dsub_rn(tm, MAGIC))) < SURE && fabs(t) < 1e9)) {
+                            const double tof_d = div_by_recip(xi, svd[j], rvd[j]);
+                            const double tof_n = div_by_recip(di, __ldg(m.neutron_speed + j), rvn);
+                            b = np_bin(__dadd_rn(tof_d, tof_n), T, run.tof_min, run.tof_max, t_step, t_scale);
+                        }
+                        TOF_CHECK(j < m.e_bins);
+                        if ((unsigned)b < (unsigned)T) atomicAdd(tofc + b, (unsigned int)cnt);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (PROF && tid == 0) {
+        const long long t = clock64();
+        atomicAdd(out.stage_cycles + 3, (unsigned long long)(t - f->t_mark));
+        f->t_mark = t;
+    }
+
+    // ---- phase 4: density (np.histogram density=True), only where the timing response of an observed bin reads it ----
+    long long cpart = 0;
+    for (int t = tid; t < T; t += NT) cpart += (long long)tofc[t];
+    const long long total_i = block_sum<long long>(cpart, reinterpret_cast<long long *>(scratch));
+    const bool degenerate = !(S > 0.0) || total_i == 0;
+    const double total = (double)total_i;
+#ifdef TOF_ZR_DEBUG
+    if (tid == 0 && w < 4) printf("zr w=%lld wide=%d S=%g total=%lld hstride=%d jlo=%d jhi=%d jbase=%d ha=%g hb=%g\n", w, f->wide, S, total_i, hstride, j_lo_all, j_hi_all, f->jbase, (double)f->hint_a, (double)f->hint_b);
+#endif
+    double *pdf = reinterpret_cast<double *>(smem_raw);    // the banded histogram region (a wide walker's cells are in global)
+    int need_lo = 0, need_hi = -1;
+    if (run.n_obs_nz > 0) {                                // obs_nz_idx ascends
+        need_lo = run.obs_nz_idx[0] + m.conv_shift - (m.n_taps - 1);
+        need_hi = run.obs_nz_idx[run.n_obs_nz - 1] + m.conv_shift;
+        need_lo = need_lo < 0 ? 0 : need_lo;
+        need_hi = need_hi > T - 1 ? T - 1 : need_hi;
+    }
+    __syncthreads();                                       // WIDE == false: the scatter has finished reading H
+    for (int t = need_lo + tid; t <= need_hi; t += NT) {
+        const unsigned int cn = tofc[t];
+        double v = 0.0;
+        if (cn) {
+            const double db = __dsub_rn(np_edge(t + 1, T, run.tof_min, run.tof_max, t_step),
+                                        np_edge(t, T, run.tof_min, run.tof_max, t_step));
+            v = __ddiv_rn(__ddiv_rn((double)cn, db), total);
+        }
+        pdf[t] = v;
+    }
+    __syncthreads();
+
+    // ---- phase 5: timing response at the observed bins + log-likelihood (adv:173-181) ------------------------
+    double lp = 0.0;
+    if (!degenerate) {
+        for (int q = tid; q < run.n_obs_nz; q += NT) {
+            const int t = run.obs_nz_idx[q];
+            double ev = 0.0;
+            for (int k = 0; k < m.n_taps; ++k) {
+                const int tt = t + m.conv_shift - k;
+                if (tt >= 0 && tt < T) ev += staps[k] * pdf[tt];
+            }
+            lp += run.obs_nz_val[q] * log(ev);
+        }
+    }
+    lp = block_sum<double>(lp, scratch);
+    if (tid == 0) {
+        double r = degenerate ? CUDART_NAN : lp;
+        if (r != r && out.nan_count) atomicAdd(out.nan_count, 1ull);
+        if (m.nan_to_neginf && r != r) r = -CUDART_INF;
+        out.lnprob[w] = r;
+    }
+    if (PROF && tid == 0) {
+        const long long t = clock64();
+        atomicAdd(out.stage_cycles + 4, (unsigned long long)(t - f->t_mark));
+        atomicAdd(out.stage_cycles + TOF_N_STAGES, 1ull);
+        f->t_mark = t;
+    }
+}
+
+template <int NT, int P, bool PROF = false>
+__global__ void __launch_bounds__(NT, 2) adv_zrank_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevRun run,
+                                                          const double *__restrict__ theta, long long n_walkers,
+                                                          const __grid_constant__ ModelOut out) {
+    extern __shared__ __align__(16) unsigned char smem_sym[];
+    unsigned char *smem_raw = smem_sym;
+    asm volatile("" : "+l"(smem_raw));                     // opaque base, still known to be shared (see adv_range_kernel)
+    __builtin_assume(__isShared(smem_raw));
+    __shared__ ZrFrame frame;
+    constexpr int RW = P + 3;
+    const int tid = threadIdx.x;
+    const int X = m.x_bins, M = m.rng_n;
+    // ---- walker-independent tables: staged once per CTA (persistent CTAs loop over walkers) ------------------
+    {
+        double *staps = reinterpret_cast<double *>(smem_raw + out.lay.staps);
+        double *sdelta = reinterpret_cast<double *>(smem_raw + out.lay.sdelta);
+        double *sbrk = reinterpret_cast<double *>(smem_raw + out.lay.sbrk);
+        const double *recg = m.rng_rec;
+        for (int j = tid; j < M; j += NT) sbrk[j] = recg[(size_t)j * RW];
+        for (int i = tid; i < m.n_taps; i += NT) staps[i] = m.taps[i];
+        const double x_start = m.ode_from_zero ? 0.0 : m.x_centers[0];
+        for (int i = tid; i < X; i += NT) sdelta[i] = m.rng_sign * (m.x_centers[i] - x_start);
+        if (PROF && tid == 0) frame.t_mark = clock64();
+    }
+    double *Hglobal = out.wide_scratch ? out.wide_scratch + (size_t)blockIdx.x * (size_t)out.split_stride : nullptr;
+    auto stage = [&](int k) {
+        if constexpr (PROF) {
+            if (tid == 0) {
+                const long long t = clock64();
+                atomicAdd(out.stage_cycles + k, (unsigned long long)(t - frame.t_mark));
+                frame.t_mark = t;
+            }
+        }
+    };
+    for (;;) {
+        const int st = zr_setup<NT, P, PROF>(&m, &run, theta, n_walkers, &out, smem_raw, &frame);
+        if (st == PLANNED_DONE) break;
+        stage(0);
+        if (st == PLANNED_SKIP) continue;
+        if (frame.wide) {
+            const double part = zr_exec<NT, P, true>(&m, &run, &out, smem_raw, &frame, Hglobal);
+            __threadfence_block();
+            __syncthreads();
+            stage(1);
+            zr_finish<NT, P, PROF, true>(&m, &run, &out, smem_raw, &frame, Hglobal, part);
+        } else {
+            const double part = zr_exec<NT, P, false>(&m, &run, &out, smem_raw, &frame, nullptr);
+            __syncthreads();
+            stage(1);
+            zr_finish<NT, P, PROF, false>(&m, &run, &out, smem_raw, &frame, nullptr, part);
+        }
+    }
+}
+
+}  // namespace tof

@@ -1,4 +1,4 @@
-// oneBD production model: tests/csi_oneBD.py.
+// oneBD production model: tests/csi_oneBD.py, and its posterior-predictive twin utilities/ppcTools_oneBD.py.
 #pragma once
 #include "simult_model.cuh"
 
@@ -64,9 +64,11 @@ __device__ inline bool np_poisson(double lam, const double *u, long long n_u, lo
     return true;
 }
 
-__host__ __device__ inline size_t onebd_smem_bytes(int NT, int X, int E, int T, int n_xs, int n_taps, int n_taps2, int stop_n,
+// `copies`: private (x,E) histogram copies (one per group of warps; NT/32 when shared memory allows, fewer for the big
+// grid of the posterior-predictive variant: 20 x 400 cells)
+__host__ __device__ inline size_t onebd_smem_bytes(int copies, int X, int E, int T, int n_xs, int n_taps, int n_taps2, int stop_n,
                                                    int lut_n) {
-    size_t d = (size_t)(NT / 32) * X * E + 4 * (size_t)T + X + E + n_xs + (size_t)(n_xs - 1) * 4 + n_taps + n_taps2 +
+    size_t d = (size_t)copies * X * E + 4 * (size_t)T + X + E + n_xs + (size_t)(n_xs - 1) * 4 + n_taps + n_taps2 +
                (size_t)X * (stop_n - 1) * 4 + X + 48;
     return d * 8 + (((size_t)lut_n + 15) / 16) * 16;
 }
@@ -84,8 +86,9 @@ __global__ void __launch_bounds__(NT) onebd_run_kernel(const DevModel m, const D
     const int T = run.tof_bins, X = m.x_bins, EB = m.e_bins, CELLS = X * EB, NS = m.stop_n - 1;
     const int tid = threadIdx.x, warp = tid >> 5;
 
-    double *Hw = reinterpret_cast<double *>(smem_raw);          // [NW][CELLS]
-    double *tofh = Hw + (size_t)NW * CELLS;                      // [T]
+    const int NC = m.onebd_copies;                               // histogram copies, 1..NW
+    double *Hw = reinterpret_cast<double *>(smem_raw);          // [NC][CELLS]
+    double *tofh = Hw + (size_t)NC * CELLS;                      // [T]
     double *pdf = tofh + T;                                      // [T]
     double *c1 = pdf + T;                                        // [T] after the causal transit convolution
     double *bg = c1 + T;                                         // [T] Poisson background realisation
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(NT) onebd_run_kernel(const DevModel m, const D
     // csi_oneBD.py:581: [eLoss, scale, s, scaleFactor_r, bgLevel_r]
     const double eLoss = th[0], scale = th[1], sshape = th[2], sf = th[3 + r], bg_level = th[m.ndim - m.n_runs + r];
 
-    for (int i = tid; i < NW * CELLS; i += NT) Hw[i] = 0.0;
+    for (int i = tid; i < NC * CELLS; i += NT) Hw[i] = 0.0;
     for (int i = tid; i < T; i += NT) tofh[i] = 0.0;
     for (int i = tid; i < X; i += NT) {
         sx[i] = m.x_centers[i];
@@ -129,7 +132,7 @@ __global__ void __launch_bounds__(NT) onebd_run_kernel(const DevModel m, const D
     xs.lut_lo = m.xs_lut_lo; xs.lut_inv = m.xs_lut_inv;
     const double e_step = (m.e_max - m.e_min) / (double)EB;
     const double e_scale = (double)EB / (m.e_max - m.e_min);
-    double *Hmine = Hw + (size_t)warp * CELLS;
+    double *Hmine = Hw + (size_t)(warp % NC) * CELLS;
 
     // ---- last loop only: the script ASSIGNS dataHist[idx,:] = hist (csi_oneBD.py:465), so earlier loops are
     //      overwritten, and e0mean is the mean of the last eZeros (489).  No redraw of E0 <= 0 here (440-447). ----
@@ -150,7 +153,9 @@ __global__ void __launch_bounds__(NT) onebd_run_kernel(const DevModel m, const D
             const double *c = sstop + ((size_t)i * NS + k) * 4;
             const double E = ((c[0] * dx0 + c[1]) * dx0 + c[2]) * dx0 + c[3];
             const int b = np_bin(E, EB, m.e_min, m.e_max, e_step, e_scale);                  // csi_oneBD.py:463
-            if (b >= 0) atomicAdd(Hmine + i * EB + b, __dmul_rn(xs_eval(E, xs), satt[i]));  // csi_oneBD.py:462
+            if (b < 0) continue;
+            if (out.unweighted) atomicAdd(Hmine + i * EB + b, 1.0);                          // ppcTools_oneBD.py:223-224 eD_atEachX
+            else atomicAdd(Hmine + i * EB + b, __dmul_rn(xs_eval(E, xs), satt[i]));          // csi_oneBD.py:462
         }
     }
     const double sum_e0 = block_sum<double>(part, scratch);
@@ -158,8 +163,14 @@ __global__ void __launch_bounds__(NT) onebd_run_kernel(const DevModel m, const D
     double *H = Hw;
     for (int c = tid; c < CELLS; c += NT) {
         double v = Hw[c];
-        for (int k = 1; k < NW; ++k) v += Hw[(size_t)k * CELLS + c];
+        for (int k = 1; k < NC; ++k) v += Hw[(size_t)k * CELLS + c];
         H[c] = v;
+    }
+    if (out.unweighted) {                                    // raw per-cell counts of the last loop, nothing else
+        __syncthreads();
+        if (out.cells)
+            for (int c = tid; c < CELLS; c += NT) out.cells[(size_t)w * CELLS + c] = (long long)H[c];
+        return;
     }
     for (int j = tid; j < EB; j += NT) {
         const double eff = __ddiv_rn(__dadd_rn(e0mean, m.e_centers[j]), 2.0);               // csi_oneBD.py:499
@@ -184,6 +195,7 @@ __global__ void __launch_bounds__(NT) onebd_run_kernel(const DevModel m, const D
     const double t_step = (run.tof_max - run.tof_min) / (double)T;
     const double t_scale = (double)T / (run.tof_max - run.tof_min);
     const double nsamp = (double)m.n_samples;
+    const int NZ = m.n_zero_deg;
     for (int idx = tid; idx < CELLS; idx += NT) {
         const double cnt = rint(__dmul_rn(H[idx], nsamp));
         if (out.cells) out.cells[(size_t)w * CELLS + idx] = (cnt == cnt) ? (long long)cnt : LLONG_MIN;
@@ -191,8 +203,17 @@ __global__ void __launch_bounds__(NT) onebd_run_kernel(const DevModel m, const D
             const int i = idx / EB, j = idx - i * EB;
             const double tof_d = __ddiv_rn(sx[i], svd[j]);
             const double tof_n = __ddiv_rn(__ldg(run.neutron_dist + i), __ldg(m.neutron_speed + j));
-            const int b = np_bin(__dadd_rn(tof_d, tof_n), T, run.tof_min, run.tof_max, t_step, t_scale);
-            if (b >= 0) atomicAdd(tofh + b, cnt);            // integer-valued doubles: exact in any order
+            const double base = __dadd_rn(tof_d, tof_n);
+            if (NZ == 0) {
+                const int b = np_bin(base, T, run.tof_min, run.tof_max, t_step, t_scale);
+                if (b >= 0) atomicAdd(tofh + b, cnt);        // integer-valued doubles: exact in any order
+            } else {                                         // ppcTools_oneBD.py:246-248: 10 zero-degree sub-times per cell
+                for (int k = 0; k < NZ; ++k) {
+                    const double tof = __dadd_rn(base, __ldg(m.zd_times + j * NZ + k));
+                    const int b = np_bin(tof, T, run.tof_min, run.tof_max, t_step, t_scale);
+                    if (b >= 0) atomicAdd(tofh + b, __dmul_rn(cnt, __ldg(m.zd_weights + j * NZ + k)));
+                }
+            }
         }
     }
     __syncthreads();

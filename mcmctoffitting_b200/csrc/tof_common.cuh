@@ -33,6 +33,9 @@ struct ModelOut {
     int split_stride;                // doubles per partial histogram
     double *split_scratch;           // [n][n_split][split_stride]
     unsigned int *split_tickets;     // [n] arrival counters (zero between calls)
+    // adv_zrank_kernel: per-CTA scratch histogram in global memory (L2) for walkers whose E-band does not fit the
+    // banded shared-memory histogram, split_stride doubles per CTA
+    double *wide_scratch;
 };
 
 }  // namespace tof

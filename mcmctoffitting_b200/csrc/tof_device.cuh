@@ -53,9 +53,14 @@ struct DevModel {
     int t1_q, t1_key_lo, t1_n, rng_degree, rng_n, rng_lut_n;
     int rng_identity;              // 1: T2 interval j is exactly E-bin j (no cross-section knot inside a bin)
     double rng_sign, rng_u_max, rng_lut_inv, e_tab_lo, e_tab_hi;
+    // rank hints of adv_zrank_kernel: rank_theta[j][i] = initial energy (keV) that reaches row i at the lower edge of
+    // T2 interval j (j = 0..rng_n), row stride rank_stride floats; walker-independent (adv_zrank.cuh)
+    const float *rank_theta;
+    int rank_stride;
     // oneBD: spline stopping table, attenuation, causal transit taps
     const double *stop_coefs, *attenuation, *taps2;
     int stop_n, n_taps2;
+    int onebd_copies;              // private (x,E) histogram copies per CTA of the oneBD kernel
     double stop_lo, stop_step, beam_energy;
 };
 
@@ -67,6 +72,9 @@ struct DevRun {
     long long n_z;
     const double *z1;            // stream 1
     long long n_z1;
+    // adv_zrank_kernel: zlut[c] = first (sorted) draw with z >= zlut_lo + c / zlut_inv, c = 0..ZR_LUT (zlut[ZR_LUT] = n_z)
+    const unsigned short *zlut;
+    double zlut_lo, zlut_inv;
     const double *obs;           // [tof_bins] (private copy, simult: 0 -> 1 applied)
     const int *obs_nz_idx;       // compacted bins with obs != 0
     const double *obs_nz_val;

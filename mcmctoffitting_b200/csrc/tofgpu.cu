@@ -28,6 +28,7 @@ struct tof_ctx {
     DevRun runs[TOF_MAX_RUNS]{};
     std::vector<void *> owned;  // device allocations freed in tof_destroy
     DeviceBuf d_theta, d_out, d_spectra, d_cells, d_counts, d_partial, d_work, d_queue, d_split, d_tickets, d_ens, d_nan, d_stage;
+    DeviceBuf d_wide, d_zlut[TOF_MAX_RUNS];   // adv_zrank_kernel: scratch histograms of wide walkers; draw-rank lookup
     // rebindable inputs: reused across tof_set_draws / tof_set_observables calls (no growth when draws are refreshed)
     DeviceBuf d_z[TOF_MAX_RUNS][2], d_obs[TOF_MAX_RUNS], d_obs_idx[TOF_MAX_RUNS], d_obs_val[TOF_MAX_RUNS];
     cudaStream_t stream = nullptr;
@@ -49,6 +50,11 @@ struct tof_ctx {
     size_t band_smem = 0;
     bool band_enabled = false;
     bool planned = false;    // banded launch runs adv_planned_kernel (FP64, <= one tile of draws, interval == E-bin)
+    // ... or adv_zrank_kernel (same conditions; shipped): one launch per call, wide walkers in a global scratch histogram
+    bool zrank = false;
+    int zr_hcap = 0, zr_rcap = 0;
+    size_t zr_smem = 0;
+    RangeLayout lay_zr{};
     RangeLayout lay_full{}, lay_band{};   // shared-memory layouts of the two launches (host-computed offsets)
     size_t simult_smem = 0, onebd_smem = 0;
     int max_smem_optin = 0;
@@ -225,7 +231,25 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 }
             }
             const long long n_work = n * out.n_split;
-            if (ctx->band_enabled && !debug) {
+            if (ctx->zrank && !debug && out.n_split == 1 && ctx->runs[run].zlut) {
+                // shipped path: ONE persistent launch, 2 CTAs/SM; walkers whose E-band does not fit shared memory keep
+                // their cell sums in this CTA's slice of an L2-resident scratch buffer (cnt[2] counts them)
+                const long long slots = (long long)ctx->stats.sm_count * 2;
+                const unsigned grid = (unsigned)std::min<long long>(n, slots);
+                const size_t stride = (size_t)c.x_bins * c.e_bins;
+                rc = ensure(ctx, ctx->d_wide, (size_t)slots * stride * sizeof(double));
+                if (rc) return rc;
+                ModelOut oz = out;
+                oz.work = cnt + 0;
+                oz.queue_count = cnt + 2;
+                oz.hcap = ctx->zr_hcap;
+                oz.rcap = ctx->zr_rcap;
+                oz.lay = ctx->lay_zr;
+                oz.split_stride = (int)stride;
+                oz.wide_scratch = static_cast<double *>(ctx->d_wide.p);
+                if (prof) adv_zrank_kernel<512, 7, true><<<grid, 512, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
+                else adv_zrank_kernel<512, 7, false><<<grid, 512, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
+            } else if (ctx->band_enabled && !debug) {
                 rc = ensure(ctx, ctx->d_queue, (size_t)n * sizeof(int));
                 if (rc) return rc;
                 // 1) banded launch: every walker whose E-band fits; the others are queued
@@ -661,6 +685,83 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
                 }
             }
         }
+        // ---- adv_zrank_kernel (shipped for single-tile draw sets): rank-hint table + its own shared-memory layout ----
+        {
+            const char *env = std::getenv("TOFGPU_RANGE_ZRANK");
+            const bool want = !(env && std::atoi(env) == 0);
+            if (want && !ctx->f32 && P == 7 && m.rng_identity && m.n_draws <= RANGE_TILE && cfg->x_bins >= 1) {
+                const int per_cta = (int)prop.sharedMemPerBlockOptin / 2 - 2048;
+                const int rcap = std::min(Mi, 128);
+                const size_t fixed = zrank_layout(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], 0, rcap, P, cfg->n_taps, Mi).total;
+                long long hcap = ((long long)per_cta - (long long)fixed) / 8;
+                hcap = std::min<long long>(hcap, (long long)cfg->x_bins * cfg->e_bins);
+                if (hcap >= (long long)cfg->x_bins * 8 && hcap >= cfg->tof_bins[0]) {
+                    ctx->zr_hcap = (int)hcap;
+                    ctx->zr_rcap = rcap;
+                    ctx->lay_zr = zrank_layout(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], (int)hcap, rcap, P, cfg->n_taps, Mi);
+                    ctx->zr_smem = ctx->lay_zr.total;
+                    int occz = 0;
+                    AdvKernel kz = adv_zrank_kernel<512, 7, false>, kzp = adv_zrank_kernel<512, 7, true>;
+                    for (AdvKernel k2 : {kz, kzp}) {
+                        CUC(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->zr_smem));
+                        CUC(cudaFuncSetAttribute(k2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                    }
+                    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occz, kz, 512, ctx->zr_smem));
+                    if (occz >= 2) {
+                        // Theta[j][i] = u^-1(U_j - delta_i): invert the T1 table u(E) on a dense grid (a hint: 1e-5 keV is plenty)
+                        auto host_t1 = [&](double E) {
+                            uint64_t bits;
+                            std::memcpy(&bits, &E, 8);
+                            const int hi = (int)(bits >> 32);
+                            const int key = hi >> (20 - cfg->t1_q);
+                            int idx = key - cfg->t1_key_lo;
+                            idx = idx < 0 ? 0 : (idx > cfg->t1_n - 1 ? cfg->t1_n - 1 : idx);
+                            const uint64_t mb = (bits & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull;
+                            double mant;
+                            std::memcpy(&mant, &mb, 8);
+                            const double cc = (double)(key & ((1 << cfg->t1_q) - 1));
+                            const double t = (mant - 1.0) * (double)(1 << (cfg->t1_q + 1)) - (2.0 * cc + 1.0);
+                            const double *k = cfg->t1_coefs + 8 * (size_t)idx;
+                            double acc = k[7];
+                            for (int q = 6; q >= 0; --q) acc = acc * t + k[q];
+                            return acc;
+                        };
+                        const int NG = 1 << 18;
+                        std::vector<double> ug(NG), eg(NG);
+                        const double e_a = cfg->e_tab_lo, e_b = cfg->e_tab_hi;
+                        double run_max = -1e300;
+                        for (int k = 0; k < NG; ++k) {
+                            eg[k] = e_a + (e_b - e_a) * ((double)k / (double)NG);
+                            double u = host_t1(eg[k]);
+                            run_max = u > run_max ? u : run_max;       // monotone up to the fit error: make it so
+                            ug[k] = run_max;
+                        }
+                        const double x_start = cfg->ode_from_zero ? 0.0 : cfg->x_centers[0];
+                        std::vector<float> th((size_t)(Mi + 1) * cfg->x_bins);
+                        for (int j = 0; j <= Mi; ++j) {
+                            const double U = cfg->rng_breaks[j];
+                            for (int i = 0; i < cfg->x_bins; ++i) {
+                                const double tq = U - cfg->rng_sign * (cfg->x_centers[i] - x_start);
+                                float v;
+                                if (!(tq >= ug[0])) v = -1e30f;
+                                else if (tq > ug[NG - 1]) v = 1e30f;
+                                else {
+                                    size_t k = std::upper_bound(ug.begin(), ug.end(), tq) - ug.begin();   // ug[k-1] <= tq < ug[k]
+                                    k = k < 1 ? 1 : (k > (size_t)NG - 1 ? (size_t)NG - 1 : k);
+                                    const double du = ug[k] - ug[k - 1];
+                                    const double fr = du > 0.0 ? (tq - ug[k - 1]) / du : 0.0;
+                                    v = (float)(eg[k - 1] + fr * (eg[k] - eg[k - 1]));
+                                }
+                                th[(size_t)j * cfg->x_bins + i] = v;
+                            }
+                        }
+                        TRY(upload(ctx, th.data(), th.size(), &m.rank_theta));
+                        m.rank_stride = cfg->x_bins;
+                        ctx->zrank = true;
+                    }
+                }
+            }
+        }
     } else if (cfg->model == TOF_MODEL_ADV) {
         if (const char *v = std::getenv("TOFGPU_ADV_VARIANT")) {
             int nt = 0, dpt = 0;
@@ -701,8 +802,15 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         m.beam_energy = cfg->beam_energy;
         int tmax = 0;
         for (int r = 0; r < cfg->n_runs; ++r) tmax = std::max(tmax, cfg->tof_bins[r]);
-        ctx->onebd_smem = onebd_smem_bytes(256, cfg->x_bins, cfg->e_bins, tmax, cfg->n_xs, cfg->n_taps, cfg->n_taps2, cfg->stop_n,
-                                           m.xs_lut_n);
+        // one private histogram copy per warp when they fit (csi_oneBD's 10 x 100 grid), fewer for the grid of the
+        // posterior-predictive variant (ppcTools_oneBD.py: 20 x 400 cells = 64 KB per copy)
+        m.onebd_copies = 256 / 32;
+        for (;;) {
+            ctx->onebd_smem = onebd_smem_bytes(m.onebd_copies, cfg->x_bins, cfg->e_bins, tmax, cfg->n_xs, cfg->n_taps, cfg->n_taps2,
+                                               cfg->stop_n, m.xs_lut_n);
+            if ((int)ctx->onebd_smem <= ctx->max_smem_optin / 2 || m.onebd_copies == 1) break;
+            m.onebd_copies /= 2;
+        }
         if ((int)ctx->onebd_smem > ctx->max_smem_optin) {
             ctx->err = "oneBD kernel needs " + std::to_string(ctx->onebd_smem) + " B of shared memory per CTA";
             return bail(TOF_ERR_CAPACITY);
@@ -753,8 +861,10 @@ void tof_destroy(tof_ctx *ctx) {
     for (void *p : ctx->owned) cudaFree(p);
     if (ctx->busy && ctx->ev_busy) cudaEventSynchronize(ctx->ev_busy);
     for (DeviceBuf *b : {&ctx->d_theta, &ctx->d_out, &ctx->d_spectra, &ctx->d_cells, &ctx->d_counts, &ctx->d_partial, &ctx->d_work,
-                         &ctx->d_queue, &ctx->d_split, &ctx->d_tickets, &ctx->d_ens, &ctx->d_nan, &ctx->d_stage})
+                         &ctx->d_queue, &ctx->d_split, &ctx->d_tickets, &ctx->d_ens, &ctx->d_nan, &ctx->d_stage, &ctx->d_wide})
         if (b->p) cudaFree(b->p);
+    for (int r = 0; r < TOF_MAX_RUNS; ++r)
+        if (ctx->d_zlut[r].p) cudaFree(ctx->d_zlut[r].p);
     for (int r = 0; r < TOF_MAX_RUNS; ++r)
         for (DeviceBuf *b : {&ctx->d_z[r][0], &ctx->d_z[r][1], &ctx->d_obs[r], &ctx->d_obs_idx[r], &ctx->d_obs_val[r]})
             if (b->p) cudaFree(b->p);
@@ -814,6 +924,32 @@ int tof_set_draws(tof_ctx *ctx, int run, int stream, const double *values, int64
         std::vector<double> sorted(values, values + n);
         std::sort(sorted.begin(), sorted.end(), [](double a, double b) { return a < b || (b != b && a == a); });
         if (int rc = upload_into(ctx, ctx->d_z[run][stream], sorted.data(), (size_t)n, &d)) return rc;
+        // adv_zrank_kernel: walker-independent rank lookup over z, zlut[c] = first draw with z >= z_lo + c*(z_hi - z_lo)/ZR_LUT
+        DevRun &rz = ctx->runs[run];
+        rz.zlut = nullptr;
+        if (ctx->zrank && n >= 1 && n <= 65535) {
+            long long n_fin = 0;
+            while (n_fin < n && std::isfinite(sorted[(size_t)n_fin])) ++n_fin;     // NaNs sort last; +-inf draws: hints off
+            const bool all_finite = n_fin == n;
+            const double z_lo = sorted[0], z_hi = sorted[(size_t)n - 1];
+            if (all_finite && z_hi > z_lo) {
+                std::vector<unsigned short> lut(ZR_LUT + 1);
+                const double inv = (double)ZR_LUT / (z_hi - z_lo);
+                size_t dpos = 0;
+                for (int cc = 0; cc <= ZR_LUT; ++cc) {
+                    const double start = z_lo + (double)cc / inv;
+                    while (dpos < (size_t)n && sorted[dpos] < start) ++dpos;
+                    lut[cc] = (unsigned short)dpos;
+                }
+                // the top entry must be "no draw" for thresholds beyond the last draw, but draws equal to z_hi sit in the
+                // last cell: lut[ZR_LUT] is the first draw with z >= z_hi, a low hint as required (never beyond the answer)
+                const unsigned short *dl = nullptr;
+                if (int rc = upload_into(ctx, ctx->d_zlut[run], lut.data(), lut.size(), &dl)) return rc;
+                rz.zlut = dl;
+                rz.zlut_lo = z_lo;
+                rz.zlut_inv = inv;
+            }
+        }
     } else {
         if (int rc = upload_into(ctx, ctx->d_z[run][stream], values, (size_t)n, &d)) return rc;
     }
@@ -897,8 +1033,9 @@ int tof_cell_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run,
 int tof_deuteron_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run, int64_t *counts) {
     if (!ctx || (n > 0 && (!theta || !counts))) return fail(ctx, TOF_ERR_INVALID, "null argument");
     if (int rc = check_run(ctx, run)) return rc;
-    if (ctx->cfg.model != TOF_MODEL_SIMULT || ctx->cfg.ode_mode != TOF_ODE_RK4)
-        return fail(ctx, TOF_ERR_INVALID, "deuteron counts are built for TOF_MODEL_SIMULT with TOF_ODE_RK4");
+    const bool simult_rk4 = ctx->cfg.model == TOF_MODEL_SIMULT && ctx->cfg.ode_mode == TOF_ODE_RK4;
+    if (!simult_rk4 && ctx->cfg.model != TOF_MODEL_ONEBD)
+        return fail(ctx, TOF_ERR_INVALID, "deuteron counts are built for TOF_MODEL_SIMULT with TOF_ODE_RK4 and for TOF_MODEL_ONEBD");
     if (n <= 0) return n == 0 ? TOF_OK : fail(ctx, TOF_ERR_INVALID, "n < 0");
     if (int rc = ready(ctx, false)) return rc;
     CU(ctx, cudaSetDevice(ctx->cfg.device));

@@ -203,7 +203,8 @@ class TofModel:
 
     def deuteron_counts(self, thetas, run: int = 0) -> np.ndarray:
         """Unweighted per-x histograms of the stopped deuteron energies of the last loop, ``[n, X, E]`` -- the
-        ``eD_atEachX`` rows of utilities/ppcTools.py:140-157 (simult model, ODE_RK4)."""
+        ``eD_atEachX`` rows of utilities/ppcTools.py:140-157 (simult model, ODE_RK4) and of
+        utilities/ppcTools_oneBD.py:214-224 (oneBD model)."""
         t = self._thetas(thetas)
         out = np.empty((t.shape[0], self.config.x_bins, self.config.e_bins), dtype=np.int64)
         self._check(self._lib.tof_deuteron_counts_batch(self._ctx, _dptr(t), t.shape[0], run,

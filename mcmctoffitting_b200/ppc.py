@@ -42,7 +42,8 @@ def ppc_bands(spectra: np.ndarray, quantiles=(0.16, 0.5, 0.84)) -> np.ndarray:
 
 def deuteron_spectra(model: TofModel, thetas: np.ndarray) -> List[np.ndarray]:
     """Per run ``[n, X, E]`` unweighted histograms of the stopped deuteron energies (last loop only, as the
-    reference keeps them: ppcTools.py:141, 151-157).  Needs the simult model with ``ode_mode=ODE_RK4``."""
+    reference keeps them: ppcTools.py:141, 151-157; ppcTools_oneBD.py:214, 223-224).  Needs the simult model with
+    ``ode_mode=ODE_RK4`` or the oneBD model (``config.onebd()`` / ``config.onebd_ppc()``)."""
     thetas = np.ascontiguousarray(thetas, dtype=np.float64)
     return [model.deuteron_counts(thetas, run=run) for run in range(model.config.n_runs)]
 
@@ -53,13 +54,15 @@ def neutron_spectrum(cell_counts: np.ndarray) -> np.ndarray:
     return np.asarray(cell_counts).sum(axis=(0, 1)).astype(np.float64)
 
 
-def sdef_sia_cumulative(cell_counts: np.ndarray, e_n_centers: np.ndarray, dist_number: int = 100) -> dict:
+def sdef_sia_cumulative(cell_counts: np.ndarray, e_n_centers: np.ndarray, dist_number: int = 100,
+                        count_format: str = "%.0f") -> dict:
     """MCNP SDEF ``SI A`` / ``SP`` cards for the neutron distribution marginalised over the cell length
     (ppcTools.makeSDEF_sia_cumulative, ppcTools.py:397-422): energies in MeV with three decimals, counts as
-    integers.  ``e_n_centers`` = ``getDDneutronEnergy(eD_binCenters)`` in keV (ppcTools.py:81)."""
+    integers.  ``e_n_centers`` = ``getDDneutronEnergy(eD_binCenters)`` in keV (ppcTools.py:81).
+    ``count_format="%.3e"`` gives the card of the oneBD twin (ppcTools_oneBD.py:406-431 writes ``{:.3e}``)."""
     spec = neutron_spectrum(cell_counts)
     if len(spec) != len(e_n_centers):
         raise ValueError("one neutron energy per E-bin is needed")
     energies = "".join(" %.3f" % (e / 1000) for e in e_n_centers)
-    weights = "".join(" %.0f" % c for c in spec)
+    weights = "".join((" " + count_format) % c for c in spec)
     return {"si": "si%d a%s" % (dist_number, energies), "sp": "sp%d%s" % (dist_number, weights)}

@@ -364,6 +364,65 @@ def onebd():
     return out
 
 
+def ppc_onebd():
+    """utilities/ppcTools_oneBD.py: the reference's own ppcTools_oneBD class (grid of initialize_oneBD: 20 x 400,
+    betheApprox stopping table, tau = 4 transit taps, 10 zero-degree sub-times) fed with a throw-away chain file;
+    generateModelData -> (TOF spectrum, eN_atEachX, eD_atEachX), seeded; then its SDEF writer (406-431)."""
+    import tempfile
+    from unittest import mock
+    from mcmctoffitting_b200.ensemble import write_chain_step
+    sys.path.insert(0, ref_loader.REFERENCE_ROOT)
+    stubs = {k: mock.MagicMock(name=k) for k in ("matplotlib", "matplotlib.pyplot", "corner")}
+    shim = ref_loader._LinspaceShim()
+    with mock.patch.dict(sys.modules, stubs):
+        np.linspace = shim
+        try:
+            import utilities.ppcTools_oneBD as P
+        finally:
+            np.linspace = shim._orig
+    path = os.path.join(tempfile.mkdtemp(), "chain.dat")
+    rs = np.random.RandomState(0)
+    for _ in range(3):
+        write_chain_step(path, rs.standard_normal((18, 9)), rs.standard_normal(18))
+    pt = P.ppcTools_oneBD(path, 1000)
+
+    def sparse(a):
+        a = np.asarray(a)
+        nz = np.flatnonzero(a)
+        return {"shape": list(a.shape), "idx": [int(i) for i in nz], "val": [int(v) for v in a.ravel()[nz]]}
+
+    out = {"x_bins": int(P.x_bins), "e_bins": int(P.eD_bins), "transit_taps": fl(P.zeroDegSpread_vals),
+           "stop_table": [fl(r) for r in P.stoppingApprox.z], "cases": []}
+    for n_ev, n_samp, seed, run, params in [(500, 2000, 5, 0, [900.0, 170.0, 0.5, 3e4, 5.0]),
+                                            (1000, 3000, 6, 2, [850.0, 300.0, 1.2, 4e4, 12.0]),
+                                            (800, 1600, 7, 1, [1000.0, 120.0, 0.3, 2e4, 0.0])]:
+        P.nEvPerLoop = n_ev
+        np.random.seed(seed)
+        tof, eN, eD = pt.generateModelData(params, P.standoffs[run], P.tof_range[run], P.tofRunBins[run], P.ddnXSinstance,
+                                           P.stoppingApprox, P.beamTiming, n_samp, True)
+        out["cases"].append({"n_ev_per_loop": n_ev, "n_samples": n_samp, "seed": seed, "run": run, "params": params,
+                             "tof": fl(tof), "eN_atEachX": sparse(eN[1:]),     # without the leading row of zeros
+                             "eD_atEachX": sparse(eD)})
+        if len(out["cases"]) == 1:
+            pt.tofData, pt.neutronSpectra = [0], [[eN[1:]]]
+            card, _, spec = pt.makeSDEF_sia_cumulative(100)
+            out["sdef_case0"] = card
+    return out
+
+
+def main_ppc_onebd():
+    gold = {"_about": "utilities/ppcTools_oneBD.py run unmodified through its own class; numpy %s" % np.__version__,
+            "ppc_onebd": ppc_onebd()}
+    path = os.path.join(ROOT, "tests", "golden", "reference_golden_ppc_onebd.json")
+    with open(path, "w") as fh:
+        json.dump(gold, fh, indent=0, separators=(",", ":"))
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__" and "--ppc-onebd" in sys.argv:
+    main_ppc_onebd()
+    sys.exit(0)
+
 if __name__ == "__main__" and "--r2" in sys.argv:
     main_r2()
     sys.exit(0)

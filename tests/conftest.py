@@ -41,5 +41,18 @@ def golden2():
 
 
 @pytest.fixture(scope="session")
+def golden_ppc_onebd():
+    """utilities/ppcTools_oneBD.py goldens (oracle/make_golden.py --ppc-onebd)."""
+    with open(os.path.join(ROOT, "tests", "golden", "reference_golden_ppc_onebd.json")) as fh:
+        return json.load(fh)["ppc_onebd"]
+
+
+def unsparse(d):
+    a = np.zeros(int(np.prod(d["shape"])), dtype=np.int64)
+    a[np.asarray(d["idx"], dtype=np.int64)] = np.asarray(d["val"], dtype=np.int64)
+    return a.reshape(d["shape"])
+
+
+@pytest.fixture(scope="session")
 def pf():
     return _pf

@@ -9,7 +9,7 @@ import warnings
 import numpy as np
 import pytest
 
-from conftest import parse_floats
+from conftest import parse_floats, unsparse
 
 pytestmark = pytest.mark.gpu
 warnings.simplefilter("ignore")
@@ -847,6 +847,42 @@ def test_onebd_reference_goldens(M, O, golden, pf):
         got = float(fn.batch([c["theta"]])[0])
         fn.model.close()
         assert rel(got, pf(c["lnprob"])) <= RTOL, (got, c["lnprob"])
+
+
+def test_ppc_onebd_reference_goldens(M, O, golden_ppc_onebd):
+    """utilities/ppcTools_oneBD.py:185-268 (the posterior-predictive twin of the oneBD model: 20 x 400 grid, 10
+    zero-degree sub-times per cell, tau = 4 transit taps, Poisson background) through the CUDA path, against the
+    outputs of the reference's own class: TOF spectrum to 1e-11, eN_atEachX and eD_atEachX bit for bit, SDEF card."""
+    g = golden_ppc_onebd
+    tab = np.array([parse_floats(r) for r in g["stop_table"]])
+    cells0 = None
+    for c in g["cases"]:
+        cfg = M.config.onebd_ppc(n_samples=c["n_samples"], n_ev_per_loop=c["n_ev_per_loop"],
+                                 stop_table=tuple(tuple(r) for r in tab))
+        assert (cfg.x_bins, cfg.e_bins) == (g["x_bins"], g["e_bins"])
+        np.testing.assert_array_equal(np.asarray(cfg.taps2), parse_floats(g["transit_taps"]))
+        r = c["run"]
+        # replay the reference's global stream: n_loops*n_ev normals, then the doubles poisson() consumes
+        rs = np.random.RandomState(c["seed"])
+        z = rs.standard_normal(cfg.n_draws)
+        u = rs.random_sample(2000)
+        p = c["params"]
+        theta = np.zeros(9)
+        theta[:3] = p[:3]
+        theta[3:6] = 1e4
+        theta[3 + r], theta[6 + r] = p[3], p[4]
+        fn = M.make_lnprob(cfg, [np.ones(n) for n in cfg.tof_bins], [z] * 3, extra_draws=[u] * 3)
+        got_s = fn.model.model_batch(theta[None, :], run=r, stage="spread")[0]
+        np.testing.assert_allclose(got_s, parse_floats(c["tof"]), rtol=1e-11)
+        got_c = fn.model.cell_counts(theta[None, :], run=r)[0]
+        assert np.array_equal(got_c, unsparse(c["eN_atEachX"]))
+        got_d = M.ppc.deuteron_spectra(fn.model, theta[None, :])[r][0]
+        assert np.array_equal(got_d, unsparse(c["eD_atEachX"]))
+        if cells0 is None:
+            cells0 = got_c
+        fn.model.close()
+    en = M.config.dd_neutron_energy(M.config.onebd_ppc().e_centers())
+    assert M.ppc.sdef_sia_cumulative(cells0[None], en, count_format="%.3e") == g["sdef_case0"]
 
 
 def test_ppc_batch_generation(M, O):

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import tof_oracle as O
-from conftest import parse_floats
+from conftest import parse_floats, unsparse
 
 warnings.simplefilter("ignore")
 
@@ -281,6 +281,32 @@ def test_ppc_goldens_from_the_reference_class(golden):
         np.testing.assert_allclose(om.model(c["params"], c["run"], draws(), None, True), parse_floats(c["tof"]), rtol=1e-13)
     from mcmctoffitting_b200 import ppc
     card = ppc.sdef_sia_cumulative(np.array([g["cases"][0]["eN_atEachX"]]), O.getDDneutronEnergy(om.eD_binCenters))
+    assert card == g["sdef_case0"]
+
+
+def test_ppc_onebd_goldens_from_the_reference_class(golden_ppc_onebd):
+    """utilities/ppcTools_oneBD.py:185-268 through its own class: TOF spectrum (10 zero-degree sub-times, tau = 4
+    transit taps, Gaussian timing, Poisson background), eN_atEachX (integer cell counts) and eD_atEachX (unweighted
+    last-loop histogram), bit for bit; and the SDEF card of 406-431."""
+    g = golden_ppc_onebd
+    tab = np.array([parse_floats(r) for r in g["stop_table"]])
+    assert np.array_equal(O.OneBDPPCModel().stop_table(), tab)
+    assert np.array_equal(O.OneBDPPCModel.zero_deg_taps(), parse_floats(g["transit_taps"]))
+    xs = O.DDNXS()
+    for c in g["cases"]:
+        m = O.OneBDPPCModel(n_ev_per_loop=c["n_ev_per_loop"], n_samples=c["n_samples"])
+        assert (m.x_bins, m.eD_bins) == (g["x_bins"], g["e_bins"])
+        rs = np.random.RandomState(c["seed"])    # the reference consumes n_loops*n_ev normals, then poisson(bg, T)
+        z_all = rs.standard_normal(m.n_loops * m.n_ev_per_loop).reshape(m.n_loops, m.n_ev_per_loop)
+        bg = rs.poisson(c["params"][4], m.tof_bins[c["run"]])
+        tof, counts = m.model(c["params"], c["run"], z_all[-1], bg, xs, tab)
+        assert np.array_equal(counts, unsparse(c["eN_atEachX"]))
+        assert np.array_equal(m.deuteron_counts(c["params"], z_all[-1], tab), unsparse(c["eD_atEachX"]))
+        assert np.array_equal(tof, parse_floats(c["tof"]))
+    from mcmctoffitting_b200 import ppc
+    m = O.OneBDPPCModel()
+    card = ppc.sdef_sia_cumulative(np.array([unsparse(g["cases"][0]["eN_atEachX"])]), O.getDDneutronEnergy(m.eD_binCenters),
+                                   count_format="%.3e")
     assert card == g["sdef_case0"]
 
 

@@ -41,19 +41,20 @@ constexpr double ZR_MIN_SPREAD = 2.0;    // keV; below this (and for reversed / 
 
 // Byte offsets of the regions of adv_zrank_kernel's dynamic shared memory (host-computed).  Order:
 //   H [hcap] f64 (later the density [T]) | draw tile u0 [RANGE_TILE] f64, later the TOF counters [T] u32 |
-//   staged T2 records [rcap][P+3] f64, later deuteron speeds and reciprocals [2][E] | taps | 40 doubles of scratch |
+//   staged T2 records [rcap][P+3] f64, later deuteron speeds, their reciprocals and 1/neutron speed [3][E] | taps |
+//   40 doubles of scratch |
 //   delta [X] | srow [X] int | hlo [X] int | interval ends [M] f64
 inline RangeLayout zrank_layout(int X, int E, int T, int hcap, int rcap, int P, int n_taps, int rng_n) {
     RangeLayout L{};
     size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
     region_a = (region_a + 15) / 16 * 16;
     size_t rec_b = (size_t)rcap * (P + 3) * 8;
-    rec_b = rec_b > (size_t)2 * E * 8 ? rec_b : (size_t)2 * E * 8;
+    rec_b = rec_b > (size_t)3 * E * 8 ? rec_b : (size_t)3 * E * 8;
     size_t o = (size_t)hcap * 8;
     L.pa = (unsigned)o;        o += region_a;
     L.rec = (unsigned)o;
     L.svd = (unsigned)o;                          // aliases the records (dead after the cell sums)
-    L.ulut = (unsigned)(o + (size_t)E * 8);       // 1/speed [E]
+    L.ulut = (unsigned)(o + (size_t)E * 8);       // 1/speed [E], followed by 1/neutron speed [E]
     o += (rec_b + 15) / 16 * 16;
     L.staps = (unsigned)o;     o += (size_t)n_taps * 8;
     L.scratch = (unsigned)o;   o += 40 * 8;
@@ -68,15 +69,34 @@ inline RangeLayout zrank_layout(int X, int E, int T, int hcap, int rcap, int P, 
 
 // per-walker scalars handed from phase to phase (static shared memory)
 struct ZrFrame {
-    long long next;          // work item fetched by thread 0
+    long long idx[2];        // work items: idx[it & 1] is this iteration's walker, the other slot receives the next one
     long long w;             // walker index
     double e0;
     int hstride, jbase;
     int band[3];             // widest row window, first / last interval of the walker
     int wide;                // 1: cell sums live in the CTA's global scratch histogram, records are read from global
     float hint_a, hint_b;    // lookup cell of a threshold energy: Theta * a + b
+    int s_ref, k_lo, n_iv, nB, wB;   // trajectory-aligned visit grid of the cell sums (see zr_exec)
+    double de, dx;           // bin widths of the (x,E) histogram (set once per CTA)
+    double umax_next;        // nextafter(u_max): right edge of the last (closed) interval (set once per CTA)
+    const unsigned short *zlut;   // draw-rank lookup of this run (set once per CTA)
     long long t_mark;        // stage timing (PROF)
 };
+
+// Sum over the CTA with ONE barrier: warp partials to `slot`, then every warp adds them with the same xor butterfly
+// (fixed order: the result is bit-identical in all threads and from run to run).  `slot` (>= NT/32 elements) must not be
+// written again before another barrier: callers alternate between two slots.
+template <typename T>
+__device__ __forceinline__ T block_sum1(T v, T *slot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    if (lane == 0) slot[warp] = v;
+    __syncthreads();
+    T t = (lane < nw) ? slot[lane] : T(0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+    return t;
+}
 
 __device__ __forceinline__ float ldg_stream_f32(const float *p) {   // read-only, do not allocate in L1
     float v;
@@ -88,7 +108,7 @@ __device__ __forceinline__ float ldg_stream_f32(const float *p) {   // read-only
 // Returns PLANNED_DONE / PLANNED_SKIP (outside the prior: -inf written) / PLANNED_RUN.  Uniform; ends with a barrier.
 template <int NT, int P, bool PROF>
 __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const double *__restrict__ theta, long long n_walkers,
-                                     const ModelOut *op, unsigned char *smem_raw, ZrFrame *f) {
+                                     const ModelOut *op, unsigned char *smem_raw, ZrFrame *f, int it) {
     __builtin_assume(__isShared(smem_raw));
     __builtin_assume(__isShared(f));
     const DevModel &m = *mp;
@@ -103,16 +123,16 @@ __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const
     int *srow = reinterpret_cast<int *>(smem_raw + out.lay.srow);
     int *hlo_s = reinterpret_cast<int *>(smem_raw + out.lay.hlo);
     const double *sbrk = reinterpret_cast<const double *>(smem_raw + out.lay.sbrk);
-    __syncthreads();                                       // the previous walker is done with shared memory
-    if (tid == 0) {
-        f->next = (long long)atomicAdd(out.work, 1ull);
+    if (tid == 0) {                                        // (every thread read the previous walker's band at the top of zr_finish)
         f->band[0] = 0;
         f->band[1] = M;
         f->band[2] = -1;
     }
-    __syncthreads();
-    const long long w = f->next;
+    __syncthreads();                                       // the previous walker is done with shared memory
+    const long long w = f->idx[it & 1];
     if (w >= n_walkers) return PLANNED_DONE;
+    // the next work item is fetched now (a global atomic: ~1 us) and read after the next iteration's first barrier
+    if (tid == 0) f->idx[(it + 1) & 1] = (long long)atomicAdd(out.work, 1ull);
     const double e0 = theta[w * m.ndim + 0];
     const double sigma0 = theta[w * m.ndim + 1];
     bool inside = true;
@@ -129,10 +149,12 @@ __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const
     const bool rev = spread < 0.0;                         // draws are sorted ascending: E0 ascends unless the spread is negative
     const double umax = m.rng_u_max;
     const int nt = (int)m.n_draws;                         // one tile
+    // energy-loss lookup of every draw (adv:128-129): u0[d] = u(e0 + spread * z_d), ascending
+    for (int d = tid; d < nt; d += NT)
+        u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? nt - 1 - d : d)))), m);
+    __syncthreads();
     // E-bins the walker can touch: the draws are sorted, first and last give the extremes
-    const double u_lo = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? nt - 1 : 0)))), m);
-    const double u_hi = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? 0 : nt - 1)))), m);
-    const double u_med = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (nt >> 1)))), m);
+    const double u_lo = u0[0], u_hi = u0[nt - 1], u_med = u0[nt >> 1];
     // every row has its own window of E-bins: [u_lo + delta_i, u_hi + delta_i], one interval of slack on both sides
     // (T1 is only monotone up to its 2e-13 cm fit error); interval j == E-bin j on this path.  srow: interval of the
     // median draw -- rows are processed along the trajectory so that the lanes of a warp have runs of similar length.
@@ -167,8 +189,6 @@ __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const
         const double *recg = m.rng_rec;
         for (int i = tid; i < (j_hi_all - jbase + 1) * RW; i += NT) rec[i] = recg[(size_t)jbase * RW + i];
     }
-    for (int d = tid; d < nt; d += NT)
-        u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? nt - 1 - d : d)))), m);
     if (tid == 0) {
         f->w = w;
         f->e0 = e0;
@@ -188,17 +208,56 @@ __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const
         }
         f->hint_a = ha;
         f->hint_b = hb;
+        // visit grid: rows are walked along the trajectory, interval j = k + (srow[row] - srow[0]); the shift is
+        // monotone in the row index.  Leftover rows (X % 32): R rows x (32/R) offsets per visit, on wB warps of their own
+        // (in proportion to their share of the visits, at least one when there are any).
+        {
+            constexpr int NW = NT / 32;
+            const int Gf = X >> 5, R = X & 31;
+            const int s_ref = srow[0], s_b = srow[X - 1] - s_ref;
+            const int s_min = s_b < 0 ? s_b : 0, s_max = s_b < 0 ? 0 : s_b;
+            const int jl = f->band[1], jh = f->band[2];
+            const int k_lo = jl - s_max;
+            const int n_iv = jh >= jl ? (jh - s_min) - k_lo + 1 : 0;
+            const int per_b = R ? 32 / R : 1;
+            const int nB = R ? (n_iv + per_b - 1) / per_b : 0;
+            int wB = 0;
+            if (R) {
+                const int den = n_iv * Gf + nB;
+                wB = (Gf && den > 0) ? (NW * nB + den / 2) / den : NW;
+                wB = wB < 1 ? 1 : (wB > NW - 1 && Gf ? NW - 1 : wB);
+            }
+            f->s_ref = s_ref;
+            f->k_lo = k_lo;
+            f->n_iv = n_iv;
+            f->nB = nB;
+            f->wB = wB;
+        }
         if (!fits && out.queue_count) atomicAdd(out.queue_count, 1ull);   // statistics: walkers kept in the scratch histogram
     }
     __syncthreads();
     return PLANNED_RUN;
 }
 
+// shared-memory accessors on 32-bit shared addresses (the phase functions receive generic pointers; spelling the
+// address space out keeps record loads and histogram stores LDS / STS without 64-bit address arithmetic)
+__device__ __forceinline__ double2 zr_lds_v2(unsigned a) {
+    double2 v;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double zr_lds(unsigned a) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void zr_sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
 // The (x,E) histogram of cross-section weights (adv:128-138) for one walker, lane = row, one (row, interval) cell per
 // lane and visit.  Returns this thread's share of sum(H * dE * dx) (adv:143).  WIDE: H and rec are global pointers.
 // Work split as in range_exec_cells: a warp keeps ONE group of 32 rows and walks the trajectory-aligned interval
 // offsets of that group with a stride; the X % 32 leftover rows get warps of their own that pack R rows x (32/R)
-// offsets per visit.
+// offsets per visit.  The rank hints of the next visit are fetched (L2) while the current one is summed.
 template <int NT, int P, bool WIDE>
 __device__ __noinline__ double zr_exec(const DevModel *mp, const DevRun *rp, const ModelOut *op, unsigned char *smem_raw,
                                        const ZrFrame *f, double *Hglobal) {
@@ -214,82 +273,80 @@ __device__ __noinline__ double zr_exec(const DevModel *mp, const DevRun *rp, con
     const double *sdelta = reinterpret_cast<const double *>(smem_raw + op->lay.sdelta);
     const int *srow = reinterpret_cast<const int *>(smem_raw + op->lay.srow);
     const int *hlo = reinterpret_cast<const int *>(smem_raw + op->lay.hlo);
-    double *H = WIDE ? Hglobal : reinterpret_cast<double *>(smem_raw);
-    const double *rec = WIDE ? m.rng_rec : reinterpret_cast<const double *>(smem_raw + op->lay.rec);
-    const int hstride = f->hstride, jbase = f->jbase;
+    const double *rec_g = m.rng_rec;                       // WIDE: records straight from global memory
+    const int hstride = f->hstride;
     const int j_lo_all = f->band[1], j_hi_all = f->band[2];
-    const float ha = f->hint_a, hb = f->hint_b;
+    // Per-walker constants are re-read from the frame where they are used (one LDS each) instead of living in
+    // registers across the polynomial loop: at 64 registers per thread that is what lets ptxas keep the four Horner
+    // chains of a trip interleaved.
+    const volatile ZrFrame *fv = f;
     const int nt = (int)m.n_draws;
     const float *theta_t = m.rank_theta;
     const int tstride = m.rank_stride;
-    const unsigned short *__restrict__ zlut = rp->zlut;
-    const double umax_next = __longlong_as_double(__double_as_longlong(m.rng_u_max) + 1);
-    const double de = (m.e_max - m.e_min) / (double)m.e_bins;
-    const double dx = (m.x_max - m.x_min) / (double)X;
     double part = 0.0;
     if (j_hi_all < j_lo_all) return part;                  // uniform: no row can be reached
     const int Gf = X >> 5, R = X & 31;
-    const int s_ref = srow[0];
-    const int s_b = srow[X - 1] - s_ref;                   // the shift is monotone in the row index
-    const int s_min = s_b < 0 ? s_b : 0, s_max = s_b < 0 ? 0 : s_b;
-    const int k_lo = j_lo_all - s_max;
-    const int n_iv = (j_hi_all - s_min) - k_lo + 1;
+    const int s_ref = f->s_ref, k_lo = f->k_lo, n_iv = f->n_iv, nB = f->nB, wB = f->wB;
     const int per_b = R ? 32 / R : 1;
-    const int nB = R ? (n_iv + per_b - 1) / per_b : 0;
-    const unsigned u0_s32 = (unsigned)__cvta_generic_to_shared(u0);
-    int wB = 0;                                            // warps for the leftover rows, in proportion to their visits
-    if (R) {
-        wB = Gf ? (NW * nB + (n_iv * Gf + nB) / 2) / (n_iv * Gf + nB) : NW;
-        wB = wB < 1 ? 1 : (wB > NW - 1 && Gf ? NW - 1 : wB);
-    }
     const int wA = NW - wB;
-#ifdef TOF_ZR_DEBUG
-    if (f->w == 0 && lane == 8) printf("exec warp=%d wide=%d Gf=%d R=%d wA=%d wB=%d n_iv=%d k_lo=%d s_ref=%d s_b=%d hstride=%d jlo=%d jhi=%d hlo[40]=%d srow[40]=%d\n", warp, (int)WIDE, Gf, R, wA, wB, n_iv, k_lo, s_ref, s_b, hstride, j_lo_all, j_hi_all, hlo[40], srow[40]);
-#endif
-    auto cell = [&](int j, bool ok, double delta, double *Hrow /* row base minus its first E-bin */, int row_lo, int row) {
-        const int col = j - row_lo;
-        const bool active = ok && (unsigned)col < (unsigned)hstride && j >= j_lo_all && j <= j_hi_all;
+    const unsigned smem_s32 = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned u0_s32 = smem_s32 + op->lay.pa;
+    const unsigned rec_s32 = smem_s32 + op->lay.rec;
+    // one (row, interval) cell: find its run of draws (hints th0 / th1 -> lookup -> short forward walks), sum the weight
+    // polynomial over the run, write the cell, accumulate the normalisation sum
+    auto cell = [&](int j, bool active, float th0, float th1, double delta, unsigned hrow_s32, double *hrow_g) {
         int d0 = 0, n = 0;
         double left = 0.0;
-#ifdef TOF_ZR_DEBUG
-        if (f->w == 0 && row == 40) printf("  visit row=%d j=%d ok=%d col=%d active=%d\n", row, j, (int)ok, col, (int)active);
-#endif
         if (active) {
-            // rank hints: first draw whose initial energy reaches the lower / upper edge of E-bin j at this row
-            const float th0 = ldg_stream_f32(theta_t + (size_t)j * tstride + row);
-            const float th1 = ldg_stream_f32(theta_t + (size_t)(j + 1) * tstride + row);
+            const float ha = fv->hint_a, hb = fv->hint_b;
+            const unsigned short *zlut = fv->zlut;
             int c0 = __float2int_rz(fmaf(th0, ha, hb)), c1 = __float2int_rz(fmaf(th1, ha, hb));
             c0 = c0 < 0 ? 0 : (c0 > ZR_LUT ? ZR_LUT : c0);
             c1 = c1 < 0 ? 0 : (c1 > ZR_LUT ? ZR_LUT : c1);
             d0 = __ldg(zlut + c0);
             int d1 = __ldg(zlut + c1);
             left = j ? brk[j - 1] : 0.0;                   // brk[j] = break that ends interval j
-            const double right = (j == M - 1) ? umax_next : brk[j];   // last interval is closed: v > u_max <=> v >= next(u_max)
+            const double right = (j == M - 1) ? fv->umax_next : brk[j];   // last interval is closed: v > u_max <=> v >= next(u_max)
             // the hints are low by construction: forward walks with the membership compare of the other range kernels
+            // (measured: loading three candidates at once instead, branch-free, is 1.5 % slower -- more instructions)
             while (d0 < nt && !(__dadd_rn(u0[d0], delta) >= left)) ++d0;
             d1 = d1 < d0 ? d0 : d1;
             while (d1 < nt && !(__dadd_rn(u0[d1], delta) >= right)) ++d1;
             n = d1 - d0;
-#ifdef TOF_ZR_DEBUG
-            if (f->w < 2 && row == 40 && (j & 7) == 0) printf("  cell w=%lld row=%d j=%d th0=%g th1=%g c0=%d c1=%d d0=%d d1=%d left=%g right=%g u0[d0]=%g delta=%g\n", f->w, row, j, (double)th0, (double)th1, c0, c1, d0, d1, left, right, d0 < nt ? u0[d0] : -1.0, delta);
-#endif
-            TOF_CHECK(d0 >= 0 && d1 <= nt && n >= 0 && (WIDE || j - jbase >= 0));
+            TOF_CHECK(d0 >= 0 && d1 <= nt && n >= 0 && (WIDE || j - fv->jbase >= 0));
         }
         const int nmax = __reduce_max_sync(FULL, n);
         if (nmax == 0) {                                   // uniform
-            if (active) Hrow[j] = 0.0;
+            if (active) {
+                if constexpr (WIDE) hrow_g[j] = 0.0;
+                else zr_sts(hrow_s32 + (unsigned)j * 8u, 0.0);
+            }
             return;
         }
         const int nmin = __reduce_min_sync(FULL, n);
         // idle lanes read the first record (valid memory, finite numbers) and multiply it by t = 0
-        const double *rj = rec + (active ? (j - jbase) * RW + 2 : 2);
+        const int ridx = active ? (j - fv->jbase) * RW + 2 : 2;
         double a[P + 1];
-        {
-            const double2 *r2 = reinterpret_cast<const double2 *>(rj);
-            a[1] = r2[0].y;
+        double a0;
+        if constexpr (WIDE) {
+            const double2 *r2 = reinterpret_cast<const double2 *>(rec_g + ridx);
+            const double2 c01 = r2[0];
+            a0 = c01.x;
+            a[1] = c01.y;
 #pragma unroll
             for (int k = 2; k <= P; k += 2) {
                 const double2 c2 = r2[k >> 1];
+                a[k] = c2.x;
+                a[k + 1] = c2.y;
+            }
+        } else {
+            const unsigned ra = rec_s32 + (unsigned)ridx * 8u;
+            const double2 c01 = zr_lds_v2(ra);
+            a0 = c01.x;
+            a[1] = c01.y;
+#pragma unroll
+            for (int k = 2; k <= P; k += 2) {
+                const double2 c2 = zr_lds_v2(ra + (unsigned)k * 8u);
                 a[k] = c2.x;
                 a[k + 1] = c2.y;
             }
@@ -312,9 +369,45 @@ __device__ __noinline__ double zr_exec(const DevModel *mp, const DevRun *rp, con
             rem -= 4;
         }
         if (active) {
-            const double val = fma((double)n, rj[0], acc);
-            Hrow[j] = val;
-            part += __dmul_rn(__dmul_rn(val, de), dx);     // adv:143
+            const double val = fma((double)n, a0, acc);
+            if constexpr (WIDE) hrow_g[j] = val;
+            else zr_sts(hrow_s32 + (unsigned)j * 8u, val);
+            part += __dmul_rn(__dmul_rn(val, fv->de), fv->dx);     // adv:143
+        }
+    };
+    // a lane bound to one row: visits j = j_first, j_first + j_step, ... (n_vis of them); the row's window of cells is
+    // [jw_lo, jw_hi] (its E-window, the walker's interval band, and `ok`)
+    auto run_row = [&](int row, bool ok, int j_first, int j_step, int n_vis) {
+        const int row_lo = hlo[row];
+        const double delta = sdelta[row];
+        int jw_lo = row_lo > j_lo_all ? row_lo : j_lo_all;
+        int jw_hi = row_lo + hstride - 1;
+        jw_hi = jw_hi < j_hi_all ? jw_hi : j_hi_all;
+        if (!ok) jw_hi = jw_lo - 1;
+        const unsigned jw_n = (unsigned)(jw_hi - jw_lo + 1);        // 0 when the window is empty
+        const unsigned hrow_s32 = smem_s32 + (unsigned)(row * hstride - row_lo) * 8u;
+        double *hrow_g = WIDE ? Hglobal + (size_t)row * hstride - row_lo : nullptr;
+        const float *th_row = theta_t + row;
+        int j = j_first;
+        bool act = (unsigned)(j - jw_lo) < jw_n && n_vis > 0;
+        float th0 = 0.0f, th1 = 0.0f;
+        if (act) {
+            th0 = ldg_stream_f32(th_row + (size_t)j * tstride);
+            th1 = ldg_stream_f32(th_row + (size_t)(j + 1) * tstride);
+        }
+        for (int v = 0; v < n_vis; ++v) {
+            const int jn = j + j_step;
+            const bool actn = (unsigned)(jn - jw_lo) < jw_n && v + 1 < n_vis;
+            float th0n = 0.0f, th1n = 0.0f;
+            if (actn) {                                    // next visit's hints: in flight while this cell is summed
+                th0n = ldg_stream_f32(th_row + (size_t)jn * tstride);
+                th1n = ldg_stream_f32(th_row + (size_t)(jn + 1) * tstride);
+            }
+            cell(j, act, th0, th1, delta, hrow_s32, hrow_g);
+            j = jn;
+            act = actn;
+            th0 = th0n;
+            th1 = th1n;
         }
     };
     if (warp < wA) {
@@ -322,29 +415,34 @@ __device__ __noinline__ double zr_exec(const DevModel *mp, const DevRun *rp, con
             const int g = warp % Gf, idx = warp / Gf;
             const int cnt = (wA - g + Gf - 1) / Gf;        // warps sharing group g
             const int row = (g << 5) + lane;
-            const int row_lo = hlo[row];
-            const double delta = sdelta[row];
-            double *Hrow = H + (size_t)row * hstride - row_lo;
-            const int jrow = k_lo + (srow[row] - s_ref);
-            for (int jj = idx; jj < n_iv; jj += cnt) cell(jrow + jj, true, delta, Hrow, row_lo, row);
+            run_row(row, true, k_lo + (srow[row] - s_ref) + idx, cnt, idx < n_iv ? (n_iv - idx + cnt - 1) / cnt : 0);
         } else {                                           // more groups than warps: stride over (offset, group) pairs
             for (int task = warp; task < n_iv * Gf; task += wA) {
                 const int jj = task / Gf;
                 const int row = ((task - jj * Gf) << 5) + lane;
-                const int row_lo = hlo[row];
-                cell(k_lo + jj + (srow[row] - s_ref), true, sdelta[row], H + (size_t)row * hstride - row_lo, row_lo, row);
+                run_row(row, true, k_lo + jj + (srow[row] - s_ref), 1, 1);
             }
         }
     } else {
         const int isub = lane / R;
         const int row = (Gf << 5) + (lane - isub * R);
-        const int row_lo = hlo[row];
-        const double delta = sdelta[row];
-        double *Hrow = H + (size_t)row * hstride - row_lo;
-        const int jrow = k_lo + isub + (srow[row] - s_ref);
-        for (int tb = warp - wA; tb < nB; tb += wB) cell(jrow + tb * per_b, isub < per_b, delta, Hrow, row_lo, row);
+        const int tb0 = warp - wA;
+        run_row(row, isub < per_b, k_lo + isub + (srow[row] - s_ref) + tb0 * per_b, wB * per_b,
+                tb0 < nB ? (nB - tb0 + wB - 1) / wB : 0);
     }
     return part;
+}
+
+// Exact paths of the scatter, taken by the few cells that sit within 1e-6 of a rounding / bin boundary: functions of
+// their own so that the common path stays short and branch-free.
+__device__ __noinline__ double zr_exact_count(double h, double S, double rS, double nsamp) {
+    return rint(__dmul_rn(div_by_recip(h, S, rS), nsamp));                                   // adv:146
+}
+__device__ __noinline__ int zr_exact_bin(double xi, double di, double vd, double rvd, double vn, double rvn, int T, double t_min,
+                                         double t_max, double t_step, double t_scale) {
+    const double tof_d = div_by_recip(xi, vd, rvd);                                          // adv:151-152
+    const double tof_n = div_by_recip(di, vn, rvn);                                          // adv:153-156
+    return np_bin(__dadd_rn(tof_d, tof_n), T, t_min, t_max, t_step, t_scale);               // adv:159
 }
 
 // Normalise (adv:143), np.rint + flight-time scatter (adv:146-159), density, timing response at the observed bins and
@@ -376,13 +474,20 @@ __device__ __noinline__ void zr_finish(const DevModel *mp, const DevRun *rp, con
     // ---- phase 2: normalise (adv:143); the products were formed where the cells were summed -----------------
     // (the caller's barrier after the cell sums: every warp is done with the draw tile and the records)
     for (int i = tid; i < T; i += NT) tofc[i] = 0u;
-    for (int j = j_lo_all + tid; j <= j_hi_all; j += NT) { // deuteron speeds of the E-bins in reach, and reciprocals
-        const double eff = __ddiv_rn(__dadd_rn(e0, m.e_centers[j]), 2.0);   // adv:151
-        const double v = speed_of(m.c, eff, m.m_d);
-        svd[j] = v;
-        rvd[j] = __ddiv_rn(1.0, v);
+    double *rvn_s = rvd + m.e_bins;                        // [E] 1/neutron speed of the E-bins in reach
+    {
+        const double *__restrict__ ec = m.e_centers;
+        const double *__restrict__ rvn_g = m.neutron_rspeed;
+        for (int j = j_lo_all + tid; j <= j_hi_all; j += NT) { // deuteron speeds of the E-bins in reach, and reciprocals
+            const double eff = __ddiv_rn(__dadd_rn(e0, ec[j]), 2.0);   // adv:151
+            const double v = speed_of(m.c, eff, m.m_d);
+            svd[j] = v;
+            rvd[j] = __ddiv_rn(1.0, v);
+            rvn_s[j] = rvn_g[j];
+        }
     }
-    const double S = block_sum<double>(part, scratch);     // includes the barrier that publishes tofc = 0 and the speeds
+    static_assert(NT <= 512, "block_sum1 slots hold 16 warp partials");
+    const double S = block_sum1<double>(part, scratch);    // includes the barrier that publishes tofc = 0 and the speeds
     if (PROF && tid == 0) {
         const long long t = clock64();
         atomicAdd(out.stage_cycles + 2, (unsigned long long)(t - f->t_mark));
@@ -390,17 +495,22 @@ __device__ __noinline__ void zr_finish(const DevModel *mp, const DevRun *rp, con
     }
 
     // ---- phase 3: quantise (adv:146) and scatter every non-empty cell to its flight time (adv:149-158) ----
-    const double t_step = (run.tof_max - run.tof_min) / (double)T;
-    const double t_scale = (double)T / (run.tof_max - run.tof_min);
+    const double t_min = run.tof_min, t_max = run.tof_max;
+    const double t_step = (t_max - t_min) / (double)T;
+    const double t_scale = (double)T / (t_max - t_min);
     const double nsamp = (double)m.n_samples;
     const double rS = __ddiv_rn(1.0, S);                    // IEEE quotients below come from this reciprocal (div_by_recip)
+    long long cpart = 0;                                    // counts this thread put into the TOF window (np.histogram's n.sum())
     if (S > 0.0 && S < CUDART_INF) {
         constexpr double MAGIC = 6755399441055744.0;        // 2^52 + 2^51: x + MAGIC - MAGIC = rint(x), low word = (int)rint(x)
         constexpr double SURE = 0.499999;                   // farther than 1e-6 from a rounding boundary
         const double k1 = __dmul_rn(rS, nsamp);
-        const double q_off = __dmul_rn(-run.tof_min, t_scale) - 0.5;
+        const double q_off = __dmul_rn(-t_min, t_scale) - 0.5;
+        const double *__restrict__ xc = m.x_centers;
+        const double *__restrict__ nd = run.neutron_dist;
+        const double *__restrict__ vn_g = m.neutron_speed;
         for (int row = warp; row < X; row += NW) {
-            const double xi = __ldg(m.x_centers + row), di = __ldg(run.neutron_dist + row);
+            const double xi = xc[row], di = nd[row];
             const int row_lo = hlo[row];
             const double *Hr = H + (size_t)row * hstride;
             int jb_hi = j_hi_all - row_lo + 1;              // cells beyond the walker's last interval were never written
@@ -414,30 +524,34 @@ __device__ __noinline__ void zr_finish(const DevModel *mp, const DevRun *rp, con
                     const double c = __dmul_rn(h, k1);
                     const double cm = __dadd_rn(c, MAGIC);
                     double cnt = __dsub_rn(cm, MAGIC);
-                    if (!(fabs(__dsub_rn(c, cnt)) < SURE && c < 1e9))
-                        cnt = rint(__dmul_rn(div_by_recip(h, S, rS), nsamp));
+                    unsigned int ci = (unsigned int)__double2loint(cm);
+                    if (__builtin_expect(!(fabs(__dsub_rn(c, cnt)) < SURE && c < 1e9), 0)) {
+                        cnt = zr_exact_count(h, S, rS, nsamp);
+                        ci = (unsigned int)cnt;
+                    }
                     if (cnt > 0.0) {
                         // TOF bin (adv:149-159).  Fast: t = (tof - tof_min) * T/(max - min) - 1/2 from reciprocals; if t
                         // is not within 1e-6 of a half-integer, rint(t) is numpy's bin (its edges are within 1e-12 bins
                         // of the uniform grid); otherwise the exact quotients and numpy's edge rule decide.
-                        const double rvn = __ldg(m.neutron_rspeed + j);
+                        const double rvn = rvn_s[j];
                         const double tof = fma(xi, rvd[j], __dmul_rn(di, rvn));
                         const double t = fma(tof, t_scale, q_off);
                         const double tm = __dadd_rn(t, MAGIC);
                         int b = __double2loint(tm);
-                        if (!(fabs(__dsub_rn(t, __dsub_rn(tm, MAGIC))) < SURE && fabs(t) < 1e9)) {
-                            const double tof_d = div_by_recip(xi, svd[j], rvd[j]);
-                            const double tof_n = div_by_recip(di, __ldg(m.neutron_speed + j), rvn);
-                            b = np_bin(__dadd_rn(tof_d, tof_n), T, run.tof_min, run.tof_max, t_step, t_scale);
-                        }
+                        if (__builtin_expect(!(fabs(__dsub_rn(t, __dsub_rn(tm, MAGIC))) < SURE && fabs(t) < 1e9), 0))
+                            b = zr_exact_bin(xi, di, svd[j], rvd[j], vn_g[j], rvn, T, t_min, t_max, t_step, t_scale);
                         TOF_CHECK(j < m.e_bins);
-                        if ((unsigned)b < (unsigned)T) atomicAdd(tofc + b, (unsigned int)cnt);
+                        if ((unsigned)b < (unsigned)T) {
+                            atomicAdd(tofc + b, ci);
+                            cpart += (long long)ci;
+                        }
                     }
                 }
             }
         }
     }
-    __syncthreads();
+    // (the barrier inside the next reduction is also the one that completes the scatter)
+    const long long total_i = block_sum1<long long>(cpart, reinterpret_cast<long long *>(scratch) + 16);
     if (PROF && tid == 0) {
         const long long t = clock64();
         atomicAdd(out.stage_cycles + 3, (unsigned long long)(t - f->t_mark));
@@ -445,9 +559,6 @@ __device__ __noinline__ void zr_finish(const DevModel *mp, const DevRun *rp, con
     }
 
     // ---- phase 4: density (np.histogram density=True), only where the timing response of an observed bin reads it ----
-    long long cpart = 0;
-    for (int t = tid; t < T; t += NT) cpart += (long long)tofc[t];
-    const long long total_i = block_sum<long long>(cpart, reinterpret_cast<long long *>(scratch));
     const bool degenerate = !(S > 0.0) || total_i == 0;
     const double total = (double)total_i;
 #ifdef TOF_ZR_DEBUG
@@ -461,8 +572,7 @@ __device__ __noinline__ void zr_finish(const DevModel *mp, const DevRun *rp, con
         need_lo = need_lo < 0 ? 0 : need_lo;
         need_hi = need_hi > T - 1 ? T - 1 : need_hi;
     }
-    __syncthreads();                                       // WIDE == false: the scatter has finished reading H
-    for (int t = need_lo + tid; t <= need_hi; t += NT) {
+    for (int t = need_lo + tid; t <= need_hi; t += NT) {    // (the scatter has finished reading H: barrier in the reduction above)
         const unsigned int cn = tofc[t];
         double v = 0.0;
         if (cn) {
@@ -487,7 +597,7 @@ __device__ __noinline__ void zr_finish(const DevModel *mp, const DevRun *rp, con
             lp += run.obs_nz_val[q] * log(ev);
         }
     }
-    lp = block_sum<double>(lp, scratch);
+    lp = block_sum1<double>(lp, scratch);
     if (tid == 0) {
         double r = degenerate ? CUDART_NAN : lp;
         if (r != r && out.nan_count) atomicAdd(out.nan_count, 1ull);
@@ -525,6 +635,13 @@ __global__ void __launch_bounds__(NT, 2) adv_zrank_kernel(const __grid_constant_
         const double x_start = m.ode_from_zero ? 0.0 : m.x_centers[0];
         for (int i = tid; i < X; i += NT) sdelta[i] = m.rng_sign * (m.x_centers[i] - x_start);
         if (PROF && tid == 0) frame.t_mark = clock64();
+        if (tid == 0) {
+            frame.de = (m.e_max - m.e_min) / (double)m.e_bins;
+            frame.dx = (m.x_max - m.x_min) / (double)X;
+            frame.umax_next = __longlong_as_double(__double_as_longlong(m.rng_u_max) + 1);
+            frame.zlut = run.zlut;
+            frame.idx[0] = (long long)atomicAdd(out.work, 1ull);
+        }
     }
     double *Hglobal = out.wide_scratch ? out.wide_scratch + (size_t)blockIdx.x * (size_t)out.split_stride : nullptr;
     auto stage = [&](int k) {
@@ -536,8 +653,8 @@ __global__ void __launch_bounds__(NT, 2) adv_zrank_kernel(const __grid_constant_
             }
         }
     };
-    for (;;) {
-        const int st = zr_setup<NT, P, PROF>(&m, &run, theta, n_walkers, &out, smem_raw, &frame);
+    for (int it = 0;; ++it) {
+        const int st = zr_setup<NT, P, PROF>(&m, &run, theta, n_walkers, &out, smem_raw, &frame, it);
         if (st == PLANNED_DONE) break;
         stage(0);
         if (st == PLANNED_SKIP) continue;

@@ -52,7 +52,7 @@ struct tof_ctx {
     bool planned = false;    // banded launch runs adv_planned_kernel (FP64, <= one tile of draws, interval == E-bin)
     // ... or adv_zrank_kernel (same conditions; shipped): one launch per call, wide walkers in a global scratch histogram
     bool zrank = false;
-    int zr_hcap = 0, zr_rcap = 0;
+    int zr_hcap = 0, zr_rcap = 0, zr_nt = 512;
     size_t zr_smem = 0;
     RangeLayout lay_zr{};
     RangeLayout lay_full{}, lay_band{};   // shared-memory layouts of the two launches (host-computed offsets)
@@ -248,6 +248,7 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 oz.split_stride = (int)stride;
                 oz.wide_scratch = static_cast<double *>(ctx->d_wide.p);
                 if (prof) adv_zrank_kernel<512, 7, true><<<grid, 512, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
+                else if (ctx->zr_nt == 384) adv_zrank_kernel<384, 7, false><<<grid, 384, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
                 else adv_zrank_kernel<512, 7, false><<<grid, 512, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
             } else if (ctx->band_enabled && !debug) {
                 rc = ensure(ctx, ctx->d_queue, (size_t)n * sizeof(int));
@@ -701,8 +702,9 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
                     ctx->lay_zr = zrank_layout(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], (int)hcap, rcap, P, cfg->n_taps, Mi);
                     ctx->zr_smem = ctx->lay_zr.total;
                     int occz = 0;
-                    AdvKernel kz = adv_zrank_kernel<512, 7, false>, kzp = adv_zrank_kernel<512, 7, true>;
-                    for (AdvKernel k2 : {kz, kzp}) {
+                    AdvKernel kz = adv_zrank_kernel<512, 7, false>, kzp = adv_zrank_kernel<512, 7, true>, kz3 = adv_zrank_kernel<384, 7, false>;
+                    if (const char *v = std::getenv("TOFGPU_ZR_THREADS")) ctx->zr_nt = std::atoi(v) == 384 ? 384 : 512;   // tuning knob
+                    for (AdvKernel k2 : {kz, kzp, kz3}) {
                         CUC(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->zr_smem));
                         CUC(cudaFuncSetAttribute(k2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                     }

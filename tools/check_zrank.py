@@ -25,7 +25,7 @@ box[:8] = [[1000.5, 0.0201], [2599.0, 0.499], [1000.5, 0.499], [2599.0, 0.0201],
 cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE)
 dev = torch.device("cuda", 0)
 res = {}
-for label, env in (("zrank", "1"), ("planned", "0")):
+for label, env in (("zrank", "1"), ("planned", "0"))[:1 if os.environ.get("ZR_ONLY") else 2]:
     os.environ["TOFGPU_RANGE_ZRANK"] = env
     fn = M.make_lnprob(cfg, obs, z, device=0)
     m = fn.model
@@ -44,6 +44,8 @@ for label, env in (("zrank", "1"), ("planned", "0")):
             {k: v for k, v in m.stats().items() if k in ("band_queued_last", "kernel_launches")}))
     m.close()
 for name, th in (("ensemble", ens), ("prior_box", box)):
+    if ("planned", name) not in res:
+        continue
     a, b = res[("zrank", name)], res[("planned", name)]
     same = (a == b) | (np.isnan(a) & np.isnan(b))
     both = np.isfinite(a) & np.isfinite(b)

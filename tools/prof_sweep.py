@@ -16,6 +16,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--prior-box", action="store_true", help="walkers uniform over the adv prior (adv:81-82) instead of the bench ensemble")
 ap.add_argument("--check", type=int, default=0)
 ap.add_argument("--seed", type=int, default=1)
+ap.add_argument("--stages", action="store_true", help="per-stage cycle shares (tof_set_stage_timing)")
 args = ap.parse_args()
 warnings.simplefilter("ignore")
 
@@ -50,6 +51,12 @@ for _ in range(args.reps):
 best = min(ms)
 print("kernel ms per call:", " ".join("%.3f" % v for v in ms))
 print("evals/s (best): %.4g   finite fraction %.3f   stats %s" % (args.n / (best * 1e-3), float(torch.isfinite(out).double().mean()), m.stats()))
+if args.stages:
+    m.set_stage_timing(True)
+    m.lnprob_batch_device(th.data_ptr(), args.n, out.data_ptr(), stream)
+    torch.cuda.synchronize()
+    print("stage profile:", m.stage_profile())
+    m.set_stage_timing(False)
 if args.check:
     from oracle import tof_oracle as O
     xs = O.DDNXS()

@@ -47,6 +47,7 @@ X_BINS, E_BINS, N_TAPS = 100, 240, 16
 FLOP_PER_EVAL_RK4 = 174 * N_DRAWS * X_BINS + 14 * X_BINS * E_BINS + 26 * E_BINS + (31 + 2 * N_TAPS) * N_TOF_BINS
 FLOP_PER_EVAL_RANGE = (18 * N_DRAWS * X_BINS + 18 * N_DRAWS + 14 * X_BINS * E_BINS + 26 * E_BINS
                        + (31 + 2 * N_TAPS) * N_TOF_BINS)
+FLOP_PER_EVAL_EXECUTED = 18 * N_DRAWS * X_BINS + 18 * N_DRAWS
 BYTES_PER_EVAL = 8 * (2 + 1)   # theta in, lnprob out
 NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
 
@@ -83,26 +84,76 @@ def _cpu_eval(theta):
     return float(_W["m"].lnprob(theta, _W["obs"], _W["z"], _W["xs"]))
 
 
-def cpu_rate(z, obs, thetas, procs, per_proc, chunksize=None):
-    """Evaluations/s of the oracle through a process pool (emcee `threads=P`, adv:300-302)."""
+def _ref_available():
+    """True where the reference tree itself can be executed (the build container, or TOF_REFERENCE_ROOT set)."""
+    try:
+        from oracle import ref_loader
+        return ref_loader.available()
+    except Exception:
+        return False
+
+
+def _ref_init(z, obs):
+    """The reference's OWN lnprob (tests/advIntermediateTOFmodel.py:115-199, executed unmodified through
+    oracle/ref_loader.py) at the sweep shape: 1024 draws per loop, one loop, 2048 TOF bins on [128, 256) ns, physical
+    mean excitation energy.  Each call draws fresh normals from numpy's global stream, as the script does."""
+    from oracle import ref_loader
+    warnings.simplefilter("ignore")
+    ns = ref_loader.load("advIntermediateTOFmodel")
+    ref = ref_loader.load_utilities()
+    ns["nEvPerLoop"] = N_DRAWS
+    ns["data_x"] = np.repeat(ns["x_binCenters"], N_DRAWS)
+    ns["tof_nBins"] = N_TOF_BINS
+    ns["tof_range"] = (128.0, 256.0)
+    ns["stoppingModel"] = ref.ionStopping.ionStopping.simpleBethe([1, 2, 8.565e-5, 1, 19.2e-3])
+    _W["ns"], _W["obs"] = ns, obs
+    np.random.seed(os.getpid() & 0xFFFF)
+
+
+def _ref_eval(theta):
+    ns = _W["ns"]
+    prior = ns["lnprior"](theta)
+    if not np.isfinite(prior):
+        return float(-np.inf)
+    return float(prior + ns["lnlike"](theta, _W["obs"], nDraws=N_DRAWS))
+
+
+def cpu_rate(z, obs, thetas, procs, per_proc, chunksize=None, kind="port"):
+    """Evaluations/s of the CPU arm through a process pool (emcee `threads=P`, adv:300-302).  kind "port": the numpy
+    oracle; kind "loader": the reference's own function bodies (only where the reference tree exists)."""
     import multiprocessing as mp
+    init, ev = (_ref_init, _ref_eval) if kind == "loader" else (_cpu_init, _cpu_eval)
     n = procs * per_proc
     sample = [list(t) for t in thetas[:n]]
     if procs == 1:
-        _cpu_init(z, obs)
-        _cpu_eval(sample[0])
+        init(z, obs)
+        ev(sample[0])
         t0 = time.perf_counter()
         for t in sample:
-            _cpu_eval(t)
+            ev(t)
         return n / (time.perf_counter() - t0)
-    with mp.get_context("fork").Pool(procs, initializer=_cpu_init, initargs=(z, obs)) as pool:
-        pool.map(_cpu_eval, sample[:procs])                       # warm-up: imports, first call
+    with mp.get_context("fork").Pool(procs, initializer=init, initargs=(z, obs)) as pool:
+        pool.map(ev, sample[:procs])                              # warm-up: imports, first call
         t0 = time.perf_counter()
         if chunksize:
-            list(pool.imap(_cpu_eval, sample, chunksize=chunksize))
+            list(pool.imap(ev, sample, chunksize=chunksize))
         else:
-            pool.map(_cpu_eval, sample)
+            pool.map(ev, sample)
         return n / (time.perf_counter() - t0)
+
+
+def oracle_check(z, obs, thetas, got, procs):
+    """Self-check of the timed ensemble: the oracle's lnprob for `thetas` against the values the GPU sampler holds."""
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(procs, initializer=_cpu_init, initargs=(z, obs)) as pool:
+        want = np.array(pool.map(_cpu_eval, [list(t) for t in thetas]))
+    both = np.isfinite(want) & np.isfinite(got)
+    same_class = (np.isfinite(want) == np.isfinite(got)) & ~(np.isnan(want) ^ np.isnan(got))
+    rel = np.abs(got[both] - want[both]) / np.abs(want[both]) if both.any() else np.zeros(0)
+    return {"n": int(len(thetas)), "n_finite": int(both.sum()), "max_rel": float(rel.max()) if rel.size else 0.0,
+            "n_outside_1e-9": int((rel > 1e-9).sum()), "n_flips": int((~same_class).sum()), "tolerance": 1e-9,
+            "what": "lnprob the sampler holds for %d randomly chosen walkers of the timed ensemble (after the timed steps) "
+                    "against the numpy oracle on the same positions and draws; n_flips = finite/-inf disagreements" % len(thetas)}
 
 
 def run_cpu_baseline():
@@ -114,12 +165,19 @@ def run_cpu_baseline():
     serial = cpu_rate(z, obs, thetas, 1, 48)
     pooled = cpu_rate(z, obs, thetas, procs, 24)
     mpi_like = cpu_rate(z, obs, thetas, max(procs - 1, 1), 24, chunksize=1) if procs > 1 else serial
-    print(json.dumps({
+    line = {
         "value": pooled, "unit": "evals/s", "cores": procs, "kind": "port",
         "sample": "%d evaluations (24 per process) of the same workload, numpy oracle" % (24 * procs),
         "serial_evals_per_s": serial, "mpi_pool_emulation_evals_per_s": mpi_like,
         "mpi_pool_emulation": "1 master + %d workers, one task per message (multiprocessing imap, chunksize=1); "
-                              "mpi4py is not installed" % max(procs - 1, 1)}))
+                              "mpi4py is not installed, so mpiTOFmodel.py's MPIPool is emulated" % max(procs - 1, 1)}
+    if _ref_available():
+        # the reference's own code (loader shim), where its tree exists: SURVEY.md 8d's CPU arm
+        line["reference_loader_evals_per_s"] = cpu_rate(z, obs, thetas, procs, 4, kind="loader")
+        line["reference_loader_serial_evals_per_s"] = cpu_rate(z, obs, thetas, 1, 6, kind="loader")
+        line["reference_loader"] = ("tests/advIntermediateTOFmodel.py lnprior + lnlike executed unmodified through "
+                                    "oracle/ref_loader.py, %d processes x 4 evaluations" % procs)
+    print(json.dumps(line))
     return 0
 
 
@@ -130,15 +188,19 @@ def run_reference_arm(args):
     from oracle import tof_oracle as O
     om, z, obs, thetas = workload(O)
     procs = os.cpu_count() or 1
-    per_proc = 24
+    # where the reference tree exists its own function bodies are timed (kind "loader"); on the GPU box, which has no
+    # /root/reference, the numpy port of the same algorithm (kind "port", ~4x faster per core than the reference)
+    kind = "loader" if _ref_available() else "port"
+    per_proc = 4 if kind == "loader" else 24
     rates = []
     for i in range(args.warmup + args.steps):
-        r = cpu_rate(z, obs, thetas[i * procs * per_proc:], procs, per_proc)
+        r = cpu_rate(z, obs, thetas[i * procs * per_proc:], procs, per_proc, kind=kind)
         if i >= args.warmup:
             rates.append(r)
     value = statistics.mean(rates)
-    sample = "%d evaluations per step (%d per process x %d processes) of the %d-walker workload" % (
-        procs * per_proc, per_proc, procs, N_WALKERS)
+    sample = "%d evaluations per step (%d per process x %d processes) of the %d-walker workload, %s" % (
+        procs * per_proc, per_proc, procs, N_WALKERS,
+        "the reference's own lnprob through oracle/ref_loader.py" if kind == "loader" else "numpy oracle (the reference tree is not on this box)")
     line = {
         "impl": "reference", "metric": "walker lnprob evals/sec (adv TOF model)", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -146,7 +208,8 @@ def run_reference_arm(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "adv TOF model sweep: %d walkers x %d TOF bins x %d MC draws" % (N_WALKERS, N_TOF_BINS, N_DRAWS),
                    "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": procs, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": procs, "kind": "reference" if kind == "loader" else "port",
+                         "sample": sample},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -302,6 +365,40 @@ def run_gpu_arm(args):
 
     finite_frac = float(torch.isfinite(lp).double().mean().item())
 
+    # ---- self-check (outside the timed region): a random sample of the timed ensemble against the oracle -----------
+    parity_sample = None
+    if rank == 0 and not args.no_parity_sample:
+        pick = np.random.RandomState(2026).choice(N_WALKERS, size=256, replace=False)
+        pos_h, lp_h = pos.cpu().numpy(), lp.cpu().numpy()
+        if f32:
+            parity_sample = {"skipped": "FP32 arm: tolerance 1e-4, see fp32_mode"}
+        else:
+            parity_sample = oracle_check(z, obs, pos_h[pick], lp_h[pick], min(os.cpu_count() or 1, 32))
+
+    # ---- burn-in regime: walkers uniform over the adv prior box (adv:81-82), one half-ensemble call ----------------
+    prior_box = None
+    if rank == 0 and not f32 and ode == M.config.ODE_RANGE:
+        rs_box = np.random.RandomState(3)
+        nb = N_WALKERS // 2 // world
+        box = np.column_stack([rs_box.uniform(1000, 2600, nb), rs_box.uniform(0.02, 0.5, nb)])
+        th_box = torch.from_numpy(box).to(device)
+        out_box = torch.empty(nb, dtype=torch.float64, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        model.set_timing(True)
+        ms_box = []
+        for i in range(4):
+            flush.zero_()
+            model.lnprob_batch_device(th_box.data_ptr(), nb, out_box.data_ptr(), stream)
+            torch.cuda.synchronize()
+            if i:
+                ms_box.append(model.last_kernel_ms())
+        model.set_timing(False)
+        st_box = model.stats()
+        prior_box = {"value": nb / (statistics.mean(ms_box) * 1e-3), "unit": "evals/s", "kernel_ms": statistics.mean(ms_box),
+                     "walkers": nb, "wide_walkers": st_box.get("wide_last"), "launches_per_call": st_box.get("model_launches_per_call"),
+                     "what": "walkers uniform over the adv prior box 1000<e0<2600, 0.02<sigma0<0.5 (a burn-in ensemble): "
+                             "most E-bands exceed the shared-memory histogram and are kept in the L2 scratch slice"}
+
     # ---- per-stage breakdown from the library's own stage timing (separate instrumented kernels, outside the
     # timed region): share of CTA cycles per stage over one ensemble step --------------------------------------
     stage_profile = None
@@ -365,12 +462,17 @@ def run_gpu_arm(args):
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE model call at this size (131072 walkers: the banded
             # launch <512,7> plus the full-size launch <1024,7> over its overflow queue), from the ncu --set full capture
             # summarised in profiles/r1_range_fp64_ncu_summary.txt; algorithmic bytes are evals * 24
-            "traffic": (3536384 * evals_per_launch // 131072) if ode == M.config.ODE_RANGE else None,
-            "traffic_source": "profiles/r1_range_fp64_ncu_summary.txt (dram read + write of both launches, scaled by walkers per launch)",
-            "kernel": ("adv_range_kernel<512,7> (banded, 2 CTAs/SM) + adv_range_kernel<1024,7> (overflow queue)"
+            "traffic": (2620928 * evals_per_launch // 131072) if ode == M.config.ODE_RANGE else None,
+            "traffic_source": "profiles/r2_zrank_fp64_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of one "
+                              "131072-walker launch, scaled by walkers per launch); algorithmic bytes are evals * 24",
+            "kernel": ("adv_zrank_kernel<512,7> (one persistent launch per call, 2 CTAs/SM)"
                        if ode == M.config.ODE_RANGE else "adv_lnprob_kernel"),
             "kernel_ms": k_ms, "evals_per_launch": evals_per_launch,
             "flop_per_eval": flop_per_eval, "flop_per_eval_rk4_formulation": FLOP_PER_EVAL_RK4,
+            # executed sample work only (per (draw, x): v, compare, dt, degree-7 Horner, accumulate = 18; T1 lookup 18 per
+            # draw), without the per-cell / per-TOF-bin terms the kernel legitimately skips for empty cells and bins
+            "flop_per_eval_executed": FLOP_PER_EVAL_EXECUTED,
+            "frac_executed": (evals_per_launch * FLOP_PER_EVAL_EXECUTED / (k_ms * 1e-3) / 1e12) / fp64_peak,
             "rk4_equivalent_tflops": evals_per_launch * FLOP_PER_EVAL_RK4 / (k_ms * 1e-3) / 1e12,
             "peak_source": "DFMA microbenchmark run in this process (tof_measure_fp64_peak)",
             "nominal_fp64_tflops": NOMINAL_FP64_TFLOPS,
@@ -398,8 +500,13 @@ def run_gpu_arm(args):
                        "l2": "flushed between timed steps (256 MiB memset outside the event bracket)",
                        "finite_lnprob_fraction": finite_frac},
             "roofline": roofline, "cpu_baseline": cpu, "fp32_mode": fp32_mode, "stage_profile": stage_profile,
+            "parity_sample": parity_sample, "prior_box": prior_box,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": N_WALKERS * 2 * 8,
-                    "d2h_bytes_per_step": N_WALKERS * 8},
+                    "d2h_bytes_per_step": N_WALKERS * 8,
+                    "what": "the reference-facing call: TofLnProb.batch = C-ABI tof_lnprob_batch with pinned HOST buffers, two calls "
+                            "of %d walkers per step as emcee's _get_lnprob issues them (H2D copy of theta, model kernel, D2H copy of "
+                            "lnprob inside the wall-clock region); %d steps, no L2 flush, without the stretch-move propose/accept "
+                            "kernels that `value` includes -- which is why it can exceed `value`" % (N_WALKERS // 2, e2e_steps)},
             "gpu_launches": launches_timed, "clocks": clock_info,
             "kernel_stats": model.stats(),
         }
@@ -423,6 +530,7 @@ def main():
     ap.add_argument("--no-fp32", action="store_true", help="skip the secondary FP32-mode measurement of the default run")
     ap.add_argument("--no-stage-profile", action="store_true", help="skip the per-stage cycle breakdown (tof_set_stage_timing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-sample", action="store_true", help="skip the oracle check of 256 timed-ensemble walkers")
     ap.add_argument("--cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_baseline:

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define TOF_ABI_VERSION 2
+#define TOF_ABI_VERSION 3
 
 #define TOF_MAX_DIM 16       /* parameters per walker (reference max: 9, simultFit.py:444-448) */
 #define TOF_MAX_RUNS 8       /* simultaneous standoff runs (reference max: 5, simultFit.py:127-131) */
@@ -243,8 +243,14 @@ typedef struct tof_stats {
     int32_t ctas_per_sm;     /* resident CTAs per SM of the main model kernel */
     int32_t band_ctas_per_sm; /* range kernel, banded launch (512 threads): resident CTAs per SM; 0 = disabled */
     int32_t band_cells;       /* ... cell-histogram capacity of the banded launch */
-    int64_t band_queued_last; /* ... walkers of the most recent call that needed the full-size launch */
+    int64_t band_queued_last; /* ... walkers of the most recent call that were queued for the second, full-size launch
+                               * (always 0 with the single-launch kernel, see model_launches_per_call) */
     int32_t fp32_active;      /* 1 when the FP32 sample stage is what the model kernel runs (see tof_precision) */
+    int32_t model_launches_per_call; /* model kernels one tof_lnprob_batch call of the adv/intermediate range path launches:
+                               * 1 with the single-launch kernel (adv_zrank_kernel: every walker, wide E-band or not, is
+                               * handled by the CTA that fetched it), 2 with the banded + overflow pair */
+    int64_t wide_last;        /* single-launch kernel: walkers of the most recent call whose (x,E) histogram did not fit
+                               * shared memory and was kept in the CTA's L2-resident scratch slice instead */
 } tof_stats;
 int tof_get_stats(const tof_ctx *ctx, tof_stats *out);
 

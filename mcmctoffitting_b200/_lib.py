@@ -8,7 +8,7 @@ import re
 from . import build as _build
 
 MAX_DIM, MAX_RUNS, MAX_MATERIALS = 16, 8, 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _dp = C.POINTER(C.c_double)
 
@@ -46,7 +46,8 @@ class TofStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("evaluations", C.c_int64), ("nan_results", C.c_int64),
                 ("sm_count", C.c_int32), ("smem_bytes", C.c_int32), ("threads", C.c_int32),
                 ("ctas_per_sm", C.c_int32), ("band_ctas_per_sm", C.c_int32), ("band_cells", C.c_int32),
-                ("band_queued_last", C.c_int64), ("fp32_active", C.c_int32)]
+                ("band_queued_last", C.c_int64), ("fp32_active", C.c_int32), ("model_launches_per_call", C.c_int32),
+                ("wide_last", C.c_int64)]
 
 
 class TofError(RuntimeError):

@@ -1151,9 +1151,13 @@ int tof_get_stats(const tof_ctx *ctx, tof_stats *out) {
     out->band_ctas_per_sm = ctx->band_enabled ? ctx->band_ctas : 0;
     out->band_cells = ctx->band_enabled ? ctx->band_hcap : 0;
     out->band_queued_last = 0;
+    out->wide_last = 0;
+    const bool single = ctx->zrank && ctx->runs[0].zlut != nullptr;
+    out->model_launches_per_call = (ctx->cfg.model == TOF_MODEL_ADV && ctx->cfg.ode_mode == TOF_ODE_RANGE)
+                                       ? ((single || !ctx->band_enabled) ? 1 : 2) : 0;
     // counters are read on the context's own stream, ordered after its last model launch (ev_busy): the host waits for
     // that launch only -- no device-wide or legacy-stream synchronisation
-    const bool want_nan = ctx->d_nan.p != nullptr, want_q = ctx->band_enabled && ctx->d_work.p != nullptr;
+    const bool want_nan = ctx->d_nan.p != nullptr, want_q = (ctx->band_enabled || single) && ctx->d_work.p != nullptr;
     if ((want_nan || want_q) && ctx->h_counters) {
         cudaSetDevice(ctx->cfg.device);
         bool ok = true;
@@ -1166,7 +1170,7 @@ int tof_get_stats(const tof_ctx *ctx, tof_stats *out) {
                                  cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess;
         if (ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess) {
             if (want_nan) out->nan_results = (int64_t)ctx->h_counters[0];
-            if (want_q) out->band_queued_last = (int64_t)ctx->h_counters[1];
+            if (want_q) (single ? out->wide_last : out->band_queued_last) = (int64_t)ctx->h_counters[1];
         }
     }
     return TOF_OK;

@@ -849,6 +849,48 @@ def test_onebd_reference_goldens(M, O, golden, pf):
         assert rel(got, pf(c["lnprob"])) <= RTOL, (got, c["lnprob"])
 
 
+def test_single_launch_kernel_equals_the_banded_pair(M, O):
+    """The shipped adv_zrank_kernel (rank hints from a walker-independent table, fused normalisation, fast-path scatter,
+    wide walkers in an L2 scratch histogram, ONE launch per call) against adv_planned_kernel + overflow launch
+    (TOFGPU_RANGE_ZRANK=0) on the bench ensemble, on prior-box walkers (mostly wide) and on the corners of the prior
+    box: same cells, same integers, so the log-likelihoods must be identical bit for bit; a sample is checked against
+    the oracle (1e-9)."""
+    om = O.sweep_model()
+    xs = O.DDNXS()
+    z = np.random.RandomState(20260101).standard_normal(1024)
+    obs = np.rint(1e5 * om.model_pdf([1050, 0.08], np.random.RandomState(7).standard_normal(1024)))
+    rs = np.random.RandomState(11)
+    ens = np.array([1050.0, 0.10]) + np.array([10, 1e-2]) * rs.standard_normal((3000, 2))
+    box = np.column_stack([rs.uniform(1000, 2600, 1000), rs.uniform(0.02, 0.5, 1000)])
+    box[:6] = [[1000.5, 0.0201], [2599.0, 0.499], [1000.5, 0.499], [2599.0, 0.0201], [999.0, 0.1], [1050.0, 0.6]]
+    thetas = np.vstack([ens, box])
+    cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE)
+    res, stats = {}, {}
+    old = os.environ.get("TOFGPU_RANGE_ZRANK")
+    try:
+        for label, env in (("single", "1"), ("pair", "0")):
+            os.environ["TOFGPU_RANGE_ZRANK"] = env
+            fn = M.make_lnprob(cfg, obs, z)
+            res[label] = fn.batch(thetas)
+            stats[label] = fn.model.stats()
+            fn.model.close()
+    finally:
+        if old is None:
+            os.environ.pop("TOFGPU_RANGE_ZRANK", None)
+        else:
+            os.environ["TOFGPU_RANGE_ZRANK"] = old
+    a, b = res["single"], res["pair"]
+    assert np.array_equal(a, b, equal_nan=True), int(np.sum(~((a == b) | (np.isnan(a) & np.isnan(b)))))
+    assert stats["single"]["model_launches_per_call"] == 1 and stats["single"]["band_queued_last"] == 0
+    assert stats["single"]["wide_last"] > 500                       # most prior-box walkers are wide
+    assert stats["pair"]["model_launches_per_call"] == 2 and stats["pair"]["band_queued_last"] > 500
+    assert a[3004] == -np.inf and a[3005] == -np.inf                # outside the prior
+    assert np.isfinite(a[:3000]).sum() > 2500
+    for k in list(range(0, 24)) + list(range(3000, 3012)):
+        want = om.lnprob(thetas[k], obs, z, xs)
+        assert (a[k] == want) or rel(float(a[k]), float(want)) <= RTOL, (k, a[k], want)
+
+
 def test_ppc_onebd_reference_goldens(M, O, golden_ppc_onebd):
     """utilities/ppcTools_oneBD.py:185-268 (the posterior-predictive twin of the oneBD model: 20 x 400 grid, 10
     zero-degree sub-times per cell, tau = 4 transit taps, Poisson background) through the CUDA path, against the

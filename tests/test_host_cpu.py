@@ -280,7 +280,17 @@ def test_reference_arm_prints_the_contract_line():
     assert line["metric"].startswith("walker lnprob evals/sec") and line["value"] > 0 and line["dtype"] == "f64"
     assert "262144 walkers" in line["config"]["workload"] and line["vs_baseline"] is None
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "evaluations" in cb["sample"]
+    # "reference": the reference's own function bodies through oracle/ref_loader.py (where /root/reference exists);
+    # "port": the numpy oracle (the GPU box)
+    from oracle import ref_loader
+    assert cb["kind"] == ("reference" if ref_loader.available() else "port")
+    assert cb["cores"] >= 1 and cb["value"] == line["value"] and "evaluations" in cb["sample"]
+    # without the reference tree the same command times the port
+    env = dict(os.environ, TOF_REFERENCE_ROOT="/nonexistent")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, cwd=root, env=env)
+    assert out.returncode == 0, out.stderr[-500:]
+    assert json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]["kind"] == "port"
     assert line["e2e"] == {"value": line["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # ranks other than 0 do no work under torchrun
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")

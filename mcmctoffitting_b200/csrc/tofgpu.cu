@@ -760,6 +760,10 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
                         TRY(upload(ctx, th.data(), th.size(), &m.rank_theta));
                         m.rank_stride = cfg->x_bins;
                         ctx->zrank = true;
+                        // what tof_get_stats reports as "the main model kernel" is now this one
+                        ctx->stats.smem_bytes = (int)ctx->zr_smem;
+                        ctx->stats.threads = ctx->zr_nt;
+                        ctx->stats.ctas_per_sm = occz;
                     }
                 }
             }

@@ -414,6 +414,31 @@ def run_gpu_arm(args):
                                  "instrumented instantiation of the same kernel" % per)
         model.set_stage_timing(False)
 
+    # ---- per-evaluation draws (the reference's own behaviour: every lnlike call draws its own normals, adv:128) ----
+    fresh_draws = None
+    if rank == 0 and not f32 and ode == M.config.ODE_RANGE:
+        fnf = M.make_lnprob(cfg, obs, None, device=local_rank, fresh_seed=20260101)
+        mf = fnf.model
+        nb = N_WALKERS // 2 // world
+        th_f = torch.from_numpy(thetas[:nb].copy()).to(device)
+        out_f = torch.empty(nb, dtype=torch.float64, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        mf.set_timing(True)
+        ms_f = []
+        for i in range(4):
+            flush.zero_()
+            mf.lnprob_batch_device(th_f.data_ptr(), nb, out_f.data_ptr(), stream)
+            torch.cuda.synchronize()
+            if i:
+                ms_f.append(mf.last_kernel_ms())
+        fresh_draws = {"value": nb / (statistics.mean(ms_f) * 1e-3), "unit": "evals/s", "kernel_ms": statistics.mean(ms_f),
+                       "walkers": nb, "finite_lnprob_fraction": float(torch.isfinite(out_f).double().mean().item()),
+                       "what": "tof_set_draw_mode(TOF_DRAWS_PER_EVALUATION): every (call, walker) draws its own 1024 sorted "
+                               "normals on the device (Philox + exponential spacings + inverse normal CDF, no sort) and is run by "
+                               "the per-walker-lookup kernels (adv_planned_kernel + overflow launch); the headline uses the bound "
+                               "draw set (common random numbers), the mode the parity goldens pin"}
+        mf.close()
+
     # ---- optional FP32 sample stage, reported beside the FP64 headline (N = 1, range formulation) ----------
     fp32_mode = None
     if world == 1 and not f32 and ode == M.config.ODE_RANGE and not args.no_fp32:
@@ -500,7 +525,7 @@ def run_gpu_arm(args):
                        "l2": "flushed between timed steps (256 MiB memset outside the event bracket)",
                        "finite_lnprob_fraction": finite_frac},
             "roofline": roofline, "cpu_baseline": cpu, "fp32_mode": fp32_mode, "stage_profile": stage_profile,
-            "parity_sample": parity_sample, "prior_box": prior_box,
+            "parity_sample": parity_sample, "prior_box": prior_box, "fresh_draws": fresh_draws,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": N_WALKERS * 2 * 8,
                     "d2h_bytes_per_step": N_WALKERS * 8,
                     "what": "the reference-facing call: TofLnProb.batch = C-ABI tof_lnprob_batch with pinned HOST buffers, two calls "

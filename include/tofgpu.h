@@ -170,6 +170,25 @@ int tof_set_observables(tof_ctx *ctx, int run, const double *counts, int nbins);
  * Host pointers; copied to the device. */
 int tof_set_draws(tof_ctx *ctx, int run, int stream, const double *values, int64_t n);
 
+/* Where the Monte-Carlo draws of an evaluation come from.
+ *   TOF_DRAWS_BOUND (default): the draw set bound with tof_set_draws, shared by all walkers and all calls (common
+ *     random numbers): bit-reproducible, the mode every parity test runs in.
+ *   TOF_DRAWS_PER_EVALUATION: what the reference does -- every lnlike call draws its own numbers from the global stream
+ *     (adv:128 np.random.normal inside generateModelData; simple:62-64), so each walker at each step sees its own noise.
+ *     The draws are generated on the device: Philox4x32-10, key = seed, counter = (index, epoch, global walker index);
+ *     `epoch` advances by one per model call made through the batch entry points (first call: epoch0, < 2^31) and is
+ *     2^31 + 2*step + half inside tof_ensemble_step / tof_ensemble_half_step, so chains do not depend on the sharding.  Normals
+ *     are inverse-CDF transforms of open uniforms; the range kernels get each walker's normals already sorted (order
+ *     statistics from exponential spacings: no sort).  tof_set_draws is not needed in this mode.
+ * Built for TOF_MODEL_SIMPLE and TOF_MODEL_ADV (TOF_ODE_RK4: any n_draws; TOF_ODE_RANGE: FP64, n_draws <= 1024). */
+typedef enum tof_draw_mode { TOF_DRAWS_BOUND = 0, TOF_DRAWS_PER_EVALUATION = 1 } tof_draw_mode;
+int tof_set_draw_mode(tof_ctx *ctx, int mode, uint64_t seed, uint64_t epoch0);
+
+/* The draws walker `walker` of model call `epoch` uses in TOF_DRAWS_PER_EVALUATION mode (HOST buffer out[n]): stream 0
+ * normals (sorted != 0: ascending, as the range kernels consume them; n <= 1024), stream 1 the simple model's uniforms.
+ * For parity checks: feed them to a CPU evaluation of the same walker. */
+int tof_generate_draws(tof_ctx *ctx, uint64_t epoch, int64_t walker, int stream, int sorted, double *out, int64_t n);
+
 /* lnprob for n walkers: theta[n][ndim] row-major -> out[n].  HOST buffers; the call copies in,
  * launches, copies out and synchronises.  Replaces n calls of lnprob (adv:191-199, simple:112-120,
  * simultFit.py:444-469), i.e. one emcee `_get_lnprob` map over a half-ensemble. */

@@ -87,8 +87,27 @@ __device__ __noinline__ int planned_setup(const DevModel *mp, const DevRun *rp, 
     const bool rev = spread < 0.0;                         // draws are sorted ascending: E0 ascends unless the spread is negative
     const double umax = m.rng_u_max;
     // E-bins the walker can touch: the draws are sorted, first and last give the extremes
-    const double u_lo = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 : 0)))), m);
-    const double u_hi = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? 0 : m.n_draws - 1)))), m);
+    double u_lo, u_hi;
+    const int nt = (int)m.n_draws;                         // one tile
+    if (run.fresh) {
+        // per-evaluation draws (tof_set_draw_mode): this walker's own sorted normals, generated in place of the tile;
+        // the sign of the spread does not matter (the normal law is symmetric): E0 ascends with |spread|
+        double *scr = reinterpret_cast<double *>(smem_raw + out.lay.scratch);
+        fresh_sorted_normals<NT>(u0, nt, run, w, 0, scr);
+        const double sp = fabs(spread);
+        double za = 0.0, zb = 0.0;
+        if (tid < nt) za = u0[tid];
+        if (tid + NT < nt) zb = u0[tid + NT];
+        __syncthreads();
+        if (tid < nt) u0[tid] = t1_eval(__dadd_rn(e0, __dmul_rn(sp, za)), m);
+        if (tid + NT < nt) u0[tid + NT] = t1_eval(__dadd_rn(e0, __dmul_rn(sp, zb)), m);
+        __syncthreads();
+        u_lo = u0[0];
+        u_hi = u0[nt - 1];
+    } else {
+        u_lo = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 : 0)))), m);
+        u_hi = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? 0 : m.n_draws - 1)))), m);
+    }
     // every row has its own window of E-bins: [u_lo + delta_i, u_hi + delta_i], one interval of slack on both sides
     // (T1 is only monotone up to its 2e-13 cm fit error); interval j == E-bin j on this path
     for (int i = tid; i < X; i += NT) {
@@ -121,9 +140,9 @@ __device__ __noinline__ int planned_setup(const DevModel *mp, const DevRun *rp, 
     const double *recg = m.rng_rec;
     for (int i = tid; i < (j_hi_all - jbase + 1) * RW; i += NT) rec[i] = recg[(size_t)jbase * RW + i];
     for (int i = tid; i < X * hstride; i += NT) H[i] = 0.0;
-    const int nt = (int)m.n_draws;                         // one tile
-    for (int d = tid; d < nt; d += NT)
-        u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? nt - 1 - d : d)))), m);
+    if (!run.fresh)
+        for (int d = tid; d < nt; d += NT)
+            u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? nt - 1 - d : d)))), m);
     if (tid == 0) {
         f->w = w;
         f->e0 = e0;

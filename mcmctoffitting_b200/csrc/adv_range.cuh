@@ -1059,8 +1059,22 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
                                                    X, M, umax, m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all, u0f, center);
                 continue;
             }
-            for (int d = tid; d < nt; d += NT)
-                u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 - (tile + d) : tile + d)))), m);
+            if (run.fresh) {
+                // per-evaluation draws (tof_set_draw_mode; one tile only, checked by the host): this walker's own sorted
+                // normals, generated in place; E0 ascends with |spread| (the normal law is symmetric)
+                fresh_sorted_normals<NT>(u0, nt, run, w, 0, scratch);
+                const double sp = fabs(spread);
+                double zv[(RANGE_TILE + NT - 1) / NT];
+#pragma unroll
+                for (int q = 0; q < (RANGE_TILE + NT - 1) / NT; ++q) zv[q] = (tid + q * NT < nt) ? u0[tid + q * NT] : 0.0;
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < (RANGE_TILE + NT - 1) / NT; ++q)
+                    if (tid + q * NT < nt) u0[tid + q * NT] = t1_eval(__dadd_rn(e0, __dmul_rn(sp, zv[q])), m);
+            } else {
+                for (int d = tid; d < nt; d += NT)
+                    u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 - (tile + d) : tile + d)))), m);
+            }
             __syncthreads();
             if (m.rng_identity && m.n_draws <= RANGE_TILE)      // one tile, one interval per E-bin: plan / execute
                 range_tile_planned<NT, P>(u0, nt, sbrk, rec, jbase, lut, ulut, RANGE_ULUT, sdelta, srow, H, hstride, hlo_s, X, M,

@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(NT) adv_lnprob_kernel(const DevModel m, const 
 #pragma unroll
         for (int k = 0; k < DPT; ++k) {
             const long long d = base + k;
-            E[k] = (d < m.n_draws) ? __dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + d))) : CUDART_NAN;
+            const double zd = (d < m.n_draws) ? (run.fresh ? fresh_normal(run, w, 0, d) : __ldg(run.z + d)) : 0.0;
+            E[k] = (d < m.n_draws) ? __dadd_rn(e0, __dmul_rn(spread, zd)) : CUDART_NAN;
         }
         double x_prev = m.ode_from_zero ? 0.0 : s.sx[0];
         for (int i = 0; i < X; ++i) {

@@ -39,8 +39,11 @@ __global__ void __launch_bounds__(NT) simple_hist_kernel(const DevModel m, const
     const long long lo = (long long)blockIdx.y * per;
     const long long hi = (lo + per < m.n_draws) ? lo + per : m.n_draws;
     for (long long d = lo + tid; d < hi; d += NT) {
-        const double x = __dmul_rn(m.cell_length, __ldg(run.z1 + d));                       // simple:62
-        const double ed = __dadd_rn(__dadd_rn(e0, __dmul_rn(e1, x)), __dmul_rn(sigma, __ldg(run.z + d)));  // simple:64
+        // draws: the bound streams, or this (call, walker)'s own (tof_set_draw_mode; the reference draws per call)
+        const double ud = run.fresh ? fresh_uniform(run, w, 0, d) : __ldg(run.z1 + d);
+        const double zd = run.fresh ? fresh_normal(run, w, 0, d) : __ldg(run.z + d);
+        const double x = __dmul_rn(m.cell_length, ud);                                      // simple:62
+        const double ed = __dadd_rn(__dadd_rn(e0, __dmul_rn(e1, x)), __dmul_rn(sigma, zd));  // simple:64
         const double rv = __ddiv_rn(__dsqrt_rn(__dmul_rn(k_mm, ed)), k_den);               // rVal (cos 0 = 1)
         const double sv = __ddiv_rn(__dadd_rn(__dmul_rn(ed, k_dm), k_q), k_den);           // sVal
         const double sq = __dadd_rn(rv, __dsqrt_rn(__dadd_rn(__dmul_rn(rv, rv), sv)));

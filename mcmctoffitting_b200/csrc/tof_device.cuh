@@ -72,6 +72,10 @@ struct DevRun {
     long long n_z;
     const double *z1;            // stream 1
     long long n_z1;
+    // per-evaluation draws generated on the device (tof_set_draw_mode): every (call, walker) has its own stream
+    int fresh;
+    unsigned long long fresh_seed, fresh_epoch;   // epoch: one per model call (or 2*step + half inside the ensemble entry points)
+    long long fresh_walker0;                       // global index of the call's first walker
     // adv_zrank_kernel: zlut[c] = first (sorted) draw with z >= zlut_lo + c / zlut_inv, c = 0..ZR_LUT (zlut[ZR_LUT] = n_z)
     const unsigned short *zlut;
     double zlut_lo, zlut_inv;
@@ -212,5 +216,79 @@ struct Philox {
         return (double)((((uint64_t)c[3] << 32) | c[2]) >> 11) * (1.0 / 9007199254740992.0);
     }
 };
+
+}  // namespace tof
+
+namespace tof {
+
+// ---- per-evaluation Monte-Carlo draws generated on the device (tof_set_draw_mode) ---------------------------------
+// The reference draws inside every lnlike call (adv:128, simple:62-64): each walker at each step sees its own noise.
+// Philox4x32-10, key = seed, counter = (pair index, epoch << 32 | global walker << 6 | run << 3 | stream): the draws of a
+// (call, walker) do not depend on how walkers are batched or sharded.
+__device__ __forceinline__ Philox fresh_philox(const DevRun &run, long long walker, int run_idx, int stream, unsigned long long pair) {
+    const unsigned long long gw = (unsigned long long)(run.fresh_walker0 + walker);
+    return Philox(run.fresh_seed, pair, (run.fresh_epoch << 32) | (gw << 6) | ((unsigned long long)run_idx << 3) | (unsigned long long)stream);
+}
+// uniform on the open interval (0, 1): (k + 1/2) * 2^-52, k < 2^52 (exact in binary64; never 0 or 1)
+__device__ __forceinline__ double philox_open01(uint32_t lo, uint32_t hi) {
+    return ((double)((((uint64_t)hi << 32) | lo) >> 12) + 0.5) * (1.0 / 4503599627370496.0);
+}
+// iid standard normal number d of this (call, walker, run): inverse-CDF of one open uniform
+__device__ __forceinline__ double fresh_normal(const DevRun &run, long long walker, int run_idx, long long d) {
+    const Philox ph = fresh_philox(run, walker, run_idx, 0, (unsigned long long)d >> 1);
+    return normcdfinv((d & 1) ? philox_open01(ph.c[2], ph.c[3]) : philox_open01(ph.c[0], ph.c[1]));
+}
+// iid uniform [0, 1) number d (stream 1 of the simple model, simple:62)
+__device__ __forceinline__ double fresh_uniform(const DevRun &run, long long walker, int run_idx, long long d) {
+    const Philox ph = fresh_philox(run, walker, run_idx, 1, (unsigned long long)d >> 1);
+    return (d & 1) ? ph.u1() : ph.u0();
+}
+
+// nt standard normals in ASCENDING order for this (call, walker), into zs (shared memory), by all NT threads of the CTA:
+// the order statistics of nt iid uniforms are S_k / S_{nt+1} with S the running sums of nt + 1 iid exponentials
+// (Renyi), so a prefix sum replaces the sort; z_k = Phi^-1(U_(k)).  Exactly the joint law of nt sorted iid normals.
+// Needs nt <= 2 * NT; scratch: >= NT/32 + 2 doubles of shared memory.  Ends with a barrier.  The result does not depend
+// on NT (two spacings per thread, the same summation order), so the banded and the full-size launch of a call, and
+// tof_generate_draws, see the same draws.
+template <int NT>
+__device__ __forceinline__ void fresh_sorted_normals(double *zs, int nt, const DevRun &run, long long walker, int run_idx,
+                                                     double *scratch) {
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Philox ph = fresh_philox(run, walker, run_idx, 2, (unsigned long long)tid);
+    // the (nt+1)-th spacing: a fixed counter, so that every thread -- and every kernel, whatever its NT -- gets the same
+    const Philox pl = fresh_philox(run, walker, run_idx, 2, 0xFFFFFFFFull);
+    const int i0 = 2 * tid, i1 = 2 * tid + 1;              // this thread's two exponentials (indices 0..nt-1)
+    const double ea = (i0 < nt) ? -log(philox_open01(ph.c[0], ph.c[1])) : 0.0;
+    const double eb = (i1 < nt) ? -log(philox_open01(ph.c[2], ph.c[3])) : 0.0;
+    const double e_last = -log(philox_open01(pl.c[0], pl.c[1]));
+    double incl = ea + eb;                                  // inclusive scan of the per-thread sums, fixed order
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += up;
+    }
+    __syncthreads();                                        // scratch may still be in use by the caller
+    if (lane == 31) scratch[warp] = incl;
+    __syncthreads();
+    double base = 0.0;
+    for (int k = 0; k < warp; ++k) base += scratch[k];
+    const double s_a = base + (incl - (ea + eb)) + ea;      // S at index i0
+    const double s_b = s_a + eb;                            // S at index i1
+    if (i0 == nt - 1) scratch[NW] = s_a;                    // the sum of the first nt spacings
+    if (i1 == nt - 1) scratch[NW] = s_b;
+    __syncthreads();
+    const double total = scratch[NW] + e_last;
+    constexpr double TOP = 1.0 - 1.0 / 9007199254740992.0;
+    if (i0 < nt) {
+        const double u = s_a / total;
+        zs[i0] = normcdfinv(u < TOP ? u : TOP);
+    }
+    if (i1 < nt) {
+        const double u = s_b / total;
+        zs[i1] = normcdfinv(u < TOP ? u : TOP);
+    }
+    __syncthreads();
+}
 
 }  // namespace tof

@@ -58,6 +58,11 @@ struct tof_ctx {
     RangeLayout lay_full{}, lay_band{};   // shared-memory layouts of the two launches (host-computed offsets)
     size_t simult_smem = 0, onebd_smem = 0;
     int max_smem_optin = 0;
+    // per-evaluation draws (tof_set_draw_mode): epoch of the next model call, key of the call being launched
+    bool fresh = false;
+    uint64_t fresh_seed = 0, fresh_epoch = 0;
+    uint64_t cur_epoch = 0;
+    int64_t cur_walker0 = 0;
     bool have_obs[TOF_MAX_RUNS]{};
     bool have_z[TOF_MAX_RUNS][2]{};
 };
@@ -163,6 +168,7 @@ int check_run(tof_ctx *ctx, int run) {
 int ready(tof_ctx *ctx, bool need_obs) {
     for (int r = 0; r < ctx->cfg.n_runs; ++r) {
         if (need_obs && !ctx->have_obs[r]) return fail(ctx, TOF_ERR_STATE, "observables not set for run " + std::to_string(r));
+        if (ctx->fresh) continue;                           // draws are generated on the device
         if (!ctx->have_z[r][0]) return fail(ctx, TOF_ERR_STATE, "draws (stream 0) not set for run " + std::to_string(r));
         if (ctx->cfg.model == TOF_MODEL_SIMPLE && !ctx->have_z[r][1])
             return fail(ctx, TOF_ERR_STATE, "uniform draws (stream 1) not set");
@@ -183,6 +189,12 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
     }
     if (ctx->stage_timing && ctx->d_stage.p) out.stage_cycles = static_cast<unsigned long long *>(ctx->d_stage.p);
     if (ctx->timing) CU(ctx, cudaEventRecord(ctx->ev0, st));
+    // the run as the kernels see it for THIS call: with per-evaluation draws it carries the call's key
+    DevRun run0 = ctx->runs[run];
+    run0.fresh = ctx->fresh ? 1 : 0;
+    run0.fresh_seed = ctx->fresh_seed;
+    run0.fresh_epoch = ctx->cur_epoch;
+    run0.fresh_walker0 = ctx->cur_walker0;
     if (c.model == TOF_MODEL_ADV) {
         if (c.ode_mode == TOF_ODE_RANGE) {
             // persistent CTAs: one per resident slot, walkers handed out through global counters.
@@ -231,7 +243,7 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 }
             }
             const long long n_work = n * out.n_split;
-            if (ctx->zrank && !debug && out.n_split == 1 && ctx->runs[run].zlut) {
+            if (ctx->zrank && !ctx->fresh && !debug && out.n_split == 1 && ctx->runs[run].zlut) {
                 // shipped path: ONE persistent launch, 2 CTAs/SM; walkers whose E-band does not fit shared memory keep
                 // their cell sums in this CTA's slice of an L2-resident scratch buffer (cnt[2] counts them)
                 const long long slots = (long long)ctx->stats.sm_count * 2;
@@ -250,7 +262,7 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 if (prof) adv_zrank_kernel<512, 7, true><<<grid, 512, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
                 else if (ctx->zr_nt == 384) adv_zrank_kernel<384, 7, false><<<grid, 384, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
                 else adv_zrank_kernel<512, 7, false><<<grid, 512, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
-            } else if (ctx->band_enabled && !debug) {
+            } else if (ctx->band_enabled && !debug && (!ctx->fresh || (ctx->planned && out.n_split == 1))) {
                 rc = ensure(ctx, ctx->d_queue, (size_t)n * sizeof(int));
                 if (rc) return rc;
                 // 1) banded launch: every walker whose E-band fits; the others are queued
@@ -265,20 +277,20 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 // many walkers x one tile of draws, one interval per E-bin: the lean cut of the same kernel
                 if (ctx->planned && out.n_split == 1) kband = prof ? adv_planned_kernel<512, 7, true> : adv_planned_kernel<512, 7, false>;
                 const long long slots_band = (long long)ctx->stats.sm_count * std::max(ctx->band_ctas, 1);
-                kband<<<(unsigned)std::min<long long>(n_work, slots_band), ctx->band_nt, ctx->band_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, ob);
+                kband<<<(unsigned)std::min<long long>(n_work, slots_band), ctx->band_nt, ctx->band_smem, st>>>(ctx->dm, run0, d_theta, n, ob);
                 // 2) full-size launch over the queue (exits at once when it is empty)
                 out.work = cnt + 1;
                 out.queue_in = static_cast<const int *>(ctx->d_queue.p);
                 out.queue_count = cnt + 2;
-                kfull<<<(unsigned)std::min<long long>(n_work, slots_full), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
+                kfull<<<(unsigned)std::min<long long>(n_work, slots_full), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, run0, d_theta, n, out);
                 ctx->stats.kernel_launches += 1;
             } else {
                 out.work = cnt + 1;
-                kfull<<<(unsigned)std::min<long long>(n_work, slots_full), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
+                kfull<<<(unsigned)std::min<long long>(n_work, slots_full), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, run0, d_theta, n, out);
             }
         } else {
             AdvKernel k = adv_variant(ctx->adv_nt, ctx->adv_dpt, c.n_materials);
-            k<<<(unsigned)n, ctx->adv_nt, ctx->adv_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, out);
+            k<<<(unsigned)n, ctx->adv_nt, ctx->adv_smem, st>>>(ctx->dm, run0, d_theta, n, out);
         }
         ctx->stats.kernel_launches += 1;
     } else if (c.model == TOF_MODEL_SIMPLE) {
@@ -291,7 +303,7 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                                                                        (ctx->dm.n_draws + 4095) / 4096));
         chunks = std::min<long long>(chunks, 65535);
         dim3 grid((unsigned)n, (unsigned)chunks);          // walkers on grid.x: no 65535 limit on the batch
-        simple_hist_kernel<256><<<grid, 256, 0, st>>>(ctx->dm, ctx->runs[0], d_theta, n,
+        simple_hist_kernel<256><<<grid, 256, 0, st>>>(ctx->dm, run0, d_theta, n,
                                                       static_cast<unsigned long long *>(ctx->d_counts.p),
                                                       out.spectra != nullptr);
         simple_finish_kernel<32><<<(unsigned)n, 32, 0, st>>>(ctx->dm, ctx->runs[0], d_theta, n,
@@ -349,6 +361,25 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
     }
     ctx->stats.evaluations += n;
     return TOF_OK;
+}
+
+// Key of the next model call when draws are generated per evaluation: calls made through the batch entry points take
+// consecutive epochs; the ensemble entry points pin (epoch, first walker) to (2*step + half, global walker index).
+void next_call_key(tof_ctx *ctx) {
+    ctx->cur_epoch = ctx->fresh_epoch++;
+    ctx->cur_walker0 = 0;
+}
+
+template <int NT>
+__global__ void fresh_draws_kernel(DevRun run, long long walker, int stream, int sorted, int n, double *out) {
+    __shared__ double zs[2 * NT];
+    __shared__ double scratch[NT / 32 + 2];
+    if (sorted) {
+        fresh_sorted_normals<NT>(zs, n, run, walker, 0, scratch);
+        for (int d = threadIdx.x; d < n; d += NT) out[d] = zs[d];
+    } else {
+        for (int d = threadIdx.x; d < n; d += NT) out[d] = stream == 1 ? fresh_uniform(run, walker, 0, d) : fresh_normal(run, walker, 0, d);
+    }
 }
 
 }  // namespace
@@ -972,6 +1003,7 @@ int tof_lnprob_batch_device(tof_ctx *ctx, const double *d_theta, int64_t n, doub
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     ModelOut o{};
     o.lnprob = d_out;
+    next_call_key(ctx);
     return launch_model(ctx, d_theta, n, 0, o, static_cast<cudaStream_t>(stream));
 }
 
@@ -987,6 +1019,7 @@ int tof_lnprob_batch(tof_ctx *ctx, const double *theta, int64_t n, double *out) 
     CU(ctx, cudaMemcpyAsync(ctx->d_theta.p, theta, tb, cudaMemcpyHostToDevice, ctx->stream));
     ModelOut o{};
     o.lnprob = static_cast<double *>(ctx->d_out.p);
+    next_call_key(ctx);
     if (int rc = launch_model(ctx, static_cast<const double *>(ctx->d_theta.p), n, 0, o, ctx->stream)) return rc;
     CU(ctx, cudaMemcpyAsync(out, ctx->d_out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1010,6 +1043,7 @@ int tof_model_batch(tof_ctx *ctx, const double *theta, int64_t n, int run, int s
     ModelOut o{};
     o.spectra = static_cast<double *>(ctx->d_spectra.p);
     o.stage = stage;
+    next_call_key(ctx);
     if (int rc = launch_model(ctx, static_cast<const double *>(ctx->d_theta.p), n, run, o, ctx->stream)) return rc;
     CU(ctx, cudaMemcpyAsync(spectra, ctx->d_spectra.p, sb, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1030,6 +1064,7 @@ int tof_cell_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run,
     CU(ctx, cudaMemcpyAsync(ctx->d_theta.p, theta, tb, cudaMemcpyHostToDevice, ctx->stream));
     ModelOut o{};
     o.cells = static_cast<long long *>(ctx->d_cells.p);
+    next_call_key(ctx);
     if (int rc = launch_model(ctx, static_cast<const double *>(ctx->d_theta.p), n, run, o, ctx->stream)) return rc;
     CU(ctx, cudaMemcpyAsync(counts, ctx->d_cells.p, cb, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1053,6 +1088,7 @@ int tof_deuteron_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int 
     ModelOut o{};
     o.cells = static_cast<long long *>(ctx->d_cells.p);
     o.unweighted = 1;
+    next_call_key(ctx);
     if (int rc = launch_model(ctx, static_cast<const double *>(ctx->d_theta.p), n, run, o, ctx->stream)) return rc;
     CU(ctx, cudaMemcpyAsync(counts, ctx->d_cells.p, cb, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1110,6 +1146,8 @@ int tof_ensemble_step(tof_ctx *ctx, double *d_pos, double *d_lnprob, int64_t n_w
             stretch_propose_kernel<<<grid, 256, 0, st>>>(sl, h, walker0, comp, h, ndim, ndim, ndim, a, seed, step0 + s, half, q, log_zz);
             ModelOut o{};
             o.lnprob = new_lp;
+            ctx->cur_epoch = (1ull << 31) | (2 * (uint64_t)(step0 + s) + (uint64_t)half);   // per-evaluation draws: independent of the sharding
+            ctx->cur_walker0 = walker0;
             if (int rc = launch_model(ctx, q, h, 0, o, st)) return rc;
             stretch_accept_kernel<<<grid, 256, 0, st>>>(sl, lp, h, walker0, q, new_lp, log_zz, ndim, ndim, 1, seed, step0 + s, half,
                                                         reinterpret_cast<long long *>(d_n_accept ? d_n_accept + walker0 : nullptr));
@@ -1141,11 +1179,51 @@ int tof_ensemble_half_step(tof_ctx *ctx, double *d_state, int64_t n_walkers, int
     stretch_propose_kernel<<<grid, 256, 0, st>>>(sl, n_own, walker0, comp, h, ndim, ld, ld, a, seed, step, half, q, log_zz);
     ModelOut o{};
     o.lnprob = new_lp;
+    ctx->cur_epoch = (1ull << 31) | (2 * (uint64_t)step + (uint64_t)half);  // per-evaluation draws: independent of the sharding
+    ctx->cur_walker0 = walker0;
     if (int rc = launch_model(ctx, q, n_own, 0, o, st)) return rc;
     stretch_accept_kernel<<<grid, 256, 0, st>>>(sl, sl + ndim, n_own, walker0, q, new_lp, log_zz, ndim, ld, ld, seed, step, half,
                                                 reinterpret_cast<long long *>(d_n_accept ? d_n_accept + walker0 : nullptr));
     ctx->stats.kernel_launches += 2;
     CU(ctx, cudaGetLastError());
+    return TOF_OK;
+}
+
+int tof_set_draw_mode(tof_ctx *ctx, int mode, uint64_t seed, uint64_t epoch0) {
+    if (!ctx) return TOF_ERR_INVALID;
+    if (mode != TOF_DRAWS_BOUND && mode != TOF_DRAWS_PER_EVALUATION) return fail(ctx, TOF_ERR_INVALID, "unknown draw mode");
+    if (mode == TOF_DRAWS_PER_EVALUATION) {
+        const tof_config &c = ctx->cfg;
+        if (c.model != TOF_MODEL_SIMPLE && c.model != TOF_MODEL_ADV)
+            return fail(ctx, TOF_ERR_INVALID, "per-evaluation draws are built for the simple and adv/intermediate models");
+        if (c.model == TOF_MODEL_ADV && c.ode_mode == TOF_ODE_RANGE && (ctx->dm.n_draws > RANGE_TILE || ctx->f32))
+            return fail(ctx, TOF_ERR_INVALID, "per-evaluation draws with TOF_ODE_RANGE need FP64 and n_draws <= " +
+                                              std::to_string(RANGE_TILE) + " (one sorted tile per walker); use TOF_ODE_RK4");
+        if (epoch0 >> 31) return fail(ctx, TOF_ERR_INVALID, "epoch0 must be < 2^31 (the upper half is used by the ensemble entry points)");
+    }
+    ctx->fresh = mode == TOF_DRAWS_PER_EVALUATION;
+    ctx->fresh_seed = seed;
+    ctx->fresh_epoch = epoch0;
+    return TOF_OK;
+}
+
+int tof_generate_draws(tof_ctx *ctx, uint64_t epoch, int64_t walker, int stream, int sorted, double *out, int64_t n) {
+    if (!ctx || !out) return fail(ctx, TOF_ERR_INVALID, "null argument");
+    if (n < 1 || stream < 0 || stream > 1) return fail(ctx, TOF_ERR_INVALID, "bad arguments");
+    if (sorted && (stream != 0 || n > 2 * 512)) return fail(ctx, TOF_ERR_INVALID, "sorted draws: stream 0, n <= 1024");
+    CU(ctx, cudaSetDevice(ctx->cfg.device));
+    DeviceBuf buf;
+    if (int rc = ensure(ctx, buf, (size_t)n * sizeof(double))) return rc;
+    DevRun r{};
+    r.fresh = 1;
+    r.fresh_seed = ctx->fresh_seed;
+    r.fresh_epoch = epoch;
+    r.fresh_walker0 = 0;
+    fresh_draws_kernel<512><<<1, 512, 0, ctx->stream>>>(r, walker, stream, sorted, (int)n, static_cast<double *>(buf.p));
+    cudaError_t e = cudaMemcpyAsync(out, buf.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(buf.p);
+    if (e != cudaSuccess) return fail(ctx, TOF_ERR_CUDA, cudaGetErrorString(e));
     return TOF_OK;
 }
 

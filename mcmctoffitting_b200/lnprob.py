@@ -67,14 +67,20 @@ class TofLnProb:
 
 
 def make_lnprob(config: ModelConfig, observables, draws, device: int = 0, extra_draws=None,
-                sort_draws: bool = False) -> TofLnProb:
+                sort_draws: bool = False, fresh_seed=None) -> TofLnProb:
     """Build the GPU context and return the reference-shaped ``lnprob`` callable.
 
     ``draws``: standard normals, ``[n_draws]`` (one run) or one array per run; for the simple model a
     pair ``(u, z)`` in the order the reference consumes its RNG (uniforms first, simple:62-65).
-    ``extra_draws``: per-run replacement normals for the simultaneous fit's rejection loop."""
+    ``extra_draws``: per-run replacement normals for the simultaneous fit's rejection loop.
+    ``draws=None`` with ``fresh_seed=<int>``: per-evaluation draws generated on the device, the reference's own
+    behaviour (every ``lnlike`` call draws from the global stream: adv:128, simple:62-64); simple and adv models."""
     model = TofModel(config, device)
-    if config.kind == cfgmod.KIND_SIMPLE:
+    if draws is None:
+        if fresh_seed is None:
+            raise ValueError("pass the Monte-Carlo draws, or fresh_seed=<int> for per-evaluation draws")
+        model.set_draw_mode(True, seed=fresh_seed)
+    elif config.kind == cfgmod.KIND_SIMPLE:
         u, z = draws
         model.set_draws(z, 0, 0)
         model.set_draws(u, 0, 1)

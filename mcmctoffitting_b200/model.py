@@ -165,6 +165,20 @@ class TofModel:
         self._check(self._lib.tof_set_draws(self._ctx, run, stream, _dptr(v), v.shape[0]))
 
     # -- evaluation -----------------------------------------------------------------------------------
+    def set_draw_mode(self, per_evaluation: bool, seed: int = 0, epoch0: int = 0) -> None:
+        """``per_evaluation=True``: every evaluation draws its own Monte-Carlo numbers on the device, as the reference
+        does inside every ``lnlike`` call (adv:128; simple:62-64) -- each walker at each step sees its own noise.
+        ``False`` (default): the bound draw set, shared by all walkers and calls (the parity mode).
+        Call ``epoch0`` is the key of the next batch call; it advances by one per call (tof_set_draw_mode)."""
+        self._check(self._lib.tof_set_draw_mode(self._ctx, 1 if per_evaluation else 0, int(seed), int(epoch0)))
+
+    def generate_draws(self, epoch: int, walker: int, n: int, stream: int = 0, sorted: bool = False) -> np.ndarray:
+        """The draws walker ``walker`` of model call ``epoch`` uses in per-evaluation mode (for parity checks)."""
+        out = np.empty(int(n), dtype=np.float64)
+        self._check(self._lib.tof_generate_draws(self._ctx, int(epoch), int(walker), int(stream), 1 if sorted else 0,
+                                                 _dptr(out), int(n)))
+        return out
+
     def _thetas(self, thetas) -> np.ndarray:
         t = _as_f64(thetas)
         if t.ndim == 1:

@@ -1214,3 +1214,108 @@ def test_range_degenerate_spreads(M, O):
         assert np.array_equal(counts[k], om.raw_tof(th, z, xs, density=False)), k
     assert cc[0].sum() > 3000 and np.count_nonzero(cc[0]) == 100      # one cell per row
     assert np.all(lp[:3] == -np.inf) and rel(float(lp[3]), float(om.lnprob(thetas[3], np.ones(2048), z, xs))) <= RTOL
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# per-evaluation draws generated on the device (tof_set_draw_mode): the reference's own behaviour (adv:128, simple:62-64)
+# ----------------------------------------------------------------------------------------------------------------------
+def test_fresh_draws_are_sorted_standard_normals(M):
+    from scipy import stats
+    cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE)
+    with M.TofModel(cfg) as m:
+        m.set_draw_mode(True, seed=99)
+        zs = np.array([m.generate_draws(7, w, 1024, sorted=True) for w in range(48)])
+        zi = np.array([m.generate_draws(7, w, 4096) for w in range(12)])
+        ui = m.generate_draws(7, 3, 4096, stream=1)
+        again = m.generate_draws(7, 5, 1024, sorted=True)
+        other = m.generate_draws(8, 5, 1024, sorted=True)
+    assert np.all(np.diff(zs, axis=1) >= 0)                        # ascending, as the range kernels consume them
+    assert np.array_equal(again, zs[5]) and not np.array_equal(other, zs[5])   # a function of (seed, epoch, walker)
+    assert len({tuple(r[:4]) for r in zs}) == 48                   # every walker has its own stream
+    for sample in (zs.ravel(), zi.ravel()):
+        assert stats.kstest(sample, "norm").pvalue > 1e-3
+        assert abs(sample.mean()) < 5 / np.sqrt(sample.size) and abs(sample.std() - 1) < 0.02
+    # the k-th order statistic of 1024 normals, averaged over walkers, against its expectation (Blom)
+    k = np.array([0, 9, 511, 1014, 1023])
+    blom = stats.norm.ppf((k + 1 - 0.375) / (1024 + 0.25))
+    assert np.all(np.abs(zs[:, k].mean(axis=0) - blom) < 5 * zs[:, k].std(axis=0) / np.sqrt(48) + 0.02)
+    assert stats.kstest(ui, "uniform").pvalue > 1e-3 and ui.min() >= 0.0 and ui.max() < 1.0
+
+
+@pytest.mark.parametrize("ode", ODE_MODES)
+def test_fresh_draw_mode_matches_the_oracle_on_the_generated_draws(M, O, ode):
+    """Per-evaluation draws: every (call, walker) gets its own numbers; fed with exactly those numbers the oracle
+    reproduces each walker's log-likelihood (1e-9).  Narrow and wide walkers (banded kernel + overflow launch)."""
+    mode = M.config.ODE_RANGE if ode == "range" else M.config.ODE_RK4
+    cfg = M.config.sweep(ode_mode=mode)
+    om = O.sweep_model(ode_scheme="exact") if ode == "range" else O.sweep_model()
+    xs = O.DDNXS()
+    obs = np.rint(1e5 * O.sweep_model().model_pdf([1050, 0.08], np.random.RandomState(7).standard_normal(1024)))
+    rs = np.random.RandomState(4)
+    thetas = np.array([1050.0, 0.10]) + np.array([10, 1e-2]) * rs.standard_normal((10, 2))
+    thetas[8], thetas[9] = [1400.0, 0.35], [999.0, 0.1]            # a wide walker; one outside the prior
+    fn = M.make_lnprob(cfg, obs, None, fresh_seed=2024)
+    fn.model.set_draw_mode(True, seed=2024, epoch0=11)
+    first = fn.batch(thetas)                                      # call epoch 11
+    second = fn.batch(thetas)                                     # call epoch 12: new noise for the same positions
+    assert first[9] == -np.inf and second[9] == -np.inf
+    fin = np.isfinite(first[:9]) & np.isfinite(second[:9])
+    assert fin.sum() >= 4 and np.all(first[:9][fin] != second[:9][fin])
+    for epoch, got in ((11, first), (12, second)):
+        for k in range(9):
+            z = fn.model.generate_draws(epoch, k, 1024, sorted=(ode == "range"))
+            want = om.lnprob(thetas[k], obs, z, xs)
+            assert (got[k] == want) or rel(float(got[k]), float(want)) <= RTOL, (epoch, k, got[k], want)
+    assert np.isfinite(first[:8]).sum() >= 6
+    fn.model.close()
+
+
+def test_fresh_draw_mode_simple_model(M, O):
+    n = 20000
+    cfg = M.config.simple(n_draws=n)
+    om = O.SimpleModel()
+    rs = np.random.RandomState(12)
+    obs = om.model_counts([1100.0, -100.0, 50.0], rs.random_sample(200000), rs.standard_normal(200000)).astype(np.float64)
+    thetas = np.array([[1100.0, -100.0, 50.0], [1111.0, -110.0, 40.0], [1090.0, -90.0, 60.0]])
+    fn = M.make_lnprob(cfg, obs, None, fresh_seed=5)
+    fn.model.set_draw_mode(True, seed=5, epoch0=3)
+    got = fn.batch(thetas)
+    for k in range(3):
+        u = fn.model.generate_draws(3, k, n, stream=1)
+        z = fn.model.generate_draws(3, k, n, stream=0)
+        want = om.lnprob(thetas[k], obs, u, z)
+        assert (got[k] == want) or rel(float(got[k]), float(want)) <= RTOL, (k, got[k], want)
+    fn.model.close()
+
+
+def test_fresh_draw_chain_agrees_statistically_with_the_cpu_chain(M, O):
+    """north_star: "chains from a fixed seed must agree statistically".  Config 1 (simple model) with per-evaluation
+    draws on the GPU against the numpy sampler driving the oracle with numpy's own fresh draws per evaluation (what the
+    reference's lnlike does, simple:62-64): posterior mean and width of every parameter agree within Monte-Carlo error."""
+    import torch
+    from mcmctoffitting_b200.ensemble import EnsembleSampler
+    from oracle.stretch_oracle import NumpyBackend
+    n, k, steps, burn = 20000, 32, 200, 60                         # (two CPU chains of this size agree to 0.2 sd)
+    cfg = M.config.simple(n_draws=n)
+    om = O.SimpleModel()
+    rs = np.random.RandomState(31)
+    obs = om.model_counts([1100.0, -100.0, 50.0], rs.random_sample(3000), rs.standard_normal(3000)).astype(np.float64)
+    p0 = np.array([1100.0, -100.0, 50.0]) + np.array([5.0, 5.0, 2.0]) * rs.standard_normal((k, 3))
+    crs = np.random.RandomState(77)
+
+    def cpu_fn(q):
+        return [om.lnprob(list(th), obs, crs.random_sample(n), crs.standard_normal(n)) for th in q]
+
+    cpu = EnsembleSampler(k, 3, backend=NumpyBackend(cpu_fn), seed=9)
+    cpu.run_mcmc(p0, steps)
+    fn = M.make_lnprob(cfg, obs, None, fresh_seed=123)
+    gpu = EnsembleSampler(k, 3, fn, seed=10)
+    gpu.run_mcmc(p0, steps)
+    fn.model.close()
+    a, b = cpu.chain[:, burn:, :].reshape(-1, 3), gpu.chain[:, burn:, :].reshape(-1, 3)
+    acc_g, acc_c = float(np.mean(gpu.acceptance_fraction)), float(np.mean(cpu.acceptance_fraction))
+    assert 0.08 < acc_g < 0.9 and 0.08 < acc_c < 0.9 and abs(acc_g - acc_c) < 0.08, (acc_g, acc_c)
+    for p in range(3):
+        sd = 0.5 * (a[:, p].std() + b[:, p].std())
+        assert abs(a[:, p].mean() - b[:, p].mean()) < 0.5 * sd, (p, a[:, p].mean(), b[:, p].mean(), sd)
+        assert 0.6 < a[:, p].std() / b[:, p].std() < 1.67, (p, a[:, p].std(), b[:, p].std())

@@ -1319,3 +1319,53 @@ def test_fresh_draw_chain_agrees_statistically_with_the_cpu_chain(M, O):
         sd = 0.5 * (a[:, p].std() + b[:, p].std())
         assert abs(a[:, p].mean() - b[:, p].mean()) < 0.5 * sd, (p, a[:, p].mean(), b[:, p].mean(), sd)
         assert 0.6 < a[:, p].std() / b[:, p].std() < 1.67, (p, a[:, p].std(), b[:, p].std())
+
+
+def test_stretch_kernels_sample_a_gaussian_on_the_gpu(M):
+    """a20 (emcee is not in the reference tree: sampler parity is statistical).  The CUDA propose / accept kernels drive an
+    analytic 9-d Gaussian target evaluated with torch on the device (the kernels take the dimension from the context:
+    the simultaneous fit has nine parameters): moments of the chain, and the acceptance fraction against the numpy
+    restatement's on the same target (emcee's stretch move, a = 2)."""
+    import torch
+    from mcmctoffitting_b200.ensemble import CudaBackend, EnsembleSampler
+    from oracle.stretch_oracle import NumpyBackend
+    dim, k, steps, burn = 9, 512, 1500, 500
+    mu = np.array([1.0, -2.0, 0.5, 10.0, -7.0, 0.0, 3.0, 100.0, -0.25])
+    sig = np.array([0.5, 2.0, 1.0, 0.1, 3.0, 1.0, 0.3, 20.0, 0.05])
+
+    class GaussBackend:
+        """propose / accept: the CUDA kernels; lnprob: the analytic target.  (No half_step_packed / ensemble_step
+        attributes, so the sampler takes the three-call path.)"""
+
+        def __init__(self, model):
+            self.cuda = CudaBackend(model)
+            self.device = self.cuda.device
+            self.mu = torch.from_numpy(mu).to(self.device)
+            self.sig = torch.from_numpy(sig).to(self.device)
+
+        def propose(self, s, walker0, comp, a, seed, step, half):       # the sampler hands strided views of its packed state
+            return self.cuda.propose(s.contiguous(), walker0, comp.contiguous(), a, seed, step, half)
+
+        def accept(self, s, lp, walker0, q, new_lp, log_zz, seed, step, half, n_accept):
+            sc, lc = s.contiguous(), lp.contiguous()
+            self.cuda.accept(sc, lc, walker0, q, new_lp, log_zz, seed, step, half, n_accept)
+            s.copy_(sc)
+            lp.copy_(lc)
+
+        def lnprob(self, q):
+            return -0.5 * (((q - self.mu) / self.sig) ** 2).sum(dim=1)
+
+    # any context gives access to the sampler kernels; the model itself is not evaluated
+    with M.TofModel(M.config.simult(n_samples=1000, n_ev_per_loop=1000)) as m:
+        be = GaussBackend(m)
+        p0 = mu + 0.1 * sig * np.random.RandomState(0).standard_normal((k, dim))
+        gpu = EnsembleSampler(k, dim, backend=be, seed=42)
+        gpu.run_mcmc(p0, steps)
+        chain = gpu.chain[:, burn:, :].reshape(-1, dim)
+        af_gpu = float(np.mean(gpu.acceptance_fraction))
+    cpu = EnsembleSampler(k, dim, backend=NumpyBackend(lambda x: -0.5 * np.sum(((x - mu) / sig) ** 2, axis=1)), seed=43)
+    cpu.run_mcmc(p0, 300)
+    af_cpu = float(np.mean(cpu.acceptance_fraction))
+    np.testing.assert_allclose((chain.mean(axis=0) - mu) / sig, 0.0, atol=0.08)
+    np.testing.assert_allclose(chain.std(axis=0) / sig, 1.0, atol=0.08)
+    assert 0.2 < af_gpu < 0.5 and abs(af_gpu - af_cpu) < 0.03, (af_gpu, af_cpu)

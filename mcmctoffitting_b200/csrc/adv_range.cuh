@@ -492,8 +492,8 @@ __device__ __forceinline__ void range_accumulate_tile(const double *u0, int nt, 
 template <int P>
 __device__ __forceinline__ void poly_run4(double &acc, unsigned addr, int r, double off, const double (&a)[P + 1]) {
     static_assert(P == 7, "poly_run4 is written for degree-7 records");
-    // Samples past the lane's run (k >= r) keep t = 0 and add q(0)*0 = 0: the loads are predicated, the arithmetic is
-    // not -- no select after the Horner chains.
+    // Samples past the lane's run (k >= r) get t = (-off) + off = 0 and add q(0)*0 = 0: the loads are predicated (a lane
+    // past its run keeps -off), the arithmetic is not -- no select before or after the Horner chains.
     asm("{\n\t"
         ".reg .pred p0, p1, p2, p3;\n\t"
         ".reg .f64 t0, t1, t2, t3, q0, q1, q2, q3;\n\t"
@@ -501,18 +501,18 @@ __device__ __forceinline__ void poly_run4(double &acc, unsigned addr, int r, dou
         "setp.gt.s32 p1, %2, 1;\n\t"
         "setp.gt.s32 p2, %2, 2;\n\t"
         "setp.gt.s32 p3, %2, 3;\n\t"
-        "mov.f64 t0, 0d0000000000000000;\n\t"
-        "mov.f64 t1, 0d0000000000000000;\n\t"
-        "mov.f64 t2, 0d0000000000000000;\n\t"
-        "mov.f64 t3, 0d0000000000000000;\n\t"
+        "mov.f64 t0, %11;\n\t"
+        "mov.f64 t1, %11;\n\t"
+        "mov.f64 t2, %11;\n\t"
+        "mov.f64 t3, %11;\n\t"
         "@p0 ld.shared.f64 t0, [%1];\n\t"
         "@p1 ld.shared.f64 t1, [%1+8];\n\t"
         "@p2 ld.shared.f64 t2, [%1+16];\n\t"
         "@p3 ld.shared.f64 t3, [%1+24];\n\t"
-        "@p0 add.rn.f64 t0, t0, %3;\n\t"
-        "@p1 add.rn.f64 t1, t1, %3;\n\t"
-        "@p2 add.rn.f64 t2, t2, %3;\n\t"
-        "@p3 add.rn.f64 t3, t3, %3;\n\t"
+        "add.rn.f64 t0, t0, %3;\n\t"
+        "add.rn.f64 t1, t1, %3;\n\t"
+        "add.rn.f64 t2, t2, %3;\n\t"
+        "add.rn.f64 t3, t3, %3;\n\t"
         "fma.rn.f64 q0, %10, t0, %9;\n\t"
         "fma.rn.f64 q1, %10, t1, %9;\n\t"
         "fma.rn.f64 q2, %10, t2, %9;\n\t"
@@ -543,7 +543,7 @@ __device__ __forceinline__ void poly_run4(double &acc, unsigned addr, int r, dou
         "fma.rn.f64 %0, q3, t3, %0;\n\t"
         "}"
         : "+d"(acc)
-        : "r"(addr), "r"(r), "d"(off), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]));
+        : "r"(addr), "r"(r), "d"(off), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(-off));
 }
 
 // Four samples, all of them inside the lane's run: no predicates at all.

@@ -377,7 +377,7 @@ def run_gpu_arm(args):
 
     # ---- burn-in regime: walkers uniform over the adv prior box (adv:81-82), one half-ensemble call ----------------
     prior_box = None
-    if rank == 0 and not f32 and ode == M.config.ODE_RANGE:
+    if rank == 0 and not f32 and ode == M.config.ODE_RANGE and not args.no_extras:
         rs_box = np.random.RandomState(3)
         nb = N_WALKERS // 2 // world
         box = np.column_stack([rs_box.uniform(1000, 2600, nb), rs_box.uniform(0.02, 0.5, nb)])
@@ -416,7 +416,7 @@ def run_gpu_arm(args):
 
     # ---- per-evaluation draws (the reference's own behaviour: every lnlike call draws its own normals, adv:128) ----
     fresh_draws = None
-    if rank == 0 and not f32 and ode == M.config.ODE_RANGE:
+    if rank == 0 and not f32 and ode == M.config.ODE_RANGE and not args.no_extras:
         fnf = M.make_lnprob(cfg, obs, None, device=local_rank, fresh_seed=20260101)
         mf = fnf.model
         nb = N_WALKERS // 2 // world
@@ -556,6 +556,7 @@ def main():
     ap.add_argument("--no-stage-profile", action="store_true", help="skip the per-stage cycle breakdown (tof_set_stage_timing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-sample", action="store_true", help="skip the oracle check of 256 timed-ensemble walkers")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (prior box, per-evaluation draws)")
     ap.add_argument("--cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_baseline:

@@ -132,6 +132,8 @@ __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const
     const long long w = f->idx[it & 1];
     if (w >= n_walkers) return PLANNED_DONE;
     // the next work item is fetched now (a global atomic: ~1 us) and read after the next iteration's first barrier
+    // (measured: dealing the first 85 % of the walkers out round-robin, without the atomic and with the next parameter
+    // vector copied in by cp.async, is 1.7 % slower -- the CTAs drift into lockstep phases)
     if (tid == 0) f->idx[(it + 1) & 1] = (long long)atomicAdd(out.work, 1ull);
     const double e0 = theta[w * m.ndim + 0];
     const double sigma0 = theta[w * m.ndim + 1];

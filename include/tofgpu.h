@@ -180,14 +180,16 @@ int tof_set_draws(tof_ctx *ctx, int run, int stream, const double *values, int64
  *     2^31 + 2*step + half inside tof_ensemble_step / tof_ensemble_half_step, so chains do not depend on the sharding.  Normals
  *     are inverse-CDF transforms of open uniforms; the range kernels get each walker's normals already sorted (order
  *     statistics from exponential spacings: no sort).  tof_set_draws is not needed in this mode.
- * Built for TOF_MODEL_SIMPLE and TOF_MODEL_ADV (TOF_ODE_RK4: any n_draws; TOF_ODE_RANGE: FP64, n_draws <= 1024). */
+ * Built for every model; adv/intermediate with TOF_ODE_RANGE needs FP64 and n_draws <= 1024 (one sorted tile per
+ * walker), the simultaneous fit needs TOF_ODE_RK4. */
 typedef enum tof_draw_mode { TOF_DRAWS_BOUND = 0, TOF_DRAWS_PER_EVALUATION = 1 } tof_draw_mode;
 int tof_set_draw_mode(tof_ctx *ctx, int mode, uint64_t seed, uint64_t epoch0);
 
-/* The draws walker `walker` of model call `epoch` uses in TOF_DRAWS_PER_EVALUATION mode (HOST buffer out[n]): stream 0
- * normals (sorted != 0: ascending, as the range kernels consume them; n <= 1024), stream 1 the simple model's uniforms.
- * For parity checks: feed them to a CPU evaluation of the same walker. */
-int tof_generate_draws(tof_ctx *ctx, uint64_t epoch, int64_t walker, int stream, int sorted, double *out, int64_t n);
+/* The draws walker `walker` of model call `epoch` uses for run `run` in TOF_DRAWS_PER_EVALUATION mode (HOST buffer
+ * out[n]): stream 0 the model's normals (sorted != 0: ascending, as the range kernels consume them; n <= 1024), stream 1
+ * uniforms (the simple model's x positions, simple:62; the oneBD model's Poisson background, csi_oneBD.py:521), stream 3
+ * the simultaneous fit's replacement normals (simultFit.py:245-252).  For parity checks: feed them to a CPU evaluation. */
+int tof_generate_draws(tof_ctx *ctx, uint64_t epoch, int64_t walker, int run, int stream, int sorted, double *out, int64_t n);
 
 /* lnprob for n walkers: theta[n][ndim] row-major -> out[n].  HOST buffers; the call copies in,
  * launches, copies out and synchronises.  Replaces n calls of lnprob (adv:191-199, simple:112-120,
@@ -207,7 +209,7 @@ int tof_cell_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run,
 
 /* Unweighted (x, E) histogram of the stopped deuteron energies of the LAST loop, [n][x_bins][e_bins]: the
  * `eD_atEachX` rows that utilities/ppcTools.py:140-157 collects for posterior-predictive checks (its leading row
- * of zeros omitted).  Built for TOF_MODEL_SIMULT with TOF_ODE_RK4 (the model ppcTools re-runs) and for
+ * of zeros omitted).  Built for TOF_MODEL_SIMULT (the model ppcTools re-runs; RK4 energies in either ode_mode) and for
  * TOF_MODEL_ONEBD (utilities/ppcTools_oneBD.py:214, 223-224). */
 int tof_deuteron_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run, int64_t *counts);
 

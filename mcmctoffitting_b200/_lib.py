@@ -69,7 +69,7 @@ SIGNATURES = {
     "tof_set_observables": (C.c_int, [_vp, C.c_int, _dp, C.c_int]),
     "tof_set_draws": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int64]),
     "tof_set_draw_mode": (C.c_int, [_vp, C.c_int, C.c_uint64, C.c_uint64]),
-    "tof_generate_draws": (C.c_int, [_vp, C.c_uint64, C.c_int64, C.c_int, C.c_int, _dp, C.c_int64]),
+    "tof_generate_draws": (C.c_int, [_vp, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, _dp, C.c_int64]),
     "tof_lnprob_batch": (C.c_int, [_vp, _dp, C.c_int64, _dp]),
     "tof_lnprob_batch_device": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),
     "tof_model_batch": (C.c_int, [_vp, _dp, C.c_int64, C.c_int, C.c_int, _dp]),

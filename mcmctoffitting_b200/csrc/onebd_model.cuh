@@ -29,8 +29,12 @@ __device__ inline double np_loggam(double x) {
     return gl;
 }
 
-// Returns false when the uniform stream runs out.
-__device__ inline bool np_poisson(double lam, const double *u, long long n_u, long long &pos, double &out) {
+// Returns false when the uniform stream runs out.  With per-evaluation draws (run.fresh) the uniforms are this (call,
+// walker, run)'s own Philox stream and never run out.
+__device__ inline bool np_poisson(double lam, const double *u_bound, long long n_bound, long long &pos, double &out, const DevRun &run,
+                                  long long walker, int run_idx) {
+    const long long n_u = run.fresh ? (1ll << 62) : n_bound;
+    auto u = [&](long long p) { return run.fresh ? fresh_uniform(run, walker, run_idx, p) : u_bound[p]; };
     if (lam == 0.0) {
         out = 0.0;
         return true;
@@ -41,7 +45,7 @@ __device__ inline bool np_poisson(double lam, const double *u, long long n_u, lo
         const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2);
         while (true) {
             if (pos + 2 > n_u) return false;
-            const double U = u[pos] - 0.5, V = u[pos + 1];
+            const double U = u(pos) - 0.5, V = u(pos + 1);
             pos += 2;
             const double us = 0.5 - fabs(U);
             const double k = floor((2 * a / us + b) * U + lam + 0.43);
@@ -57,7 +61,7 @@ __device__ inline bool np_poisson(double lam, const double *u, long long n_u, lo
     double X = 0.0, prod = 1.0;
     while (true) {
         if (pos + 1 > n_u) return false;
-        prod *= u[pos++];
+        prod *= u(pos++);
         if (prod > enlam) X += 1.0; else break;
     }
     out = X;
@@ -141,7 +145,8 @@ __global__ void __launch_bounds__(NT) onebd_run_kernel(const DevModel m, const D
     const double inv_step = 1.0 / m.stop_step;
     double part = 0.0;
     for (long long d = tid; d < m.n_ev_per_loop; d += NT) {
-        const double E0 = __dsub_rn(m.beam_energy, __dadd_rn(__dmul_rn(exp(__dmul_rn(sshape, __ldg(z + d))), scale), eLoss));
+        const double zd = run.fresh ? fresh_normal(run, w, r, (m.n_loops - 1) * m.n_ev_per_loop + d) : __ldg(z + d);
+        const double E0 = __dsub_rn(m.beam_energy, __dadd_rn(__dmul_rn(exp(__dmul_rn(sshape, zd)), scale), eLoss));
         part += E0;
         // betheApprox.evalStopped (ionStopping.py:132-136): FITPACK clamps the argument to the grid
         double a = E0 < m.stop_lo ? m.stop_lo : (E0 > stop_hi ? stop_hi : E0);
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(NT) onebd_run_kernel(const DevModel m, const D
         long long pos = 0;
         for (int t = 0; t < T; ++t) {
             double k = 0.0;
-            if (!np_poisson(bg_level, run.z1, run.n_z1, pos, k)) {
+            if (!np_poisson(bg_level, run.z1, run.n_z1, pos, k, run, w, r)) {
                 bg_ok = false;
                 k = CUDART_NAN;
             }

@@ -164,13 +164,15 @@ __global__ void __launch_bounds__(NT) simult_run_kernel(const DevModel m, const 
     bool exhausted = false;
     for (long long loop = 0; loop < m.n_loops; ++loop) {
         const double *src = run.z + loop * m.n_ev_per_loop;
+        long long fresh_base = loop * m.n_ev_per_loop;       // per-evaluation draws (tof_set_draw_mode): index into the stream
+        int fresh_stream = 0;
         long long count = m.n_ev_per_loop;
         double loop_sum = 0.0;
         while (count > 0) {
             long long nbad = 0;
             double part = 0.0;
             for (long long d = tid; d < count; d += NT) {
-                const double z = __ldg(src + d);
+                const double z = run.fresh ? fresh_normal(run, w, r, fresh_base + d, fresh_stream) : __ldg(src + d);
                 double E = __dsub_rn(beamE, __dadd_rn(__dmul_rn(exp(__dmul_rn(sshape, z)), scale), eLoss));
                 if (E <= 0.0) {
                     ++nbad;
@@ -197,11 +199,13 @@ __global__ void __launch_bounds__(NT) simult_run_kernel(const DevModel m, const 
             const long long nbad_tot = block_sum<long long>(nbad, reinterpret_cast<long long *>(scratch));
             loop_sum += block_sum<double>(part, scratch);
             if (nbad_tot == 0) break;
-            if (extra_pos + nbad_tot > run.n_z1) {          // replacement stream exhausted
+            if (!run.fresh && extra_pos + nbad_tot > run.n_z1) {   // replacement stream exhausted
                 exhausted = true;
                 break;
             }
             src = run.z1 + extra_pos;
+            fresh_base = extra_pos;
+            fresh_stream = 3;
             extra_pos += nbad_tot;
             count = nbad_tot;
         }

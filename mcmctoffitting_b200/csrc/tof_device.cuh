@@ -233,9 +233,10 @@ __device__ __forceinline__ Philox fresh_philox(const DevRun &run, long long walk
 __device__ __forceinline__ double philox_open01(uint32_t lo, uint32_t hi) {
     return ((double)((((uint64_t)hi << 32) | lo) >> 12) + 0.5) * (1.0 / 4503599627370496.0);
 }
-// iid standard normal number d of this (call, walker, run): inverse-CDF of one open uniform
-__device__ __forceinline__ double fresh_normal(const DevRun &run, long long walker, int run_idx, long long d) {
-    const Philox ph = fresh_philox(run, walker, run_idx, 0, (unsigned long long)d >> 1);
+// iid standard normal number d of this (call, walker, run): inverse-CDF of one open uniform.  stream 0: the model's
+// draws (adv:128, simultFit.py:244, csi_oneBD.py:438); stream 3: the simultaneous fit's replacement draws (245-252)
+__device__ __forceinline__ double fresh_normal(const DevRun &run, long long walker, int run_idx, long long d, int stream = 0) {
+    const Philox ph = fresh_philox(run, walker, run_idx, stream, (unsigned long long)d >> 1);
     return normcdfinv((d & 1) ? philox_open01(ph.c[2], ph.c[3]) : philox_open01(ph.c[0], ph.c[1]));
 }
 // iid uniform [0, 1) number d (stream 1 of the simple model, simple:62)

@@ -57,6 +57,7 @@ struct tof_ctx {
     RangeLayout lay_zr{};
     RangeLayout lay_full{}, lay_band{};   // shared-memory layouts of the two launches (host-computed offsets)
     size_t simult_smem = 0, onebd_smem = 0;
+    size_t simult_rk4_smem = 0;   // range-mode contexts: the RK4 kernel still serves the unweighted deuteron histograms
     int max_smem_optin = 0;
     // per-evaluation draws (tof_set_draw_mode): epoch of the next model call, key of the call being launched
     bool fresh = false;
@@ -311,7 +312,11 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
         ctx->stats.kernel_launches += 2;
     } else if (c.model == TOF_MODEL_ONEBD) {
         DevRunSet rs;
-        for (int r = 0; r < TOF_MAX_RUNS; ++r) rs.r[r] = ctx->runs[r];
+        for (int r = 0; r < TOF_MAX_RUNS; ++r) {
+            rs.r[r] = ctx->runs[r];
+            rs.r[r].fresh = run0.fresh; rs.r[r].fresh_seed = run0.fresh_seed; rs.r[r].fresh_epoch = run0.fresh_epoch;
+            rs.r[r].fresh_walker0 = run0.fresh_walker0;
+        }
         const bool debug = out.spectra != nullptr || out.cells != nullptr;
         if (debug) {
             onebd_run_kernel<256><<<(unsigned)n, 256, ctx->onebd_smem, st>>>(ctx->dm, rs, d_theta, n, out, run);
@@ -327,12 +332,18 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
         }
     } else if (c.model == TOF_MODEL_SIMULT) {
         DevRunSet rs;
-        for (int r = 0; r < TOF_MAX_RUNS; ++r) rs.r[r] = ctx->runs[r];
+        for (int r = 0; r < TOF_MAX_RUNS; ++r) {
+            rs.r[r] = ctx->runs[r];
+            rs.r[r].fresh = run0.fresh; rs.r[r].fresh_seed = run0.fresh_seed; rs.r[r].fresh_epoch = run0.fresh_epoch;
+            rs.r[r].fresh_walker0 = run0.fresh_walker0;
+        }
         const bool debug = out.spectra != nullptr || out.cells != nullptr;
         const bool rng = c.ode_mode == TOF_ODE_RANGE;
         if (debug) {
-            if (rng) simult_range_kernel<256, 7><<<(unsigned)n, 256, ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, out, run);
-            else simult_run_kernel<256><<<(unsigned)n, 256, ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, out, run);
+            // eD_atEachX (ppcTools.py:151-157) is an unweighted histogram of stopped energies: the RK4 kernel produces it in
+            // either mode (the range kernel never forms per-sample energies)
+            if (rng && !out.unweighted) simult_range_kernel<256, 7><<<(unsigned)n, 256, ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, out, run);
+            else simult_run_kernel<256><<<(unsigned)n, 256, rng ? ctx->simult_rk4_smem : ctx->simult_smem, st>>>(ctx->dm, rs, d_theta, n, out, run);
             ctx->stats.kernel_launches += 1;
         } else {
             int rc = ensure(ctx, ctx->d_partial, (size_t)n * c.n_runs * sizeof(double));
@@ -371,14 +382,15 @@ void next_call_key(tof_ctx *ctx) {
 }
 
 template <int NT>
-__global__ void fresh_draws_kernel(DevRun run, long long walker, int stream, int sorted, int n, double *out) {
+__global__ void fresh_draws_kernel(DevRun run, long long walker, int run_idx, int stream, int sorted, int n, double *out) {
     __shared__ double zs[2 * NT];
     __shared__ double scratch[NT / 32 + 2];
     if (sorted) {
-        fresh_sorted_normals<NT>(zs, n, run, walker, 0, scratch);
+        fresh_sorted_normals<NT>(zs, n, run, walker, run_idx, scratch);
         for (int d = threadIdx.x; d < n; d += NT) out[d] = zs[d];
     } else {
-        for (int d = threadIdx.x; d < n; d += NT) out[d] = stream == 1 ? fresh_uniform(run, walker, 0, d) : fresh_normal(run, walker, 0, d);
+        for (int d = threadIdx.x; d < n; d += NT)
+            out[d] = stream == 1 ? fresh_uniform(run, walker, run_idx, d) : fresh_normal(run, walker, run_idx, d, stream);
     }
 }
 
@@ -877,6 +889,11 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         if (use_range) {
             CUC(cudaFuncSetAttribute(simult_range_kernel<256, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->simult_smem));
             CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simult_range_kernel<256, 7>, 256, ctx->simult_smem));
+            ctx->simult_rk4_smem = simult_smem_bytes(256, cfg->x_bins, cfg->e_bins, tmax, cfg->n_xs, cfg->n_taps, m.xs_lut_n);
+            if ((int)ctx->simult_rk4_smem <= ctx->max_smem_optin)
+                CUC(cudaFuncSetAttribute(simult_run_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->simult_rk4_smem));
+            else
+                ctx->simult_rk4_smem = 0;
         } else {
             CUC(cudaFuncSetAttribute(simult_run_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->simult_smem));
             CUC(cudaFuncSetAttribute(simult_run_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1074,9 +1091,9 @@ int tof_cell_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run,
 int tof_deuteron_counts_batch(tof_ctx *ctx, const double *theta, int64_t n, int run, int64_t *counts) {
     if (!ctx || (n > 0 && (!theta || !counts))) return fail(ctx, TOF_ERR_INVALID, "null argument");
     if (int rc = check_run(ctx, run)) return rc;
-    const bool simult_rk4 = ctx->cfg.model == TOF_MODEL_SIMULT && ctx->cfg.ode_mode == TOF_ODE_RK4;
-    if (!simult_rk4 && ctx->cfg.model != TOF_MODEL_ONEBD)
-        return fail(ctx, TOF_ERR_INVALID, "deuteron counts are built for TOF_MODEL_SIMULT with TOF_ODE_RK4 and for TOF_MODEL_ONEBD");
+    const bool simult_ok = ctx->cfg.model == TOF_MODEL_SIMULT && (ctx->cfg.ode_mode == TOF_ODE_RK4 || ctx->simult_rk4_smem > 0);
+    if (!simult_ok && ctx->cfg.model != TOF_MODEL_ONEBD)
+        return fail(ctx, TOF_ERR_INVALID, "deuteron counts are built for TOF_MODEL_SIMULT and TOF_MODEL_ONEBD");
     if (n <= 0) return n == 0 ? TOF_OK : fail(ctx, TOF_ERR_INVALID, "n < 0");
     if (int rc = ready(ctx, false)) return rc;
     CU(ctx, cudaSetDevice(ctx->cfg.device));
@@ -1194,8 +1211,9 @@ int tof_set_draw_mode(tof_ctx *ctx, int mode, uint64_t seed, uint64_t epoch0) {
     if (mode != TOF_DRAWS_BOUND && mode != TOF_DRAWS_PER_EVALUATION) return fail(ctx, TOF_ERR_INVALID, "unknown draw mode");
     if (mode == TOF_DRAWS_PER_EVALUATION) {
         const tof_config &c = ctx->cfg;
-        if (c.model != TOF_MODEL_SIMPLE && c.model != TOF_MODEL_ADV)
-            return fail(ctx, TOF_ERR_INVALID, "per-evaluation draws are built for the simple and adv/intermediate models");
+        if (c.model == TOF_MODEL_SIMULT && c.ode_mode == TOF_ODE_RANGE)
+            return fail(ctx, TOF_ERR_INVALID, "per-evaluation draws for the simultaneous fit need TOF_ODE_RK4 (the range kernel "
+                                              "wants every loop's draws sorted)");
         if (c.model == TOF_MODEL_ADV && c.ode_mode == TOF_ODE_RANGE && (ctx->dm.n_draws > RANGE_TILE || ctx->f32))
             return fail(ctx, TOF_ERR_INVALID, "per-evaluation draws with TOF_ODE_RANGE need FP64 and n_draws <= " +
                                               std::to_string(RANGE_TILE) + " (one sorted tile per walker); use TOF_ODE_RK4");
@@ -1207,9 +1225,10 @@ int tof_set_draw_mode(tof_ctx *ctx, int mode, uint64_t seed, uint64_t epoch0) {
     return TOF_OK;
 }
 
-int tof_generate_draws(tof_ctx *ctx, uint64_t epoch, int64_t walker, int stream, int sorted, double *out, int64_t n) {
+int tof_generate_draws(tof_ctx *ctx, uint64_t epoch, int64_t walker, int run, int stream, int sorted, double *out, int64_t n) {
     if (!ctx || !out) return fail(ctx, TOF_ERR_INVALID, "null argument");
-    if (n < 1 || stream < 0 || stream > 1) return fail(ctx, TOF_ERR_INVALID, "bad arguments");
+    if (n < 1 || (stream != 0 && stream != 1 && stream != 3) || run < 0 || run >= TOF_MAX_RUNS)
+        return fail(ctx, TOF_ERR_INVALID, "bad arguments");
     if (sorted && (stream != 0 || n > 2 * 512)) return fail(ctx, TOF_ERR_INVALID, "sorted draws: stream 0, n <= 1024");
     CU(ctx, cudaSetDevice(ctx->cfg.device));
     DeviceBuf buf;
@@ -1219,7 +1238,7 @@ int tof_generate_draws(tof_ctx *ctx, uint64_t epoch, int64_t walker, int stream,
     r.fresh_seed = ctx->fresh_seed;
     r.fresh_epoch = epoch;
     r.fresh_walker0 = 0;
-    fresh_draws_kernel<512><<<1, 512, 0, ctx->stream>>>(r, walker, stream, sorted, (int)n, static_cast<double *>(buf.p));
+    fresh_draws_kernel<512><<<1, 512, 0, ctx->stream>>>(r, walker, run, stream, sorted, (int)n, static_cast<double *>(buf.p));
     cudaError_t e = cudaMemcpyAsync(out, buf.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(buf.p);

@@ -172,10 +172,11 @@ class TofModel:
         Call ``epoch0`` is the key of the next batch call; it advances by one per call (tof_set_draw_mode)."""
         self._check(self._lib.tof_set_draw_mode(self._ctx, 1 if per_evaluation else 0, int(seed), int(epoch0)))
 
-    def generate_draws(self, epoch: int, walker: int, n: int, stream: int = 0, sorted: bool = False) -> np.ndarray:
-        """The draws walker ``walker`` of model call ``epoch`` uses in per-evaluation mode (for parity checks)."""
+    def generate_draws(self, epoch: int, walker: int, n: int, stream: int = 0, sorted: bool = False, run: int = 0) -> np.ndarray:
+        """The draws walker ``walker`` of model call ``epoch`` uses for ``run`` in per-evaluation mode (for parity checks):
+        stream 0 normals, 1 uniforms, 3 the simultaneous fit's replacement normals."""
         out = np.empty(int(n), dtype=np.float64)
-        self._check(self._lib.tof_generate_draws(self._ctx, int(epoch), int(walker), int(stream), 1 if sorted else 0,
+        self._check(self._lib.tof_generate_draws(self._ctx, int(epoch), int(walker), int(run), int(stream), 1 if sorted else 0,
                                                  _dptr(out), int(n)))
         return out
 

@@ -738,6 +738,11 @@ def test_ppc_reference_goldens(M, O, golden):
         assert np.array_equal(fn.model.deuteron_counts(theta, run=r)[0], np.array(c["eD_atEachX"]))
         np.testing.assert_allclose(fn.model.model_batch(theta, run=r, stage="spread")[0], parse_floats(c["tof"]), rtol=1e-11)
         fn.model.close()
+        # a range-mode context serves eD_atEachX too (the RK4 kernel forms the per-sample energies in either mode)
+        cfg_r = M.config.simult(x_bins=g["x_bins"], e_bins=g["e_bins"], ode_mode=M.config.ODE_RANGE, **kw)
+        fn = M.make_lnprob(cfg_r, [np.ones(t) for t in cfg_r.tof_bins], z_main, extra_draws=z_extra)
+        assert np.array_equal(fn.model.deuteron_counts(theta, run=r)[0], np.array(c["eD_atEachX"]))
+        fn.model.close()
 
 
 def test_simult_reference_goldens(M, O, golden, pf):
@@ -1369,3 +1374,54 @@ def test_stretch_kernels_sample_a_gaussian_on_the_gpu(M):
     np.testing.assert_allclose((chain.mean(axis=0) - mu) / sig, 0.0, atol=0.08)
     np.testing.assert_allclose(chain.std(axis=0) / sig, 1.0, atol=0.08)
     assert 0.2 < af_gpu < 0.5 and abs(af_gpu - af_cpu) < 0.03, (af_gpu, af_cpu)
+
+
+def test_fresh_draw_mode_simult_and_onebd(M, O):
+    """Per-evaluation draws for the simultaneous fit (RK4; lognormal losses + its own replacement stream for the E0 <= 0
+    redraws, simultFit.py:243-252) and the oneBD model (normals of the last loop + the uniforms numpy's Poisson sampler
+    consumes, csi_oneBD.py:438, 521): the oracle fed with each evaluation's generated numbers reproduces it (1e-9)."""
+    xs = O.DDNXS()
+    # ---- simultaneous fit -------------------------------------------------------------------------------------------
+    cfg = M.config.simult(n_samples=3000, n_ev_per_loop=1000)
+    om = O.SimultModel(n_samples=3000, n_ev_per_loop=1000)
+    z_main, z_extra = _simult_tables(O, cfg, 5)
+    theta_star = [1878.4, 850, 170, 0.5, 3e4, 2e4, 2e4, 4e4, 4e4]
+    td = O.TableDraws(z_main, z_extra)
+    obs = [np.rint(om.model(theta_star[:4] + [theta_star[4 + r]], r, td, xs)) for r in range(5)]
+    thetas = np.array([theta_star, [1825.0, 1000, 300, 1.2, 3e4, 2e4, 2e4, 4e4, 4e4]])   # the second one redraws ~20 %
+    fn = M.make_lnprob(cfg, obs, None, fresh_seed=8)
+    fn.model.set_draw_mode(True, seed=8, epoch0=2)
+    got = fn.batch(thetas)
+    again = fn.batch(thetas)
+    assert np.all(got != again)
+    for epoch, vals in ((2, got), (3, again)):
+        for k in range(2):
+            zm = [fn.model.generate_draws(epoch, k, cfg.n_draws, run=r).reshape(cfg.n_loops, cfg.n_ev_per_loop) for r in range(5)]
+            ze = [fn.model.generate_draws(epoch, k, 4000, run=r, stream=3) for r in range(5)]
+            want = om.lnprob(list(thetas[k]), obs, O.TableDraws(zm, ze), xs)
+            assert rel(float(vals[k]), float(want)) <= RTOL, (epoch, k, vals[k], want)
+    fn.model.close()
+    with pytest.raises(M.TofError):                          # the range kernel wants sorted loops: refused loudly
+        M.make_lnprob(M.config.simult(n_samples=3000, n_ev_per_loop=1000, ode_mode=M.config.ODE_RANGE), obs, None, fresh_seed=8)
+    # ---- oneBD ----------------------------------------------------------------------------------------------------------
+    n_ev, n_samp = 2000, 6000
+    cfg = M.config.onebd(n_samples=n_samp, n_ev_per_loop=n_ev)
+    om = O.OneBDModel(n_samples=n_samp, n_ev_per_loop=n_ev)
+    tab = om.stop_table()
+    rs = np.random.RandomState(21)
+    theta_star = [900.0, 170.0, 0.5, 3e4, 2e4, 4e4, 5.0, 12.0, 0.0]
+    obs = []
+    for r in range(3):
+        p = om.run_params(theta_star, r)
+        ev, _ = om.model(p, r, rs.standard_normal(n_ev), rs.poisson(p[4], 25), xs, tab)
+        obs.append(np.rint(ev))
+    thetas = np.array([theta_star, [1200.0, 300.0, 0.8, 5e4, 1e4, 2e4, 0.5, 30.0, 250.0]])
+    fn = M.make_lnprob(cfg, obs, None, fresh_seed=9)
+    fn.model.set_draw_mode(True, seed=9, epoch0=40)
+    got = fn.batch(thetas)
+    for k in range(2):
+        z_last = [fn.model.generate_draws(40, k, cfg.n_draws, run=r)[-n_ev:] for r in range(3)]
+        u = [fn.model.generate_draws(40, k, 4000, run=r, stream=1) for r in range(3)]
+        want = _onebd_oracle_lnprob(O, om, thetas[k], obs, z_last, u, xs, tab)
+        assert rel(float(got[k]), float(want)) <= RTOL, (k, got[k], want)
+    fn.model.close()

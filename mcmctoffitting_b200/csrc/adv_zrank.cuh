@@ -294,29 +294,22 @@ __device__ __forceinline__ double zr_exec(const DevModel *mp, const DevRun *rp, 
     const unsigned smem_s32 = (unsigned)__cvta_generic_to_shared(smem_raw);
     const unsigned u0_s32 = smem_s32 + op->lay.pa;
     const unsigned rec_s32 = smem_s32 + op->lay.rec;
-    // one (row, interval) cell: find its run of draws (hints th0 / th1 -> lookup -> short forward walks), sum the weight
-    // polynomial over the run, write the cell, accumulate the normalisation sum
-    auto cell = [&](int j, bool active, float th0, float th1, double delta, unsigned hrow_s32, double *hrow_g) {
-        int d0 = 0, n = 0;
-        double left = 0.0;
-        if (active) {
-            const float ha = fv->hint_a, hb = fv->hint_b;
-            const unsigned short *zlut = fv->zlut;
-            int c0 = __float2int_rz(fmaf(th0, ha, hb)), c1 = __float2int_rz(fmaf(th1, ha, hb));
-            c0 = c0 < 0 ? 0 : (c0 > ZR_LUT ? ZR_LUT : c0);
-            c1 = c1 < 0 ? 0 : (c1 > ZR_LUT ? ZR_LUT : c1);
-            d0 = __ldg(zlut + c0);
-            int d1 = __ldg(zlut + c1);
-            left = j ? brk[j - 1] : 0.0;                   // brk[j] = break that ends interval j
-            const double right = (j == M - 1) ? fv->umax_next : brk[j];   // last interval is closed: v > u_max <=> v >= next(u_max)
-            // the hints are low by construction: forward walks with the membership compare of the other range kernels
-            // (measured: loading three candidates at once instead, branch-free, is 1.5 % slower -- more instructions)
-            while (d0 < nt && !(__dadd_rn(u0[d0], delta) >= left)) ++d0;
-            d1 = d1 < d0 ? d0 : d1;
-            while (d1 < nt && !(__dadd_rn(u0[d1], delta) >= right)) ++d1;
-            n = d1 - d0;
-            TOF_CHECK(d0 >= 0 && d1 <= nt && n >= 0 && (WIDE || j - fv->jbase >= 0));
-        }
+    // ---- finding a cell's run of draws: hint -> lookup -> short forward walk -------------------------------------
+    // lower edge of interval j in u (j == M: the upper end of the last, closed, interval: v > u_max <=> v >= next(u_max))
+    auto edge_of = [&](int j) -> double { return j == 0 ? 0.0 : (j >= M ? fv->umax_next : brk[j - 1]); };
+    auto hint = [&](float th) -> int {
+        int c = __float2int_rz(fmaf(th, fv->hint_a, fv->hint_b));
+        c = c < 0 ? 0 : (c > ZR_LUT ? ZR_LUT : c);
+        return (int)__ldg(fv->zlut + c);
+    };
+    // the hints are low by construction: forward walks with the membership compare of the other range kernels
+    // (measured: loading three candidates at once instead, branch-free, is 1.5 % slower -- more instructions)
+    auto walk = [&](int d, double edge, double delta) -> int {
+        while (d < nt && !(__dadd_rn(u0[d], delta) >= edge)) ++d;
+        return d;
+    };
+    // ---- summing a cell: the weight polynomial over draws [d0, d0 + n), the cell store, the normalisation sum -------
+    auto sum_cell = [&](int j, bool active, int d0, int n, double left, double delta, unsigned hrow_s32, double *hrow_g) {
         const int nmax = __reduce_max_sync(FULL, n);
         if (nmax == 0) {                                   // uniform
             if (active) {
@@ -377,39 +370,114 @@ __device__ __forceinline__ double zr_exec(const DevModel *mp, const DevRun *rp, 
             part += __dmul_rn(__dmul_rn(val, fv->de), fv->dx);     // adv:143
         }
     };
-    // a lane bound to one row: visits j = j_first, j_first + j_step, ... (n_vis of them); the row's window of cells is
-    // [jw_lo, jw_hi] (its E-window, the walker's interval band, and `ok`)
-    auto run_row = [&](int row, bool ok, int j_first, int j_step, int n_vis) {
+    // one (row, interval) cell per lane and visit
+    auto cell = [&](int j, bool active, float th0, float th1, double delta, unsigned hrow_s32, double *hrow_g) {
+        int d0 = 0, n = 0;
+        double left = 0.0;
+        if (active) {
+            left = edge_of(j);
+            d0 = walk(hint(th0), left, delta);
+            const int h1 = hint(th1);
+            const int d1 = walk(h1 < d0 ? d0 : h1, edge_of(j + 1), delta);
+            n = d1 - d0;
+            TOF_CHECK(d0 >= 0 && d1 <= nt && n >= 0 && (WIDE || j - fv->jbase >= 0));
+        }
+        sum_cell(j, active, d0, n, left, delta, hrow_s32, hrow_g);
+    };
+    // a lane bound to one row: the row's window of cells [jw_lo, jw_lo + jw_n) (its E-window, the walker's interval band,
+    // and `ok`), its addresses
+    struct RowState {
+        double delta;
+        int jw_lo;
+        unsigned jw_n, hrow_s32;
+        double *hrow_g;
+        const float *th_row;
+    };
+    auto row_state = [&](int row, bool ok) {
+        RowState r;
         const int row_lo = hlo[row];
-        const double delta = sdelta[row];
-        int jw_lo = row_lo > j_lo_all ? row_lo : j_lo_all;
+        r.delta = sdelta[row];
+        r.jw_lo = row_lo > j_lo_all ? row_lo : j_lo_all;
         int jw_hi = row_lo + hstride - 1;
         jw_hi = jw_hi < j_hi_all ? jw_hi : j_hi_all;
-        if (!ok) jw_hi = jw_lo - 1;
-        const unsigned jw_n = (unsigned)(jw_hi - jw_lo + 1);        // 0 when the window is empty
-        const unsigned hrow_s32 = smem_s32 + (unsigned)(row * hstride - row_lo) * 8u;
-        double *hrow_g = WIDE ? Hglobal + (size_t)row * hstride - row_lo : nullptr;
-        const float *th_row = theta_t + row;
+        if (!ok) jw_hi = r.jw_lo - 1;
+        r.jw_n = (unsigned)(jw_hi - r.jw_lo + 1);          // 0 when the window is empty
+        r.hrow_s32 = smem_s32 + (unsigned)(row * hstride - row_lo) * 8u;
+        r.hrow_g = WIDE ? Hglobal + (size_t)row * hstride - row_lo : nullptr;
+        r.th_row = theta_t + row;
+        return r;
+    };
+    // visits j = j_first, j_first + j_step, ... (n_vis of them), one cell each
+    auto run_row = [&](int row, bool ok, int j_first, int j_step, int n_vis) {
+        const RowState r = row_state(row, ok);
         int j = j_first;
-        bool act = (unsigned)(j - jw_lo) < jw_n && n_vis > 0;
+        bool act = (unsigned)(j - r.jw_lo) < r.jw_n && n_vis > 0;
         float th0 = 0.0f, th1 = 0.0f;
         if (act) {
-            th0 = ldg_stream_f32(th_row + (size_t)j * tstride);
-            th1 = ldg_stream_f32(th_row + (size_t)(j + 1) * tstride);
+            th0 = ldg_stream_f32(r.th_row + (size_t)j * tstride);
+            th1 = ldg_stream_f32(r.th_row + (size_t)(j + 1) * tstride);
         }
         for (int v = 0; v < n_vis; ++v) {
             const int jn = j + j_step;
-            const bool actn = (unsigned)(jn - jw_lo) < jw_n && v + 1 < n_vis;
+            const bool actn = (unsigned)(jn - r.jw_lo) < r.jw_n && v + 1 < n_vis;
             float th0n = 0.0f, th1n = 0.0f;
             if (actn) {                                    // next visit's hints: in flight while this cell is summed
-                th0n = ldg_stream_f32(th_row + (size_t)jn * tstride);
-                th1n = ldg_stream_f32(th_row + (size_t)(jn + 1) * tstride);
+                th0n = ldg_stream_f32(r.th_row + (size_t)jn * tstride);
+                th1n = ldg_stream_f32(r.th_row + (size_t)(jn + 1) * tstride);
             }
-            cell(j, act, th0, th1, delta, hrow_s32, hrow_g);
+            cell(j, act, th0, th1, r.delta, r.hrow_s32, r.hrow_g);
             j = jn;
             act = actn;
             th0 = th0n;
             th1 = th1n;
+        }
+    };
+    // visits of PAIRS of adjacent cells (j, j + 1), j = j_first, j_first + j_step, ...: the end of the first run is the
+    // start of the second, so a pair costs three edge searches instead of four, and they are independent of each other
+    auto run_row_pairs = [&](int row, int j_first, int j_step, int n_vis) {
+        const RowState r = row_state(row, true);
+        int j = j_first;
+        bool actA = (unsigned)(j - r.jw_lo) < r.jw_n && n_vis > 0, actB = (unsigned)(j + 1 - r.jw_lo) < r.jw_n && n_vis > 0;
+        float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+        if (actA || actB) {
+            t0 = ldg_stream_f32(r.th_row + (size_t)j * tstride);
+            t1 = ldg_stream_f32(r.th_row + (size_t)(j + 1) * tstride);
+            t2 = ldg_stream_f32(r.th_row + (size_t)(j + 2) * tstride);
+        }
+        for (int v = 0; v < n_vis; ++v) {
+            const int jn = j + j_step;
+            const bool more = v + 1 < n_vis;
+            const bool actAn = (unsigned)(jn - r.jw_lo) < r.jw_n && more, actBn = (unsigned)(jn + 1 - r.jw_lo) < r.jw_n && more;
+            float t0n = 0.0f, t1n = 0.0f, t2n = 0.0f;
+            if (actAn || actBn) {                          // next visit's hints: in flight while these cells are summed
+                t0n = ldg_stream_f32(r.th_row + (size_t)jn * tstride);
+                t1n = ldg_stream_f32(r.th_row + (size_t)(jn + 1) * tstride);
+                t2n = ldg_stream_f32(r.th_row + (size_t)(jn + 2) * tstride);
+            }
+            int e0 = 0, e1 = 0, e2 = 0;
+            double edge0 = 0.0, edge1 = 0.0;
+            if (actA || actB) {
+                edge1 = edge_of(j + 1);
+                int h1 = hint(t1);
+                if (actA) {
+                    edge0 = edge_of(j);
+                    e0 = walk(hint(t0), edge0, r.delta);
+                    h1 = h1 < e0 ? e0 : h1;
+                }
+                e1 = walk(h1, edge1, r.delta);
+                if (actB) {
+                    const int h2 = hint(t2);
+                    e2 = walk(h2 < e1 ? e1 : h2, edge_of(j + 2), r.delta);
+                }
+            }
+            sum_cell(j, actA, e0, actA ? e1 - e0 : 0, edge0, r.delta, r.hrow_s32, r.hrow_g);
+            sum_cell(j + 1, actB, e1, actB ? e2 - e1 : 0, edge1, r.delta, r.hrow_s32, r.hrow_g);
+            j = jn;
+            actA = actAn;
+            actB = actBn;
+            t0 = t0n;
+            t1 = t1n;
+            t2 = t2n;
         }
     };
     if (warp < wA) {
@@ -417,7 +485,8 @@ __device__ __forceinline__ double zr_exec(const DevModel *mp, const DevRun *rp, 
             const int g = warp % Gf, idx = warp / Gf;
             const int cnt = (wA - g + Gf - 1) / Gf;        // warps sharing group g
             const int row = (g << 5) + lane;
-            run_row(row, true, k_lo + (srow[row] - s_ref) + idx, cnt, idx < n_iv ? (n_iv - idx + cnt - 1) / cnt : 0);
+            const int n_pr = (n_iv + 1) >> 1;              // pairs of adjacent trajectory offsets
+            run_row_pairs(row, k_lo + (srow[row] - s_ref) + 2 * idx, 2 * cnt, idx < n_pr ? (n_pr - idx + cnt - 1) / cnt : 0);
         } else {                                           // more groups than warps: stride over (offset, group) pairs
             for (int task = warp; task < n_iv * Gf; task += wA) {
                 const int jj = task / Gf;

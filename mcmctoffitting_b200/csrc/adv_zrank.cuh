@@ -434,6 +434,7 @@ __device__ __forceinline__ double zr_exec(const DevModel *mp, const DevRun *rp, 
     };
     // visits of PAIRS of adjacent cells (j, j + 1), j = j_first, j_first + j_step, ...: the end of the first run is the
     // start of the second, so a pair costs three edge searches instead of four, and they are independent of each other
+    // (+1.5 %; a generic K-cells-per-visit version with K = 2, 3, 4 was measured 2.5 - 3 % slower than this one)
     auto run_row_pairs = [&](int row, int j_first, int j_step, int n_vis) {
         const RowState r = row_state(row, true);
         int j = j_first;

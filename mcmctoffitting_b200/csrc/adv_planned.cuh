@@ -111,7 +111,7 @@ __device__ __noinline__ int planned_setup(const DevModel *mp, const DevRun *rp, 
     // every row has its own window of E-bins: [u_lo + delta_i, u_hi + delta_i], one interval of slack on both sides
     // (T1 is only monotone up to its 2e-13 cm fit error); interval j == E-bin j on this path
     for (int i = tid; i < X; i += NT) {
-        double vmin = (u_lo > -CUDART_INF ? u_lo : 0.0) + sdelta[i];   // -inf draws: the lowest in-range v is 0
+        double vmin = u_lo > -CUDART_INF ? u_lo + sdelta[i] : 0.0;     // -inf draws: the lowest in-range v is 0 (whatever the sign of delta)
         double vmax = u_hi + sdelta[i];
         vmin = vmin > 0.0 ? vmin : 0.0;
         vmax = vmax < umax ? vmax : umax;

@@ -51,7 +51,7 @@ inline RangeLayout range_layout(int X, int E, int T, int hcap, int rcap, int P, 
     RangeLayout L;
     size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
     region_a = (region_a + 15) / 16 * 16;
-    size_t o = (size_t)hcap * 8;
+    size_t o = ((size_t)hcap * 8 + 15) / 16 * 16;         // what follows is read with 16-byte loads
     L.pa = (unsigned)o;        o += region_a;
     L.rec = (unsigned)o;       o += range_rec_doubles(rcap, P) * 8;
     L.svd = (unsigned)o;       o += (size_t)E * 8;
@@ -935,7 +935,7 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) adv_range_kernel(cons
         // every row has its own window of E-bins: [u_lo + delta_i, u_hi + delta_i], one interval of slack on both
         // sides (T1 is only monotone up to its 2e-13 cm fit error)
         for (int i = tid; i < X; i += NT) {
-            double vmin = (u_lo > -CUDART_INF ? u_lo : 0.0) + sdelta[i];   // -inf draws: the lowest in-range v is 0
+            double vmin = u_lo > -CUDART_INF ? u_lo + sdelta[i] : 0.0;     // -inf draws: the lowest in-range v is 0 (whatever the sign of delta)
             double vmax = u_hi + sdelta[i];
             vmin = vmin > 0.0 ? vmin : 0.0;
             vmax = vmax < umax ? vmax : umax;

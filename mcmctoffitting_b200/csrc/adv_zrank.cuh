@@ -50,7 +50,7 @@ inline RangeLayout zrank_layout(int X, int E, int T, int hcap, int rcap, int P, 
     region_a = (region_a + 15) / 16 * 16;
     size_t rec_b = (size_t)rcap * (P + 3) * 8;
     rec_b = rec_b > (size_t)3 * E * 8 ? rec_b : (size_t)3 * E * 8;
-    size_t o = (size_t)hcap * 8;
+    size_t o = ((size_t)hcap * 8 + 15) / 16 * 16;         // what follows is read with 16-byte loads
     L.pa = (unsigned)o;        o += region_a;
     L.rec = (unsigned)o;
     L.svd = (unsigned)o;                          // aliases the records (dead after the cell sums)
@@ -162,7 +162,7 @@ __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const
     // median draw -- rows are processed along the trajectory so that the lanes of a warp have runs of similar length.
     for (int i = tid; i < X; i += NT) {
         const double dl = sdelta[i];
-        double vmin = (u_lo > -CUDART_INF ? u_lo : 0.0) + dl;   // -inf draws: the lowest in-range v is 0
+        double vmin = u_lo > -CUDART_INF ? u_lo + dl : 0.0;     // -inf draws: the lowest in-range v is 0 (whatever the sign of delta)
         double vmax = u_hi + dl;
         vmin = vmin > 0.0 ? vmin : 0.0;
         vmax = vmax < umax ? vmax : umax;
@@ -592,26 +592,29 @@ __device__ __noinline__ void zr_finish(const DevModel *mp, const DevRun *rp, con
                 const int j = row_lo + jb;
                 const double h = Hr[jb];
                 if (h != 0.0) {
-                    // cnt = rint(RN(RN(h/S) * N)) (adv:146).  Fast: c = h * RN(rS*N) is within 2 ulp of the product the
-                    // reference rounds; if it is not within 1e-6 of a half-integer both round to the same integer.
+                    // Two independent chains, both formed before any branch so that they overlap:
+                    // (1) cnt = rint(RN(RN(h/S) * N)) (adv:146).  Fast: c = h * RN(rS*N) is within 2 ulp of the product the
+                    //     reference rounds; if it is not within 1e-6 of a half-integer both round to the same integer.
                     const double c = __dmul_rn(h, k1);
                     const double cm = __dadd_rn(c, MAGIC);
                     double cnt = __dsub_rn(cm, MAGIC);
                     unsigned int ci = (unsigned int)__double2loint(cm);
-                    if (__builtin_expect(!(fabs(__dsub_rn(c, cnt)) < SURE && c < 1e9), 0)) {
+                    const bool sure_c = fabs(__dsub_rn(c, cnt)) < SURE && c < 1e9;
+                    // (2) TOF bin (adv:149-159).  Fast: t = (tof - tof_min) * T/(max - min) - 1/2 from reciprocals; if t is
+                    //     not within 1e-6 of a half-integer, rint(t) is numpy's bin (its edges are within 1e-12 bins of the
+                    //     uniform grid); otherwise the exact quotients and numpy's edge rule decide.
+                    const double rvn = rvn_s[j];
+                    const double tof = fma(xi, rvd[j], __dmul_rn(di, rvn));
+                    const double t = fma(tof, t_scale, q_off);
+                    const double tm = __dadd_rn(t, MAGIC);
+                    int b = __double2loint(tm);
+                    const bool sure_b = fabs(__dsub_rn(t, __dsub_rn(tm, MAGIC))) < SURE && fabs(t) < 1e9;
+                    if (__builtin_expect(!sure_c, 0)) {
                         cnt = zr_exact_count(h, S, rS, nsamp);
                         ci = (unsigned int)cnt;
                     }
                     if (cnt > 0.0) {
-                        // TOF bin (adv:149-159).  Fast: t = (tof - tof_min) * T/(max - min) - 1/2 from reciprocals; if t
-                        // is not within 1e-6 of a half-integer, rint(t) is numpy's bin (its edges are within 1e-12 bins
-                        // of the uniform grid); otherwise the exact quotients and numpy's edge rule decide.
-                        const double rvn = rvn_s[j];
-                        const double tof = fma(xi, rvd[j], __dmul_rn(di, rvn));
-                        const double t = fma(tof, t_scale, q_off);
-                        const double tm = __dadd_rn(t, MAGIC);
-                        int b = __double2loint(tm);
-                        if (__builtin_expect(!(fabs(__dsub_rn(t, __dsub_rn(tm, MAGIC))) < SURE && fabs(t) < 1e9), 0))
+                        if (__builtin_expect(!sure_b, 0))
                             b = zr_exact_bin(xi, di, svd[j], rvd[j], vn_g[j], rvn, T, t_min, t_max, t_step, t_scale);
                         TOF_CHECK(j < m.e_bins);
                         if ((unsigned)b < (unsigned)T) {

@@ -707,6 +707,7 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
             const size_t fixed = range_smem_bytes(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], 0, rcap, P, cfg->n_taps, cfg->rng_lut_n, Mi);
             long long hcap = ((long long)per_cta - (long long)fixed) / 8;
             hcap = std::min<long long>(hcap, (long long)cfg->x_bins * cfg->e_bins - 1);
+            hcap &= ~1LL;                                   // the records behind the histogram are read with 16-byte loads
             if (want && kband && hcap >= (long long)cfg->x_bins * 8 && hcap >= cfg->tof_bins[0]) {
                 ctx->band_hcap = (int)hcap;
                 ctx->band_rcap = rcap;
@@ -739,6 +740,7 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
                 const size_t fixed = zrank_layout(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], 0, rcap, P, cfg->n_taps, Mi).total;
                 long long hcap = ((long long)per_cta - (long long)fixed) / 8;
                 hcap = std::min<long long>(hcap, (long long)cfg->x_bins * cfg->e_bins);
+                hcap &= ~1LL;                               // the records behind the histogram are read with 16-byte loads
                 if (hcap >= (long long)cfg->x_bins * 8 && hcap >= cfg->tof_bins[0]) {
                     ctx->zr_hcap = (int)hcap;
                     ctx->zr_rcap = rcap;
@@ -995,6 +997,8 @@ int tof_set_draws(tof_ctx *ctx, int run, int stream, const double *values, int64
                     while (dpos < (size_t)n && sorted[dpos] < start) ++dpos;
                     lut[cc] = (unsigned short)dpos;
                 }
+                if (const char *v = std::getenv("TOFGPU_ZR_NOHINT"))   // debugging aid: every search walks from draw 0
+                    if (std::atoi(v)) std::fill(lut.begin(), lut.end(), (unsigned short)0);
                 // the top entry must be "no draw" for thresholds beyond the last draw, but draws equal to z_hi sit in the
                 // last cell: lut[ZR_LUT] is the first draw with z >= z_hi, a low hint as required (never beyond the answer)
                 const unsigned short *dl = nullptr;

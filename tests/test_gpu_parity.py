@@ -896,6 +896,52 @@ def test_single_launch_kernel_equals_the_banded_pair(M, O):
         assert (a[k] == want) or rel(float(a[k]), float(want)) <= RTOL, (k, a[k], want)
 
 
+@pytest.mark.parametrize("shape", ["300draws", "20rows", "as_written", "fewbins"])
+def test_single_launch_kernel_other_shapes(M, O, shape):
+    """adv_zrank_kernel away from the benchmark shape: a partial tile of draws, fewer rows than a warp (no full group of
+    32 rows: every warp takes the leftover path), the as-written medium (dE/dx > 0: the energies RISE along the cell, the
+    thresholds are mirrored) and coarse TOF binning -- against the banded pair (bit for bit) and the oracle (1e-9)."""
+    kw, okw = {}, {}
+    if shape == "300draws":
+        kw, okw = dict(n_samples=300, n_ev_per_loop=300), dict(n_samples=300, n_ev_per_loop=300)
+    elif shape == "20rows":
+        kw, okw = dict(x_bins=20), dict(x_bins=20)
+    elif shape == "as_written":
+        kw, okw = dict(mean_excitation=19.2), dict(mean_excitation=19.2)
+    elif shape == "fewbins":
+        kw, okw = dict(tof_bins=(64,), tof_ranges=((150.0, 250.0),)), dict(tof_bins=64, tof_min=150.0, tof_max=250.0)
+    cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE, **kw)
+    om = O.sweep_model(ode_scheme="exact", **okw)
+    xs = O.DDNXS()
+    z = np.random.RandomState(3).standard_normal(cfg.n_draws)
+    obs = np.rint(2e4 * om.model_pdf([1050, 0.09], np.random.RandomState(7).standard_normal(cfg.n_draws)))
+    rs = np.random.RandomState(2)
+    thetas = np.vstack([np.array([1050.0, 0.10]) + np.array([10, 1e-2]) * rs.standard_normal((60, 2)),
+                        np.column_stack([rs.uniform(1000, 2600, 20), rs.uniform(0.02, 0.5, 20)])])
+    res = {}
+    old = os.environ.get("TOFGPU_RANGE_ZRANK")
+    try:
+        for label, env in (("single", "1"), ("pair", "0")):
+            os.environ["TOFGPU_RANGE_ZRANK"] = env
+            fn = M.make_lnprob(cfg, obs, z)
+            res[label] = fn.batch(thetas)
+            if label == "single":
+                assert fn.model.stats()["model_launches_per_call"] == 1
+                one = fn.batch(thetas[:1])                 # a single walker: a grid of one CTA
+                assert one[0] == res[label][0] or (np.isnan(one[0]) and np.isnan(res[label][0]))
+            fn.model.close()
+    finally:
+        if old is None:
+            os.environ.pop("TOFGPU_RANGE_ZRANK", None)
+        else:
+            os.environ["TOFGPU_RANGE_ZRANK"] = old
+    a, b = res["single"], res["pair"]
+    assert np.array_equal(a, b, equal_nan=True), int(np.sum(~((a == b) | (np.isnan(a) & np.isnan(b)))))
+    for k in list(range(0, 10)) + [60, 61, 62]:
+        want = om.lnprob(thetas[k], obs, z, xs)
+        assert (a[k] == want) or (np.isnan(a[k]) and np.isnan(want)) or rel(float(a[k]), float(want)) <= RTOL, (k, a[k], want)
+
+
 def test_ppc_onebd_reference_goldens(M, O, golden_ppc_onebd):
     """utilities/ppcTools_oneBD.py:185-268 (the posterior-predictive twin of the oneBD model: 20 x 400 grid, 10
     zero-degree sub-times per cell, tau = 4 transit taps, Poisson background) through the CUDA path, against the

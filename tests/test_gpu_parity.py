@@ -710,11 +710,15 @@ def test_ppc_deuteron_spectra_and_sdef_card(M, O):
     card = ppc.sdef_sia_cumulative(cells[0], e_n)
     assert [int(v) for v in card["sp"].split()[1:]] == list(cells[0].sum(axis=(0, 1)))
     assert card["si"].split()[2] == "%.3f" % (e_n[0] / 1000)
-    # the range-table context refuses the request loudly instead of answering with another scheme
+    # a range-table context answers too: the per-sample energies come from the RK4 kernel in either mode (round 2)
     fr = M.make_lnprob(M.config.simult(n_samples=3000, n_ev_per_loop=1000, ode_mode=M.config.ODE_RANGE),
                        [np.ones(t) for t in cfg.tof_bins], [z.ravel() for z in z_main], extra_draws=z_extra)
-    with pytest.raises(Exception):
-        fr.model.deuteron_counts(thetas)
+    assert np.array_equal(fr.model.deuteron_counts(thetas, run=3), spectra[3])
+    # ... the adv model has no such quantity in the reference and refuses loudly
+    fa = M.make_lnprob(M.config.sweep(), np.ones(2048), np.zeros(1024))
+    with pytest.raises(M.TofError):
+        fa.model.deuteron_counts(np.array([[1050.0, 0.1]]))
+    fa.model.close()
     fr.model.close()
     fn.model.close()
 

@@ -558,7 +558,7 @@ __device__ __noinline__ void zr_finish(const DevModel *mp, const DevRun *rp, con
             rvn_s[j] = rvn_g[j];
         }
     }
-    static_assert(NT <= 512, "block_sum1 slots hold 16 warp partials");
+    static_assert(NT <= 640, "the two block_sum1 slots share 40 doubles of scratch");
     const double S = block_sum1<double>(part, scratch);    // includes the barrier that publishes tofc = 0 and the speeds
     if (PROF && tid == 0) {
         const long long t = clock64();
@@ -627,7 +627,7 @@ __device__ __noinline__ void zr_finish(const DevModel *mp, const DevRun *rp, con
         }
     }
     // (the barrier inside the next reduction is also the one that completes the scatter)
-    const long long total_i = block_sum1<long long>(cpart, reinterpret_cast<long long *>(scratch) + 16);
+    const long long total_i = block_sum1<long long>(cpart, reinterpret_cast<long long *>(scratch) + NT / 32);
     if (PROF && tid == 0) {
         const long long t = clock64();
         atomicAdd(out.stage_cycles + 3, (unsigned long long)(t - f->t_mark));

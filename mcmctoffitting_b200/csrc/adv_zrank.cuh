@@ -37,7 +37,10 @@ namespace tof {
 
 constexpr int ZR_LUT = 4096;             // cells of the draw-rank lookup over z (entries: ZR_LUT + 1)
 constexpr float ZR_BIAS = 0.25f;         // cells the hint is lowered by (float rounding of the hint << 0.25 cell)
-constexpr double ZR_MIN_SPREAD = 2.0;    // keV; below this (and for reversed / degenerate spreads) hints are off
+// keV; below this (and for reversed / degenerate spreads) hints are off.  Error budget of a hint in lookup cells, worst case
+// at spread = 8 keV with thresholds near 2600 keV: float rounding of Theta (1.6e-4 keV), of Theta*a + b (|b| ~ 2e5:
+// 0.008 cells) and of the FMA -- together < 0.03 cells against the 0.25-cell bias.
+constexpr double ZR_MIN_SPREAD = 8.0;
 
 // Byte offsets of the regions of adv_zrank_kernel's dynamic shared memory (host-computed).  Order:
 //   H [hcap] f64 (later the density [T]) | draw tile u0 [RANGE_TILE] f64, later the TOF counters [T] u32 |
@@ -207,6 +210,7 @@ __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const
             const double inv = 1.0 / spread;
             ha = (float)(run.zlut_inv * inv);
             hb = (float)((-e0 * inv - run.zlut_lo) * run.zlut_inv - (double)ZR_BIAS);
+            if (!(ha < 1e6f) || !(fabsf(hb) < 1e9f)) ha = hb = 0.0f;   // a degenerate draw set: no hints (walk from draw 0)
         }
         f->hint_a = ha;
         f->hint_b = hb;

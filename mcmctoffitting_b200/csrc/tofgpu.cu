@@ -989,7 +989,7 @@ int tof_set_draws(tof_ctx *ctx, int run, int stream, const double *values, int64
             while (n_fin < n && std::isfinite(sorted[(size_t)n_fin])) ++n_fin;     // NaNs sort last; +-inf draws: hints off
             const bool all_finite = n_fin == n;
             const double z_lo = sorted[0], z_hi = sorted[(size_t)n - 1];
-            if (all_finite && z_hi > z_lo) {
+            if (all_finite && z_hi - z_lo > 1e-3) {                // (a degenerate draw set gets no lookup: the banded pair runs)
                 std::vector<unsigned short> lut(ZR_LUT + 1);
                 const double inv = (double)ZR_LUT / (z_hi - z_lo);
                 size_t dpos = 0;

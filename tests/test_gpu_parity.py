@@ -900,7 +900,7 @@ def test_single_launch_kernel_equals_the_banded_pair(M, O):
         assert (a[k] == want) or rel(float(a[k]), float(want)) <= RTOL, (k, a[k], want)
 
 
-@pytest.mark.parametrize("shape", ["300draws", "20rows", "as_written", "fewbins"])
+@pytest.mark.parametrize("shape", ["300draws", "20rows", "as_written", "fewbins", "tiny_spread"])
 def test_single_launch_kernel_other_shapes(M, O, shape):
     """adv_zrank_kernel away from the benchmark shape: a partial tile of draws, fewer rows than a warp (no full group of
     32 rows: every warp takes the leftover path), the as-written medium (dE/dx > 0: the energies RISE along the cell, the
@@ -914,6 +914,9 @@ def test_single_launch_kernel_other_shapes(M, O, shape):
         kw, okw = dict(mean_excitation=19.2), dict(mean_excitation=19.2)
     elif shape == "fewbins":
         kw, okw = dict(tof_bins=(64,), tof_ranges=((150.0, 250.0),)), dict(tof_bins=64, tof_min=150.0, tof_max=250.0)
+    elif shape == "tiny_spread":                             # a prior that admits spreads below ZR_MIN_SPREAD: hints off
+        pr = ((1000.0, 2600.0), (1e-5, 0.5))
+        kw, okw = dict(prior=pr), dict(prior=pr)
     cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE, **kw)
     om = O.sweep_model(ode_scheme="exact", **okw)
     xs = O.DDNXS()
@@ -922,6 +925,9 @@ def test_single_launch_kernel_other_shapes(M, O, shape):
     rs = np.random.RandomState(2)
     thetas = np.vstack([np.array([1050.0, 0.10]) + np.array([10, 1e-2]) * rs.standard_normal((60, 2)),
                         np.column_stack([rs.uniform(1000, 2600, 20), rs.uniform(0.02, 0.5, 20)])])
+    if shape == "tiny_spread":
+        thetas[:10, 1] = [1e-4, 5e-4, 1e-3, 2e-3, 4e-3, 7e-3, 7.7e-3, 1e-2, 2e-5, 3e-3]      # spreads 0.02 .. 10 keV
+        thetas[:10, 0] = 1050.3 + np.arange(10)
     res = {}
     old = os.environ.get("TOFGPU_RANGE_ZRANK")
     try:

@@ -373,7 +373,16 @@ def run_gpu_arm(args):
         if f32:
             parity_sample = {"skipped": "FP32 arm: tolerance 1e-4, see fp32_mode"}
         else:
-            parity_sample = oracle_check(z, obs, pos_h[pick], lp_h[pick], min(os.cpu_count() or 1, 32))
+            # in a fresh interpreter: no fork of a process that holds a CUDA context
+            import subprocess
+            import tempfile
+            with tempfile.TemporaryDirectory() as td:
+                path = os.path.join(td, "sample.npz")
+                np.savez(path, thetas=pos_h[pick], got=lp_h[pick])
+                res = subprocess.run([sys.executable, os.path.abspath(__file__), "--oracle-check", path], stdout=subprocess.PIPE,
+                                     text=True, timeout=900)
+            parity_sample = (json.loads(res.stdout.strip().splitlines()[-1]) if res.returncode == 0 and res.stdout.strip()
+                             else {"error": "rc=%d" % res.returncode})
 
     # ---- burn-in regime: walkers uniform over the adv prior box (adv:81-82), one half-ensemble call ----------------
     prior_box = None
@@ -558,9 +567,16 @@ def main():
     ap.add_argument("--no-parity-sample", action="store_true", help="skip the oracle check of 256 timed-ensemble walkers")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (prior box, per-evaluation draws)")
     ap.add_argument("--cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--oracle-check", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_baseline:
         return run_cpu_baseline()
+    if args.oracle_check:
+        from oracle import tof_oracle as O
+        _, z, obs, _ = workload(O)
+        with np.load(args.oracle_check) as f:
+            print(json.dumps(oracle_check(z, obs, f["thetas"], f["got"], min(os.cpu_count() or 1, 32))))
+        return 0
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_gpu_arm(args)

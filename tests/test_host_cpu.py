@@ -299,6 +299,36 @@ def test_reference_arm_prints_the_contract_line():
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
+def test_bench_self_check_leg_counts_deviations(tmp_path):
+    """bench.py --oracle-check (the leg behind `parity_sample`): oracle values pass, a perturbed one and a finite / -inf
+    flip are counted."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    om, z, obs, thetas = bench.workload(O)
+    xs = O.DDNXS()
+    th = np.vstack([thetas[:3], [[1050.0, 0.08], [1052.0, 0.081]]])
+    got = np.array([om.lnprob(t, obs, z, xs) for t in th])
+    assert np.isfinite(got).sum() >= 2
+    fin = np.flatnonzero(np.isfinite(got))
+    bad = got.copy()
+    bad[fin[0]] *= 1 + 1e-6                      # outside 1e-9
+    bad[fin[1]] = -np.inf                        # a flip
+    out = {}
+    for name, arr in (("good", got), ("bad", bad)):
+        path = str(tmp_path / (name + ".npz"))
+        np.savez(path, thetas=th, got=arr)
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--oracle-check", path], stdout=subprocess.PIPE,
+                           text=True, timeout=300, cwd=root)
+        assert r.returncode == 0
+        out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["good"]["n_outside_1e-9"] == 0 and out["good"]["n_flips"] == 0 and out["good"]["max_rel"] <= 1e-12
+    assert out["bad"]["n_outside_1e-9"] == 1 and out["bad"]["n_flips"] == 1
+
+
 def test_gpu_arm_refuses_to_run_without_a_device():
     import subprocess
     import sys

@@ -80,6 +80,7 @@ struct ZrFrame {
     int wide;                // 1: cell sums live in the CTA's global scratch histogram, records are read from global
     float hint_a, hint_b;    // lookup cell of a threshold energy: Theta * a + b
     int s_ref, k_lo, n_iv, nB, wB;   // trajectory-aligned visit grid of the cell sums (see zr_exec)
+    double spread;           // sigma0 * e0 (multi-tile kernel: the draws are staged tile by tile)
     double de, dx;           // bin widths of the (x,E) histogram (set once per CTA)
     double umax_next;        // nextafter(u_max): right edge of the last (closed) interval (set once per CTA)
     const unsigned short *zlut;   // draw-rank lookup of this run (set once per CTA)
@@ -750,6 +751,337 @@ __global__ void __launch_bounds__(NT, 2) adv_zrank_kernel(const __grid_constant_
             stage(1);
             zr_finish<NT, P, PROF, false>(&m, &run, &out, smem_raw, &frame, nullptr, part);
         }
+    }
+}
+
+// ================================================================================================================
+// Many draws per walker (n_draws > RANGE_TILE; the reference's own default is 1e5 - 1e6): adv_zrank_multi_kernel
+// ================================================================================================================
+// The sorted draws are taken a tile of RANGE_TILE at a time.  A tile of a big draw set is a narrow slice of the energy
+// distribution: for a given row it touches one to three E-bins, so a (row, E-bin) run is hundreds of consecutive draws
+// and the polynomial loop is all there is -- 11 instructions per 32 samples against 34 for the warp-private streaming
+// walk of adv_range_kernel (which re-derives the interval of every sample; ncu: 11.0 M warp-instructions per walker at
+// 1e5 draws).  Lane = row as in zr_exec; the runs of a tile are found by binary search in the tile (no hints needed:
+// the search is ~1 % of a run's polynomial work); every run is split over the warps that share the group of rows and
+// the partial sums meet in the cell with atomics (as in the streaming walk, the summation order of those few partials
+// is not fixed).  Normalisation, scatter, density and likelihood are zr_finish.
+template <int NT, int P>
+__device__ __noinline__ int zrm_setup(const DevModel *mp, const DevRun *rp, const double *__restrict__ theta, long long n_walkers,
+                                      const ModelOut *op, unsigned char *smem_raw, ZrFrame *f, int it, double *Hglobal) {
+    __builtin_assume(__isShared(smem_raw));
+    __builtin_assume(__isShared(f));
+    const DevModel &m = *mp;
+    const DevRun &run = *rp;
+    const ModelOut &out = *op;
+    constexpr int RW = P + 3;
+    const int tid = threadIdx.x;
+    const int X = m.x_bins, M = m.rng_n;
+    double *H = reinterpret_cast<double *>(smem_raw);
+    double *rec = reinterpret_cast<double *>(smem_raw + out.lay.rec);
+    const double *sdelta = reinterpret_cast<const double *>(smem_raw + out.lay.sdelta);
+    int *hlo_s = reinterpret_cast<int *>(smem_raw + out.lay.hlo);
+    const double *sbrk = reinterpret_cast<const double *>(smem_raw + out.lay.sbrk);
+    if (tid == 0) {
+        f->band[0] = 0;
+        f->band[1] = M;
+        f->band[2] = -1;
+    }
+    __syncthreads();                                       // the previous walker is done with shared memory
+    const long long w = f->idx[it & 1];
+    if (w >= n_walkers) return PLANNED_DONE;
+    if (tid == 0) f->idx[(it + 1) & 1] = (long long)atomicAdd(out.work, 1ull);
+    const double e0 = theta[w * m.ndim + 0];
+    const double sigma0 = theta[w * m.ndim + 1];
+    bool inside = true;
+    for (int p = 0; p < m.ndim; ++p) {
+        const double v = theta[w * m.ndim + p];
+        inside = inside && (m.prior_strict ? (m.prior_lo[p] < v && v < m.prior_hi[p])
+                                           : !(v < m.prior_lo[p] || v > m.prior_hi[p]));
+    }
+    if (!inside) {                                         // adv:191-195: the model is never evaluated outside the prior
+        if (tid == 0) out.lnprob[w] = -CUDART_INF;
+        return PLANNED_SKIP;
+    }
+    const double spread = __dmul_rn(sigma0, e0);          // adv:128
+    const bool rev = spread < 0.0;
+    const double umax = m.rng_u_max;
+    // E-bins the walker can touch: the draws are sorted, first and last give the extremes
+    const double u_lo = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 : 0)))), m);
+    const double u_hi = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? 0 : m.n_draws - 1)))), m);
+    for (int i = tid; i < X; i += NT) {
+        const double dl = sdelta[i];
+        double vmin = u_lo > -CUDART_INF ? u_lo + dl : 0.0;     // -inf draws: the lowest in-range v is 0
+        double vmax = u_hi + dl;
+        vmin = vmin > 0.0 ? vmin : 0.0;
+        vmax = vmax < umax ? vmax : umax;
+        int j_lo = 0, j_hi = 0;
+        if (vmax >= vmin) {
+            j_lo = range_interval(vmin, sbrk, m.rng_lut, m.rng_lut_inv, m.rng_lut_n, M);
+            j_hi = range_interval(vmax, sbrk, m.rng_lut, m.rng_lut_inv, m.rng_lut_n, M);
+            j_lo = j_lo > 0 ? j_lo - 1 : 0;
+            j_hi = j_hi < M - 1 ? j_hi + 1 : M - 1;
+            atomicMin(&f->band[1], j_lo);
+            atomicMax(&f->band[2], j_hi);
+        }
+        hlo_s[i] = j_lo;
+        atomicMax(&f->band[0], j_hi - j_lo + 1);
+    }
+    __syncthreads();
+    const int hstride = f->band[0];
+    const int j_lo_all = f->band[2] >= 0 ? f->band[1] : 0, j_hi_all = f->band[2] >= 0 ? f->band[2] : 0;
+    const int jbase = j_lo_all > 0 ? j_lo_all - 1 : 0;
+    const bool fits = (long long)X * hstride <= out.hcap && (j_hi_all - jbase + 1) <= out.rcap;
+    if (fits) {
+        const double *recg = m.rng_rec;
+        for (int i = tid; i < (j_hi_all - jbase + 1) * RW; i += NT) rec[i] = recg[(size_t)jbase * RW + i];
+        for (int i = tid; i < X * hstride; i += NT) H[i] = 0.0;
+    } else {
+        for (int i = tid; i < X * hstride; i += NT) Hglobal[i] = 0.0;
+    }
+    if (tid == 0) {
+        f->w = w;
+        f->e0 = e0;
+        f->spread = spread;
+        f->hstride = hstride;
+        f->jbase = fits ? jbase : 0;
+        f->wide = fits ? 0 : 1;
+        if (f->band[2] < 0) {
+            f->band[1] = 0;
+            f->band[2] = -1;
+        }
+        if (!fits && out.queue_count) atomicAdd(out.queue_count, 1ull);
+    }
+    __syncthreads();
+    return PLANNED_RUN;
+}
+
+// All tiles of one walker: (x,E) histogram of cross-section weights (adv:128-138), accumulated into H.
+//
+// Work split inside a tile: the warps that share a group of 32 rows each take a contiguous slice [A, B) of the tile's
+// draws -- the SAME slice for every lane (= row) of the warp, so all lanes have the same number of samples.  A row's
+// slice lies in one E-bin unless one of the bin's edges falls inside it (a quarter of the rows per tile, one slice in
+// five): every lane sums the first segment of its slice in lockstep (the main pass: full four-sample trips only), and
+// the few leftover segments are then summed one after the other by all 32 lanes together (strided over the segment's
+// draws, coefficients broadcast by shuffle, warp sum).  Letting those rows run a second lockstep pass instead doubled
+// the polynomial work (measured: 10.0 M warp-instructions per walker at 1e5 draws, against 11.0 M for the streaming walk).
+template <int NT, int P, bool WIDE>
+__device__ __forceinline__ void zrm_exec(const DevModel &m, const DevRun &run, const ModelOut &out, unsigned char *smem_raw,
+                                         const ZrFrame *f, double *Hglobal) {
+    constexpr int RW = P + 3;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int X = m.x_bins, M = m.rng_n;
+    double *u0 = reinterpret_cast<double *>(smem_raw + out.lay.pa);
+    double *Hs = reinterpret_cast<double *>(smem_raw);
+    const double *brk = reinterpret_cast<const double *>(smem_raw + out.lay.sbrk);
+    const double *sdelta = reinterpret_cast<const double *>(smem_raw + out.lay.sdelta);
+    const int *hlo = reinterpret_cast<const int *>(smem_raw + out.lay.hlo);
+    const double *rec_s = reinterpret_cast<const double *>(smem_raw + out.lay.rec);
+    const double *rec_g = m.rng_rec;
+    const volatile ZrFrame *fv = f;
+    const int hstride = f->hstride;
+    const int j_lo_all = f->band[1], j_hi_all = f->band[2];
+    if (j_hi_all < j_lo_all) return;                       // uniform: no row can be reached
+    const double e0 = f->e0, spread = f->spread, umax = m.rng_u_max;
+    const bool rev = spread < 0.0;
+    const unsigned smem_s32 = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned u0_s32 = smem_s32 + out.lay.pa;
+    // warps -> groups of 32 rows; the X % 32 leftover rows get one warp that packs R rows x (32/R) sub-slices
+    const int Gf = X >> 5, R = X & 31;
+    const int wB = R ? (Gf ? 1 : NW) : 0, wA = NW - wB;
+    int row, parts, part;
+    bool lane_ok = true;
+    if (warp < wA) {
+        const int g = warp % Gf, q = warp / Gf;
+        row = (g << 5) + lane;
+        parts = (wA - g + Gf - 1) / Gf;                    // warps sharing group g
+        part = q;
+    } else {
+        const int per_b = 32 / R, sub = lane / R;
+        row = (Gf << 5) + (lane - sub * R);
+        parts = wB * per_b;
+        part = (warp - wA) * per_b + sub;
+        lane_ok = sub < per_b;
+    }
+    const double delta = sdelta[row];
+    const int hbase = row * hstride - hlo[row];            // H index of (row, E-bin j) is hbase + j
+    const int row_lo = hlo[row];
+    auto edge_of = [&](int j) -> double { return j == 0 ? 0.0 : (j >= M ? fv->umax_next : brk[j - 1]); };
+    // first draw d in [lo, hi) with RN(u0[d] + dl) >= edge (hi when there is none): the membership compare of every range
+    // kernel, by bisection
+    auto first_ge = [&](int lo, int hi, double edge, double dl) -> int {
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__dadd_rn(u0[mid], dl) >= edge) hi = mid;
+            else lo = mid + 1;
+        }
+        return lo;
+    };
+    auto load_record = [&](int j, double (&a)[P + 1], double &a0) {
+        const int ridx = (j - fv->jbase) * RW + 2;
+        const double2 *r2 = reinterpret_cast<const double2 *>((WIDE ? rec_g : rec_s) + ridx);
+        const double2 c01 = r2[0];
+        a0 = c01.x;
+        a[0] = 0.0;                                        // the constant term is added once per run
+        a[1] = c01.y;
+#pragma unroll
+        for (int k = 2; k <= P; k += 2) {
+            const double2 c2 = r2[k >> 1];
+            a[k] = c2.x;
+            a[k + 1] = c2.y;
+        }
+    };
+    auto add_cell = [&](int hidx, double val) {
+        if constexpr (WIDE) atomicAdd(Hglobal + hidx, val);
+        else atomicAdd(Hs + hidx, val);
+    };
+    for (long long tile = 0; tile < m.n_draws; tile += RANGE_TILE) {
+        const int nt = (int)((m.n_draws - tile < RANGE_TILE) ? (m.n_draws - tile) : RANGE_TILE);
+        __syncthreads();                                   // the previous tile is consumed
+        int n_neg = 0, n_pos = 0;                          // draws outside the energy table: -inf first, +inf last
+        for (int d = tid; d < RANGE_TILE; d += NT) {
+            double u = CUDART_INF;
+            if (d < nt) {
+                u = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? m.n_draws - 1 - (tile + d) : tile + d)))), m);
+                u0[d] = u;
+            }
+            n_neg += __syncthreads_count(d < nt && !(u > -CUDART_INF));
+            n_pos += __syncthreads_count(d < nt && u >= CUDART_INF);
+        }
+        const int v_lo = n_neg, v_hi = nt - n_pos;         // finite part of the tile (NaN counts as -inf)
+        if (v_hi <= v_lo) continue;                        // uniform
+        // this lane's slice of the tile's draws, and its first in-range draw
+        const int nf = v_hi - v_lo;
+        int sB = v_lo + ((part + 1) * nf) / parts;
+        int s = v_lo + (part * nf) / parts;
+        if (!lane_ok) sB = s;
+        s = first_ge(s, sB, 0.0, delta);                   // samples below the histogram range (v < 0) are skipped
+        // E-bin of the first sample of the slice (edges: the compare rule, so range_interval's answer is the cell)
+        int j = 0;
+        if (s < sB) {
+            const double v = __dadd_rn(u0[s], delta);
+            if (v > umax) s = sB;                          // the whole slice is beyond the range (sorted)
+            else j = range_interval(v, brk, m.rng_lut, m.rng_lut_inv, m.rng_lut_n, M);
+        }
+        // ---- main pass: every lane sums the first segment of its slice (up to the next edge) in lockstep --------
+        {
+            const bool act = s < sB && (unsigned)(j - row_lo) < (unsigned)hstride;
+            const int s1 = (s < sB) ? first_ge(s, sB, edge_of(j + 1), delta) : sB;
+            const int n = act ? s1 - s : 0;
+            const int nmax = __reduce_max_sync(FULL, n);
+            if (nmax > 0) {
+                const int nmin = __reduce_min_sync(FULL, n);
+                double a[P + 1], a0;
+                load_record(act ? j : fv->jbase, a, a0);
+                const double off = delta - (act ? edge_of(j) : 0.0);
+                double acc = 0.0;
+                unsigned addr = u0_s32 + (unsigned)s * 8u;
+                const int tfull = nmin >> 2;
+#pragma unroll 1
+                for (int t = tfull; t > 0; --t) {
+                    poly_full4<P>(acc, addr, off, a);
+                    addr += 32u;
+                }
+                int rem = n - (tfull << 2);
+#pragma unroll 1
+                for (int t = ((nmax + 3) >> 2) - tfull; t > 0; --t) {
+                    poly_run4<P>(acc, addr, rem, off, a);
+                    addr += 32u;
+                    rem -= 4;
+                }
+                if (n > 0) add_cell(hbase + j, fma((double)n, a0, acc));
+            }
+            s = s1;
+            ++j;
+        }
+        // ---- leftover segments (a bin edge inside the slice), one at a time, all 32 lanes on each ------------------
+        for (;;) {
+            const bool more = s < sB && j < M;
+            const unsigned pending = __ballot_sync(FULL, more);
+            if (pending == 0u) break;                      // uniform
+            const int src = __ffs(pending) - 1;
+            // the owner finds the end of its segment, then hands the segment to the warp
+            int s1 = 0;
+            if (lane == src) s1 = first_ge(s, sB, edge_of(j + 1), delta);
+            const int seg_s = __shfl_sync(FULL, s, src), seg_e = __shfl_sync(FULL, s1, src), seg_j = __shfl_sync(FULL, j, src);
+            const double seg_delta = __shfl_sync(FULL, delta, src);
+            const int seg_h = __shfl_sync(FULL, hbase, src), seg_row_lo = __shfl_sync(FULL, row_lo, src);
+            const int seg_n = seg_e - seg_s;
+            if (seg_n > 0 && (unsigned)(seg_j - seg_row_lo) < (unsigned)hstride) {
+                double a[P + 1], a0;
+                load_record(seg_j, a, a0);
+                const double off = seg_delta - edge_of(seg_j);
+                const int ch = (seg_n + 31) >> 5;          // consecutive samples per lane
+                const int la = seg_s + lane * ch;
+                int n = seg_e - la;
+                n = n < 0 ? 0 : (n > ch ? ch : n);
+                double acc = 0.0;
+                unsigned addr = u0_s32 + (unsigned)(la < seg_e ? la : seg_s) * 8u;
+                int rem = n;
+#pragma unroll 1
+                for (int t = (ch + 3) >> 2; t > 0; --t) {
+                    poly_run4<P>(acc, addr, rem, off, a);
+                    addr += 32u;
+                    rem -= 4;
+                }
+                acc = fma((double)n, a0, acc);
+                acc = warp_sum(acc);
+                if (lane == 0) add_cell(seg_h + seg_j, acc);
+            }
+            if (lane == src) {
+                s = s1;
+                ++j;
+            }
+        }
+    }
+}
+
+template <int NT, int P>
+__global__ void __launch_bounds__(NT, 2) adv_zrank_multi_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevRun run,
+                                                                const double *__restrict__ theta, long long n_walkers,
+                                                                const __grid_constant__ ModelOut out) {
+    extern __shared__ __align__(16) unsigned char smem_sym[];
+    unsigned char *smem_raw = smem_sym;
+    asm volatile("" : "+l"(smem_raw));
+    __builtin_assume(__isShared(smem_raw));
+    __shared__ ZrFrame frame;
+    constexpr int RW = P + 3;
+    const int tid = threadIdx.x;
+    const int X = m.x_bins, M = m.rng_n;
+    {
+        double *staps = reinterpret_cast<double *>(smem_raw + out.lay.staps);
+        double *sdelta = reinterpret_cast<double *>(smem_raw + out.lay.sdelta);
+        double *sbrk = reinterpret_cast<double *>(smem_raw + out.lay.sbrk);
+        const double *recg = m.rng_rec;
+        for (int j = tid; j < M; j += NT) sbrk[j] = recg[(size_t)j * RW];
+        for (int i = tid; i < m.n_taps; i += NT) staps[i] = m.taps[i];
+        const double x_start = m.ode_from_zero ? 0.0 : m.x_centers[0];
+        for (int i = tid; i < X; i += NT) sdelta[i] = m.rng_sign * (m.x_centers[i] - x_start);
+        if (tid == 0) {
+            frame.de = (m.e_max - m.e_min) / (double)m.e_bins;
+            frame.dx = (m.x_max - m.x_min) / (double)X;
+            frame.umax_next = __longlong_as_double(__double_as_longlong(m.rng_u_max) + 1);
+            frame.zlut = nullptr;
+            frame.idx[0] = (long long)atomicAdd(out.work, 1ull);
+        }
+    }
+    double *Hglobal = out.wide_scratch ? out.wide_scratch + (size_t)blockIdx.x * (size_t)out.split_stride : nullptr;
+    for (int it = 0;; ++it) {
+        const int st = zrm_setup<NT, P>(&m, &run, theta, n_walkers, &out, smem_raw, &frame, it, Hglobal);
+        if (st == PLANNED_DONE) break;
+        if (st == PLANNED_SKIP) continue;
+        const bool wide = frame.wide != 0;
+        if (wide) zrm_exec<NT, P, true>(m, run, out, smem_raw, &frame, Hglobal);
+        else zrm_exec<NT, P, false>(m, run, out, smem_raw, &frame, nullptr);
+        __threadfence_block();
+        __syncthreads();
+        // normalisation sum (adv:143) over the walker's cells, then phases 3-5
+        const double *H = wide ? Hglobal : reinterpret_cast<const double *>(smem_raw);
+        const int ncell = X * frame.hstride;
+        double part = 0.0;
+        for (int i = tid; i < ncell; i += NT) part += __dmul_rn(__dmul_rn(H[i], frame.de), frame.dx);
+        if (wide) zr_finish<NT, P, false, true>(&m, &run, &out, smem_raw, &frame, Hglobal, part);
+        else zr_finish<NT, P, false, false>(&m, &run, &out, smem_raw, &frame, nullptr, part);
     }
 }
 

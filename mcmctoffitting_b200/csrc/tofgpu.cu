@@ -52,6 +52,8 @@ struct tof_ctx {
     bool planned = false;    // banded launch runs adv_planned_kernel (FP64, <= one tile of draws, interval == E-bin)
     // ... or adv_zrank_kernel (same conditions; shipped): one launch per call, wide walkers in a global scratch histogram
     bool zrank = false;
+    bool zrank_multi = false;   // ... adv_zrank_multi_kernel for draw sets of more than one tile (no draw split)
+    int last_model_launches = 0;   // model kernels the most recent adv/intermediate range call launched
     int zr_hcap = 0, zr_rcap = 0, zr_nt = 512;
     size_t zr_smem = 0;
     RangeLayout lay_zr{};
@@ -244,7 +246,24 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 }
             }
             const long long n_work = n * out.n_split;
-            if (ctx->zrank && !ctx->fresh && !debug && out.n_split == 1 && ctx->runs[run].zlut) {
+            if (ctx->zrank_multi && !ctx->fresh && !debug && !prof && out.n_split == 1) {
+                // big draw sets, enough walkers to fill the machine: tiles of sorted draws, long runs (one launch)
+                const long long slots = (long long)ctx->stats.sm_count * 2;
+                const unsigned grid = (unsigned)std::min<long long>(n, slots);
+                const size_t stride = (size_t)c.x_bins * c.e_bins;
+                rc = ensure(ctx, ctx->d_wide, (size_t)slots * stride * sizeof(double));
+                if (rc) return rc;
+                ModelOut oz = out;
+                oz.work = cnt + 0;
+                oz.queue_count = cnt + 2;
+                oz.hcap = ctx->zr_hcap;
+                oz.rcap = ctx->zr_rcap;
+                oz.lay = ctx->lay_zr;
+                oz.split_stride = (int)stride;
+                oz.wide_scratch = static_cast<double *>(ctx->d_wide.p);
+                adv_zrank_multi_kernel<512, 7><<<grid, 512, ctx->zr_smem, st>>>(ctx->dm, run0, d_theta, n, oz);
+                ctx->last_model_launches = 1;
+            } else if (ctx->zrank && !ctx->fresh && !debug && out.n_split == 1 && ctx->runs[run].zlut) {
                 // shipped path: ONE persistent launch, 2 CTAs/SM; walkers whose E-band does not fit shared memory keep
                 // their cell sums in this CTA's slice of an L2-resident scratch buffer (cnt[2] counts them)
                 const long long slots = (long long)ctx->stats.sm_count * 2;
@@ -263,6 +282,7 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 if (prof) adv_zrank_kernel<512, 7, true><<<grid, 512, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
                 else if (ctx->zr_nt == 384) adv_zrank_kernel<384, 7, false><<<grid, 384, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
                 else adv_zrank_kernel<512, 7, false><<<grid, 512, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
+                ctx->last_model_launches = 1;
             } else if (ctx->band_enabled && !debug && (!ctx->fresh || (ctx->planned && out.n_split == 1))) {
                 rc = ensure(ctx, ctx->d_queue, (size_t)n * sizeof(int));
                 if (rc) return rc;
@@ -285,9 +305,11 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 out.queue_count = cnt + 2;
                 kfull<<<(unsigned)std::min<long long>(n_work, slots_full), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, run0, d_theta, n, out);
                 ctx->stats.kernel_launches += 1;
+                ctx->last_model_launches = 2;
             } else {
                 out.work = cnt + 1;
                 kfull<<<(unsigned)std::min<long long>(n_work, slots_full), ctx->rng_nt, ctx->adv_smem, st>>>(ctx->dm, run0, d_theta, n, out);
+                ctx->last_model_launches = 1;
             }
         } else {
             AdvKernel k = adv_variant(ctx->adv_nt, ctx->adv_dpt, c.n_materials);
@@ -734,7 +756,8 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
         {
             const char *env = std::getenv("TOFGPU_RANGE_ZRANK");
             const bool want = !(env && std::atoi(env) == 0);
-            if (want && !ctx->f32 && P == 7 && m.rng_identity && m.n_draws <= RANGE_TILE && cfg->x_bins >= 1) {
+            const bool multi = m.n_draws > RANGE_TILE;       // big draw sets: adv_zrank_multi_kernel (tiles, no hint tables)
+            if (want && !ctx->f32 && P == 7 && m.rng_identity && cfg->x_bins >= 1 && (!multi || cfg->x_bins <= 32 * (512 / 32 - 1))) {
                 const int per_cta = (int)prop.sharedMemPerBlockOptin / 2 - 2048;
                 const int rcap = std::min(Mi, 128);
                 const size_t fixed = zrank_layout(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], 0, rcap, P, cfg->n_taps, Mi).total;
@@ -755,7 +778,14 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
                         CUC(cudaFuncSetAttribute(k2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                     }
                     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occz, kz, 512, ctx->zr_smem));
-                    if (occz >= 2) {
+                    if (multi) {
+                        AdvKernel km = adv_zrank_multi_kernel<512, 7>;
+                        CUC(cudaFuncSetAttribute(km, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->zr_smem));
+                        CUC(cudaFuncSetAttribute(km, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                        int occm = 0;
+                        CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occm, km, 512, ctx->zr_smem));
+                        ctx->zrank_multi = occm >= 2;
+                    } else if (occz >= 2) {
                         // Theta[j][i] = u^-1(U_j - delta_i): invert the T1 table u(E) on a dense grid (a hint: 1e-5 keV is plenty)
                         auto host_t1 = [&](double E) {
                             uint64_t bits;
@@ -1258,9 +1288,10 @@ int tof_get_stats(const tof_ctx *ctx, tof_stats *out) {
     out->band_cells = ctx->band_enabled ? ctx->band_hcap : 0;
     out->band_queued_last = 0;
     out->wide_last = 0;
-    const bool single = ctx->zrank && ctx->runs[0].zlut != nullptr;
-    out->model_launches_per_call = (ctx->cfg.model == TOF_MODEL_ADV && ctx->cfg.ode_mode == TOF_ODE_RANGE)
-                                       ? ((single || !ctx->band_enabled) ? 1 : 2) : 0;
+    // (before the first call: what a production call of this context will launch)
+    const bool single = ctx->last_model_launches ? ctx->last_model_launches == 1
+                                                 : ((ctx->zrank && ctx->runs[0].zlut != nullptr) || ctx->zrank_multi || !ctx->band_enabled);
+    out->model_launches_per_call = (ctx->cfg.model == TOF_MODEL_ADV && ctx->cfg.ode_mode == TOF_ODE_RANGE) ? (single ? 1 : 2) : 0;
     // counters are read on the context's own stream, ordered after its last model launch (ev_busy): the host waits for
     // that launch only -- no device-wide or legacy-stream synchronisation
     const bool want_nan = ctx->d_nan.p != nullptr, want_q = (ctx->band_enabled || single) && ctx->d_work.p != nullptr;

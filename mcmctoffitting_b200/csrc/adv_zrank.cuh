@@ -864,6 +864,9 @@ __device__ __noinline__ int zrm_setup(const DevModel *mp, const DevRun *rp, cons
 // the few leftover segments are then summed one after the other by all 32 lanes together (strided over the segment's
 // draws, coefficients broadcast by shuffle, warp sum).  Letting those rows run a second lockstep pass instead doubled
 // the polynomial work (measured: 10.0 M warp-instructions per walker at 1e5 draws, against 11.0 M for the streaming walk).
+// Measured alternatives, both slower than this (81.6 K evals/s at 4096 walkers x 1e5 draws): double-buffered tiles with
+// one barrier per tile and the next tile staged ahead (77.4 K); warp-private chunks of 128 draws with no CTA barrier at
+// all in the draw loop (76.6 K: the energy-loss lookups are repeated by every group of rows, per-chunk overheads).
 template <int NT, int P, bool WIDE>
 __device__ __forceinline__ void zrm_exec(const DevModel &m, const DevRun &run, const ModelOut &out, unsigned char *smem_raw,
                                          const ZrFrame *f, double *Hglobal) {

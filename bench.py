@@ -448,6 +448,35 @@ def run_gpu_arm(args):
                                "draw set (common random numbers), the mode the parity goldens pin"}
         mf.close()
 
+    # ---- the reference's own adv configuration (BASELINE.json configs[3]): 4096 walkers x 1e5 draws, 50 TOF bins ------
+    adv_c3 = None
+    if rank == 0 and world == 1 and not f32 and ode == M.config.ODE_RANGE and not args.no_extras:
+        cfg3 = M.config.adv(0, ode_mode=M.config.ODE_RANGE, mean_excitation=19.2e-3)
+        rs3 = np.random.RandomState(5)
+        fn3 = M.make_lnprob(cfg3, np.ones(cfg3.tof_bins[0]), rs3.standard_normal(cfg3.n_draws), device=local_rank)
+        m3 = fn3.model
+        # observables: a realisation of the model at the script's region of interest (made with the library: a timing figure)
+        real = np.rint(1e4 * m3.model_batch(np.array([[1050.0, 0.10]]), run=0, stage="spread")[0])
+        fn3.bind_observables(real)
+        n3 = 4096
+        th3 = torch.from_numpy(np.array([1050.0, 0.10]) + np.array([5.0, 5e-3]) * rs3.standard_normal((n3, 2))).to(device)
+        out3 = torch.empty(n3, dtype=torch.float64, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        m3.set_timing(True)
+        ms3 = []
+        for i in range(3):
+            m3.lnprob_batch_device(th3.data_ptr(), n3, out3.data_ptr(), stream)
+            torch.cuda.synchronize()
+            if i:
+                ms3.append(m3.last_kernel_ms())
+        adv_c3 = {"value": n3 / (statistics.mean(ms3) * 1e-3), "unit": "evals/s", "kernel_ms": statistics.mean(ms3), "walkers": n3,
+                  "draws_per_walker": cfg3.n_draws, "finite_lnprob_fraction": float(torch.isfinite(out3).double().mean().item()),
+                  "launches_per_call": m3.stats().get("model_launches_per_call"),
+                  "what": "tests/advIntermediateTOFmodel.py at its own sizes (BASELINE.json configs[3]: 4096 walkers, nDraws 1e5, "
+                          "100 x 240 grid, 50 TOF bins), physical mean excitation energy; kernel time of one ensemble-sized call "
+                          "(adv_zrank_multi_kernel: tiles of sorted draws)"}
+        m3.close()
+
     # ---- optional FP32 sample stage, reported beside the FP64 headline (N = 1, range formulation) ----------
     fp32_mode = None
     if world == 1 and not f32 and ode == M.config.ODE_RANGE and not args.no_fp32:
@@ -534,7 +563,7 @@ def run_gpu_arm(args):
                        "l2": "flushed between timed steps (256 MiB memset outside the event bracket)",
                        "finite_lnprob_fraction": finite_frac},
             "roofline": roofline, "cpu_baseline": cpu, "fp32_mode": fp32_mode, "stage_profile": stage_profile,
-            "parity_sample": parity_sample, "prior_box": prior_box, "fresh_draws": fresh_draws,
+            "parity_sample": parity_sample, "prior_box": prior_box, "fresh_draws": fresh_draws, "adv_config3": adv_c3,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": N_WALKERS * 2 * 8,
                     "d2h_bytes_per_step": N_WALKERS * 8,
                     "what": "the reference-facing call: TofLnProb.batch = C-ABI tof_lnprob_batch with pinned HOST buffers, two calls "

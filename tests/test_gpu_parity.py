@@ -900,7 +900,7 @@ def test_single_launch_kernel_equals_the_banded_pair(M, O):
         assert (a[k] == want) or rel(float(a[k]), float(want)) <= RTOL, (k, a[k], want)
 
 
-@pytest.mark.parametrize("shape", ["300draws", "20rows", "as_written", "fewbins", "tiny_spread"])
+@pytest.mark.parametrize("shape", ["300draws", "20rows", "as_written", "fewbins", "tiny_spread", "3000draws", "3000draws_as_written"])
 def test_single_launch_kernel_other_shapes(M, O, shape):
     """adv_zrank_kernel away from the benchmark shape: a partial tile of draws, fewer rows than a warp (no full group of
     32 rows: every warp takes the leftover path), the as-written medium (dE/dx > 0: the energies RISE along the cell, the
@@ -914,6 +914,10 @@ def test_single_launch_kernel_other_shapes(M, O, shape):
         kw, okw = dict(mean_excitation=19.2), dict(mean_excitation=19.2)
     elif shape == "fewbins":
         kw, okw = dict(tof_bins=(64,), tof_ranges=((150.0, 250.0),)), dict(tof_bins=64, tof_min=150.0, tof_max=250.0)
+    elif shape.startswith("3000draws"):                      # three tiles, the last one partial: adv_zrank_multi_kernel
+        kw, okw = dict(n_samples=3000, n_ev_per_loop=3000), dict(n_samples=3000, n_ev_per_loop=3000)
+        if shape.endswith("as_written"):
+            kw["mean_excitation"] = okw["mean_excitation"] = 19.2
     elif shape == "tiny_spread":                             # a prior that admits spreads below ZR_MIN_SPREAD: hints off
         pr = ((1000.0, 2600.0), (1e-5, 0.5))
         kw, okw = dict(prior=pr), dict(prior=pr)
@@ -946,7 +950,13 @@ def test_single_launch_kernel_other_shapes(M, O, shape):
         else:
             os.environ["TOFGPU_RANGE_ZRANK"] = old
     a, b = res["single"], res["pair"]
-    assert np.array_equal(a, b, equal_nan=True), int(np.sum(~((a == b) | (np.isnan(a) & np.isnan(b)))))
+    if shape.startswith("3000draws"):
+        # partial sums of a cell meet with atomics in both kernels: same cells up to the order of a few additions
+        assert np.array_equal(np.isfinite(a), np.isfinite(b)) and np.array_equal(np.isnan(a), np.isnan(b))
+        fin = np.isfinite(a)
+        assert np.all(np.abs(a[fin] - b[fin]) <= RTOL * np.abs(b[fin]))
+    else:
+        assert np.array_equal(a, b, equal_nan=True), int(np.sum(~((a == b) | (np.isnan(a) & np.isnan(b)))))
     for k in list(range(0, 10)) + [60, 61, 62]:
         want = om.lnprob(thetas[k], obs, z, xs)
         assert (a[k] == want) or (np.isnan(a[k]) and np.isnan(want)) or rel(float(a[k]), float(want)) <= RTOL, (k, a[k], want)

@@ -81,6 +81,8 @@ struct ZrFrame {
     float hint_a, hint_b;    // lookup cell of a threshold energy: Theta * a + b
     int s_ref, k_lo, n_iv, nB, wB;   // trajectory-aligned visit grid of the cell sums (see zr_exec)
     double spread;           // sigma0 * e0 (multi-tile kernel: the draws are staged tile by tile)
+    int split;               // multi-tile kernel with few walkers: which share of the tiles this CTA sums
+    int last;                // ... whether this CTA arrived last and finishes the walker
     double de, dx;           // bin widths of the (x,E) histogram (set once per CTA)
     double umax_next;        // nextafter(u_max): right edge of the last (closed) interval (set once per CTA)
     const unsigned short *zlut;   // draw-rank lookup of this run (set once per CTA)
@@ -787,7 +789,11 @@ __device__ __noinline__ int zrm_setup(const DevModel *mp, const DevRun *rp, cons
         f->band[2] = -1;
     }
     __syncthreads();                                       // the previous walker is done with shared memory
-    const long long w = f->idx[it & 1];
+    // a work item is (walker, split): with few walkers and a big draw set, n_split CTAs share one walker's tiles
+    const int NS = out.n_split > 1 ? out.n_split : 1;
+    const long long item = f->idx[it & 1];
+    const long long w = item / NS;
+    const int split = (int)(item - w * NS);
     if (w >= n_walkers) return PLANNED_DONE;
     if (tid == 0) f->idx[(it + 1) & 1] = (long long)atomicAdd(out.work, 1ull);
     const double e0 = theta[w * m.ndim + 0];
@@ -842,6 +848,7 @@ __device__ __noinline__ int zrm_setup(const DevModel *mp, const DevRun *rp, cons
         f->w = w;
         f->e0 = e0;
         f->spread = spread;
+        f->split = split;
         f->hstride = hstride;
         f->jbase = fits ? jbase : 0;
         f->wide = fits ? 0 : 1;
@@ -849,7 +856,7 @@ __device__ __noinline__ int zrm_setup(const DevModel *mp, const DevRun *rp, cons
             f->band[1] = 0;
             f->band[2] = -1;
         }
-        if (!fits && out.queue_count) atomicAdd(out.queue_count, 1ull);
+        if (!fits && split == 0 && out.queue_count) atomicAdd(out.queue_count, 1ull);
     }
     __syncthreads();
     return PLANNED_RUN;
@@ -938,7 +945,8 @@ __device__ __forceinline__ void zrm_exec(const DevModel &m, const DevRun &run, c
         if constexpr (WIDE) atomicAdd(Hglobal + hidx, val);
         else atomicAdd(Hs + hidx, val);
     };
-    for (long long tile = 0; tile < m.n_draws; tile += RANGE_TILE) {
+    const int NS = out.n_split > 1 ? out.n_split : 1;
+    for (long long tile = (long long)f->split * RANGE_TILE; tile < m.n_draws; tile += (long long)NS * RANGE_TILE) {
         const int nt = (int)((m.n_draws - tile < RANGE_TILE) ? (m.n_draws - tile) : RANGE_TILE);
         __syncthreads();                                   // the previous tile is consumed
         int n_neg = 0, n_pos = 0;                          // draws outside the energy table: -inf first, +inf last
@@ -1078,9 +1086,32 @@ __global__ void __launch_bounds__(NT, 2) adv_zrank_multi_kernel(const __grid_con
         else zrm_exec<NT, P, false>(m, run, out, smem_raw, &frame, nullptr);
         __threadfence_block();
         __syncthreads();
+        const int ncell = X * frame.hstride;
+        if (out.n_split > 1) {
+            // partial histogram -> L2-resident scratch; the CTA that arrives last adds the partials in split order (a fixed
+            // order: the sum does not depend on which CTA finishes last) and carries on alone
+            const int NS = out.n_split;
+            const long long w = frame.w;
+            double *Hmine = wide ? Hglobal : reinterpret_cast<double *>(smem_raw);
+            double *part_out = out.split_scratch + ((size_t)w * NS + frame.split) * (size_t)out.split_stride;
+            for (int i = tid; i < ncell; i += NT) part_out[i] = Hmine[i];
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) frame.last = (atomicAdd(out.split_tickets + w, 1u) == (unsigned)(NS - 1)) ? 1 : 0;
+            __syncthreads();
+            if (!frame.last) continue;
+            __threadfence();
+            const double *base_in = out.split_scratch + (size_t)w * NS * (size_t)out.split_stride;
+            for (int i = tid; i < ncell; i += NT) {
+                double v = 0.0;
+                for (int k = 0; k < NS; ++k) v += __ldcg(base_in + (size_t)k * out.split_stride + i);
+                Hmine[i] = v;
+            }
+            if (tid == 0) out.split_tickets[w] = 0u;       // ready for the next call
+            __syncthreads();
+        }
         // normalisation sum (adv:143) over the walker's cells, then phases 3-5
         const double *H = wide ? Hglobal : reinterpret_cast<const double *>(smem_raw);
-        const int ncell = X * frame.hstride;
         double part = 0.0;
         for (int i = tid; i < ncell; i += NT) part += __dmul_rn(__dmul_rn(H[i], frame.de), frame.dx);
         if (wide) zr_finish<NT, P, false, true>(&m, &run, &out, smem_raw, &frame, Hglobal, part);

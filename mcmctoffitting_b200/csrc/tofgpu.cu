@@ -246,10 +246,10 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 }
             }
             const long long n_work = n * out.n_split;
-            if (ctx->zrank_multi && !ctx->fresh && !debug && !prof && out.n_split == 1) {
-                // big draw sets, enough walkers to fill the machine: tiles of sorted draws, long runs (one launch)
+            if (ctx->zrank_multi && !ctx->fresh && !debug && !prof) {
+                // big draw sets: tiles of sorted draws, long runs (one launch); with few walkers n_split CTAs share a walker
                 const long long slots = (long long)ctx->stats.sm_count * 2;
-                const unsigned grid = (unsigned)std::min<long long>(n, slots);
+                const unsigned grid = (unsigned)std::min<long long>(n_work, slots);
                 const size_t stride = (size_t)c.x_bins * c.e_bins;
                 rc = ensure(ctx, ctx->d_wide, (size_t)slots * stride * sizeof(double));
                 if (rc) return rc;

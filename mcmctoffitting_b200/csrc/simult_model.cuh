@@ -247,6 +247,165 @@ __device__ __forceinline__ void smem_sort(double *a, int n, int cap) {
     }
 }
 
+// Phase 1 for one tile of a BIG sorted draw set (the simultaneous fit draws 50 000 per loop): the tile is a narrow slice
+// of the energy distribution, a row's slice of it lies in one E-bin unless a bin edge falls inside, so runs are long and
+// the polynomial loop is nearly all there is.  Same scheme as adv_zrank_multi_kernel (adv_zrank.cuh): lane = row (with
+// fewer than 32 rows: R rows x (32/R) sub-slices per warp), every lane of a warp sums the first segment of its slice in
+// lockstep, leftover segments are summed one after the other by all 32 lanes; partial sums of a cell meet with atomics.
+// Membership rule RN(u0[d] + delta) >= edge as everywhere.  Full-width histogram H[X][EB], all T2 records staged.
+// Called by all threads of the CTA; no barrier inside.
+template <int NT, int P>
+__device__ __forceinline__ void simult_tile_long(const double *u0, int nt, const double *brk, const double *rec, const unsigned short *lut,
+                                                 const double *sdelta, double *H, int EB, int X, int M, double umax, double lut_inv,
+                                                 int lut_n) {
+    constexpr int RW = P + 3;
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // finite part of the sorted tile: -inf (redrawn / NaN) first, +inf last
+    int v_lo = 0, v_hi = nt;
+    if (!(u0[0] > -CUDART_INF) || u0[nt - 1] >= CUDART_INF) {
+        int lo = 0, hi = nt;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (u0[mid] > -CUDART_INF) hi = mid;
+            else lo = mid + 1;
+        }
+        v_lo = lo;
+        hi = nt;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (u0[mid] >= CUDART_INF) hi = mid;
+            else lo = mid + 1;
+        }
+        v_hi = lo;
+    }
+    if (v_hi <= v_lo) return;                              // uniform
+    const int Gf = X >> 5, R = X & 31;
+    const int wB = R ? (Gf ? 1 : NW) : 0, wA = NW - wB;
+    int row, parts, part;
+    bool lane_ok = true;
+    if (warp < wA) {
+        const int g = warp % Gf, q = warp / Gf;
+        row = (g << 5) + lane;
+        parts = (wA - g + Gf - 1) / Gf;
+        part = q;
+        if (g >= wA) return;                               // (more groups of rows than warps: not a simultFit shape)
+    } else {
+        const int per_b = 32 / R, sub = lane / R;
+        row = (Gf << 5) + (lane - sub * R);
+        parts = wB * per_b;
+        part = (warp - wA) * per_b + sub;
+        lane_ok = sub < per_b;
+    }
+    const double delta = sdelta[row];
+    const int hbase = row * EB;
+    const double umax_next = __longlong_as_double(__double_as_longlong(umax) + 1);
+    const unsigned u0_s32 = (unsigned)__cvta_generic_to_shared(u0);
+    auto edge_of = [&](int j) -> double { return j == 0 ? 0.0 : (j >= M ? umax_next : brk[j - 1]); };
+    auto first_ge = [&](int lo, int hi, double edge, double dl) -> int {
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__dadd_rn(u0[mid], dl) >= edge) hi = mid;
+            else lo = mid + 1;
+        }
+        return lo;
+    };
+    auto load_record = [&](int j, double (&a)[P + 1], double &a0, int &bin) {
+        const double2 *r2 = reinterpret_cast<const double2 *>(rec + j * RW);
+        bin = __double2loint(r2[0].y);
+        const double2 c01 = r2[1];
+        a0 = c01.x;
+        a[0] = 0.0;
+        a[1] = c01.y;
+#pragma unroll
+        for (int k = 2; k <= P; k += 2) {
+            const double2 c2 = r2[1 + (k >> 1)];
+            a[k] = c2.x;
+            a[k + 1] = c2.y;
+        }
+    };
+    const int nf = v_hi - v_lo;
+    int s = v_lo + (part * nf) / parts, sB = v_lo + ((part + 1) * nf) / parts;
+    if (!lane_ok) sB = s;
+    if (s < sB && !(__dadd_rn(u0[s], delta) >= 0.0)) s = first_ge(s, sB, 0.0, delta);   // below the histogram range
+    int j = 0;
+    if (s < sB) {
+        const double v = __dadd_rn(u0[s], delta);
+        if (v > umax) s = sB;
+        else j = range_interval(v, brk, lut, lut_inv, lut_n, M);
+    }
+    {   // main pass: the first segment of every lane's slice, in lockstep
+        const bool act = s < sB;
+        int s1 = sB;
+        if (act && __dadd_rn(u0[sB - 1], delta) >= edge_of(j + 1)) s1 = first_ge(s, sB, edge_of(j + 1), delta);
+        const int n = act ? s1 - s : 0;
+        const int nmax = __reduce_max_sync(FULL, n);
+        if (nmax > 0) {
+            const int nmin = __reduce_min_sync(FULL, n);
+            double a[P + 1], a0;
+            int bin;
+            load_record(act ? j : 0, a, a0, bin);
+            const double off = delta - (act ? edge_of(j) : 0.0);
+            double acc = 0.0;
+            unsigned addr = u0_s32 + (unsigned)s * 8u;
+            const int tfull = nmin >> 2;
+#pragma unroll 1
+            for (int t = tfull; t > 0; --t) {
+                poly_full4<P>(acc, addr, off, a);
+                addr += 32u;
+            }
+            int rem = n - (tfull << 2);
+#pragma unroll 1
+            for (int t = ((nmax + 3) >> 2) - tfull; t > 0; --t) {
+                poly_run4<P>(acc, addr, rem, off, a);
+                addr += 32u;
+                rem -= 4;
+            }
+            if (n > 0) atomicAdd(H + hbase + bin, fma((double)n, a0, acc));
+        }
+        s = s1;
+        ++j;
+    }
+    for (;;) {   // leftover segments (an interval edge inside the slice), one at a time, all 32 lanes on each
+        const bool more = s < sB && j < M;
+        const unsigned pending = __ballot_sync(FULL, more);
+        if (pending == 0u) break;
+        const int src = __ffs(pending) - 1;
+        int s1 = 0;
+        if (lane == src) s1 = first_ge(s, sB, edge_of(j + 1), delta);
+        const int seg_s = __shfl_sync(FULL, s, src), seg_e = __shfl_sync(FULL, s1, src), seg_j = __shfl_sync(FULL, j, src);
+        const double seg_delta = __shfl_sync(FULL, delta, src);
+        const int seg_h = __shfl_sync(FULL, hbase, src);
+        const int seg_n = seg_e - seg_s;
+        if (seg_n > 0) {
+            double a[P + 1], a0;
+            int bin;
+            load_record(seg_j, a, a0, bin);
+            const double off = seg_delta - edge_of(seg_j);
+            const int ch = (seg_n + 31) >> 5;
+            const int la = seg_s + lane * ch;
+            int n = seg_e - la;
+            n = n < 0 ? 0 : (n > ch ? ch : n);
+            double acc = 0.0;
+            unsigned addr = u0_s32 + (unsigned)(la < seg_e ? la : seg_s) * 8u;
+            int rem = n;
+#pragma unroll 1
+            for (int t = (ch + 3) >> 2; t > 0; --t) {
+                poly_run4<P>(acc, addr, rem, off, a);
+                addr += 32u;
+                rem -= 4;
+            }
+            acc = fma((double)n, a0, acc);
+            acc = warp_sum(acc);
+            if (lane == 0) atomicAdd(H + seg_h + bin, acc);
+        }
+        if (lane == src) {
+            s = s1;
+            ++j;
+        }
+    }
+}
+
 __host__ __device__ inline size_t simult_range_smem_bytes(int X, int E, int T, int rng_n, int P, int n_taps, int lut_n) {
     size_t d = (size_t)X * E + 2 * (size_t)T + RANGE_TILE + (size_t)rng_n * (P + 3) + X + E + n_taps + 48 + X;
     return d * 8 + (((size_t)lut_n * 2 + 15) / 16) * 16 + SIMULT_ULUT * 2 + (((size_t)X * 4 + 15) / 16) * 16 + (size_t)rng_n * 8 + 32;
@@ -337,8 +496,13 @@ __global__ void __launch_bounds__(NT, 4) simult_range_kernel(const DevModel m, c
                     while (cap < nt) cap <<= 1;
                     smem_sort<NT>(u0, nt, cap);
                 }
-                range_accumulate_tile<NT, P>(u0, nt, sbrk, rec, 0, lut, ulut, SIMULT_ULUT, sdelta, srow, H, EB, nullptr, X, M, m.rng_u_max,
-                                             m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all);
+                // long runs (a tile of a 50 000-draw loop is a narrow energy slice): the lean routine; short tiles of
+                // replacement draws and split E-bins go through the general one
+                if (nt >= 256 && X <= 32 * (NT / 32))
+                    simult_tile_long<NT, P>(u0, nt, sbrk, rec, lut, sdelta, H, EB, X, M, m.rng_u_max, m.rng_lut_inv, m.rng_lut_n);
+                else
+                    range_accumulate_tile<NT, P>(u0, nt, sbrk, rec, 0, lut, ulut, SIMULT_ULUT, sdelta, srow, H, EB, nullptr, X, M, m.rng_u_max,
+                                                 m.rng_lut_inv, m.rng_lut_n, bin_lo_all, bin_hi_all);
             }
             const long long nbad_tot = block_sum<long long>(nbad, reinterpret_cast<long long *>(scratch));
             loop_sum += block_sum<double>(part, scratch);

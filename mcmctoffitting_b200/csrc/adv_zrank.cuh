@@ -35,11 +35,11 @@
 
 namespace tof {
 
-constexpr int ZR_LUT = 4096;             // cells of the draw-rank lookup over z (entries: ZR_LUT + 1)
+constexpr int ZR_LUT = 8192;             // cells of the draw-rank lookup over z (entries: ZR_LUT + 1); 4096: -0.5 %, 16384: same
 constexpr float ZR_BIAS = 0.25f;         // cells the hint is lowered by (float rounding of the hint << 0.25 cell)
 // keV; below this (and for reversed / degenerate spreads) hints are off.  Error budget of a hint in lookup cells, worst case
-// at spread = 8 keV with thresholds near 2600 keV: float rounding of Theta (1.6e-4 keV), of Theta*a + b (|b| ~ 2e5:
-// 0.008 cells) and of the FMA -- together < 0.03 cells against the 0.25-cell bias.
+// at spread = 8 keV with thresholds near 2600 keV: float rounding of Theta (1.6e-4 keV = 0.025 cells), of b (|b| ~ 4e5:
+// 0.016 cells) and of the FMA (0.016) -- together < 0.06 cells against the 0.25-cell bias.
 constexpr double ZR_MIN_SPREAD = 8.0;
 
 // Byte offsets of the regions of adv_zrank_kernel's dynamic shared memory (host-computed).  Order:

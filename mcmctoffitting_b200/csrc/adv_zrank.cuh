@@ -873,7 +873,8 @@ __device__ __noinline__ int zrm_setup(const DevModel *mp, const DevRun *rp, cons
 // the polynomial work (measured: 10.0 M warp-instructions per walker at 1e5 draws, against 11.0 M for the streaming walk).
 // Measured alternatives, both slower than this (81.6 K evals/s at 4096 walkers x 1e5 draws): double-buffered tiles with
 // one barrier per tile and the next tile staged ahead (77.4 K); warp-private chunks of 128 draws with no CTA barrier at
-// all in the draw loop (76.6 K: the energy-loss lookups are repeated by every group of rows, per-chunk overheads).
+// all in the draw loop (76.6 K: the energy-loss lookups are repeated by every group of rows, per-chunk overheads); ten
+// slices per group handed out through a shared counter instead of one static slice per warp (80.5 K).
 template <int NT, int P, bool WIDE>
 __device__ __forceinline__ void zrm_exec(const DevModel &m, const DevRun &run, const ModelOut &out, unsigned char *smem_raw,
                                          const ZrFrame *f, double *Hglobal) {
@@ -1000,6 +1001,7 @@ __device__ __forceinline__ void zrm_exec(const DevModel &m, const DevRun &run, c
                     addr += 32u;
                     rem -= 4;
                 }
+                TOF_CHECK(n == 0 || (s >= v_lo && s1 <= v_hi && hbase + j >= 0 && hbase + j < X * hstride && (WIDE || j - fv->jbase >= 0)));
                 if (n > 0) add_cell(hbase + j, fma((double)n, a0, acc));
             }
             s = s1;
@@ -1037,6 +1039,7 @@ __device__ __forceinline__ void zrm_exec(const DevModel &m, const DevRun &run, c
                 }
                 acc = fma((double)n, a0, acc);
                 acc = warp_sum(acc);
+                TOF_CHECK(seg_s >= v_lo && seg_e <= v_hi && seg_h + seg_j >= 0 && seg_h + seg_j < X * hstride);
                 if (lane == 0) add_cell(seg_h + seg_j, acc);
             }
             if (lane == src) {

@@ -361,6 +361,7 @@ __device__ __forceinline__ void simult_tile_long(const double *u0, int nt, const
                 addr += 32u;
                 rem -= 4;
             }
+            TOF_CHECK(n == 0 || (bin >= 0 && bin < EB && s >= v_lo && s1 <= v_hi));
             if (n > 0) atomicAdd(H + hbase + bin, fma((double)n, a0, acc));
         }
         s = s1;
@@ -397,6 +398,7 @@ __device__ __forceinline__ void simult_tile_long(const double *u0, int nt, const
             }
             acc = fma((double)n, a0, acc);
             acc = warp_sum(acc);
+            TOF_CHECK(bin >= 0 && bin < EB && seg_s >= v_lo && seg_e <= v_hi);
             if (lane == 0) atomicAdd(H + seg_h + bin, acc);
         }
         if (lane == src) {

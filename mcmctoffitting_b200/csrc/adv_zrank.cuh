@@ -26,7 +26,10 @@
 //    launch at 1 CTA/SM: the same CTA keeps their cell sums in an L2-resident scratch histogram (WIDE instantiation
 //    of the same phase functions) -- one launch per call, no serial tail.
 //
-// Used for: FP64, n_draws <= RANGE_TILE, one T2 interval per E-bin (rng_identity), production output (lnprob only).
+// Used for: FP64, n_draws <= RANGE_TILE, one T2 interval per E-bin (rng_identity), production output (lnprob only),
+// bound draws.  The second kernel of this file, adv_zrank_multi_kernel, serves bigger draw sets (the reference's own
+// 1e5 - 1e6 draws per evaluation) with the same phase functions after the cell sums.  Debug outputs, the FP32 mode,
+// split E-bins and per-evaluation draws stay with adv_range_kernel / adv_planned_kernel.
 #pragma once
 #include "adv_planned.cuh"
 #ifdef TOF_ZR_DEBUG

@@ -247,6 +247,11 @@ __device__ __forceinline__ void smem_sort(double *a, int n, int cap) {
     }
 }
 
+// draws staged at a time by simult_range_kernel: with ten rows a warp packs 10 rows x 3 sub-slices, 24 sub-slices per row
+// over the CTA's eight warps -- 2048 draws give every lane a run of ~85 samples (1024: the per-tile searches cost as much
+// as the polynomial work)
+constexpr int SIMULT_TILE = 2048;
+
 // Phase 1 for one tile of a BIG sorted draw set (the simultaneous fit draws 50 000 per loop): the tile is a narrow slice
 // of the energy distribution, a row's slice of it lies in one E-bin unless a bin edge falls inside, so runs are long and
 // the polynomial loop is nearly all there is.  Same scheme as adv_zrank_multi_kernel (adv_zrank.cuh): lane = row (with
@@ -409,7 +414,7 @@ __device__ __forceinline__ void simult_tile_long(const double *u0, int nt, const
 }
 
 __host__ __device__ inline size_t simult_range_smem_bytes(int X, int E, int T, int rng_n, int P, int n_taps, int lut_n) {
-    size_t d = (size_t)X * E + 2 * (size_t)T + RANGE_TILE + (size_t)rng_n * (P + 3) + X + E + n_taps + 48 + X;
+    size_t d = (size_t)X * E + 2 * (size_t)T + SIMULT_TILE + (size_t)rng_n * (P + 3) + X + E + n_taps + 48 + X;
     return d * 8 + (((size_t)lut_n * 2 + 15) / 16) * 16 + SIMULT_ULUT * 2 + (((size_t)X * 4 + 15) / 16) * 16 + (size_t)rng_n * 8 + 32;
 }
 
@@ -430,8 +435,8 @@ __global__ void __launch_bounds__(NT, 4) simult_range_kernel(const DevModel m, c
     double *H = reinterpret_cast<double *>(smem_raw);            // [CELLS]
     double *tofh = H + CELLS;                                    // [T]
     double *pdf = tofh + T;                                      // [T]
-    double *u0 = pdf + T;                                        // [RANGE_TILE]
-    double *rec = u0 + RANGE_TILE;                               // [M][RW]
+    double *u0 = pdf + T;                                        // [SIMULT_TILE]
+    double *rec = u0 + SIMULT_TILE;                              // [M][RW]
     double *sx = rec + (size_t)M * RW;                           // [X]
     double *svd = sx + X;                                        // [E]
     double *staps = svd + EB;
@@ -477,11 +482,19 @@ __global__ void __launch_bounds__(NT, 4) simult_range_kernel(const DevModel m, c
         while (count > 0) {
             long long nbad = 0;
             double part = 0.0;
-            for (long long tile = 0; tile < count; tile += RANGE_TILE) {
-                const int nt = (int)((count - tile < RANGE_TILE) ? (count - tile) : RANGE_TILE);
+            for (long long tile = 0; tile < count; tile += SIMULT_TILE) {
+                const int nt = (int)((count - tile < SIMULT_TILE) ? (count - tile) : SIMULT_TILE);
                 __syncthreads();
-                for (int d = tid; d < nt; d += NT) {
-                    const double z = __ldg(src + tile + d);
+                // the tile's draws are fetched first (independent loads in flight), then transformed
+                constexpr int ZPT = SIMULT_TILE / NT;
+                double zz[ZPT];
+#pragma unroll
+                for (int q = 0; q < ZPT; ++q) zz[q] = (tid + q * NT < nt) ? __ldg(src + tile + tid + q * NT) : 0.0;
+#pragma unroll
+                for (int q = 0; q < ZPT; ++q) {
+                    const int d = tid + q * NT;
+                    if (d >= nt) break;
+                    const double z = zz[q];
                     const double E = __dsub_rn(beamE, __dadd_rn(__dmul_rn(exp(__dmul_rn(sshape, z)), scale), eLoss));
                     double u = -CUDART_INF;                      // redrawn (E <= 0) or NaN: contributes nothing
                     if (E <= 0.0) {

@@ -44,19 +44,24 @@ constexpr float ZR_BIAS = 0.25f;         // cells the hint is lowered by (float 
 // at spread = 8 keV with thresholds near 2600 keV: float rounding of Theta (1.6e-4 keV = 0.025 cells), of b (|b| ~ 4e5:
 // 0.016 cells) and of the FMA (0.016) -- together < 0.06 cells against the 0.25-cell bias.
 constexpr double ZR_MIN_SPREAD = 8.0;
+// Scalars the cell sums re-read at every use (they do not fit in registers next to four Horner chains) sit right below
+// the draw tile, whose shared-memory address is live in a register anyway: one LDS with an immediate offset each.
+constexpr int ZR_MIRROR = 32;            // bytes: de f64 @-32 | dx f64 @-24 | jbase s32 @-16 | hint_a, hint_b f32 @-8
 
 // Byte offsets of the regions of adv_zrank_kernel's dynamic shared memory (host-computed).  Order:
-//   H [hcap] f64 (later the density [T]) | draw tile u0 [RANGE_TILE] f64, later the TOF counters [T] u32 |
+//   H [hcap] f64 (later the density [T]) | ZR_MIRROR bytes | draw tile u0 [RANGE_TILE + 1] f64, later the TOF counters [T] u32 |
 //   staged T2 records [rcap][P+3] f64, later deuteron speeds, their reciprocals and 1/neutron speed [3][E] | taps |
 //   40 doubles of scratch |
-//   delta [X] | srow [X] int | hlo [X] int | interval ends [M] f64
+//   delta [X] | srow [X] int | hlo [X] int | 0.0 | interval ends [M] f64 (the last one replaced by nextafter(u_max):
+//   range_interval never reads it, the edge lookup of the cell sums does)
 inline RangeLayout zrank_layout(int X, int E, int T, int hcap, int rcap, int P, int n_taps, int rng_n) {
     RangeLayout L{};
-    size_t region_a = (size_t)T * 4 > (size_t)RANGE_TILE * 8 ? (size_t)T * 4 : (size_t)RANGE_TILE * 8;
+    size_t region_a = (size_t)T * 4 > (size_t)(RANGE_TILE + 1) * 8 ? (size_t)T * 4 : (size_t)(RANGE_TILE + 1) * 8;   // + the +inf sentinel behind the draws
     region_a = (region_a + 15) / 16 * 16;
     size_t rec_b = (size_t)rcap * (P + 3) * 8;
     rec_b = rec_b > (size_t)3 * E * 8 ? rec_b : (size_t)3 * E * 8;
     size_t o = ((size_t)hcap * 8 + 15) / 16 * 16;         // what follows is read with 16-byte loads
+    o += ZR_MIRROR;                                       // per-walker scalars of the cell sums, at fixed offsets below u0
     L.pa = (unsigned)o;        o += region_a;
     L.rec = (unsigned)o;
     L.svd = (unsigned)o;                          // aliases the records (dead after the cell sums)
@@ -67,6 +72,7 @@ inline RangeLayout zrank_layout(int X, int E, int T, int hcap, int rcap, int P, 
     L.sdelta = (unsigned)o;    o += (size_t)X * 8;
     L.srow = (unsigned)o;      o += (size_t)X * 4;
     L.hlo = (unsigned)o;       o += (size_t)(X + (X & 1)) * 4;
+    o += 8;                                       // sbrk[-1] = 0: sbrk[j - 1] is the lower edge of interval j for every j in [0, M]
     L.sbrk = (unsigned)o;      o += (size_t)rng_n * 8;
     L.lut = L.sbin = 0;
     L.total = (unsigned)(o + 16);
@@ -87,7 +93,6 @@ struct ZrFrame {
     int split;               // multi-tile kernel with few walkers: which share of the tiles this CTA sums
     int last;                // ... whether this CTA arrived last and finishes the walker
     double de, dx;           // bin widths of the (x,E) histogram (set once per CTA)
-    double umax_next;        // nextafter(u_max): right edge of the last (closed) interval (set once per CTA)
     const unsigned short *zlut;   // draw-rank lookup of this run (set once per CTA)
     long long t_mark;        // stage timing (PROF)
 };
@@ -144,6 +149,18 @@ __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const
     // (measured: dealing the first 85 % of the walkers out round-robin, without the atomic and with the next parameter
     // vector copied in by cp.async, is 1.7 % slower -- the CTAs drift into lockstep phases)
     if (tid == 0) f->idx[(it + 1) & 1] = (long long)atomicAdd(out.work, 1ull);
+    // the draws do not depend on the walker: fetched before the parameter vector is looked at, so that both loads fly together
+    const int nt = (int)m.n_draws;                         // one tile
+    constexpr int DPT = (1024 + NT - 1) / NT;              // draws per thread (zrank_layout caps the tile at 1024 draws)
+    double zf[DPT], zb[DPT];                               // z[d] and z[nt - 1 - d]: the order depends on the sign of the spread
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+        const int d = tid + q * NT;
+        zf[q] = d < nt ? __ldg(run.z + d) : 0.0;
+        zb[q] = d < nt ? __ldg(run.z + (nt - 1 - d)) : 0.0;
+    }
+    const double z_first = __ldg(run.z), z_last = __ldg(run.z + (nt - 1)), z_mid_f = __ldg(run.z + (nt >> 1)),
+                 z_mid_b = __ldg(run.z + (nt - 1 - (nt >> 1)));
     const double e0 = theta[w * m.ndim + 0];
     const double sigma0 = theta[w * m.ndim + 1];
     bool inside = true;
@@ -159,16 +176,25 @@ __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const
     const double spread = __dmul_rn(sigma0, e0);          // adv:128
     const bool rev = spread < 0.0;                         // draws are sorted ascending: E0 ascends unless the spread is negative
     const double umax = m.rng_u_max;
-    const int nt = (int)m.n_draws;                         // one tile
     // energy-loss lookup of every draw (adv:128-129): u0[d] = u(e0 + spread * z_d), ascending
-    for (int d = tid; d < nt; d += NT)
-        u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, __ldg(run.z + (rev ? nt - 1 - d : d)))), m);
-    __syncthreads();
-    // E-bins the walker can touch: the draws are sorted, first and last give the extremes
-    const double u_lo = u0[0], u_hi = u0[nt - 1], u_med = u0[nt >> 1];
+#pragma unroll
+    for (int q = 0; q < DPT; ++q) {
+        const int d = tid + q * NT;
+        if (d < nt) u0[d] = t1_eval(__dadd_rn(e0, __dmul_rn(spread, rev ? zb[q] : zf[q])), m);
+    }
+    if (tid == 0) u0[nt] = CUDART_INF;                     // sentinel: the forward walks of the cell sums stop here
+    // E-bins the walker can touch: the draws are sorted, first and last give the extremes.  The row threads evaluate
+    // these three draws themselves (the same expression as the staged copy: identical bits) instead of waiting for
+    // the staged array behind a barrier.
     // every row has its own window of E-bins: [u_lo + delta_i, u_hi + delta_i], one interval of slack on both sides
     // (T1 is only monotone up to its 2e-13 cm fit error); interval j == E-bin j on this path.  srow: interval of the
     // median draw -- rows are processed along the trajectory so that the lanes of a warp have runs of similar length.
+    double u_lo = 0.0, u_hi = 0.0, u_med = 0.0;
+    if (tid < X) {
+        u_lo = t1_eval(__dadd_rn(e0, __dmul_rn(spread, rev ? z_last : z_first)), m);
+        u_hi = t1_eval(__dadd_rn(e0, __dmul_rn(spread, rev ? z_first : z_last)), m);
+        u_med = t1_eval(__dadd_rn(e0, __dmul_rn(spread, rev ? z_mid_b : z_mid_f)), m);
+    }
     for (int i = tid; i < X; i += NT) {
         const double dl = sdelta[i];
         double vmin = u_lo > -CUDART_INF ? u_lo + dl : 0.0;     // -inf draws: the lowest in-range v is 0 (whatever the sign of delta)
@@ -220,6 +246,12 @@ __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const
         }
         f->hint_a = ha;
         f->hint_b = hb;
+        {
+            unsigned char *mir = smem_raw + out.lay.pa;
+            reinterpret_cast<float *>(mir - 8)[0] = ha;
+            reinterpret_cast<float *>(mir - 8)[1] = hb;
+            *reinterpret_cast<int *>(mir - 16) = fits ? jbase : 0;
+        }
         // visit grid: rows are walked along the trajectory, interval j = k + (srow[row] - srow[0]); the shift is
         // monotone in the row index.  Leftover rows (X % 32): R rows x (32/R) offsets per visit, on wB warps of their own
         // (in proportion to their share of the visits, at least one when there are any).
@@ -306,16 +338,20 @@ __device__ __forceinline__ double zr_exec(const DevModel *mp, const DevRun *rp, 
     const unsigned rec_s32 = smem_s32 + op->lay.rec;
     // ---- finding a cell's run of draws: hint -> lookup -> short forward walk -------------------------------------
     // lower edge of interval j in u (j == M: the upper end of the last, closed, interval: v > u_max <=> v >= next(u_max))
-    auto edge_of = [&](int j) -> double { return j == 0 ? 0.0 : (j >= M ? fv->umax_next : brk[j - 1]); };
+    auto edge_of = [&](int j) -> double { return brk[j - 1]; };   // 0 <= j <= M (see the staging of sbrk)
+    const unsigned short *zlut = rp->zlut;
     auto hint = [&](float th) -> int {
-        int c = __float2int_rz(fmaf(th, fv->hint_a, fv->hint_b));
+        float ha, hb;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+-8];" : "=f"(ha), "=f"(hb) : "r"(u0_s32));
+        int c = __float2int_rz(fmaf(th, ha, hb));
         c = c < 0 ? 0 : (c > ZR_LUT ? ZR_LUT : c);
-        return (int)__ldg(fv->zlut + c);
+        return (int)__ldg(zlut + c);
     };
     // the hints are low by construction: forward walks with the membership compare of the other range kernels
     // (measured: loading three candidates at once instead, branch-free, is 1.5 % slower -- more instructions)
+    // (u0[nt] = +inf ends every walk: no bound check)
     auto walk = [&](int d, double edge, double delta) -> int {
-        while (d < nt && !(__dadd_rn(u0[d], delta) >= edge)) ++d;
+        while (!(__dadd_rn(u0[d], delta) >= edge)) ++d;
         return d;
     };
     // ---- summing a cell: the weight polynomial over draws [d0, d0 + n), the cell store, the normalisation sum -------
@@ -330,7 +366,9 @@ __device__ __forceinline__ double zr_exec(const DevModel *mp, const DevRun *rp, 
         }
         const int nmin = __reduce_min_sync(FULL, n);
         // idle lanes read the first record (valid memory, finite numbers) and multiply it by t = 0
-        const int ridx = active ? (j - fv->jbase) * RW + 2 : 2;
+        int jb;
+        asm volatile("ld.shared.s32 %0, [%1+-16];" : "=r"(jb) : "r"(u0_s32));
+        const int ridx = active ? (j - jb) * RW + 2 : 2;
         double a[P + 1];
         double a0;
         if constexpr (WIDE) {
@@ -377,7 +415,10 @@ __device__ __forceinline__ double zr_exec(const DevModel *mp, const DevRun *rp, 
             const double val = fma((double)n, a0, acc);
             if constexpr (WIDE) hrow_g[j] = val;
             else zr_sts(hrow_s32 + (unsigned)j * 8u, val);
-            part += __dmul_rn(__dmul_rn(val, fv->de), fv->dx);     // adv:143
+            double de, dx;
+            asm volatile("ld.shared.f64 %0, [%1+-32];" : "=d"(de) : "r"(u0_s32));
+            asm volatile("ld.shared.f64 %0, [%1+-24];" : "=d"(dx) : "r"(u0_s32));
+            part += __dmul_rn(__dmul_rn(val, de), dx);             // adv:143
         }
     };
     // one (row, interval) cell per lane and visit
@@ -716,7 +757,11 @@ __global__ void __launch_bounds__(NT, 2) adv_zrank_kernel(const __grid_constant_
         double *sdelta = reinterpret_cast<double *>(smem_raw + out.lay.sdelta);
         double *sbrk = reinterpret_cast<double *>(smem_raw + out.lay.sbrk);
         const double *recg = m.rng_rec;
-        for (int j = tid; j < M; j += NT) sbrk[j] = recg[(size_t)j * RW];
+        // lower edge of interval j = sbrk[j - 1], j in [0, M]: 0 in front, and the upper end of the last (closed) interval
+        // as the first double above it (v > u_max <=> v >= next(u_max))
+        for (int j = tid; j < M; j += NT)
+            sbrk[j] = j == M - 1 ? __longlong_as_double(__double_as_longlong(m.rng_u_max) + 1) : recg[(size_t)j * RW];
+        if (tid == 0) sbrk[-1] = 0.0;
         for (int i = tid; i < m.n_taps; i += NT) staps[i] = m.taps[i];
         const double x_start = m.ode_from_zero ? 0.0 : m.x_centers[0];
         for (int i = tid; i < X; i += NT) sdelta[i] = m.rng_sign * (m.x_centers[i] - x_start);
@@ -724,8 +769,9 @@ __global__ void __launch_bounds__(NT, 2) adv_zrank_kernel(const __grid_constant_
         if (tid == 0) {
             frame.de = (m.e_max - m.e_min) / (double)m.e_bins;
             frame.dx = (m.x_max - m.x_min) / (double)X;
-            frame.umax_next = __longlong_as_double(__double_as_longlong(m.rng_u_max) + 1);
             frame.zlut = run.zlut;
+            reinterpret_cast<double *>(smem_raw + out.lay.pa - 32)[0] = frame.de;     // ZR_MIRROR
+            reinterpret_cast<double *>(smem_raw + out.lay.pa - 32)[1] = frame.dx;
             frame.idx[0] = (long long)atomicAdd(out.work, 1ull);
         }
     }
@@ -920,7 +966,7 @@ __device__ __forceinline__ void zrm_exec(const DevModel &m, const DevRun &run, c
     const double delta = sdelta[row];
     const int hbase = row * hstride - hlo[row];            // H index of (row, E-bin j) is hbase + j
     const int row_lo = hlo[row];
-    auto edge_of = [&](int j) -> double { return j == 0 ? 0.0 : (j >= M ? fv->umax_next : brk[j - 1]); };
+    auto edge_of = [&](int j) -> double { return brk[j - 1]; };   // 0 <= j <= M (see the staging of sbrk)
     // first draw d in [lo, hi) with RN(u0[d] + dl) >= edge (hi when there is none): the membership compare of every range
     // kernel, by bisection
     auto first_ge = [&](int lo, int hi, double edge, double dl) -> int {
@@ -1070,14 +1116,17 @@ __global__ void __launch_bounds__(NT, 2) adv_zrank_multi_kernel(const __grid_con
         double *sdelta = reinterpret_cast<double *>(smem_raw + out.lay.sdelta);
         double *sbrk = reinterpret_cast<double *>(smem_raw + out.lay.sbrk);
         const double *recg = m.rng_rec;
-        for (int j = tid; j < M; j += NT) sbrk[j] = recg[(size_t)j * RW];
+        // lower edge of interval j = sbrk[j - 1], j in [0, M]: 0 in front, and the upper end of the last (closed) interval
+        // as the first double above it (v > u_max <=> v >= next(u_max))
+        for (int j = tid; j < M; j += NT)
+            sbrk[j] = j == M - 1 ? __longlong_as_double(__double_as_longlong(m.rng_u_max) + 1) : recg[(size_t)j * RW];
+        if (tid == 0) sbrk[-1] = 0.0;
         for (int i = tid; i < m.n_taps; i += NT) staps[i] = m.taps[i];
         const double x_start = m.ode_from_zero ? 0.0 : m.x_centers[0];
         for (int i = tid; i < X; i += NT) sdelta[i] = m.rng_sign * (m.x_centers[i] - x_start);
         if (tid == 0) {
             frame.de = (m.e_max - m.e_min) / (double)m.e_bins;
             frame.dx = (m.x_max - m.x_min) / (double)X;
-            frame.umax_next = __longlong_as_double(__double_as_longlong(m.rng_u_max) + 1);
             frame.zlut = nullptr;
             frame.idx[0] = (long long)atomicAdd(out.work, 1ull);
         }

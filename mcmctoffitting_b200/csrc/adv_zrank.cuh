@@ -46,6 +46,7 @@ constexpr float ZR_BIAS = 0.25f;         // cells the hint is lowered by (float 
 constexpr double ZR_MIN_SPREAD = 8.0;
 // Scalars the cell sums re-read at every use (they do not fit in registers next to four Horner chains) sit right below
 // the draw tile, whose shared-memory address is live in a register anyway: one LDS with an immediate offset each.
+constexpr int ZR_TPITCH = 128;           // floats per row of the threshold table when the cell has at most that many rows
 constexpr int ZR_MIRROR = 32;            // bytes: de f64 @-32 | dx f64 @-24 | jbase s32 @-16 | hint_a, hint_b f32 @-8
 
 // Byte offsets of the regions of adv_zrank_kernel's dynamic shared memory (host-computed).  Order:
@@ -302,7 +303,7 @@ __device__ __forceinline__ void zr_sts(unsigned a, double v) { asm volatile("st.
 // Work split as in range_exec_cells: a warp keeps ONE group of 32 rows and walks the trajectory-aligned interval
 // offsets of that group with a stride; the X % 32 leftover rows get warps of their own that pack R rows x (32/R)
 // offsets per visit.  The rank hints of the next visit are fetched (L2) while the current one is summed.
-template <int NT, int P, bool WIDE>
+template <int NT, int P, bool WIDE, int TP>
 __device__ __forceinline__ double zr_exec(const DevModel *mp, const DevRun *rp, const ModelOut *op, unsigned char *smem_raw,
                                        const ZrFrame *f, double *Hglobal) {
     __builtin_assume(__isShared(smem_raw));
@@ -326,7 +327,7 @@ __device__ __forceinline__ double zr_exec(const DevModel *mp, const DevRun *rp, 
     const volatile ZrFrame *fv = f;
     const int nt = (int)m.n_draws;
     const float *theta_t = m.rank_theta;
-    const int tstride = m.rank_stride;
+    const int tstride = TP > 0 ? TP : m.rank_stride;      // TP: the pitch as a compile-time constant (immediate load offsets)
     double part = 0.0;
     if (j_hi_all < j_lo_all) return part;                  // uniform: no row can be reached
     const int Gf = X >> 5, R = X & 31;
@@ -464,17 +465,20 @@ __device__ __forceinline__ double zr_exec(const DevModel *mp, const DevRun *rp, 
         int j = j_first;
         bool act = (unsigned)(j - r.jw_lo) < r.jw_n && n_vis > 0;
         float th0 = 0.0f, th1 = 0.0f;
+        const float *pt = r.th_row + (ptrdiff_t)j * tstride;
+        const int pstep = j_step * tstride;
         if (act) {
-            th0 = ldg_stream_f32(r.th_row + (size_t)j * tstride);
-            th1 = ldg_stream_f32(r.th_row + (size_t)(j + 1) * tstride);
+            th0 = ldg_stream_f32(pt);
+            th1 = ldg_stream_f32(pt + tstride);
         }
         for (int v = 0; v < n_vis; ++v) {
             const int jn = j + j_step;
+            pt += pstep;
             const bool actn = (unsigned)(jn - r.jw_lo) < r.jw_n && v + 1 < n_vis;
             float th0n = 0.0f, th1n = 0.0f;
             if (actn) {                                    // next visit's hints: in flight while this cell is summed
-                th0n = ldg_stream_f32(r.th_row + (size_t)jn * tstride);
-                th1n = ldg_stream_f32(r.th_row + (size_t)(jn + 1) * tstride);
+                th0n = ldg_stream_f32(pt);
+                th1n = ldg_stream_f32(pt + tstride);
             }
             cell(j, act, th0, th1, r.delta, r.hrow_s32, r.hrow_g);
             j = jn;
@@ -491,20 +495,23 @@ __device__ __forceinline__ double zr_exec(const DevModel *mp, const DevRun *rp, 
         int j = j_first;
         bool actA = (unsigned)(j - r.jw_lo) < r.jw_n && n_vis > 0, actB = (unsigned)(j + 1 - r.jw_lo) < r.jw_n && n_vis > 0;
         float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+        const float *pt = r.th_row + (ptrdiff_t)j * tstride;
+        const int pstep = j_step * tstride;
         if (actA || actB) {
-            t0 = ldg_stream_f32(r.th_row + (size_t)j * tstride);
-            t1 = ldg_stream_f32(r.th_row + (size_t)(j + 1) * tstride);
-            t2 = ldg_stream_f32(r.th_row + (size_t)(j + 2) * tstride);
+            t0 = ldg_stream_f32(pt);
+            t1 = ldg_stream_f32(pt + tstride);
+            t2 = ldg_stream_f32(pt + 2 * tstride);
         }
         for (int v = 0; v < n_vis; ++v) {
             const int jn = j + j_step;
+            pt += pstep;
             const bool more = v + 1 < n_vis;
             const bool actAn = (unsigned)(jn - r.jw_lo) < r.jw_n && more, actBn = (unsigned)(jn + 1 - r.jw_lo) < r.jw_n && more;
             float t0n = 0.0f, t1n = 0.0f, t2n = 0.0f;
             if (actAn || actBn) {                          // next visit's hints: in flight while these cells are summed
-                t0n = ldg_stream_f32(r.th_row + (size_t)jn * tstride);
-                t1n = ldg_stream_f32(r.th_row + (size_t)(jn + 1) * tstride);
-                t2n = ldg_stream_f32(r.th_row + (size_t)(jn + 2) * tstride);
+                t0n = ldg_stream_f32(pt);
+                t1n = ldg_stream_f32(pt + tstride);
+                t2n = ldg_stream_f32(pt + 2 * tstride);
             }
             int e0 = 0, e1 = 0, e2 = 0;
             double edge0 = 0.0, edge1 = 0.0;
@@ -739,7 +746,7 @@ __device__ __noinline__ void zr_finish(const DevModel *mp, const DevRun *rp, con
     }
 }
 
-template <int NT, int P, bool PROF = false>
+template <int NT, int P, bool PROF = false, int TP = 0>
 __global__ void __launch_bounds__(NT, 2) adv_zrank_kernel(const __grid_constant__ DevModel m, const __grid_constant__ DevRun run,
                                                           const double *__restrict__ theta, long long n_walkers,
                                                           const __grid_constant__ ModelOut out) {
@@ -791,13 +798,13 @@ __global__ void __launch_bounds__(NT, 2) adv_zrank_kernel(const __grid_constant_
         stage(0);
         if (st == PLANNED_SKIP) continue;
         if (frame.wide) {
-            const double part = zr_exec<NT, P, true>(&m, &run, &out, smem_raw, &frame, Hglobal);
+            const double part = zr_exec<NT, P, true, TP>(&m, &run, &out, smem_raw, &frame, Hglobal);
             __threadfence_block();
             __syncthreads();
             stage(1);
             zr_finish<NT, P, PROF, true>(&m, &run, &out, smem_raw, &frame, Hglobal, part);
         } else {
-            const double part = zr_exec<NT, P, false>(&m, &run, &out, smem_raw, &frame, nullptr);
+            const double part = zr_exec<NT, P, false, TP>(&m, &run, &out, smem_raw, &frame, nullptr);
             __syncthreads();
             stage(1);
             zr_finish<NT, P, PROF, false>(&m, &run, &out, smem_raw, &frame, nullptr, part);

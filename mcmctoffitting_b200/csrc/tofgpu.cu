@@ -280,7 +280,7 @@ int launch_model(tof_ctx *ctx, const double *d_theta, long long n, int run, Mode
                 oz.split_stride = (int)stride;
                 oz.wide_scratch = static_cast<double *>(ctx->d_wide.p);
                 if (prof) adv_zrank_kernel<512, 7, true><<<grid, 512, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
-                else if (ctx->zr_nt == 384) adv_zrank_kernel<384, 7, false><<<grid, 384, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
+                else if (ctx->dm.rank_stride == ZR_TPITCH) adv_zrank_kernel<512, 7, false, ZR_TPITCH><<<grid, 512, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
                 else adv_zrank_kernel<512, 7, false><<<grid, 512, ctx->zr_smem, st>>>(ctx->dm, ctx->runs[run], d_theta, n, oz);
                 ctx->last_model_launches = 1;
             } else if (ctx->band_enabled && !debug && (!ctx->fresh || (ctx->planned && out.n_split == 1))) {
@@ -770,9 +770,8 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
                     ctx->lay_zr = zrank_layout(cfg->x_bins, cfg->e_bins, cfg->tof_bins[0], (int)hcap, rcap, P, cfg->n_taps, Mi);
                     ctx->zr_smem = ctx->lay_zr.total;
                     int occz = 0;
-                    AdvKernel kz = adv_zrank_kernel<512, 7, false>, kzp = adv_zrank_kernel<512, 7, true>, kz3 = adv_zrank_kernel<384, 7, false>;
-                    // tuning knob; measured on the benchmark shape: 384 threads / 80 registers -9 %, 576 threads / 56 registers -13 %
-                    if (const char *v = std::getenv("TOFGPU_ZR_THREADS")) ctx->zr_nt = std::atoi(v) == 384 ? 384 : 512;
+                    // (measured on the benchmark shape: 384 threads / 80 registers -9 %, 576 threads / 56 registers -13 %)
+                    AdvKernel kz = adv_zrank_kernel<512, 7, false>, kzp = adv_zrank_kernel<512, 7, true>, kz3 = adv_zrank_kernel<512, 7, false, ZR_TPITCH>;
                     for (AdvKernel k2 : {kz, kzp, kz3}) {
                         CUC(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->zr_smem));
                         CUC(cudaFuncSetAttribute(k2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -815,7 +814,10 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
                             ug[k] = run_max;
                         }
                         const double x_start = cfg->ode_from_zero ? 0.0 : cfg->x_centers[0];
-                        std::vector<float> th((size_t)(Mi + 1) * cfg->x_bins);
+                        // rows j = -1 .. M + 1 (a pair visit prefetches j, j + 1, j + 2 around its window; the pad rows are
+                        // read by idle lanes only); up to ZR_TPITCH rows of the cell the pitch is that compile-time constant
+                        const int pitch = cfg->x_bins <= ZR_TPITCH ? ZR_TPITCH : cfg->x_bins;
+                        std::vector<float> th((size_t)(Mi + 3) * pitch, 1e30f);
                         for (int j = 0; j <= Mi; ++j) {
                             const double U = cfg->rng_breaks[j];
                             for (int i = 0; i < cfg->x_bins; ++i) {
@@ -830,11 +832,12 @@ int tof_create(const tof_config *cfg, tof_ctx **out) {
                                     const double fr = du > 0.0 ? (tq - ug[k - 1]) / du : 0.0;
                                     v = (float)(eg[k - 1] + fr * (eg[k] - eg[k - 1]));
                                 }
-                                th[(size_t)j * cfg->x_bins + i] = v;
+                                th[(size_t)(j + 1) * pitch + i] = v;
                             }
                         }
                         TRY(upload(ctx, th.data(), th.size(), &m.rank_theta));
-                        m.rank_stride = cfg->x_bins;
+                        m.rank_theta += pitch;                   // row 0 of the view = interval 0
+                        m.rank_stride = pitch;
                         ctx->zrank = true;
                         // what tof_get_stats reports as "the main model kernel" is now this one
                         ctx->stats.smem_bytes = (int)ctx->zr_smem;

@@ -85,6 +85,18 @@ __device__ __forceinline__ int range_interval(double v, const double *brk, const
     return j;
 }
 
+// range_interval in two steps, so that a caller can put the table loads of several lookups in flight together
+__device__ __forceinline__ int range_lut_guess(double v, const unsigned short *lut, double lut_inv, int lut_n) {
+    int c = (int)(v * lut_inv);
+    c = c < 0 ? 0 : (c > lut_n - 1 ? lut_n - 1 : c);
+    return lut[c];
+}
+__device__ __forceinline__ int range_refine(double v, int j, const double *brk, int M) {
+    while (j + 1 < M && v >= brk[j]) ++j;
+    while (j > 0 && v < brk[j - 1]) --j;
+    return j;
+}
+
 // u0 = u(E0): T1 cell from the exponent/mantissa bits, degree-7 Horner in t in [-1, 1].
 __device__ __forceinline__ double t1_eval(double E0, const DevModel &m) {
     double t;

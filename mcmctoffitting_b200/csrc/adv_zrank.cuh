@@ -202,10 +202,16 @@ __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const
         double vmax = u_hi + dl;
         vmin = vmin > 0.0 ? vmin : 0.0;
         vmax = vmax < umax ? vmax : umax;
+        double vm = __dadd_rn(u_med, dl);
+        vm = vm < 0.0 ? 0.0 : (vm > umax ? umax : vm);    // NaN (median draw outside the table) -> any interval
+        // the three table lookups of the row fly together (range_interval = lookup + refinement against the breaks)
+        const int g_lo = range_lut_guess(vmin, m.rng_lut, m.rng_lut_inv, m.rng_lut_n);
+        const int g_hi = range_lut_guess(vmax, m.rng_lut, m.rng_lut_inv, m.rng_lut_n);
+        const int g_md = range_lut_guess(vm, m.rng_lut, m.rng_lut_inv, m.rng_lut_n);
         int j_lo = 0, j_hi = 0;
         if (vmax >= vmin) {                               // otherwise this row gets nothing: any window will do
-            j_lo = range_interval(vmin, sbrk, m.rng_lut, m.rng_lut_inv, m.rng_lut_n, M);
-            j_hi = range_interval(vmax, sbrk, m.rng_lut, m.rng_lut_inv, m.rng_lut_n, M);
+            j_lo = range_refine(vmin, g_lo, sbrk, M);
+            j_hi = range_refine(vmax, g_hi, sbrk, M);
             j_lo = j_lo > 0 ? j_lo - 1 : 0;
             j_hi = j_hi < M - 1 ? j_hi + 1 : M - 1;
             atomicMin(&f->band[1], j_lo);
@@ -213,9 +219,21 @@ __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const
         }
         hlo_s[i] = j_lo;
         atomicMax(&f->band[0], j_hi - j_lo + 1);
-        double vm = __dadd_rn(u_med, dl);
-        vm = vm < 0.0 ? 0.0 : (vm > umax ? umax : vm);    // NaN (median draw outside the table) -> any interval
-        srow[i] = (vm == vm) ? range_interval(vm, sbrk, m.rng_lut, m.rng_lut_inv, m.rng_lut_n, M) : 0;
+        srow[i] = (vm == vm) ? range_refine(vm, g_md, sbrk, M) : 0;
+    }
+    if (tid == NT - 1) {                                   // (a thread of the last warp: the row loop keeps the first ones busy)
+        // rank hint of a threshold energy Th: cell = ((Th - e0)/spread - z_lo) * z_inv - bias
+        float ha = 0.0f, hb = 0.0f;
+        if (spread >= ZR_MIN_SPREAD && spread < 1e30 && run.zlut != nullptr) {
+            const double inv = 1.0 / spread;
+            ha = (float)(run.zlut_inv * inv);
+            hb = (float)((-e0 * inv - run.zlut_lo) * run.zlut_inv - (double)ZR_BIAS);
+            if (!(ha < 1e6f) || !(fabsf(hb) < 1e9f)) ha = hb = 0.0f;   // a degenerate draw set: no hints (walk from draw 0)
+        }
+        f->hint_a = ha;
+        f->hint_b = hb;
+        reinterpret_cast<float *>(smem_raw + out.lay.pa - 8)[0] = ha;   // ZR_MIRROR
+        reinterpret_cast<float *>(smem_raw + out.lay.pa - 8)[1] = hb;
     }
     __syncthreads();
     const int hstride = f->band[0];
@@ -237,22 +255,7 @@ __device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const
             f->band[1] = 0;
             f->band[2] = -1;
         }
-        // rank hint of a threshold energy Th: cell = ((Th - e0)/spread - z_lo) * z_inv - bias
-        float ha = 0.0f, hb = 0.0f;
-        if (spread >= ZR_MIN_SPREAD && spread < 1e30 && run.zlut != nullptr) {
-            const double inv = 1.0 / spread;
-            ha = (float)(run.zlut_inv * inv);
-            hb = (float)((-e0 * inv - run.zlut_lo) * run.zlut_inv - (double)ZR_BIAS);
-            if (!(ha < 1e6f) || !(fabsf(hb) < 1e9f)) ha = hb = 0.0f;   // a degenerate draw set: no hints (walk from draw 0)
-        }
-        f->hint_a = ha;
-        f->hint_b = hb;
-        {
-            unsigned char *mir = smem_raw + out.lay.pa;
-            reinterpret_cast<float *>(mir - 8)[0] = ha;
-            reinterpret_cast<float *>(mir - 8)[1] = hb;
-            *reinterpret_cast<int *>(mir - 16) = fits ? jbase : 0;
-        }
+        *reinterpret_cast<int *>(smem_raw + out.lay.pa - 16) = fits ? jbase : 0;   // ZR_MIRROR
         // visit grid: rows are walked along the trajectory, interval j = k + (srow[row] - srow[0]); the shift is
         // monotone in the row index.  Leftover rows (X % 32): R rows x (32/R) offsets per visit, on wB warps of their own
         // (in proportion to their share of the visits, at least one when there are any).

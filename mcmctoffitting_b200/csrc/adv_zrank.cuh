@@ -122,7 +122,7 @@ __device__ __forceinline__ float ldg_stream_f32(const float *p) {   // read-only
 // Work fetch, prior, per-row E-window, record staging, energy-loss lookup of the draws (adv:128-129), hint constants.
 // Returns PLANNED_DONE / PLANNED_SKIP (outside the prior: -inf written) / PLANNED_RUN.  Uniform; ends with a barrier.
 template <int NT, int P, bool PROF>
-__device__ __noinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const double *__restrict__ theta, long long n_walkers,
+__device__ __forceinline__ int zr_setup(const DevModel *mp, const DevRun *rp, const double *__restrict__ theta, long long n_walkers,
                                      const ModelOut *op, unsigned char *smem_raw, ZrFrame *f, int it) {
     __builtin_assume(__isShared(smem_raw));
     __builtin_assume(__isShared(f));
@@ -582,7 +582,7 @@ __device__ __noinline__ int zr_exact_bin(double xi, double di, double vd, double
 // log-likelihood (adv:160-181).  Same integers and the same floating-point results as adv_range_kernel's phases 2-5
 // given the same cell sums; `part` is this thread's share of the normalisation sum.
 template <int NT, int P, bool PROF, bool WIDE>
-__device__ __noinline__ void zr_finish(const DevModel *mp, const DevRun *rp, const ModelOut *op, unsigned char *smem_raw,
+__device__ __forceinline__ void zr_finish(const DevModel *mp, const DevRun *rp, const ModelOut *op, unsigned char *smem_raw,
                                        ZrFrame *f, double *Hglobal, double part) {
     __builtin_assume(__isShared(smem_raw));
     __builtin_assume(__isShared(f));

@@ -522,10 +522,10 @@ def run_gpu_arm(args):
         achieved = evals_per_launch * flop_per_eval / (k_ms * 1e-3) / 1e12
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE model call at this size (131072 walkers: the banded
-            # launch <512,7> plus the full-size launch <1024,7> over its overflow queue), from the ncu --set full capture
-            # summarised in profiles/r1_range_fp64_ncu_summary.txt; algorithmic bytes are evals * 24
-            "traffic": (2910464 * evals_per_launch // 131072) if ode == M.config.ODE_RANGE else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE model call at this size (131072 walkers, one launch of
+            # adv_zrank_kernel), from the ncu --set full capture summarised in profiles/r2_zrank_fp64_ncu_summary.txt;
+            # algorithmic bytes are evals * 24
+            "traffic": (2586368 * evals_per_launch // 131072) if ode == M.config.ODE_RANGE else None,
             "traffic_source": "profiles/r2_zrank_fp64_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of one "
                               "131072-walker launch, scaled by walkers per launch); algorithmic bytes are evals * 24",
             "kernel": ("adv_zrank_kernel<512,7> (one persistent launch per call, 2 CTAs/SM)"

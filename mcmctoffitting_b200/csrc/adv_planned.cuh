@@ -3,10 +3,12 @@
 // Same model, tables, shared-memory layout and arithmetic as adv_range_kernel (adv_range.cuh); what differs is how the
 // code is cut.  adv_range_kernel is one function: every phase of a walker is inlined into the persistent loop, the
 // compiler keeps the union of their live values in 64 registers, spills, re-derives pointers inside hot loops and
-// serialises the polynomial's Horner chains.  Here every phase is a function of its own (__noinline__ on purpose: a
-// call is a register-allocation firewall) and the few per-walker scalars cross phases through a small frame in shared
-// memory, so that the hot loop -- range_exec_cells -- is allocated almost alone and ptxas keeps four Horner chains in
-// flight per lane (dependent DFMA latency on B200: 8.8 cycles, issue interval 2.2: tools/dfma_latency.cu).
+// serialises the polynomial's Horner chains.  Here the hot loop -- range_exec_cells -- is a function of its own
+// (__noinline__ on purpose: a call is a register-allocation firewall) and the few per-walker scalars cross phases through
+// a small frame in shared memory, so that it is allocated almost alone and ptxas keeps four Horner chains in flight per
+// lane (dependent DFMA latency on B200: 8.8 cycles, issue interval 2.2: tools/dfma_latency.cu).  The set-up and finish
+// phases are inlined into the kernel: out of line they read the kernel parameters through generic pointers (LD.E
+// instead of constant-bank operands), which cost adv_zrank_kernel 8 % (measured there).
 //
 // Used for: FP64, n_draws <= RANGE_TILE, one T2 interval per E-bin (rng_identity), production output (lnprob only).
 // Everything else (debug spectra / cell counts, big or multi-tile draw sets, FP32 mode, draw splits, split E-bins) and
@@ -44,7 +46,7 @@ __device__ __forceinline__ void planned_stage_done(PlannedFrame *f, unsigned lon
 // prior: -inf written; band too wide: queued for the full-size launch), PLANNED_RUN with the frame filled and the tile
 // of u0 values staged otherwise.  Uniform over the CTA; ends with a barrier.
 template <int NT, int P, bool PROF>
-__device__ __noinline__ int planned_setup(const DevModel *mp, const DevRun *rp, const double *__restrict__ theta, long long n_walkers,
+__device__ __forceinline__ int planned_setup(const DevModel *mp, const DevRun *rp, const double *__restrict__ theta, long long n_walkers,
                                           const ModelOut *op, unsigned char *smem_raw, PlannedFrame *f) {
     __builtin_assume(__isShared(smem_raw));
     __builtin_assume(__isShared(f));
@@ -157,7 +159,7 @@ __device__ __noinline__ int planned_setup(const DevModel *mp, const DevRun *rp, 
 // Phases 2-5 of a walker: normalise (adv:143), np.rint + flight-time scatter (adv:146-159), density, timing response at
 // the observed bins and log-likelihood (adv:160-181).  Same arithmetic, in the same order, as adv_range_kernel.
 template <int NT, int P, bool PROF>
-__device__ __noinline__ void planned_finish(const DevModel *mp, const DevRun *rp, const ModelOut *op, unsigned char *smem_raw,
+__device__ __forceinline__ void planned_finish(const DevModel *mp, const DevRun *rp, const ModelOut *op, unsigned char *smem_raw,
                                             PlannedFrame *f) {
     __builtin_assume(__isShared(smem_raw));
     __builtin_assume(__isShared(f));

@@ -827,7 +827,7 @@ __global__ void __launch_bounds__(NT, 2) adv_zrank_kernel(const __grid_constant_
 // the partial sums meet in the cell with atomics (as in the streaming walk, the summation order of those few partials
 // is not fixed).  Normalisation, scatter, density and likelihood are zr_finish.
 template <int NT, int P>
-__device__ __noinline__ int zrm_setup(const DevModel *mp, const DevRun *rp, const double *__restrict__ theta, long long n_walkers,
+__device__ __forceinline__ int zrm_setup(const DevModel *mp, const DevRun *rp, const double *__restrict__ theta, long long n_walkers,
                                       const ModelOut *op, unsigned char *smem_raw, ZrFrame *f, int it, double *Hglobal) {
     __builtin_assume(__isShared(smem_raw));
     __builtin_assume(__isShared(f));

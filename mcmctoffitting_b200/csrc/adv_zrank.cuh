@@ -14,7 +14,9 @@
 //    reached by a short forward walk with the usual compare.  The hint only has to be low and close; the membership
 //    rule is untouched, so the cells are the ones adv_range_kernel / adv_planned_kernel produce, bit for bit.
 //    This removes the per-walker lookup build, the plan pass (18 % of the instructions of adv_planned_kernel), its
-//    barrier and the slot hand-over through the histogram.
+//    barrier and the slot hand-over through the histogram.  In memory Theta is interval-major (a warp's lanes = 32
+//    rows at nearby intervals share cache lines; row-major was measured 17 % slower), with pad rows around it and, for
+//    cells of up to ZR_TPITCH rows, a compile-time pitch: the three thresholds of a visit are one pointer + immediates.
 //  * the normalisation sum S = sum(H * dE * dx) (adv:143) is accumulated by the lane that produces a cell (no second
 //    pass over the histogram), and every cell of a row's window is written, zero or not (no histogram reset).
 //  * scatter (adv:146-159): rint(H/S * N) and the TOF bin of a cell are first formed from reciprocals (two products);
@@ -25,6 +27,10 @@
 //  * walkers whose E-band does not fit the banded histogram (sigma0 >~ 0.2) no longer wait for a second, full-size
 //    launch at 1 CTA/SM: the same CTA keeps their cell sums in an L2-resident scratch histogram (WIDE instantiation
 //    of the same phase functions) -- one launch per call, no serial tail.
+//  * the phases are __forceinline__ functions of one kernel body: out of line they would receive the kernel parameters
+//    by pointer and read every field with a generic load (measured: 8 % slower, with a stack frame for the calls).
+//    What keeps the polynomial loop's registers free instead: per-walker scalars are re-read from shared memory where
+//    they are used -- from a small mirror at fixed offsets below the draw tile (ZR_MIRROR), whose address is live anyway.
 //
 // Used for: FP64, n_draws <= RANGE_TILE, one T2 interval per E-bin (rng_identity), production output (lnprob only),
 // bound draws.  The second kernel of this file, adv_zrank_multi_kernel, serves bigger draw sets (the reference's own

@@ -60,7 +60,7 @@ inline RangeLayout range_layout(int X, int E, int T, int hcap, int rcap, int P, 
     L.sdelta = (unsigned)o;    o += (size_t)X * 8;
     L.lut = (unsigned)o;       o += (size_t)((lut_n + 7) / 8) * 8 * 2;
     L.ulut = (unsigned)o;      o += range_ulut_bytes(E);
-    L.srow = (unsigned)o;      o += (size_t)X * 4;
+    L.srow = (unsigned)o;      o += (size_t)(X + (X & 1)) * 4;   // (odd X: keeps what follows 8-byte aligned)
     L.hlo = (unsigned)o;       o += (size_t)(X + (X & 1)) * 4;
     L.sbrk = (unsigned)o;      o += (size_t)rng_n * 8;
     L.sbin = (unsigned)o;      o += (((size_t)rng_n * 2 + 15) / 16) * 16;

@@ -77,7 +77,7 @@ inline RangeLayout zrank_layout(int X, int E, int T, int hcap, int rcap, int P, 
     L.staps = (unsigned)o;     o += (size_t)n_taps * 8;
     L.scratch = (unsigned)o;   o += 40 * 8;
     L.sdelta = (unsigned)o;    o += (size_t)X * 8;
-    L.srow = (unsigned)o;      o += (size_t)X * 4;
+    L.srow = (unsigned)o;      o += (size_t)(X + (X & 1)) * 4;   // (odd X: keeps what follows 8-byte aligned)
     L.hlo = (unsigned)o;       o += (size_t)(X + (X & 1)) * 4;
     o += 8;                                       // sbrk[-1] = 0: sbrk[j - 1] is the lower edge of interval j for every j in [0, M]
     L.sbrk = (unsigned)o;      o += (size_t)rng_n * 8;

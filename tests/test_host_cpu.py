@@ -408,3 +408,60 @@ def test_div_by_recip_restated_is_correctly_rounded():
         cases.append((a, b))
     for a, b in cases:
         assert div_by_recip(a, b, 1.0 / b) == a / b, (a, b)
+
+
+def test_shared_memory_layouts_stay_aligned(tmp_path):
+    """range_layout / zrank_layout (host-computed byte offsets of the kernels' dynamic shared memory): every region keeps
+    the alignment its accesses need for any cell shape -- 16 bytes where records are read with LDS.128, 8 for doubles.
+    Regression: an odd x_bins used to leave the interval breaks 4-byte aligned ("misaligned address" on the GPU).
+    The two functions are host code in the kernel headers: compiled into a small host program with nvcc and run here."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    csrc = os.path.join(os.path.dirname(M.__file__), "csrc")
+    src = tmp_path / "layouts.cu"
+    src.write_text(r'''
+#include "adv_zrank.cuh"
+#include <cstdio>
+using namespace tof;
+static int bad = 0;
+static void need(unsigned off, unsigned a, const char *what, int X, int E, int T, int hcap) {
+    if (off % a) { if (bad++ < 10) std::printf("%s = %u not %u-aligned (X=%d E=%d T=%d hcap=%d)\n", what, off, a, X, E, T, hcap); }
+}
+int main() {
+    const int Es[] = {50, 120, 240, 241}, Ts[] = {50, 64, 2048, 2049, 4001};
+    long n = 0;
+    for (int X = 1; X <= 300; ++X) for (int E : Es) for (int T : Ts) for (int hk = 0; hk < 3; ++hk) {
+        const int hcap = hk == 0 ? X * 8 : (hk == 1 ? X * E : X * 8 + 2 * hk + 1);
+        for (int taps : {7, 16}) {
+            const RangeLayout z = zrank_layout(X, E, T, hcap, E < 128 ? E : 128, 7, taps, E);
+            need(z.pa, 16, "zrank pa", X, E, T, hcap);  need(z.rec, 16, "zrank rec", X, E, T, hcap);
+            need(z.svd, 8, "zrank svd", X, E, T, hcap);  need(z.ulut, 8, "zrank ulut", X, E, T, hcap);
+            need(z.staps, 8, "zrank staps", X, E, T, hcap);  need(z.scratch, 8, "zrank scratch", X, E, T, hcap);
+            need(z.sdelta, 8, "zrank sdelta", X, E, T, hcap);  need(z.srow, 4, "zrank srow", X, E, T, hcap);
+            need(z.hlo, 4, "zrank hlo", X, E, T, hcap);  need(z.sbrk, 8, "zrank sbrk", X, E, T, hcap);
+            if (z.pa < (unsigned)hcap * 8u + ZR_MIRROR || z.total < z.sbrk + (unsigned)E * 8u) { ++bad; std::printf("zrank extents X=%d\n", X); }
+            const RangeLayout r = range_layout(X, E, T, hcap, E < 128 ? E : 128, 7, taps, 1000 + X, E);
+            need(r.pa, 16, "range pa", X, E, T, hcap);  need(r.rec, 16, "range rec", X, E, T, hcap);
+            need(r.svd, 8, "range svd", X, E, T, hcap);  need(r.staps, 8, "range staps", X, E, T, hcap);
+            need(r.scratch, 8, "range scratch", X, E, T, hcap);  need(r.sdelta, 8, "range sdelta", X, E, T, hcap);
+            need(r.lut, 2, "range lut", X, E, T, hcap);  need(r.ulut, 4, "range ulut", X, E, T, hcap);
+            need(r.srow, 4, "range srow", X, E, T, hcap);  need(r.hlo, 4, "range hlo", X, E, T, hcap);
+            need(r.sbrk, 8, "range sbrk", X, E, T, hcap);  need(r.sbin, 2, "range sbin", X, E, T, hcap);
+            if (r.total < r.sbin + (unsigned)E * 2u) { ++bad; std::printf("range extents X=%d\n", X); }
+            n += 2;
+        }
+    }
+    std::printf("%ld layouts, %d misaligned\n", n, bad);
+    return bad ? 1 : 0;
+}
+''')
+    exe = tmp_path / "layouts"
+    cmd = [nvcc, "-std=c++17", "-O0", "-gencode", "arch=compute_100a,code=sm_100a", "-I", csrc, "-o", str(exe), str(src)]
+    comp = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert comp.returncode == 0, comp.stderr[-2000:]
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout[-2000:]
+    assert "0 misaligned" in run.stdout

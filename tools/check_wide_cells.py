@@ -17,6 +17,9 @@ for xb, eb in ((160, 120), (129, 150), (33, 240)):
         os.environ["TOFGPU_RANGE_ZRANK"] = env
         cfg = M.config.sweep(ode_mode=M.config.ODE_RANGE, x_bins=xb, e_bins=eb)
         fn = M.make_lnprob(cfg, obs, z)
+        if os.environ.get("REALISTIC_OBS"):                 # observables = a model realisation: finite log-likelihoods
+            real = np.rint(1e4 * fn.model.model_batch(np.array([[1050.0, 0.10]]), run=0, stage="spread")[0])
+            fn.bind_observables(real)
         try:
             res[label] = fn.batch(th)
         except Exception as e:
